@@ -1,0 +1,219 @@
+/* synthobs_b200 — C-ABI of the B200 (sm_100a) hot paths of SynthObs.
+ *
+ * The reference (stephenmwilkins/SynthObs) is pure Python/NumPy and has no FFI of
+ * its own: the drop-in boundary is the Python call surface of
+ * synthobs.sed.models / synthobs.morph.images.  This header is the boundary one
+ * level below it: every entry point replaces one Python hot loop of the reference
+ * (cited per function, paths relative to the reference root) and is what a
+ * ctypes/cffi binding in the reference would bind (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain C: raw pointers, int64 sizes, no torch / C++ types.
+ *  - pointers are DEVICE pointers unless the parameter is documented "host".
+ *  - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and
+ *    asynchronous unless documented "synchronises".
+ *  - the caller allocates every input, output and workspace buffer; nothing is
+ *    allocated, retained or freed behind the ABI (except cached TMA descriptors
+ *    and kernel attributes, which hold no user memory).
+ *  - return value: 0 = ok, >0 = cudaError_t of the failing CUDA call,
+ *    <0 = SO_ERR_* argument error.  Nothing throws across the ABI.
+ *  - particle inputs are float64, exactly what the reference API receives
+ *    (np.load of X, Y, Ages, ..., synthobs/core.py:17-22); index decisions are
+ *    made in float64 (bit-exact against np.argmin), values are computed in FP32.
+ */
+#ifndef SYNTHOBS_B200_H
+#define SYNTHOBS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO_OK 0
+#define SO_ERR_BAD_ARG (-1)
+#define SO_ERR_TOO_LARGE (-2)
+#define SO_ERR_WORKSPACE (-3)
+#define SO_ERR_UNSUPPORTED (-4)
+
+#define SO_MAX_FILTERS 32 /* filters per so_sed_broadband launch (smem tables) */
+#define SO_TILE 64        /* image tile edge in pixels (so_img_*) */
+
+/* library / build identification; returns a static string */
+const char* so_version(void);
+/* 1 if a CUDA device of compute capability 10.x is present, else 0 */
+int so_device_ok(void);
+
+/* ------------------------------------------------------------------------- */
+/* SED path                                                                   */
+/* ------------------------------------------------------------------------- */
+
+/* K1+K3 — nearest-grid-point SSP lookup + per-particle broadband luminosity/flux
+ * + per-galaxy sums.  Replaces the particle loops of generate_Lnu_array /
+ * generate_Fnu_array (synthobs/sed/models.py:88-135, :153-200) for ALL filters in
+ * one pass, and the np.sum of generate_Lnu / generate_Fnu (:74-85, :139-150).
+ *
+ * NGP index: the reference does ia = argmin|log10age_grid - (log10(Age)+6)|
+ * (:108-114).  That decision is monotone in Age, so the host pre-computes, with
+ * the SAME NumPy/libm expression, the float64 thresholds age_thr[na-1] (smallest
+ * Age that maps to node i+1) and z_thr[nz-1]; the kernel only compares float64
+ * values, which reproduces np.argmin bit-exactly without a device log10.
+ * young_thr = smallest Age with log10(Age)+6 >= log10t_BC (:124).
+ *
+ *   masses, ages, metals : [n] float64
+ *   tau_ism, tau_bc      : [n] float64 or NULL (= zeros, :92-93)
+ *   seg_offsets          : [n_seg+1] int64 CSR offsets of the galaxies, or NULL
+ *                          with n_seg = 1 (one galaxy = all particles)
+ *   age_thr [na-1], z_thr [nz-1] : float64 thresholds (device)
+ *   age_guess_a, age_guess_b     : optional closed-form first guess of the age
+ *                          node, floor(log2f(Age)*a + b), for log-uniform age grids;
+ *                          it is always corrected against age_thr, so it affects
+ *                          speed only.  a = 0 selects a binary search.
+ *   tab_inc, tab_tn      : [n_filters, na*nz] float32: stellar_incident and
+ *                          (stellar_transmitted + nebular) per filter (:131-133)
+ *   k_ism, k_bc          : HOST [n_filters] float64 dust-curve value at the filter
+ *                          pivot wavelength (:95-101), or NULL when the model has
+ *                          no such dust (T = 1)
+ *   out_pf               : [n_filters, n] float32 per-particle values or NULL
+ *   out_sums             : [n_seg, n_filters] float64 per-galaxy sums or NULL
+ *   out_cell             : [n] int32 = ia*nz + iZ + (young ? 65536 : 0) or NULL
+ *   workspace            : so_sed_broadband_workspace_bytes(n, n_seg, n_filters)
+ */
+int64_t so_sed_broadband_workspace_bytes(int64_t n, int64_t n_seg, int32_t n_filters);
+int so_sed_broadband(const double* masses, const double* ages, const double* metals,
+                     const double* tau_ism, const double* tau_bc, int64_t n,
+                     const int64_t* seg_offsets, int64_t n_seg,
+                     const double* age_thr, int32_t na, const double* z_thr, int32_t nz, double young_thr,
+                     double age_guess_a, double age_guess_b,
+                     const float* tab_inc, const float* tab_tn, int32_t n_filters,
+                     const double* k_ism, const double* k_bc, double fesc,
+                     float* out_pf, double* out_sums, int32_t* out_cell,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K2 — per-galaxy grid-weight histogram H[n_seg, 2*na*nz] (old cells then young
+ * cells), H = sum of particle masses per SSP cell: the left operand of the
+ * dust-free contractions of generate_SED (synthobs/sed/models.py:277,281,295,
+ * 306-307) and of generate_log10Q (:206-221).  `cell` is so_sed_broadband's
+ * out_cell.  ld_h >= 2*na*nz is the row stride of H in floats.  H_lo (optional)
+ * receives the TF32 residual of H for the 3xTF32 GEMM. */
+int64_t so_sed_hist_workspace_bytes(int64_t n_seg, int32_t ncell);
+int so_sed_hist(const double* masses, const int32_t* cell, int64_t n,
+                const int64_t* seg_offsets, int64_t n_seg, int32_t ncell,
+                float* H, float* H_lo, int64_t ld_h,
+                void* workspace, int64_t workspace_bytes, void* stream);
+
+/* split x into TF32-exact hi and lo = x - hi (elementwise), for the 3xTF32 GEMM */
+int so_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+
+/* K4/K5 — C[M,N] = A[M,K] * B[N,K]^T in error-compensated 3xTF32 on the tcgen05
+ * tensor cores (FP32 accumulate in TMEM): A*B = Ahi*Bhi + Ahi*Blo + Alo*Bhi.
+ * Replaces the dense contractions  hist x SSP-grid  (generate_SED dust-free
+ * spectra, synthobs/sed/models.py:277-310),  grid x filter-weights
+ * (create_Lnu_grid / create_Fnu_grid, :39-67) and  spectra x filter-weights.
+ * All operands are K-major (row-major with K contiguous), float32, 16-byte
+ * aligned; lda/ldb/ldc are row strides in elements, multiples of 4.
+ * M, N, K arbitrary (TMA zero-fills out-of-range tiles). */
+int so_gemm_3xtf32(const float* A_hi, const float* A_lo, int64_t lda,
+                   const float* B_hi, const float* B_lo, int64_t ldb,
+                   float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream);
+/* same product on the FP32 FMA pipe (one operand set, no split); used to validate
+ * the tensor-core kernel on the device and for very small problems */
+int so_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb,
+                float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream);
+
+/* K6 — dust-attenuated spectra of generate_SED (synthobs/sed/models.py:285-310):
+ * BC, total and no_HII_no_BC need T_i(lambda) = exp(-tauV_i * k(lambda)) per
+ * particle and wavelength, which does not factor through the histogram.
+ * Particles must be sorted by cell (`order` = permutation, `cell_sorted` the
+ * sorted keys).  grid_inc / grid_tn: [2? no: ncell, n_lam] float32 rows
+ * (stellar_incident, transmitted+nebular).  k_ism_lam / k_bc_lam: [n_lam] float32
+ * or NULL.  Outputs [n_lam] float32 each (NULL = not wanted). */
+int64_t so_sed_dust_spectra_workspace_bytes(int64_t n, int32_t n_lam);
+int so_sed_dust_spectra(const double* masses, const double* tau_ism, const double* tau_bc,
+                        const int32_t* cell_sorted, const int32_t* order, int64_t n,
+                        const float* grid_inc, const float* grid_tn, int32_t ncell, int32_t n_lam,
+                        const float* k_ism_lam, const float* k_bc_lam, double fesc,
+                        float* out_bc, float* out_total, float* out_nohii,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Imaging path                                                               */
+/* ------------------------------------------------------------------------- */
+
+/* K8a — selection + nearest-pixel index.  Replaces images.core's selection
+ * (synthobs/morph/images.py:47-50) and the per-particle argmin of :67.
+ * G = the float64 np.linspace pixel centres (uploaded by the host so the device
+ * compares against the very same values).  ix/iy = argmin|G - x| (first minimum)
+ * or -1 when the particle is outside |x| < half_width & |y| < half_width. */
+int so_img_ngp_index(const double* X, const double* Y, int64_t n,
+                     const double* G, int32_t ndim, double half_width,
+                     int32_t* ix, int32_t* iy, void* stream);
+
+/* K7 — distance to the k-th nearest neighbour in 2-D, counting the particle
+ * itself as the first (cKDTree.query(k)[..., -1], synthobs/morph/images.py:83-85).
+ * Only particles with ix >= 0 take part; dk = 0 for the others.  dk = +inf when
+ * k exceeds the number of selected particles.  Exact (uniform-grid ring search
+ * with a conservative stopping rule), float64.  Synchronises once (reads the
+ * selected count back). */
+int64_t so_knn_workspace_bytes(int64_t n, int32_t k);
+int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
+                        int32_t k, double half_width, double* dk,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K8b..K9 — kernel-smoothed deposition.  Replaces the adaptive loop of
+ * images.core (synthobs/morph/images.py:87-97): per particle a Gaussian of
+ * FWHM = max(dk, 0.01), normalised by its SUM OVER THE IMAGE PIXELS, times L.
+ * Also produces the NGP products of :66-69 (`simple`, `hist`) when requested.
+ *
+ * Truncation: the Gaussian is evaluated on the pixel box +-W around the NGP
+ * pixel, W = ceil(support_sigmas * sigma / pitch), clipped to the image, and
+ * normalised over that same box (flux is conserved exactly as in the
+ * reference); support_sigmas <= 0 means full image support (reference
+ * semantics; affordable for small images).  A particle whose largest float64
+ * term exp(-d^2/2 sigma^2) underflows to 0 is dropped, as the reference does
+ * (`if sgauss > 0`, :97).
+ *
+ * Two phases because the number of (particle, tile) pairs is data dependent:
+ *   so_img_plan      computes per-particle records + pair counts; synchronises
+ *                    and returns the pair count in *n_pairs (host).
+ *   so_img_deposit   bins the pairs per 64x64 tile (stable radix sort: bit-exact,
+ *                    order-deterministic tile lists), accumulates each tile in
+ *                    shared memory/registers (no global atomics) and writes every
+ *                    pixel once.
+ *
+ *   L        : [n_chan, n] float64 weights (n_chan images share positions/sigma)
+ *   dk       : [n] float64 k-th neighbour distance, or NULL for NGP only
+ *   data     : [n_chan, ndim, ndim] float32 smoothed images (row = y) or NULL
+ *   simple   : [n_chan, ndim, ndim] float32 NGP images or NULL
+ *   hist     : [ndim, ndim] float32 NGP counts or NULL
+ *   tile_ids / pair_pids (optional, for the tile-assignment parity test):
+ *              [n_pairs] int32 sorted pair list as used by the kernel
+ *   stats    : HOST double[4]: pairs, in-support (particle,pixel) deposits
+ *              evaluated, selected particles, dropped particles  (or NULL)
+ */
+int64_t so_img_plan_workspace_bytes(int64_t n);
+int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X, const double* Y,
+                const double* dk, int64_t n, const double* G, int32_t ndim,
+                double support_sigmas, void* plan_workspace, int64_t plan_workspace_bytes,
+                int64_t* n_pairs, double* stats, void* stream);
+int64_t so_img_deposit_workspace_bytes(int64_t n, int64_t n_pairs, int32_t ndim, int32_t n_chan);
+int so_img_deposit(const void* plan_workspace, const double* L, int64_t n, int32_t n_chan,
+                   int32_t ndim, int64_t n_pairs,
+                   float* data, float* simple, float* hist,
+                   int32_t* tile_ids, int32_t* pair_pids,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K11 — rebin by block SUM (synthobs/morph/images.py:19-22): in [n_img, n*s, n*s]
+ * -> out [n_img, n, n]. */
+int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int32_t s, void* stream);
+
+/* elementwise helper for the PSF step (K10): out = a * b on interleaved complex
+ * float32 spectra, b broadcast over the leading n_img images.  The FFTs
+ * themselves are cuFFT through torch.fft (convolve_fft of images.py:78,202). */
+int so_complex_mul_bcast(const float* a, const float* b, float* out, int64_t n_complex, int32_t n_img,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNTHOBS_B200_H */

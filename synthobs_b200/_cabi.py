@@ -1,0 +1,106 @@
+"""ctypes binding of libsynthobs_b200.so (the C-ABI declared in include/synthobs_b200.h).
+
+This is the only place Python touches the CUDA kernels.  There is no CPU path:
+if the library is missing the import fails with the build command, and every
+compute entry point raises when no sm_100 device is present.  PyTorch is used by
+the callers only for device memory, streams and torch.distributed.
+"""
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libsynthobs_b200.so')
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        'synthobs_b200: %s not found. Build it first: `python -m synthobs_b200.build` '
+        '(or __graft_entry__.build()). There is no CPU fallback.' % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+P = c_void_p
+I64 = c_int64
+I32 = c_int32
+D = c_double
+
+# name -> (restype, argtypes); must list every symbol declared in include/synthobs_b200.h
+SIGNATURES = {
+    'so_version': (c_char_p, []),
+    'so_device_ok': (c_int, []),
+    'so_sed_broadband_workspace_bytes': (I64, [I64, I64, I32]),
+    'so_sed_broadband': (c_int, [P, P, P, P, P, I64, P, I64, P, I32, P, I32, D, D, D, P, P, I32,
+                                 POINTER(c_double), POINTER(c_double), D, P, P, P, P, I64, P]),
+    'so_sed_hist_workspace_bytes': (I64, [I64, I32]),
+    'so_sed_hist': (c_int, [P, P, I64, P, I64, I32, P, P, I64, P, I64, P]),
+    'so_split_tf32': (c_int, [P, P, P, I64, P]),
+    'so_gemm_3xtf32': (c_int, [P, P, I64, P, P, I64, P, I64, I64, I64, I64, P]),
+    'so_gemm_f32': (c_int, [P, I64, P, I64, P, I64, I64, I64, I64, P]),
+    'so_sed_dust_spectra_workspace_bytes': (I64, [I64, I32]),
+    'so_sed_dust_spectra': (c_int, [P, P, P, P, P, I64, P, P, I32, I32, P, P, D, P, P, P, P, I64, P]),
+    'so_img_ngp_index': (c_int, [P, P, I64, P, I32, D, P, P, P]),
+    'so_knn_workspace_bytes': (I64, [I64, I32]),
+    'so_knn_kth_distance': (c_int, [P, P, P, I64, I32, D, P, P, I64, P]),
+    'so_img_plan_workspace_bytes': (I64, [I64]),
+    'so_img_plan': (c_int, [P, P, P, P, P, I64, P, I32, D, P, I64, POINTER(c_int64), POINTER(c_double), P]),
+    'so_img_deposit_workspace_bytes': (I64, [I64, I64, I32, I32]),
+    'so_img_deposit': (c_int, [P, P, I64, I32, I32, I64, P, P, P, P, P, P, I64, P]),
+    'so_img_rebin': (c_int, [P, P, I32, I32, I32, P]),
+    'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, P]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+_ERR = {-1: 'SO_ERR_BAD_ARG', -2: 'SO_ERR_TOO_LARGE', -3: 'SO_ERR_WORKSPACE', -4: 'SO_ERR_UNSUPPORTED'}
+
+
+class SynthObsCudaError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise SynthObsCudaError('%s failed: %s' % (what, _ERR.get(rc, rc)))
+    raise SynthObsCudaError('%s failed: CUDA error %d' % (what, rc))
+
+
+_device_checked = False
+
+
+def require_device():
+    """Fail loudly when there is no B200-class device: no CPU fallback exists."""
+    global _device_checked
+    if _device_checked:
+        return
+    import torch
+    if not torch.cuda.is_available() or not lib.so_device_ok():
+        raise SynthObsCudaError('synthobs_b200 needs a CUDA device of compute capability 10.x (B200); '
+                                'none is visible and there is no CPU fallback')
+    _device_checked = True
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_doubles(values):
+    if values is None:
+        return None
+    arr = (c_double * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def version():
+    return lib.so_version().decode()

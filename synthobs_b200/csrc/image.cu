@@ -1,0 +1,622 @@
+// Imaging hot path (sm_100a): nearest-pixel index, tile binning, kernel-smoothed
+// deposition, rebin.
+//
+// Reference behaviour reproduced (paths relative to the reference root):
+//   synthobs/morph/images.py:47-50   selection |x|,|y| < width/2
+//   synthobs/morph/images.py:66-69   NGP histogram (simple, hist)
+//   synthobs/morph/images.py:87-97   adaptive Gaussian deposit, normalised by its sum over the image
+//   synthobs/morph/images.py:19-22   rebin (block sum)
+//
+// Design: the Gaussian is separable, so one particle's contribution to a
+// 64x64 tile is a rank-1 update  tile += (w * ey) (x) ex.  Particles are binned per tile with a
+// stable radix sort (deterministic lists), each work item (tile, chunk of the tile's list) keeps
+// its 64x64 accumulator in registers (8x4 per thread, 128 threads), stages the per-particle
+// factor vectors in shared memory, and writes its tile exactly once with plain stores; tiles
+// split over several items are summed by a second kernel in fixed order.  No global atomics
+// touch pixels.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kT = SO_TILE;          // tile edge
+constexpr int kDepThreads = 128;     // deposit CTA
+constexpr int kP = 32;               // particles staged per phase
+
+struct PlanView {
+    float* ux;        // (x - G[ix]) / pitch
+    float* uy;
+    float* cpx;       // log2(e) * pitch^2 / (2 sigma^2)
+    float* wnorm;     // 1 / (Sx * Sy), 0 for dropped particles
+    int32_t* ix;
+    int32_t* iy;
+    int32_t* W;       // support half width in pixels
+    int64_t* offs;    // [n+1] pair offsets (exclusive scan of the tile counts)
+    unsigned long long* stats;  // [4] pairs, deposits, selected, dropped
+    void* cub_tmp;
+    int64_t cub_tmp_bytes;
+};
+
+static int64_t scan_tmp_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceScan::ExclusiveSum((void*)nullptr, b, (int64_t*)nullptr, (int64_t*)nullptr, (int)(n + 1));
+    return (int64_t)b;
+}
+
+static PlanView carve_plan(void* ws, int64_t bytes, int64_t n, bool* ok) {
+    SoArena a(ws, bytes);
+    PlanView v;
+    v.ux = a.take<float>(n);
+    v.uy = a.take<float>(n);
+    v.cpx = a.take<float>(n);
+    v.wnorm = a.take<float>(n);
+    v.ix = a.take<int32_t>(n);
+    v.iy = a.take<int32_t>(n);
+    v.W = a.take<int32_t>(n);
+    v.offs = a.take<int64_t>(n + 1);
+    v.stats = a.take<unsigned long long>(4);
+    v.cub_tmp_bytes = scan_tmp_bytes(n);
+    v.cub_tmp = a.take<char>(v.cub_tmp_bytes);
+    if (ok) *ok = a.ok();
+    return v;
+}
+
+__global__ void ngp_index_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n,
+                                 const double* __restrict__ G, int ndim, double hw,
+                                 int32_t* __restrict__ ix, int32_t* __restrict__ iy) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = X[i], y = Y[i];
+    const bool sel = (fabs(x) < hw) && (fabs(y) < hw);   // images.py:47 (strict)
+    int rx = -1, ry = -1;
+    if (sel) {
+        const double g0 = G[0];
+        const double inv = (ndim > 1) ? (double)(ndim - 1) / (G[ndim - 1] - g0) : 0.0;
+        const double v[2] = {x, y};
+        int r[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            int k0 = (int)floor((v[a] - g0) * inv + 0.5);
+            k0 = max(0, min(ndim - 1, k0));
+            // literal first-minimum argmin over the neighbourhood of the closed-form guess,
+            // on the same float64 G values the reference compares (images.py:67)
+            int lo = max(0, k0 - 2), hi = min(ndim - 1, k0 + 2);
+            int best = lo;
+            double bd = fabs(G[lo] - v[a]);
+            for (int k = lo + 1; k <= hi; ++k) {
+                const double d = fabs(G[k] - v[a]);
+                if (d < bd) { bd = d; best = k; }
+            }
+            r[a] = best;
+        }
+        rx = r[0]; ry = r[1];
+    }
+    ix[i] = rx; iy[i] = ry;
+}
+
+// one warp per particle: support box, normalisation sums, tile count
+__global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ ix_in, const int32_t* __restrict__ iy_in,
+                                                   const double* __restrict__ X, const double* __restrict__ Y,
+                                                   const double* __restrict__ dk, int64_t n,
+                                                   const double* __restrict__ G, int ndim, double R,
+                                                   PlanView pv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long my_dep = 0, my_sel = 0, my_drop = 0, my_pairs = 0;
+    if (p < n) {
+        const int ip = ix_in[p], jp = iy_in[p];
+        int64_t count = 0;
+        float ux = 0.f, uy = 0.f, cpx = 0.f, wn = 0.f;
+        int W = 0;
+        if (ip >= 0) {
+            const double pitch = (ndim > 1) ? (G[ndim - 1] - G[0]) / (double)(ndim - 1) : 1.0;
+            const double dx0 = X[p] - G[ip], dy0 = Y[p] - G[jp];
+            bool dropped = false;
+            if (dk) {
+                const double fwhm = fmax(dk[p], 0.01);               // images.py:89
+                const double sigma = __ddiv_rn(fwhm, 2.355);         // images.py:91
+                const double two_s2 = __dmul_rn(2.0, __dmul_rn(sigma, sigma));
+                // the reference drops the particle when every float64 term underflows (images.py:95-97)
+                const double amin = __ddiv_rn(__dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0)), two_s2);
+                dropped = exp(-amin) <= 0.0;
+                const double c = 1.4426950408889634 * pitch * pitch / two_s2;
+                cpx = (float)c;
+                if (R > 0.0) {
+                    const double w = ceil(__ddiv_rn(__dmul_rn(R, sigma), pitch));
+                    W = (w >= (double)ndim) ? ndim : (int)w;
+                } else {
+                    W = ndim;
+                }
+                if (!(sigma < __longlong_as_double(0x7ff0000000000000LL))) W = ndim;
+            }
+            ux = (float)(dx0 / pitch);
+            uy = (float)(dy0 / pitch);
+            if (dropped || !dk) W = dk ? 0 : 0;
+            const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
+            const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
+            if (dk && !dropped) {
+                float sx = 0.f, sy = 0.f;
+                for (int k = kx0 + lane; k <= kx1; k += 32) {
+                    const float fk = (float)k;
+                    sx += exp2f(-cpx * fk * (fk - 2.f * ux));
+                }
+                for (int k = ky0 + lane; k <= ky1; k += 32) {
+                    const float fk = (float)k;
+                    sy += exp2f(-cpx * fk * (fk - 2.f * uy));
+                }
+                sx = warp_sum(sx);
+                sy = warp_sum(sy);
+                wn = 1.0f / (sx * sy);
+                my_dep = (unsigned long long)(kx1 - kx0 + 1) * (unsigned long long)(ky1 - ky0 + 1);
+            }
+            const int tx0 = (ip + kx0) / kT, tx1 = (ip + kx1) / kT;
+            const int ty0 = (jp + ky0) / kT, ty1 = (jp + ky1) / kT;
+            count = (int64_t)(tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+            my_sel = 1;
+            my_drop = dropped ? 1 : 0;
+            my_pairs = (unsigned long long)count;
+        }
+        if (lane == 0) {
+            pv.ux[p] = ux; pv.uy[p] = uy; pv.cpx[p] = cpx; pv.wnorm[p] = wn;
+            pv.ix[p] = ip; pv.iy[p] = jp; pv.W[p] = W;
+            pv.offs[p] = count;
+            if (p == n - 1) pv.offs[n] = 0;
+        }
+    }
+    // statistics (integer atomics on 4 counters; never on pixels)
+    if (lane != 0) { my_dep = 0; my_sel = 0; my_drop = 0; my_pairs = 0; }
+    __shared__ unsigned long long s[4];
+    if (threadIdx.x < 4) s[threadIdx.x] = 0;
+    __syncthreads();
+    if (my_sel) {
+        atomicAdd(&s[0], my_pairs); atomicAdd(&s[1], my_dep); atomicAdd(&s[2], my_sel); atomicAdd(&s[3], my_drop);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s[threadIdx.x]) atomicAdd(&pv.stats[threadIdx.x], s[threadIdx.x]);
+}
+
+// one warp per particle: write its (tile, pid) pairs at offs[p].. (row-major over the tile box)
+__global__ void __launch_bounds__(256) expand_kernel(PlanView pv, int64_t n, int ndim, int ntx,
+                                                     int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= n) return;
+    const int ip = pv.ix[p];
+    if (ip < 0) return;
+    const int jp = pv.iy[p], W = pv.W[p];
+    const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
+    const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
+    const int tx0 = (ip + kx0) / kT, tx1 = (ip + kx1) / kT;
+    const int ty0 = (jp + ky0) / kT, ty1 = (jp + ky1) / kT;
+    const int nx = tx1 - tx0 + 1;
+    const int cnt = nx * (ty1 - ty0 + 1);
+    const int64_t o = pv.offs[p];
+    for (int q = lane; q < cnt; q += 32) {
+        const int ty = ty0 + q / nx, tx = tx0 + q % nx;
+        keys[o + q] = ty * ntx + tx;
+        vals[o + q] = (int32_t)p;
+    }
+}
+
+// tile_start[t] = first sorted pair with key >= t  (t in [0, ntiles])
+__global__ void tile_start_kernel(const int32_t* __restrict__ keys, int64_t n_pairs, int ntiles,
+                                  int64_t* __restrict__ tile_start) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    int64_t lo = 0, hi = n_pairs;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    tile_start[t] = lo;
+}
+
+// items per tile -> exclusive scan (single CTA) ; item -> tile map
+__global__ void __launch_bounds__(1024) tile_item_scan_kernel(const int64_t* __restrict__ tile_start, int ntiles,
+                                                              int64_t chunk, int64_t* __restrict__ item_start) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int t = base + tid;
+        int64_t v = 0;
+        if (t < ntiles) v = (tile_start[t + 1] - tile_start[t] + chunk - 1) / chunk;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int64_t incl = x + (warp > 0 ? s_warp[warp - 1] : 0) + s_carry;
+        if (t < ntiles) item_start[t] = incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (tid == 0) item_start[ntiles] = s_carry;
+}
+
+__global__ void item_tile_kernel(const int64_t* __restrict__ item_start, int ntiles, int64_t max_items,
+                                 int32_t* __restrict__ item_tile) {
+    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= max_items || it >= item_start[ntiles]) return;
+    int lo = 0, hi = ntiles;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (item_start[mid] <= it) lo = mid; else hi = mid;
+    }
+    item_tile[it] = lo;
+}
+
+struct DepositParams {
+    PlanView pv;
+    const double* L;          // [C, n]
+    int64_t n;
+    int ndim, ntx, ntiles;
+    const int32_t* pids;      // sorted pair list
+    const int64_t* tile_start;
+    const int64_t* item_start;
+    const int32_t* item_tile;
+    int64_t chunk;
+    float* data;              // [C, ndim, ndim]
+    float* partial;           // [max_items, C, kT*kT]
+};
+
+__global__ void __launch_bounds__(kDepThreads) deposit_kernel(const DepositParams p) {
+    const int64_t item = blockIdx.x;
+    const int chan = blockIdx.y;
+    if (item >= p.item_start[p.ntiles]) return;
+    const int tile = p.item_tile[item];
+    const int64_t t0 = p.tile_start[tile], t1 = p.tile_start[tile + 1];
+    const int64_t start = t0 + (item - p.item_start[tile]) * p.chunk;
+    const int64_t end = min(t1, start + p.chunk);
+    const bool single = (p.item_start[tile + 1] - p.item_start[tile]) == 1;
+    const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
+
+    __shared__ __align__(16) float sA[kP][kT];   // w * ey over the tile rows
+    __shared__ __align__(16) float sB[kP][kT];   // ex over the tile columns
+    __shared__ float s_u[2][kP], s_c[kP], s_w[kP];
+    __shared__ int s_i[2][kP], s_W[kP];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tyi = tid >> 4, txi = tid & 15;     // 8 x 16 threads, 8 rows x 4 cols each
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+    const double* Lc = p.L + (size_t)chan * p.n;
+    for (int64_t base = start; base < end; base += kP) {
+        const int np = (int)min((int64_t)kP, end - base);
+        if (tid < np) {
+            const int pid = p.pids[base + tid];
+            s_u[0][tid] = p.pv.ux[pid];
+            s_u[1][tid] = p.pv.uy[pid];
+            s_c[tid] = p.pv.cpx[pid];
+            s_w[tid] = (float)(Lc[pid] * (double)p.pv.wnorm[pid]);
+            s_i[0][tid] = p.pv.ix[pid];
+            s_i[1][tid] = p.pv.iy[pid];
+            s_W[tid] = p.pv.W[pid];
+        }
+        __syncthreads();
+        // phase A: factor vectors. thread t < 64 -> row t (y axis, weighted); t >= 64 -> column t-64
+        {
+            const int axis = (tid < kT) ? 1 : 0;
+            const int t = tid & (kT - 1);
+            const int pix = (axis ? py0 : px0) + t;
+            for (int q = 0; q < np; ++q) {
+                const int k = pix - s_i[axis][q];
+                float v = 0.f;
+                if (abs(k) <= s_W[q] && pix < p.ndim) {
+                    const float fk = (float)k;
+                    v = exp2f(-s_c[q] * fk * (fk - 2.f * s_u[axis][q]));
+                    if (axis) v *= s_w[q];
+                }
+                if (axis) sA[q][t] = v; else sB[q][t] = v;
+            }
+        }
+        __syncthreads();
+        // phase B: rank-1 updates; a warp skips particles whose rows miss its 16-row band
+        const int band0 = py0 + warp * 16, band1 = band0 + 15;
+        for (int q = 0; q < np; ++q) {
+            const int jp = s_i[1][q], W = s_W[q];
+            if (jp + W < band0 || jp - W > band1) continue;
+            const float4 a0 = *reinterpret_cast<const float4*>(&sA[q][tyi * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sA[q][tyi * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&sB[q][txi * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], bb[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+
+    if (single) {
+        float* img = p.data + (size_t)chan * p.ndim * p.ndim;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int row = py0 + tyi * 8 + r;
+            if (row >= p.ndim) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col = px0 + txi * 4 + c;
+                if (col < p.ndim) img[(size_t)row * p.ndim + col] = acc[r][c];
+            }
+        }
+    } else {
+        float* out = p.partial + ((size_t)item * gridDim.y + chan) * (kT * kT);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            *reinterpret_cast<float4*>(&out[(tyi * 8 + r) * kT + txi * 4]) =
+                make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+}
+
+// tiles with 0 items -> zeros, 1 item -> already written, >1 -> ordered sum of the partial tiles
+__global__ void __launch_bounds__(256) tile_reduce_kernel(const DepositParams p, int n_chan) {
+    const int tile = blockIdx.x, chan = blockIdx.y;
+    const int64_t i0 = p.item_start[tile], i1 = p.item_start[tile + 1];
+    if (i1 - i0 == 1) return;
+    const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
+    float* img = p.data + (size_t)chan * p.ndim * p.ndim;
+    for (int e = threadIdx.x; e < kT * kT; e += 256) {
+        float s = 0.f;
+        for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
+        const int row = py0 + e / kT, col = px0 + e % kT;
+        if (row < p.ndim && col < p.ndim) img[(size_t)row * p.ndim + col] = s;
+    }
+}
+
+// NGP products: one CTA per tile; shared-memory accumulation (float64 sums, integer counts)
+__global__ void __launch_bounds__(256) ngp_tile_kernel(const DepositParams p, int n_chan, float* __restrict__ simple,
+                                                       float* __restrict__ hist) {
+    __shared__ double s_sum[kT * kT];
+    __shared__ unsigned int s_cnt[kT * kT];
+    const int tile = blockIdx.x;
+    const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
+    const int64_t t0 = p.tile_start[tile], t1 = p.tile_start[tile + 1];
+    for (int chan = 0; chan < (simple ? n_chan : 1); ++chan) {
+        for (int e = threadIdx.x; e < kT * kT; e += 256) { s_sum[e] = 0.0; s_cnt[e] = 0; }
+        __syncthreads();
+        const double* Lc = p.L ? p.L + (size_t)chan * p.n : nullptr;
+        for (int64_t q = t0 + threadIdx.x; q < t1; q += 256) {
+            const int pid = p.pids[q];
+            const int lx = p.pv.ix[pid] - px0, ly = p.pv.iy[pid] - py0;
+            if (lx >= 0 && lx < kT && ly >= 0 && ly < kT) {   // the particle's own tile only
+                if (simple) atomicAdd(&s_sum[ly * kT + lx], Lc[pid]);
+                atomicAdd(&s_cnt[ly * kT + lx], 1u);
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < kT * kT; e += 256) {
+            const int row = py0 + e / kT, col = px0 + e % kT;
+            if (row < p.ndim && col < p.ndim) {
+                if (simple) simple[((size_t)chan * p.ndim + row) * p.ndim + col] = (float)s_sum[e];
+                if (hist && chan == 0) hist[(size_t)row * p.ndim + col] = (float)s_cnt[e];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void rebin_kernel(const float* __restrict__ in, float* __restrict__ out, int n_out, int s) {
+    const int img = blockIdx.z;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= n_out || oy >= n_out) return;
+    const size_t nin = (size_t)n_out * s;
+    const float* src = in + (size_t)img * nin * nin;
+    // images.py:22 sums the last axis first (columns within the block), then the rows
+    float tot = 0.f;
+    for (int r = 0; r < s; ++r) {
+        float rs = 0.f;
+        for (int c = 0; c < s; ++c) rs += src[((size_t)oy * s + r) * nin + (size_t)ox * s + c];
+        tot += rs;
+    }
+    out[((size_t)img * n_out + oy) * n_out + ox] = tot;
+}
+
+__global__ void complex_mul_kernel(const float2* __restrict__ a, const float2* __restrict__ b,
+                                   float2* __restrict__ out, int64_t nc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    const float2 x = a[(size_t)blockIdx.y * nc + i], y = b[i];
+    out[(size_t)blockIdx.y * nc + i] = make_float2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+}
+
+struct DepositLayout {
+    int32_t *keys0, *vals0, *keys1, *vals1;
+    int64_t *tile_start, *item_start;
+    int32_t* item_tile;
+    float* partial;
+    void* cub_tmp;
+    int64_t cub_tmp_bytes;
+    int64_t chunk, max_items;
+    int ntx, ntiles;
+};
+
+static int64_t sort_tmp_bytes(int64_t n_pairs) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_pairs, 0, 32);
+    return (int64_t)b;
+}
+
+static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n_pairs, int ndim, int n_chan, bool* ok) {
+    DepositLayout d;
+    d.ntx = (ndim + kT - 1) / kT;
+    d.ntiles = d.ntx * d.ntx;
+    // aim for ~16 work items per SM (but never below one staging phase worth of particles)
+    const int64_t target = 16 * 148;
+    int64_t chunk = (n_pairs + target - 1) / target;
+    chunk = (chunk + kP - 1) / kP * kP;
+    if (chunk < 4 * kP) chunk = 4 * kP;
+    d.chunk = chunk;
+    d.max_items = n_pairs / chunk + d.ntiles + 1;
+    SoArena a(ws, bytes);
+    d.keys0 = a.take<int32_t>(n_pairs);
+    d.vals0 = a.take<int32_t>(n_pairs);
+    d.keys1 = a.take<int32_t>(n_pairs);
+    d.vals1 = a.take<int32_t>(n_pairs);
+    d.tile_start = a.take<int64_t>(d.ntiles + 1);
+    d.item_start = a.take<int64_t>(d.ntiles + 1);
+    d.item_tile = a.take<int32_t>(d.max_items);
+    d.partial = a.take<float>(d.max_items * n_chan * kT * kT);
+    d.cub_tmp_bytes = sort_tmp_bytes(n_pairs > 0 ? n_pairs : 1);
+    d.cub_tmp = a.take<char>(d.cub_tmp_bytes);
+    if (ok) *ok = a.ok();
+    if (!ws) d.cub_tmp_bytes = a.used;   // total, for the size query
+    return d;
+}
+
+}  // namespace
+
+extern "C" int so_img_ngp_index(const double* X, const double* Y, int64_t n, const double* G, int32_t ndim,
+                                double half_width, int32_t* ix, int32_t* iy, void* stream) {
+    if (n < 0 || ndim < 1 || !G) return SO_ERR_BAD_ARG;
+    if (n == 0) return SO_OK;
+    ngp_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, Y, n, G, ndim, half_width, ix, iy);
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
+
+extern "C" int64_t so_img_plan_workspace_bytes(int64_t n) {
+    SoArena a(nullptr, 0);
+    bool ok;
+    (void)ok;
+    // replicate carve_plan's accounting with a null base
+    a.take<float>(n); a.take<float>(n); a.take<float>(n); a.take<float>(n);
+    a.take<int32_t>(n); a.take<int32_t>(n); a.take<int32_t>(n);
+    a.take<int64_t>(n + 1);
+    a.take<unsigned long long>(4);
+    a.take<char>(scan_tmp_bytes(n));
+    return a.used + 256;
+}
+
+extern "C" int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X, const double* Y,
+                           const double* dk, int64_t n, const double* G, int32_t ndim,
+                           double support_sigmas, void* plan_workspace, int64_t plan_workspace_bytes,
+                           int64_t* n_pairs, double* stats, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0 || ndim < 1 || !G || !ix || !iy || !X || !Y || !n_pairs) return SO_ERR_BAD_ARG;
+    if (n >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
+    bool ok = false;
+    PlanView pv = carve_plan(plan_workspace, plan_workspace_bytes, n, &ok);
+    if (!ok || !plan_workspace) return SO_ERR_WORKSPACE;
+    SO_CUDA(cudaMemsetAsync(pv.stats, 0, 4 * sizeof(unsigned long long), st));
+    *n_pairs = 0;
+    if (n == 0) {
+        if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0.0;
+        return SO_OK;
+    }
+    const int64_t threads = n * 32;
+    plan_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ix, iy, X, Y, dk, n, G, ndim, support_sigmas, pv);
+    SO_LAUNCH_CHECK();
+    size_t tmp = (size_t)pv.cub_tmp_bytes;
+    SO_CUDA(cub::DeviceScan::ExclusiveSum(pv.cub_tmp, tmp, pv.offs, pv.offs, (int)(n + 1), st));
+    unsigned long long h[4];
+    int64_t total = 0;
+    SO_CUDA(cudaMemcpyAsync(&total, pv.offs + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SO_CUDA(cudaMemcpyAsync(h, pv.stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SO_CUDA(cudaStreamSynchronize(st));
+    *n_pairs = total;
+    if (stats) for (int i = 0; i < 4; ++i) stats[i] = (double)h[i];
+    return SO_OK;
+}
+
+extern "C" int64_t so_img_deposit_workspace_bytes(int64_t n, int64_t n_pairs, int32_t ndim, int32_t n_chan) {
+    (void)n;
+    DepositLayout d = carve_deposit(nullptr, 0, n_pairs, ndim, n_chan, nullptr);
+    return d.cub_tmp_bytes + 256;
+}
+
+extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64_t n, int32_t n_chan,
+                              int32_t ndim, int64_t n_pairs,
+                              float* data, float* simple, float* hist,
+                              int32_t* tile_ids, int32_t* pair_pids,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0 || ndim < 1 || n_chan < 1 || n_pairs < 0 || !plan_workspace) return SO_ERR_BAD_ARG;
+    if (n_pairs >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
+    if ((data || simple) && !L) return SO_ERR_BAD_ARG;
+    bool ok = false;
+    PlanView pv = carve_plan(const_cast<void*>(plan_workspace), (int64_t)1 << 60, n, &ok);
+    DepositLayout d = carve_deposit(workspace, workspace_bytes, n_pairs, ndim, n_chan, &ok);
+    if (!ok || !workspace) return SO_ERR_WORKSPACE;
+    const size_t img_bytes = (size_t)ndim * ndim * sizeof(float);
+    if (n_pairs == 0) {
+        if (data) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
+        if (simple) SO_CUDA(cudaMemsetAsync(simple, 0, img_bytes * n_chan, st));
+        if (hist) SO_CUDA(cudaMemsetAsync(hist, 0, img_bytes, st));
+        return SO_OK;
+    }
+    const int64_t pthreads = n * 32;
+    expand_kernel<<<(unsigned)((pthreads + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, d.keys0, d.vals0);
+    SO_LAUNCH_CHECK();
+    int bits = 1;
+    while ((1 << bits) < d.ntiles) ++bits;
+    size_t tmp = (size_t)d.cub_tmp_bytes;
+    SO_CUDA(cub::DeviceRadixSort::SortPairs(d.cub_tmp, tmp, d.keys0, d.keys1, d.vals0, d.vals1, (int)n_pairs, 0, bits, st));
+    tile_start_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.keys1, n_pairs, d.ntiles, d.tile_start);
+    SO_LAUNCH_CHECK();
+    if (tile_ids) SO_CUDA(cudaMemcpyAsync(tile_ids, d.keys1, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToDevice, st));
+    if (pair_pids) SO_CUDA(cudaMemcpyAsync(pair_pids, d.vals1, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToDevice, st));
+
+    DepositParams p{};
+    p.pv = pv; p.L = L; p.n = n; p.ndim = ndim; p.ntx = d.ntx; p.ntiles = d.ntiles;
+    p.pids = d.vals1; p.tile_start = d.tile_start; p.item_start = d.item_start; p.item_tile = d.item_tile;
+    p.chunk = d.chunk; p.data = data; p.partial = d.partial;
+    if (data) {
+        tile_item_scan_kernel<<<1, 1024, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start);
+        SO_LAUNCH_CHECK();
+        item_tile_kernel<<<(unsigned)((d.max_items + 255) / 256), 256, 0, st>>>(d.item_start, d.ntiles, d.max_items,
+                                                                              d.item_tile);
+        SO_LAUNCH_CHECK();
+        dim3 grid((unsigned)d.max_items, (unsigned)n_chan);
+        deposit_kernel<<<grid, kDepThreads, 0, st>>>(p);
+        SO_LAUNCH_CHECK();
+        dim3 rgrid((unsigned)d.ntiles, (unsigned)n_chan);
+        tile_reduce_kernel<<<rgrid, 256, 0, st>>>(p, n_chan);
+        SO_LAUNCH_CHECK();
+    }
+    if (simple || hist) {
+        ngp_tile_kernel<<<(unsigned)d.ntiles, 256, 0, st>>>(p, n_chan, simple, hist);
+        SO_LAUNCH_CHECK();
+    }
+    return SO_OK;
+}
+
+extern "C" int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int32_t s, void* stream) {
+    if (n_img < 1 || n_out < 1 || s < 1) return SO_ERR_BAD_ARG;
+    dim3 block(32, 8), grid((n_out + 31) / 32, (n_out + 7) / 8, n_img);
+    rebin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, n_out, s);
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
+
+extern "C" int so_complex_mul_bcast(const float* a, const float* b, float* out, int64_t n_complex, int32_t n_img,
+                                    void* stream) {
+    if (n_complex < 1 || n_img < 1) return SO_ERR_BAD_ARG;
+    dim3 grid((unsigned)((n_complex + 255) / 256), (unsigned)n_img);
+    complex_mul_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)a, (const float2*)b, (float2*)out, n_complex);
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}

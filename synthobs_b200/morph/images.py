@@ -1,0 +1,356 @@
+"""synthobs.morph.images — same public API as the reference module
+(reference: synthobs/morph/images.py) for the particle -> image hot path:
+rebin, core, observed(...).particle, particle.  The per-particle Python loops of
+the reference are CUDA kernels here (include/synthobs_b200.h); there is no CPU
+path.
+
+Deliberate behaviours kept from the reference:
+  * observed.particle recentres the caller's X, Y IN PLACE (images.py:183-187);
+  * particle(..., offsets=True) draws from the global np.random (images.py:265-267);
+  * particle() passes yoffset_pix = xoffset_pix (images.py:282);
+  * img.data IS img.simple when there is no smoothing (images.py:103);
+  * pixel pitch is width/(ndim-1) because G = linspace(-w/2, w/2, ndim) (images.py:53).
+Difference, stated: the adaptive Gaussian is truncated at SUPPORT_SIGMAS sigma
+(default 7: the dropped tail is < 2.3e-11 of a particle's peak) and normalised
+over that truncated box, so total flux is conserved exactly as in the reference;
+SUPPORT_SIGMAS = 0 evaluates every pixel like the reference does.  ('adaptive', 1)
+raises IndexError in the reference (images.py:89 on a scalar); here it means
+FWHM = 0.01 for every particle.
+"""
+
+from ctypes import c_double, c_int64
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from .. import device as dv
+
+try:
+    import flare.observatories as _obs   # type: ignore
+    filter_info = _obs.filter_info
+except Exception:
+    filter_info = {}     # offline: callers register {'<filter>': {'pixel_scale': arcsec}}
+
+SUPPORT_SIGMAS = 7.0
+
+
+class empty():
+    pass
+
+
+# --------------------------------------------------------------------------
+# building blocks on device tensors
+# --------------------------------------------------------------------------
+
+def pixel_grid(resolution, ndim):
+    width = ndim * resolution                                   # images.py:39
+    return width, np.linspace(-width / 2., width / 2., ndim)    # images.py:53
+
+
+def rebin_device(img, n_out):
+    """[..., n*s, n*s] float32 CUDA -> [..., n, n] block sums (K11)."""
+    _cabi.require_device()
+    shape = img.shape
+    nin = shape[-1]
+    s = nin // n_out
+    if shape[-2] != nin or s * n_out != nin:
+        raise ValueError('cannot rebin %s to (%d, %d)' % (tuple(shape), n_out, n_out))
+    x = img.reshape(-1, nin, nin).contiguous()
+    out = torch.empty((x.shape[0], n_out, n_out), dtype=torch.float32, device=x.device)
+    _cabi.check(_cabi.lib.so_img_rebin(_cabi.ptr(x), _cabi.ptr(out), x.shape[0], n_out, s, _cabi.stream()),
+                'so_img_rebin')
+    return out.reshape(shape[:-2] + (n_out, n_out))
+
+
+def rebin(arr, new_shape):
+    """reference: images.py:19-22 — block SUM to new_shape."""
+    if new_shape[0] != new_shape[1] or arr.shape[0] != arr.shape[1]:
+        raise ValueError('rebin: square images only')
+    if dv.is_device_tensor(arr):
+        return rebin_device(arr.to(torch.float32), new_shape[0])
+    return dv.to_host(rebin_device(dv.to_dev(arr, torch.float32), new_shape[0]))
+
+
+def convolve_fft_device(img, kernel):
+    """astropy.convolution.convolve_fft with its defaults (zero fill, kernel
+    normalised to unit sum and centred on element n//2, output cropped to the
+    image; see oracle/ref_loader.py for the restated identity) as a batched
+    cuFFT step (K10).  img: [..., n, n] float32 CUDA; kernel: [nk, nk] host
+    float64 array (normalised in float64) or CUDA tensor."""
+    import scipy.fft as sfft
+    _cabi.require_device()
+    if isinstance(kernel, torch.Tensor):
+        k = kernel.to(img.device, torch.float64)
+        k = (k / k.sum()).to(torch.float32)
+    else:
+        kh = np.asarray(kernel, dtype=np.float64)
+        k = dv.to_dev((kh / kh.sum()).astype(np.float32), torch.float32)
+    n_y, n_x = img.shape[-2], img.shape[-1]
+    py = sfft.next_fast_len(n_y + k.shape[0] - 1, real=True)
+    px = sfft.next_fast_len(n_x + k.shape[1] - 1, real=True)
+    x = img.reshape(-1, n_y, n_x)
+    A = torch.fft.rfft2(x, s=(py, px))
+    K = torch.fft.rfft2(k, s=(py, px))
+    prod = torch.empty_like(A)
+    _cabi.check(_cabi.lib.so_complex_mul_bcast(_cabi.ptr(torch.view_as_real(A)), _cabi.ptr(torch.view_as_real(K)),
+                                               _cabi.ptr(torch.view_as_real(prod)), A.shape[-2] * A.shape[-1],
+                                               A.shape[0], _cabi.stream()), 'so_complex_mul_bcast')
+    full = torch.fft.irfft2(prod, s=(py, px))
+    oy, ox = k.shape[0] // 2, k.shape[1] // 2
+    out = full[:, oy:oy + n_y, ox:ox + n_x].contiguous()
+    return out.reshape(img.shape)
+
+
+def convolve_fft(array, kernel):
+    if dv.is_device_tensor(array):
+        return convolve_fft_device(array.to(torch.float32), kernel)
+    return dv.to_host(convolve_fft_device(dv.to_dev(array, torch.float32), kernel))
+
+
+def ngp_index_device(Xd, Yd, Gd, ndim, half_width):
+    n = Xd.numel()
+    ix = torch.empty(n, dtype=torch.int32, device=Xd.device)
+    iy = torch.empty(n, dtype=torch.int32, device=Xd.device)
+    _cabi.check(_cabi.lib.so_img_ngp_index(_cabi.ptr(Xd), _cabi.ptr(Yd), n, _cabi.ptr(Gd), ndim, float(half_width),
+                                           _cabi.ptr(ix), _cabi.ptr(iy), _cabi.stream()), 'so_img_ngp_index')
+    return ix, iy
+
+
+def knn_device(Xd, Yd, ix, k, half_width):
+    """distance to the k-th neighbour (self = first) among the selected particles (K7)."""
+    n = Xd.numel()
+    dk = torch.empty(n, dtype=torch.float64, device=Xd.device)
+    wsb = _cabi.lib.so_knn_workspace_bytes(n, int(k))
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_knn_kth_distance(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), n, int(k),
+                                              float(half_width), _cabi.ptr(dk), _cabi.ptr(ws), wsb, _cabi.stream()),
+                'so_knn_kth_distance')
+    return dk
+
+
+def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
+                   support_sigmas=None, dk=None, return_pairs=False):
+    """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
+    CUDA (C images sharing positions).  Returns dict of float32 CUDA tensors:
+    data [C, ndim, ndim] (adaptive only), simple [C, ndim, ndim], hist [ndim, ndim],
+    plus ix, iy, dk and the stats (pairs, deposits, selected, dropped)."""
+    _cabi.require_device()
+    if Ld.dim() == 1:
+        Ld = Ld.reshape(1, -1)
+    Ld = Ld.contiguous()
+    C, n = Ld.shape
+    width, G = pixel_grid(resolution, ndim)
+    Gd = dv.to_dev(G)
+    ix, iy = ngp_index_device(Xd, Yd, Gd, ndim, width / 2.)
+    adaptive = adaptive_k is not None
+    if adaptive and dk is None:
+        dk = knn_device(Xd, Yd, ix, adaptive_k, width / 2.)
+    R = SUPPORT_SIGMAS if support_sigmas is None else support_sigmas
+    pws_b = _cabi.lib.so_img_plan_workspace_bytes(n)
+    pws = dv.workspace(pws_b)
+    n_pairs = c_int64(0)
+    stats = (c_double * 4)()
+    _cabi.check(_cabi.lib.so_img_plan(_cabi.ptr(ix), _cabi.ptr(iy), _cabi.ptr(Xd), _cabi.ptr(Yd),
+                                      _cabi.ptr(dk) if adaptive else None, n, _cabi.ptr(Gd), ndim, float(R),
+                                      _cabi.ptr(pws), pws_b, n_pairs, stats, _cabi.stream()), 'so_img_plan')
+    npairs = n_pairs.value
+    dev = Xd.device
+    data = torch.empty((C, ndim, ndim), dtype=torch.float32, device=dev) if (adaptive and want_data) else None
+    simple = torch.empty((C, ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
+    hist = torch.empty((ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
+    tiles = torch.empty(npairs, dtype=torch.int32, device=dev) if return_pairs else None
+    pids = torch.empty(npairs, dtype=torch.int32, device=dev) if return_pairs else None
+    wsb = _cabi.lib.so_img_deposit_workspace_bytes(n, npairs, ndim, C)
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_img_deposit(_cabi.ptr(pws), _cabi.ptr(Ld), n, C, ndim, npairs,
+                                         _cabi.ptr(data), _cabi.ptr(simple), _cabi.ptr(hist),
+                                         _cabi.ptr(tiles), _cabi.ptr(pids), _cabi.ptr(ws), wsb, _cabi.stream()),
+                'so_img_deposit')
+    return {'data': data, 'simple': simple, 'hist': hist, 'ix': ix, 'iy': iy, 'dk': dk, 'G': G,
+            'stats': {'pairs': stats[0], 'deposits': stats[1], 'selected': stats[2], 'dropped': stats[3]},
+            'tiles': tiles, 'pids': pids}
+
+
+def _parse_smoothing(smoothing):
+    if smoothing:
+        return smoothing[0], smoothing[1]
+    return False, None
+
+
+def core_device(Xd, Yd, Ld, resolution=0.1, ndim=100, smoothing=False, want_ngp=True):
+    """images.core for [C, n] weights on the device; returns (data, simple, hist, info)."""
+    method, scale = _parse_smoothing(smoothing)
+    if method == 'adaptive':
+        r = deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=int(scale), want_ngp=want_ngp)
+        return r['data'], r['simple'], r['hist'], r
+    r = deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_ngp=True)
+    if method == 'convolved_gaussian':
+        width, G = pixel_grid(resolution, ndim)
+        Gx, Gy = np.meshgrid(G, G)
+        sigma = scale / 2.355                                              # images.py:74
+        gauss = np.exp(-((Gx ** 2 + Gy ** 2) / (2.0 * sigma ** 2)))       # images.py:75
+        gauss /= np.sum(gauss)
+        data = convolve_fft_device(r['simple'], gauss)                    # images.py:78
+    else:
+        data = r['simple']                                                 # images.py:103
+    return data, r['simple'], r['hist'], r
+
+
+# --------------------------------------------------------------------------
+# reference API
+# --------------------------------------------------------------------------
+
+def core(X, Y, L, resolution=0.1, ndim=100, smoothing=False, verbose=False):
+    """reference: images.py:28-105.  X, Y, resolution and the smoothing scale in
+    the same units (default physical kpc).  Returns an object with .hist,
+    .simple, .data ([ndim, ndim], row = y, column = x)."""
+    host = not any(dv.is_device_tensor(a) for a in (X, Y, L))
+    Xd, Yd, Ld = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L)
+    data, simple, hist, info = core_device(Xd, Yd, Ld, resolution, ndim, smoothing)
+    if verbose:
+        method, _ = _parse_smoothing(smoothing)
+        print('*' * 5, 'CORE')
+        print('width: {0:.2f} kpc'.format(ndim * resolution))
+        print('ndim: {0:.2f} '.format(ndim))
+        print('resolution: {0:.2f} '.format(resolution))
+        print('N_particles: {0:.2f} '.format(info['stats']['selected']))
+        print('smoothing method: {0} '.format(method))
+    img = empty()
+    same = data is simple
+    if host:
+        img.hist = dv.to_host(hist)
+        img.simple = dv.to_host(simple[0])
+        img.data = img.simple if same else dv.to_host(data[0])
+    else:
+        img.hist, img.simple = hist, simple[0]
+        img.data = img.simple if same else data[0]
+    img.info = info['stats']
+    return img
+
+
+def _median_inplace_shift(A, offset):
+    """A -= median(A); A += offset, in place on the caller's array (images.py:183-187)."""
+    if isinstance(A, torch.Tensor):
+        srt = torch.sort(A.reshape(-1)).values
+        m = A.numel()
+        med = srt[m // 2] if m % 2 else 0.5 * (srt[m // 2 - 1] + srt[m // 2])   # np.median semantics
+        A -= med
+        A += offset
+    else:
+        A -= np.median(A)
+        A += offset
+
+
+class observed():
+    """reference: images.py:112-213 (geometry + .particle)."""
+
+    def __init__(self, filter, cosmo, z, target_width_arcsec, resampling_factor=False, pixel_scale=False,
+                 smoothing=False, PSF=False, super_sampling=4, verbose=False, xoffset_pix=0.0, yoffset_pix=0.0):
+
+        self.filter = filter
+        self.target_width_arcsec = target_width_arcsec
+        self.resampling_factor = resampling_factor
+        self.pixel_scale = pixel_scale
+        self.smoothing = smoothing
+        self.PSF = PSF
+        self.verbose = verbose
+        self.super_sampling = super_sampling
+
+        self.native_pixel_scale = filter_info[self.filter]['pixel_scale']
+
+        if self.resampling_factor:
+            self.pixel_scale = self.native_pixel_scale / self.resampling_factor
+        elif self.pixel_scale:
+            self.resampling_factor = self.native_pixel_scale / self.pixel_scale
+        else:
+            self.pixel_scale = self.native_pixel_scale
+            self.resampling_factor = 1.0
+
+        self.arcsec_per_proper_kpc = cosmo.arcsec_per_kpc_proper(z).value
+        self.pixel_scale_kpc = self.pixel_scale / self.arcsec_per_proper_kpc
+        self.ndim = int(self.target_width_arcsec / self.pixel_scale)
+        self.width_arcsec = self.ndim * self.pixel_scale
+        self.width = self.width_arcsec / self.arcsec_per_proper_kpc
+        self.resolution = self.pixel_scale_kpc / self.super_sampling
+        self.ndim_super = self.ndim * self.super_sampling
+        self.xoffset = xoffset_pix * self.pixel_scale_kpc
+        self.yoffset = yoffset_pix * self.pixel_scale_kpc
+
+        if verbose:
+            print('*' * 5, 'OBSERVED')
+            print('z: {0}'.format(z))
+            print('"/kpc: {0:.2f}'.format(self.arcsec_per_proper_kpc))
+            print('-' * 10)
+            print('target width/": {0:.2f}'.format(self.target_width_arcsec))
+            print('width/": {0:.2f}'.format(self.width_arcsec))
+            print('width/kpc: {0:.2f}'.format(self.width))
+            print('-' * 10)
+            print('native pixel scale/": {0:.2f}'.format(self.native_pixel_scale))
+            print('pixel scale/": {0:.2f}'.format(self.pixel_scale))
+            print('pixel scale/kpc: {0:.2f}'.format(self.pixel_scale_kpc))
+            print('super sampling: {0:.2f}'.format(self.super_sampling))
+            print('resolution/kpc: {0:.2f}'.format(self.resolution))
+            print('ndim: {0:.2f}'.format(self.ndim))
+            print('-' * 10)
+
+    def psf_kernel(self):
+        xx = yy = np.linspace(-(self.width_arcsec / self.native_pixel_scale / 2.),
+                              (self.width_arcsec / self.native_pixel_scale / 2.), self.ndim_super)   # images.py:198
+        return self.PSF.f(xx, yy)                                                                   # images.py:200
+
+    def particle_device(self, Xd, Yd, Ld, dk=None):
+        """Device pipeline after recentring: deposit -> PSF FFT convolution -> rebin.
+        Ld: [C, n].  Returns dict of float32 CUDA tensors."""
+        method, scale = _parse_smoothing(self.smoothing)
+        if method == 'adaptive':
+            r = deposit_device(Xd, Yd, Ld, self.resolution, self.ndim_super, adaptive_k=int(scale), want_ngp=False,
+                               dk=dk)
+            no_psf = r['data']
+        else:
+            no_psf, _, _, r = core_device(Xd, Yd, Ld, self.resolution, self.ndim_super, self.smoothing)
+        conv = convolve_fft_device(no_psf, self.psf_kernel())                                       # images.py:202
+        return {'super_no_PSF': no_psf, 'super_data': conv,
+                'no_PSF': rebin_device(no_psf, self.ndim), 'data': rebin_device(conv, self.ndim),  # images.py:210-211
+                'info': r}
+
+    def particle(self, X, Y, L):
+        host = not any(dv.is_device_tensor(a) for a in (X, Y, L))
+        _median_inplace_shift(X, self.xoffset)     # mutates the caller's arrays, as the reference does
+        _median_inplace_shift(Y, self.yoffset)
+        Xd, Yd, Ld = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L)
+        r = self.particle_device(Xd, Yd, Ld)
+        conv = (lambda t: dv.to_host(t[0])) if host else (lambda t: t[0])
+        imgs = empty()
+        imgs.super = empty()
+        imgs.super.no_PSF = conv(r['super_no_PSF'])
+        imgs.super.data = conv(r['super_data'])
+        imgs.img = empty()
+        imgs.img.pixel_scale = self.pixel_scale
+        imgs.img.pixel_scale_kpc = self.pixel_scale_kpc
+        imgs.img.no_PSF = conv(r['no_PSF'])
+        imgs.img.data = conv(r['data'])
+        return imgs
+
+
+def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=False, pixel_scale=False,
+             smoothing=False, PSFs=False, super_sampling=10, verbose=False, offsets=False):
+    """reference: images.py:263-286 — one observed image per filter."""
+    if offsets:
+        xoffset_pix_base = np.random.random() - 0.5
+        yoffset_pix_base = np.random.random() - 0.5
+    else:
+        xoffset_pix_base = yoffset_pix_base = 0.0
+
+    max_pixel_scale = np.max([filter_info[filter]['pixel_scale'] for filter in filters])
+
+    IMGs = {}
+    for filter in filters:
+        xoffset_pix = xoffset_pix_base * (max_pixel_scale / filter_info[filter]['pixel_scale'])
+        yoffset_pix = yoffset_pix_base * (max_pixel_scale / filter_info[filter]['pixel_scale'])  # noqa: F841 (unused upstream too)
+        imgs = observed(filter, cosmo, z, target_width_arcsec, resampling_factor=resampling_factor,
+                        pixel_scale=pixel_scale, smoothing=smoothing, PSF=PSFs[filter],
+                        super_sampling=super_sampling, verbose=verbose, xoffset_pix=xoffset_pix,
+                        yoffset_pix=xoffset_pix).particle(X, Y, L[filter])
+        IMGs[filter] = imgs.img
+    return IMGs

@@ -1,0 +1,202 @@
+"""GPU parity: the CUDA imaging path (through the C-ABI) against the golden vectors written
+by the unmodified reference and against the oracle.
+
+Tolerances: NGP pixel indices, counts and particle->tile assignment bit-exact; images within
+1e-5 of the image peak per pixel and 1e-5 relative in L2 (FP32; see DESIGN.md for why a
+truncated-support gather cannot be per-pixel relative in empty regions); total flux 1e-6."""
+
+import numpy as np
+import pytest
+
+from oracle import image_oracle
+from synthobs_b200 import synthetic
+
+import _cases
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_image_close(a, b, tol=1e-5):
+    peak = np.abs(b).max()
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() <= tol * peak, (np.abs(a - b).max() / peak)
+    assert np.linalg.norm(a - b) <= tol * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize('tag', _cases.IMG_CASES)
+def test_core_matches_reference(tag):
+    from synthobs_b200.morph import images
+    g = _cases.load('img_' + tag)
+    sm = _cases.smoothing_of(g)
+    img = images.core(g['X'].copy(), g['Y'].copy(), g['L'].copy(), resolution=float(g['resolution']),
+                      ndim=int(g['ndim']), smoothing=sm)
+    assert img.hist.dtype == np.float64
+    assert np.array_equal(img.hist, g['hist'])
+    np.testing.assert_allclose(img.simple, g['simple'], rtol=2e-7, atol=0)
+    assert_image_close(img.data, g['data'])
+    assert img.data.sum() == pytest.approx(g['data'].sum(), rel=2e-6)
+    if not sm:
+        assert img.data is img.simple          # images.py:103
+
+
+@pytest.mark.parametrize('tag', ['adaptive16', 'adaptive_odd', 'adaptive_kbig', 'adaptive_underflow'])
+def test_full_support_is_per_pixel_relative(tag):
+    """SUPPORT_SIGMAS = 0 evaluates every pixel like the reference: per-pixel relative 1e-5
+    wherever the value is representable in FP32 relative to the peak."""
+    from synthobs_b200.morph import images
+    g = _cases.load('img_' + tag)
+    old = images.SUPPORT_SIGMAS
+    images.SUPPORT_SIGMAS = 0.0
+    try:
+        img = images.core(g['X'].copy(), g['Y'].copy(), g['L'].copy(), resolution=float(g['resolution']),
+                          ndim=int(g['ndim']), smoothing=_cases.smoothing_of(g))
+    finally:
+        images.SUPPORT_SIGMAS = old
+    ref = g['data']
+    big = ref > 1e-25 * ref.max()
+    np.testing.assert_allclose(img.data[big], ref[big], rtol=2e-5)
+    assert_image_close(img.data, ref)
+
+
+def test_pixel_indices_bit_exact():
+    import torch
+    from synthobs_b200.morph import images
+    from synthobs_b200 import device as dv
+    g = _cases.load('img_indices')
+    width, G = images.pixel_grid(float(g['resolution']), int(g['ndim']))
+    x = g['x']
+    ix, iy = images.ngp_index_device(dv.to_dev(x), dv.to_dev(np.full_like(x, 0.123)), dv.to_dev(G), int(g['ndim']),
+                                     width / 2.)
+    assert np.array_equal(ix.cpu().numpy(), g['idx'])
+    # large random + midpoints on a big grid vs the oracle's literal argmin
+    width, G = images.pixel_grid(0.013, 1024)
+    rng = np.random.default_rng(0)
+    mids = 0.5 * (G[:-1] + G[1:])
+    xs = np.concatenate([rng.uniform(-width / 2, width / 2, 200000), mids, np.nextafter(mids, 9), np.nextafter(mids, -9),
+                         [width / 2, -width / 2, np.nextafter(width / 2, 0), np.nan]])
+    ys = np.zeros_like(xs)
+    ix, iy = images.ngp_index_device(dv.to_dev(xs), dv.to_dev(ys), dv.to_dev(G), 1024, width / 2.)
+    sel = image_oracle.select(xs, ys, width)
+    ref = np.full(xs.size, -1)
+    ref[sel] = image_oracle.ngp_pixels(G, xs[sel])
+    assert np.array_equal(ix.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize('n,k', [(3000, 16), (20000, 8), (500, 1), (64, 64), (40, 50)])
+def test_knn_distance_matches_ckdtree(n, k):
+    from synthobs_b200.morph import images
+    from synthobs_b200 import device as dv
+    p = synthetic.particles(n, seed=n + k)
+    X, Y = p['X'], p['Y']
+    X[:5] = X[5:10]          # exact duplicates
+    Y[:5] = Y[5:10]
+    hw = 4.0
+    width, G = images.pixel_grid(2 * hw / 100, 100)
+    Xd, Yd = dv.to_dev(X), dv.to_dev(Y)
+    ix, _ = images.ngp_index_device(Xd, Yd, dv.to_dev(G), 100, hw)
+    dk = images.knn_device(Xd, Yd, ix, k, hw).cpu().numpy()
+    sel = image_oracle.select(X, Y, 2 * hw)
+    ref = image_oracle.kth_neighbour_distance(X[sel], Y[sel], k) if k <= sel.sum() else np.full(sel.sum(), np.inf)
+    assert np.array_equal(dk[~sel], np.zeros((~sel).sum()))
+    np.testing.assert_allclose(dk[sel], ref, rtol=4e-16, atol=0)
+
+
+def test_tile_assignment_bit_exact():
+    from synthobs_b200.morph import images
+    from synthobs_b200 import device as dv
+    g = _cases.load('img_adaptive8f')
+    ndim, res = 200, 0.02
+    X, Y, L = g['X'], g['Y'], g['L']
+    r = images.deposit_device(dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L), res, ndim, adaptive_k=8, return_pairs=True)
+    o = image_oracle.core(X, Y, L, resolution=res, ndim=ndim, smoothing=('adaptive', 8), return_aux=True)
+    sel = o['aux']['sel']
+    ix = r['ix'].cpu().numpy()
+    iy = r['iy'].cpu().numpy()
+    assert np.array_equal(ix >= 0, sel)
+    assert np.array_equal(ix[sel], o['aux']['i']) and np.array_equal(iy[sel], o['aux']['j'])
+    G = o['aux']['G']
+    pitch = (G[-1] - G[0]) / (ndim - 1)
+    dk = r['dk'].cpu().numpy()[sel]
+    np.testing.assert_allclose(dk, o['aux']['dk'], rtol=4e-16)
+    W = image_oracle.support_halfwidth(dk, pitch, images.SUPPORT_SIGMAS)
+    tiles, pids = image_oracle.tile_pairs(o['aux']['i'], o['aux']['j'], W, ndim, 64)
+    gid = np.nonzero(sel)[0]
+    assert np.array_equal(r['tiles'].cpu().numpy(), tiles)
+    assert np.array_equal(r['pids'].cpu().numpy(), gid[pids])
+    assert r['stats']['pairs'] == tiles.size
+    assert_image_close(r['data'][0].cpu().numpy().astype(np.float64), o['data'])
+
+
+def test_oracle_parity_larger_seeded_case_and_determinism():
+    """1e4 particles, 100x100 (BASELINE config 1 shape) vs the oracle; twice -> bitwise equal"""
+    from synthobs_b200.morph import images
+    p = synthetic.particles(10000, seed=1)
+    L = p['Masses']
+    a = images.core(p['X'], p['Y'], L, resolution=0.1, ndim=100, smoothing=('adaptive', 16))
+    b = images.core(p['X'], p['Y'], L, resolution=0.1, ndim=100, smoothing=('adaptive', 16))
+    assert np.array_equal(a.data, b.data)
+    o = image_oracle.core(p['X'], p['Y'], L, resolution=0.1, ndim=100, smoothing=('adaptive', 16), return_aux=True)
+    assert np.array_equal(a.hist, o['hist'])
+    assert_image_close(a.data, o['data'])
+    assert a.data.sum() == pytest.approx(L[o['aux']['sel']].sum(), rel=2e-6)      # flux conservation
+
+
+def test_multi_channel_and_empty():
+    import torch
+    from synthobs_b200.morph import images
+    from synthobs_b200 import device as dv
+    p = synthetic.particles(4000, seed=5)
+    L = np.stack([p['Masses'], p['Masses'] * np.random.default_rng(1).random(4000), np.zeros(4000)])
+    r = images.deposit_device(dv.to_dev(p['X']), dv.to_dev(p['Y']), dv.to_dev(L), 0.05, 160, adaptive_k=8)
+    for c in range(3):
+        o = image_oracle.core(p['X'], p['Y'], L[c], resolution=0.05, ndim=160, smoothing=('adaptive', 8))
+        if c < 2:
+            assert_image_close(r['data'][c].cpu().numpy().astype(np.float64), o['data'])
+        else:
+            assert float(r['data'][c].abs().max()) == 0.0
+    # nothing selected
+    img = images.core(np.array([100.0, -100.0]), np.array([0.0, 0.0]), np.array([1.0, 1.0]), ndim=30,
+                      smoothing=('adaptive', 4))
+    assert img.data.shape == (30, 30) and img.data.sum() == 0 and img.hist.sum() == 0
+    img = images.core(np.zeros(0), np.zeros(0), np.zeros(0), ndim=30, smoothing=('adaptive', 4))
+    assert img.data.sum() == 0
+
+
+def test_rebin_and_convolve():
+    from synthobs_b200.morph import images
+    rng = np.random.default_rng(2)
+    a = rng.random((120, 120))
+    np.testing.assert_allclose(images.rebin(a, (40, 40)), image_oracle.rebin(a, (40, 40)), rtol=1e-6)
+    assert images.rebin(a, (40, 40)).sum() == pytest.approx(a.sum(), rel=1e-6)
+    for nk in (120, 121, 33):
+        k = rng.random((nk, nk))
+        ref = image_oracle.convolve_fft_same(a, k)
+        got = images.convolve_fft(a, k)
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_observed_matches_reference():
+    from synthobs_b200.morph import images
+    g = _cases.load('img_observed')
+    cosmo = synthetic.FixedCosmology(arcsec_per_kpc=float(g['arcsec_per_kpc']))
+    filters = ['JWST.NIRCAM.F150W', 'JWST.NIRCAM.F356W']
+    images.filter_info.update({'JWST.NIRCAM.F150W': {'pixel_scale': 0.031}, 'JWST.NIRCAM.F356W': {'pixel_scale': 0.063}})
+    PSFs = {f: synthetic.GaussianPSF(fw) for f, fw in zip(filters, g['fwhm'])}
+    X, Y = g['X'].copy(), g['Y'].copy()
+    o = images.observed(filters[0], cosmo, float(g['z']), float(g['width_arcsec']), smoothing=('adaptive', 8.),
+                        PSF=PSFs[filters[0]], super_sampling=int(g['super_sampling']), xoffset_pix=0.25,
+                        yoffset_pix=-0.4).particle(X, Y, g['L_0'])
+    assert np.array_equal(X, g['obs_X_after']) and np.array_equal(Y, g['obs_Y_after'])   # in-place recentring
+    assert o.img.pixel_scale == float(g['obs_pixel_scale'])
+    assert_image_close(o.super.no_PSF, g['obs_super_no_PSF'])
+    assert_image_close(o.super.data, g['obs_super_data'])
+    assert_image_close(o.img.no_PSF, g['obs_no_PSF'])
+    assert_image_close(o.img.data, g['obs_data'])
+    X, Y = g['X'].copy(), g['Y'].copy()
+    L = {f: g['L_%d' % i] for i, f in enumerate(filters)}
+    IMGs = images.particle(X, Y, L, filters, cosmo, float(g['z']), float(g['width_arcsec']),
+                           smoothing=('adaptive', 8.), PSFs=PSFs, super_sampling=int(g['super_sampling']))
+    assert np.array_equal(X, g['multi_X_after'])
+    for i, f in enumerate(filters):
+        assert_image_close(IMGs[f].data, g['multi_%d_data' % i])
+        assert_image_close(IMGs[f].no_PSF, g['multi_%d_no_PSF' % i])

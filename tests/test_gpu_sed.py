@@ -1,0 +1,192 @@
+"""GPU parity: the CUDA SED path (through the C-ABI) against the golden vectors written by
+the unmodified reference and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): NGP indices bit-exact; per-particle values and
+spectra within 1e-5 relative (FP32); per-galaxy filter sums within 1e-4."""
+
+import io
+import contextlib
+
+import numpy as np
+import pytest
+
+from oracle import sed_oracle
+from synthobs_b200 import providers, synthetic
+
+import _cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL_PARTICLE = 1e-5
+RTOL_SUM = 1e-4
+
+
+def make_model(grid, dust_ISM=False, dust_BC=False):
+    from synthobs_b200.sed import models
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = models.define_model(grid)
+    m.dust_ISM, m.dust_BC = dust_ISM, dust_BC
+    return m
+
+
+def set_golden_tables(model, g, F, kind):
+    from synthobs_b200.sed import models
+    tabs = {}
+    for fi, f in enumerate(F['filters']):
+        e = models.empty()
+        for c in sed_oracle.COMPONENTS:
+            setattr(e, c, g['tab_%d_%s' % (fi, c)])
+        tabs[f] = e
+    if kind == 'Fnu':
+        tabs['z'] = float(g['z'])
+        model.Fnu = tabs
+    else:
+        model.Lnu = tabs
+
+
+@pytest.mark.parametrize('tag', _cases.SED_CASES)
+def test_filter_tables_match_reference(tag):
+    """create_Lnu_grid / create_Fnu_grid (K4 contraction) vs the reference's trapz tables"""
+    g, grid, F, dI, dB, kw = _cases.sed_inputs(tag)
+    model = make_model(grid, dI, dB)
+    if bool(g['observed']):
+        model.create_Fnu_grid(F, float(g['z']), synthetic.FixedCosmology(dl_cm=float(g['dl_cm'])))
+        tabs = model.Fnu
+    else:
+        model.create_Lnu_grid(F)
+        tabs = model.Lnu
+    for fi, f in enumerate(F['filters']):
+        for c in sed_oracle.COMPONENTS:
+            ref = g['tab_%d_%s' % (fi, c)]
+            np.testing.assert_allclose(getattr(tabs[f], c), ref, rtol=RTOL_PARTICLE, atol=1e-7 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize('tag', _cases.SED_CASES)
+@pytest.mark.parametrize('own_tables', [False, True])
+def test_broadband_matches_reference(tag, own_tables):
+    from synthobs_b200.sed import models
+    g, grid, F, dI, dB, kw = _cases.sed_inputs(tag)
+    model = make_model(grid, dI, dB)
+    observed = bool(g['observed'])
+    kind = 'Fnu' if observed else 'Lnu'
+    if own_tables:
+        if observed:
+            model.create_Fnu_grid(F, float(g['z']), synthetic.FixedCosmology(dl_cm=float(g['dl_cm'])))
+        else:
+            model.create_Lnu_grid(F)
+    else:
+        set_golden_tables(model, g, F, kind)
+    gen_arr = models.generate_Fnu_array if observed else models.generate_Lnu_array
+    gen_sum = models.generate_Fnu if observed else models.generate_Lnu
+    args = (g['Masses'], g['Ages'], g['Metallicities'])
+    for fi, f in enumerate(F['filters']):
+        arr = gen_arr(model, F, f, *args, **kw)
+        ref = g['arr_%d' % fi]
+        assert arr.dtype == np.float64 and arr.shape == ref.shape
+        np.testing.assert_allclose(arr, ref, rtol=RTOL_PARTICLE, atol=1e-30)
+    sums = gen_sum(model, F, *args, **kw)
+    np.testing.assert_allclose([sums[f] for f in F['filters']], g['sums'], rtol=RTOL_SUM)
+    # property: generate_Lnu == sum of generate_Lnu_array (models.py:83)
+    allf = models.generate_Lnu_arrays(model, F, *args, kind=kind, **kw)
+    np.testing.assert_allclose([allf[f].sum() for f in F['filters']], [sums[f] for f in F['filters']], rtol=1e-6)
+
+
+def test_ngp_indices_bit_exact():
+    from synthobs_b200.sed import models
+    g = _cases.load('sed_indices')
+    grid = synthetic.ssp_grid(**_cases.GRID_KW)
+    model = make_model(grid)
+    ia, iZ, young = models.ngp_cells(model, g['Ages'], g['Metallicities'], 7.0)
+    assert np.array_equal(ia, g['ia'])
+    assert np.array_equal(iZ, g['iZ'])
+    assert np.array_equal(young, g['young'])
+
+
+def test_ngp_indices_bit_exact_large_random_and_nonuniform_grid():
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=8)
+    grid['log10age'] = np.sort(6.0 + 5.0 * np.random.default_rng(3).random(51))   # non-uniform: binary-search path
+    model = make_model(grid)
+    rng = np.random.default_rng(4)
+    A = 10 ** rng.uniform(-1, 5.5, 1 << 20)
+    Z = 10 ** rng.uniform(-6, -1, 1 << 20)
+    ia, iZ, young = models.ngp_cells(model, A, Z, 7.2)
+    ra, rz, la = sed_oracle.ngp_indices(grid['log10age'], grid['log10Z'], A, Z)
+    assert np.array_equal(ia, ra) and np.array_equal(iZ, rz)
+    assert np.array_equal(young, la < 7.2)
+
+
+def test_batch_equals_loop_over_galaxies():
+    """segmented entry point == a Python loop of single-galaxy oracle calls"""
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=200)
+    simple = ('simple', {'slope': -1.0})
+    model = make_model(grid, simple, simple)
+    F = synthetic.filter_set(grid['lam'], n_filters=10)
+    model.create_Lnu_grid(F)
+    b = synthetic.galaxy_batch(37, n_min=1, n_max=9000, seed=7)
+    off = b['offsets']
+    out = models.generate_Lnu_batch(model, F, b['Masses'], b['Ages'], b['Metallicities'], off,
+                                    tauVs_ISM=b['tauVs_ISM'], tauVs_BC=b['tauVs_BC'], fesc=0.2)
+    assert out.shape == (37, 10)
+    tabs = {f: {c: getattr(model.Lnu[f], c) for c in sed_oracle.COMPONENTS} for f in F['filters']}
+    kI = {f: providers.simple({'slope': -1.0}).tau(F[f].pivwv()) for f in F['filters']}
+    for gi in range(37):
+        s, e = off[gi], off[gi + 1]
+        ref = sed_oracle.broadband(tabs, F['filters'], grid['log10age'], grid['log10Z'], b['Masses'][s:e],
+                                   b['Ages'][s:e], b['Metallicities'][s:e], tauVs_ISM=b['tauVs_ISM'][s:e],
+                                   tauVs_BC=b['tauVs_BC'][s:e], k_ISM=kI, k_BC=kI, fesc=0.2)
+        np.testing.assert_allclose(out[gi], [ref[f] for f in F['filters']], rtol=RTOL_SUM)
+
+
+def test_many_filters_and_device_inputs():
+    import torch
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=400)
+    model = make_model(grid, ('simple', {'slope': -1.0}), False)
+    F = synthetic.filter_set(grid['lam'], n_filters=37, kind='gauss')   # > SO_MAX_FILTERS: two launches
+    model.create_Lnu_grid(F)
+    p = synthetic.particles(5000, seed=9)
+    dev = {k: torch.from_numpy(p[k]).cuda() for k in ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM')}
+    out = models.generate_Lnu_batch(model, F, dev['Masses'], dev['Ages'], dev['Metallicities'],
+                                    np.array([0, 5000]), tauVs_ISM=dev['tauVs_ISM'])
+    assert out.is_cuda and out.shape == (1, 37)
+    tabs = {f: {c: getattr(model.Lnu[f], c) for c in sed_oracle.COMPONENTS} for f in F['filters']}
+    kI = {f: providers.simple({'slope': -1.0}).tau(F[f].pivwv()) for f in F['filters']}
+    ref = sed_oracle.broadband(tabs, F['filters'], grid['log10age'], grid['log10Z'], p['Masses'], p['Ages'],
+                               p['Metallicities'], tauVs_ISM=p['tauVs_ISM'], k_ISM=kI)
+    np.testing.assert_allclose(out.cpu().numpy()[0], [ref[f] for f in F['filters']], rtol=RTOL_SUM)
+
+
+@pytest.mark.parametrize('tag', _cases.SED_CASES)
+def test_log10Q_and_spectra_match_reference(tag):
+    from synthobs_b200.sed import models
+    g, grid, F, dI, dB, kw = _cases.sed_inputs(tag)
+    model = make_model(grid, dI, dB)
+    args = (g['Masses'], g['Ages'], g['Metallicities'])
+    assert models.generate_log10Q(model, *args) == pytest.approx(float(g['log10Q']), rel=1e-6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        o = models.generate_SED(model, *args, **kw)
+    for k in ('stellar', 'intrinsic', 'BC', 'total', 'no_HII_no_BC'):
+        ref = g['sed_' + k]
+        got = getattr(o, k).lnu
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=RTOL_PARTICLE, atol=1e-6 * np.abs(ref).max(), err_msg=k)
+    ok = np.isfinite(g['sed_tau_relV']) & (g['sed_intrinsic'] > 1e-6 * g['sed_intrinsic'].max())
+    np.testing.assert_allclose(o.f_esc[ok], g['sed_f_esc'][ok], rtol=1e-4)
+
+
+def test_empty_and_tiny_inputs():
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=64)
+    model = make_model(grid)
+    F = synthetic.filter_set(grid['lam'], n_filters=3)
+    model.create_Lnu_grid(F)
+    z = np.zeros(0)
+    out = models.generate_Lnu(model, F, z, z, z)
+    assert all(out[f] == 0.0 for f in F['filters'])
+    one = models.generate_Lnu_array(model, F, F['filters'][0], np.array([1e6]), np.array([5.0]), np.array([0.01]))
+    tab = {c: getattr(model.Lnu[F['filters'][0]], c) for c in sed_oracle.COMPONENTS}
+    ref = sed_oracle.broadband_array(tab, grid['log10age'], grid['log10Z'], np.array([1e6]), np.array([5.0]),
+                                     np.array([0.01]))
+    np.testing.assert_allclose(one, ref, rtol=RTOL_PARTICLE)

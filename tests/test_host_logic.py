@@ -1,0 +1,72 @@
+"""CPU: host-side logic of the API mirror (thresholds, filter weights, geometry)."""
+
+import numpy as np
+import pytest
+
+from oracle import image_oracle, sed_oracle
+from synthobs_b200 import synthetic
+from synthobs_b200.sed import models
+
+import _cases
+
+
+def _count(thr, v):
+    r = (v[:, None] >= thr[None, :]).sum(1)
+    r[~(v < np.inf)] = 0
+    return r
+
+
+def test_thresholds_reproduce_reference_indices():
+    g = _cases.load('sed_indices')
+    grid = synthetic.ssp_grid(**_cases.GRID_KW)
+    ta = models.ngp_thresholds(grid['log10age'], 6.0)
+    tz = models.ngp_thresholds(grid['log10Z'], 0.0)
+    assert np.array_equal(_count(ta, g['Ages']), g['ia'])
+    assert np.array_equal(_count(tz, g['Metallicities']), g['iZ'])
+    yt = models.young_threshold(7.0)
+    assert np.array_equal((g['Ages'] < yt) & (g['Ages'] >= 0), g['young'])
+
+
+def test_thresholds_random_dense():
+    grid = synthetic.ssp_grid(n_lam=8)
+    rng = np.random.default_rng(0)
+    A = 10 ** rng.uniform(-2, 6, 200000)
+    Z = 10 ** rng.uniform(-7, 0, 200000)
+    ia, iZ, la = sed_oracle.ngp_indices(grid['log10age'], grid['log10Z'], A, Z)
+    assert np.array_equal(_count(models.ngp_thresholds(grid['log10age'], 6.0), A), ia)
+    assert np.array_equal(_count(models.ngp_thresholds(grid['log10Z'], 0.0), Z), iZ)
+    for t in (6.5, 7.0, 7.3, 8.0):
+        yt = models.young_threshold(t)
+        assert np.array_equal(A < yt, la < t)
+
+
+def test_trapz_weights_identity():
+    rng = np.random.default_rng(1)
+    x = np.sort(rng.uniform(0, 10, 200))
+    y = rng.random(200)
+    assert np.trapezoid(y, x=x) == pytest.approx(np.sum(models.trapz_weights(x) * y), rel=1e-14)
+
+
+def test_filter_weight_fold_equals_reference_expression():
+    """create_Lnu_grid's W-matrix formulation == the reference's trapz expression (float64)."""
+    grid = synthetic.ssp_grid(n_lam=200)
+    sed_oracle.ensure_incident(grid)
+    F = synthetic.filter_set(grid['lam'], n_filters=3)
+    ref = sed_oracle.lnu_grid(grid, F)
+    for f in F['filters']:
+        w = models.trapz_weights(F[f].lam) * F[f].T / np.trapezoid(F[f].T, x=F[f].lam)
+        mine = grid['nebular'] @ w
+        np.testing.assert_allclose(mine, ref[f]['nebular'], rtol=1e-13)
+
+
+def test_observed_geometry_matches_oracle():
+    from synthobs_b200.morph import images
+    images.filter_info['T.F'] = {'pixel_scale': 0.031}
+    cosmo = synthetic.FixedCosmology()
+    for kw in (dict(), dict(resampling_factor=2.0), dict(pixel_scale=0.05)):
+        o = images.observed('T.F', cosmo, 8.0, 1.7, super_sampling=3, xoffset_pix=0.3, yoffset_pix=-0.2, **kw)
+        g = image_oracle.observed_geometry(0.031, cosmo.arcsec_per_kpc, 1.7, super_sampling=3, xoffset_pix=0.3,
+                                           yoffset_pix=-0.2, **kw)
+        for k in ('pixel_scale', 'pixel_scale_kpc', 'ndim', 'width_arcsec', 'width', 'resolution', 'ndim_super',
+                  'xoffset', 'yoffset', 'resampling_factor'):
+            assert getattr(o, k) == g[k], k
