@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the two SynthObs hot paths on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  Primary record: BASELINE.json config[1]
+(SED_fluxes-style: galaxies of 1e5 particles, BPASS-shape grid 51x13x9000, ISM+BC LOS
+dust, 10 broadband filters), batched so one step streams more than L2 from HBM.
+`value` = galaxy SEDs x filters / s with inputs resident in HBM; `e2e` = the same through
+the public API with pinned HOST inputs (H2D + D2H inside the timed region).
+Secondary record under "imaging": BASELINE.json config[2] (1e6 particles, 8 filters,
+512x512 observed-frame images, super-sampling 2, adaptive smoothing, PSF convolution).
+Multi-GPU: one process per GPU, galaxies/objects sharded by rank, no data-path collective
+(weak scaling); time = max over ranks.
+
+--impl reference times the CPU restatement of the reference (oracle/, NumPy, the reference is
+pure Python so there is nothing to compile into oracle/_ref) on bounded samples of the same
+workload on the host cores.
+"""
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PER_GALAXY = 100000
+N_FILTERS = 10
+N_LAM = 9000
+GALAXIES_PER_GPU = 256          # 2.56e7 particles, 1.02 GB of float64 inputs per step (>> 126 MB L2)
+IMG_PARTICLES = 1000000
+IMG_FILTERS = 8
+IMG_NDIM = 512
+IMG_SS = 2
+IMG_K = 8
+Z = 8.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            p = json.load(fh)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, smax, reasons = [], [], set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax.append(mx)
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        if not sm:
+            sm = [float(x[1].split(',')[1]) for x in self.lines[-3:]] if self.lines else [0.0]
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)) if smax else 0.0,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def setup_model(n_lam=N_LAM, n_filters=N_FILTERS):
+    from synthobs_b200 import synthetic
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=n_lam, seed=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = models.define_model(grid)
+    model.dust_ISM = ('simple', {'slope': -1.0})
+    model.dust_BC = ('simple', {'slope': -1.0})
+    F = synthetic.filter_set(model.lam * (1. + Z), n_filters=n_filters, kind='gauss', lo=12000., hi=50000.,
+                             prefix='JWST.FAKE.')
+    cosmo = synthetic.FixedCosmology()
+    model.create_Fnu_grid(F, Z, cosmo)
+    return model, F, cosmo
+
+
+# ------------------------------------------------------------------ ours (GPU)
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from synthobs_b200 import _cabi, synthetic
+    from synthobs_b200.morph import images
+    from synthobs_b200.sed import models
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    _cabi.require_device()
+    dev = torch.device('cuda', local)
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- SED workload (primary)
+    model, F, cosmo = setup_model()
+    G = GALAXIES_PER_GPU
+    batch = synthetic.galaxy_batch(G, fixed_n=N_PER_GALAXY, seed=100 + rank)
+    keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
+    host = {k: torch.from_numpy(batch[k]).pin_memory() for k in keys}
+    offsets = torch.from_numpy(batch['offsets'])
+    d = {k: host[k].to(dev) for k in keys}
+    d_off = offsets.to(dev)
+    n_part = d['Masses'].numel()
+    kw_names = dict(fesc=0.0, log10t_BC=7.0)
+
+    def sed_step_device():
+        return models.generate_Fnu_batch(model, F, d['Masses'], d['Ages'], d['Metallicities'], d_off,
+                                         tauVs_ISM=d['tauVs_ISM'], tauVs_BC=d['tauVs_BC'], **kw_names)
+
+    def sed_step_e2e():
+        # public API with HOST (pinned) inputs: H2D of the five particle arrays + kernels + D2H of [G, F]
+        out = models.generate_Fnu_batch(model, F, host['Masses'], host['Ages'], host['Metallicities'], offsets,
+                                        tauVs_ISM=host['tauVs_ISM'], tauVs_BC=host['tauVs_BC'], **kw_names)
+        return out
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        out = sed_step_device()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        out = sed_step_device()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    sed_value = world * G * N_FILTERS / (ms_step * 1e-3)
+    algo_bytes = 40.0 * n_part                     # 5 float64 arrays read once
+    achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # e2e
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        sed_step_e2e()
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        res = sed_step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.time() - t0) * 1e3 / e2e_steps)
+    e2e_value = world * G * N_FILTERS / (e2e_ms * 1e-3)
+    h2d = int(sum(host[k].numel() * 8 for k in keys) + offsets.numel() * 8)
+    d2h = int(G * N_FILTERS * 8)
+
+    # ---------------- imaging workload (secondary, config[2])
+    imaging = None
+    if not args.no_imaging:
+        imaging = run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak)
+    sampler.stop()
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_sed(batch, model, F, budget_s=12.0)
+        if imaging is not None:
+            imaging['cpu_baseline'] = cpu_baseline_imaging(budget_s=12.0)
+
+    if rank == 0:
+        rec = {
+            'metric': 'galaxy SEDs x filters / s', 'value': sed_value, 'unit': 'galaxy_SEDs_x_filters/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 values, f64 index compares',
+            'data': 'synthetic',
+            'config': {'workload': 'config[1] SED_fluxes: %d galaxies/GPU x 1e5 particles, BPASS-shape grid 51x13x%d, '
+                                   'ISM+BC LOS dust, %d filters; one segmented so_sed_broadband pass per step' %
+                                   (G, N_LAM, N_FILTERS),
+                       'particles_per_step_per_gpu': n_part, 'l2_policy': 'inputs (1.02 GB/step) larger than L2',
+                       'parallelism': 'galaxies sharded by rank, no collective'},
+            'particles_per_s': world * n_part / (ms_step * 1e-3),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                         'kernel': 'sed_broadband_kernel<12>', 'algorithmic_bytes_per_particle': 40,
+                         'note': 'duration = whole step (4 launches: item scan, item map, broadband, per-galaxy '
+                                 'reduce), so the fraction is a lower bound for the streaming kernel'},
+            'e2e': {'value': e2e_value, 'unit': 'galaxy_SEDs_x_filters/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
+            'gpu_launches': 4 * args.steps,
+            'clocks': clocks,
+            'cpu_baseline': cpu,
+            'imaging': imaging,
+        }
+        print(json.dumps(rec))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
+    import torch
+    from synthobs_b200 import synthetic
+    from synthobs_b200.morph import images
+    p = synthetic.particles(IMG_PARTICLES, seed=200 + rank, scale_kpc=3.0)
+    filters = ['JWST.NIRCAM.B%d' % i for i in range(IMG_FILTERS)]
+    for f in filters:
+        images.filter_info[f] = {'pixel_scale': 0.031}
+    cosmo = synthetic.FixedCosmology()
+    width_arcsec = IMG_NDIM * 0.031 + 1e-9
+    rng = np.random.default_rng(7 + rank)
+    Lh = np.stack([p['Masses'] * (0.5 + rng.random(IMG_PARTICLES)) for _ in filters])
+    PSFs = {f: synthetic.GaussianPSF(1.5 + 0.2 * i) for i, f in enumerate(filters)}
+    Xh = torch.from_numpy(p['X']).pin_memory()
+    Yh = torch.from_numpy(p['Y']).pin_memory()
+    Lh_t = torch.from_numpy(Lh).pin_memory()
+    Xd, Yd, Ld = Xh.to(dev), Yh.to(dev), Lh_t.to(dev)
+    obs = [images.observed(f, cosmo, Z, width_arcsec, smoothing=('adaptive', float(IMG_K)), PSF=PSFs[f],
+                           super_sampling=IMG_SS) for f in filters]
+    assert obs[0].ndim == IMG_NDIM, obs[0].ndim
+    stats = {}
+
+    def step_device(Xd, Yd, Ld):
+        X = Xd - torch.median(Xd)            # recentring (images.py:183-184) on device copies
+        Y = Yd - torch.median(Yd)
+        r = images.particle_device_multi(obs, X, Y, Ld)
+        stats.update(r['stats'])
+        return r['data']
+
+    def step_e2e():
+        out = step_device(Xh.to(dev, non_blocking=True), Yh.to(dev, non_blocking=True), Lh_t.to(dev, non_blocking=True))
+        return out.cpu()
+
+    for _ in range(3):
+        step_device(Xd, Yd, Ld)
+    barrier()
+    steps = max(3, min(args.steps, 10))
+    import torch.cuda as tc
+    e0, e1 = tc.Event(enable_timing=True), tc.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_device(Xd, Yd, Ld)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.time()
+    for _ in range(steps):
+        step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.time() - t0) * 1e3 / steps)
+    deposits = stats.get('deposits', 0.0) * IMG_FILTERS
+    nsel = stats.get('selected', 0.0)
+    ref_equiv = nsel * (IMG_NDIM * IMG_SS) ** 2 * IMG_FILTERS
+    return {
+        'metric': 'particles/sec imaged', 'unit': 'particles/s (all %d filter images)' % IMG_FILTERS,
+        'value': world * IMG_PARTICLES / (ms * 1e-3), 'ms_per_step': ms,
+        'particle_filter_images_per_s': world * IMG_PARTICLES * IMG_FILTERS / (ms * 1e-3),
+        'deposits_evaluated_per_s': world * deposits / (ms * 1e-3),
+        'reference_equivalent_deposits_per_s': world * ref_equiv / (ms * 1e-3),
+        'config': {'workload': 'config[2] observed-frame: %d particles, %d filters, %dx%d, super_sampling %d, '
+                               "('adaptive', %d), Gaussian PSF FFT convolution, rebin" %
+                               (IMG_PARTICLES, IMG_FILTERS, IMG_NDIM, IMG_NDIM, IMG_SS, IMG_K),
+                   'support_sigmas': images.SUPPORT_SIGMAS, 'pairs_particle_tile': stats.get('pairs'),
+                   'selected': nsel, 'deposits_per_filter': stats.get('deposits')},
+        'e2e': {'value': world * IMG_PARTICLES / (e2e_ms * 1e-3), 'unit': 'particles/s', 'ms_per_step': e2e_ms,
+                'h2d_bytes_per_step': int(IMG_PARTICLES * 8 * (2 + IMG_FILTERS)),
+                'd2h_bytes_per_step': int(IMG_FILTERS * IMG_NDIM * IMG_NDIM * 4)},
+    }
+
+
+# ------------------------------------------------------------------ CPU baselines (oracle port)
+
+def cpu_baseline_sed(batch, model, F, budget_s=12.0):
+    from oracle import sed_oracle
+    from synthobs_b200 import providers
+    tabs = {f: {c: getattr(model.Fnu[f], c) for c in sed_oracle.COMPONENTS} for f in F['filters']}
+    grid = model.grid
+    k = {f: float(providers.simple({'slope': -1.0}).tau(F[f].pivwv() / (1. + Z))) for f in F['filters']}
+    off = batch['offsets']
+    done, t0 = 0, time.time()
+    while time.time() - t0 < budget_s and done < len(off) - 1:
+        s, e = off[done], off[done + 1]
+        sed_oracle.broadband(tabs, F['filters'], grid['log10age'], grid['log10Z'], batch['Masses'][s:e],
+                             batch['Ages'][s:e], batch['Metallicities'][s:e], tauVs_ISM=batch['tauVs_ISM'][s:e],
+                             tauVs_BC=batch['tauVs_BC'][s:e], k_ISM=k, k_BC=k, fesc=0.0)
+        done += 1
+    dt = time.time() - t0
+    return {'value': done * len(F['filters']) / dt, 'unit': 'galaxy_SEDs_x_filters/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d galaxies x 1e5 particles x %d filters with oracle/sed_oracle.broadband (vectorised '
+                      'NumPy restatement of generate_Fnu; the reference itself is a per-particle Python loop, '
+                      '~1e5 particle-filters/s) in %.1f s; host has %d cores' % (done, len(F['filters']), dt,
+                                                                               os.cpu_count())}
+
+
+def cpu_baseline_imaging(budget_s=12.0, n_sample=4000):
+    from oracle import image_oracle
+    from synthobs_b200 import synthetic
+    p = synthetic.particles(IMG_PARTICLES, seed=200, scale_kpc=3.0)
+    cosmo = synthetic.FixedCosmology()
+    g = image_oracle.observed_geometry(0.031, cosmo.arcsec_per_kpc, IMG_NDIM * 0.031 + 1e-9, super_sampling=IMG_SS)
+    width, G = image_oracle.pixel_grid(g['resolution'], g['ndim_super'])
+    X, Y = p['X'] - np.median(p['X']), p['Y'] - np.median(p['Y'])
+    t0 = time.time()
+    dk = image_oracle.kth_neighbour_distance(X, Y, IMG_K)
+    t_knn = time.time() - t0
+    idx = np.random.default_rng(0).choice(IMG_PARTICLES, n_sample, replace=False)
+    t0 = time.time()
+    done = 0
+    for s in range(0, n_sample, 500):
+        sl = idx[s:s + 500]
+        image_oracle.adaptive_separable(G, X[sl], Y[sl], p['Masses'][sl], dk[sl], chunk=500)
+        done += sl.size
+        if time.time() - t0 > budget_s:
+            break
+    t_dep = time.time() - t0
+    per_particle = t_dep / done
+    total = t_knn + per_particle * IMG_PARTICLES * IMG_FILTERS
+    return {'value': IMG_PARTICLES / total, 'unit': 'particles/s (all %d filter images)' % IMG_FILTERS, 'cores': 1,
+            'kind': 'port',
+            'sample': 'cKDTree k=%d on all 1e6 particles (%.2f s, all cores) + oracle adaptive_separable (NumPy/BLAS '
+                      'restatement, full-image support like the reference) on %d particles at %dx%d: %.3f ms/particle, '
+                      'extrapolated x%d particles x %d filters; PSF FFT and rebin not included' %
+                      (IMG_K, t_knn, done, g['ndim_super'], g['ndim_super'], per_particle * 1e3, IMG_PARTICLES,
+                       IMG_FILTERS)}
+
+
+# ------------------------------------------------------------------ reference arm
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    from oracle import sed_oracle
+    from synthobs_b200 import providers, synthetic
+    grid = synthetic.ssp_grid(n_lam=N_LAM, seed=0)
+    sed_oracle.ensure_incident(grid)
+    F = synthetic.filter_set(grid['lam'] * (1. + Z), n_filters=N_FILTERS, kind='gauss', lo=12000., hi=50000.,
+                             prefix='JWST.FAKE.')
+    cosmo = synthetic.FixedCosmology()
+    t0 = time.time()
+    tabs = sed_oracle.fnu_grid(grid, F, Z, cosmo.dl_cm, providers.madau)
+    t_setup = time.time() - t0
+    k = {f: float(providers.simple({'slope': -1.0}).tau(F[f].pivwv() / (1. + Z))) for f in F['filters']}
+    per_step = 4      # galaxies per step: bounded sample of the 256-galaxy step
+    batch = synthetic.galaxy_batch(per_step, fixed_n=N_PER_GALAXY, seed=100)
+    off = batch['offsets']
+
+    def step():
+        for gi in range(per_step):
+            s, e = off[gi], off[gi + 1]
+            sed_oracle.broadband(tabs, F['filters'], grid['log10age'], grid['log10Z'], batch['Masses'][s:e],
+                                 batch['Ages'][s:e], batch['Metallicities'][s:e], tauVs_ISM=batch['tauVs_ISM'][s:e],
+                                 tauVs_BC=batch['tauVs_BC'][s:e], k_ISM=k, k_BC=k, fesc=0.0)
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    steps = min(args.steps, 10)
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t0) / steps
+    value = per_step * N_FILTERS / dt
+    rec = {
+        'impl': 'reference', 'metric': 'galaxy SEDs x filters / s', 'value': value,
+        'unit': 'galaxy_SEDs_x_filters/s', 'n_gpus': world, 'steps': steps, 'warmup': min(args.warmup, 2),
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': 'config[1] SED_fluxes: galaxies of 1e5 particles, BPASS-shape grid 51x13x%d, ISM+BC '
+                               'LOS dust, %d filters; each step = %d galaxies (bounded sample of the GPU arm\'s '
+                               '%d-galaxy step)' % (N_LAM, N_FILTERS, per_step, GALAXIES_PER_GPU),
+                   'table_setup_s': t_setup},
+        'cpu_baseline': {'value': value, 'unit': 'galaxy_SEDs_x_filters/s', 'cores': 1, 'kind': 'port',
+                         'sample': 'oracle/sed_oracle.broadband (vectorised NumPy restatement of '
+                                   'generate_Fnu; NumPy runs this on one core), %d galaxies per step; host has %d '
+                                   'cores' % (per_step, os.cpu_count())},
+        'e2e': {'value': value, 'unit': 'galaxy_SEDs_x_filters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(rec))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-imaging', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -208,10 +208,11 @@ int so_img_deposit(const void* plan_workspace, const double* L, int64_t n, int32
 int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int32_t s, void* stream);
 
 /* elementwise helper for the PSF step (K10): out = a * b on interleaved complex
- * float32 spectra, b broadcast over the leading n_img images.  The FFTs
+ * float32 spectra; a, out: [n_img, n_complex]; b: [n_complex] broadcast over the
+ * images (b_per_image = 0) or [n_img, n_complex] (b_per_image = 1).  The FFTs
  * themselves are cuFFT through torch.fft (convolve_fft of images.py:78,202). */
 int so_complex_mul_bcast(const float* a, const float* b, float* out, int64_t n_complex, int32_t n_img,
-                         void* stream);
+                         int32_t b_per_image, void* stream);
 
 #ifdef __cplusplus
 }

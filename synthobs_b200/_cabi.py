@@ -47,7 +47,7 @@ SIGNATURES = {
     'so_img_deposit_workspace_bytes': (I64, [I64, I64, I32, I32]),
     'so_img_deposit': (c_int, [P, P, I64, I32, I32, I64, P, P, P, P, P, P, I64, P]),
     'so_img_rebin': (c_int, [P, P, I32, I32, I32, P]),
-    'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, P]),
+    'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, I32, P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

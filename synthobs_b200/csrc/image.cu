@@ -435,10 +435,10 @@ __global__ void rebin_kernel(const float* __restrict__ in, float* __restrict__ o
 }
 
 __global__ void complex_mul_kernel(const float2* __restrict__ a, const float2* __restrict__ b,
-                                   float2* __restrict__ out, int64_t nc) {
+                                   float2* __restrict__ out, int64_t nc, int b_per_image) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nc) return;
-    const float2 x = a[(size_t)blockIdx.y * nc + i], y = b[i];
+    const float2 x = a[(size_t)blockIdx.y * nc + i], y = b[(b_per_image ? (size_t)blockIdx.y * nc : 0) + i];
     out[(size_t)blockIdx.y * nc + i] = make_float2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
 }
 
@@ -516,7 +516,7 @@ extern "C" int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X
                            double support_sigmas, void* plan_workspace, int64_t plan_workspace_bytes,
                            int64_t* n_pairs, double* stats, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (n < 0 || ndim < 1 || !G || !ix || !iy || !X || !Y || !n_pairs) return SO_ERR_BAD_ARG;
+    if (n < 0 || ndim < 1 || !G || !n_pairs || (n > 0 && (!ix || !iy || !X || !Y))) return SO_ERR_BAD_ARG;
     if (n >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
     bool ok = false;
     PlanView pv = carve_plan(plan_workspace, plan_workspace_bytes, n, &ok);
@@ -613,10 +613,11 @@ extern "C" int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t 
 }
 
 extern "C" int so_complex_mul_bcast(const float* a, const float* b, float* out, int64_t n_complex, int32_t n_img,
-                                    void* stream) {
+                                    int32_t b_per_image, void* stream) {
     if (n_complex < 1 || n_img < 1) return SO_ERR_BAD_ARG;
     dim3 grid((unsigned)((n_complex + 255) / 256), (unsigned)n_img);
-    complex_mul_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)a, (const float2*)b, (float2*)out, n_complex);
+    complex_mul_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)a, (const float2*)b, (float2*)out, n_complex,
+                                                               b_per_image);
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

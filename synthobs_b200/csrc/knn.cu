@@ -179,9 +179,9 @@ extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32
                                    int32_t k, double half_width, double* dk,
                                    void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return SO_OK;
     if (n < 0 || k < 1 || !(half_width > 0.0) || !X || !Y || !ix || !dk) return SO_ERR_BAD_ARG;
     if (n >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
-    if (n == 0) return SO_OK;
     bool ok = false;
     KnnLayout l = carve_knn(workspace, workspace_bytes, n, &ok);
     if (!ok || !workspace) return SO_ERR_WORKSPACE;

@@ -382,7 +382,7 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (n < 0 || n_seg < 1 || na < 1 || nz < 1 || n_filters < 1) return SO_ERR_BAD_ARG;
     if (na - 1 > kMaxThr || nz - 1 > kMaxThr || (int64_t)na * nz > 65535) return SO_ERR_TOO_LARGE;
-    if (!masses || !ages || !metals || !tab_inc || !tab_tn || (na > 1 && !age_thr) || (nz > 1 && !z_thr))
+    if (n > 0 && (!masses || !ages || !metals || !tab_inc || !tab_tn || (na > 1 && !age_thr) || (nz > 1 && !z_thr)))
         return SO_ERR_BAD_ARG;
     if (n == 0) {
         if (out_sums) SO_CUDA(cudaMemsetAsync(out_sums, 0, sizeof(double) * n_seg * n_filters, st));
@@ -468,6 +468,7 @@ extern "C" int so_sed_hist(const double* masses, const int32_t* cell, int64_t n,
     cudaStream_t st = (cudaStream_t)stream;
     if (n < 0 || n_seg < 1 || ncell < 1 || !H || ld_h < 2 * (int64_t)ncell) return SO_ERR_BAD_ARG;
     if (!seg_offsets && n_seg != 1) return SO_ERR_BAD_ARG;
+    if (n > 0 && (!masses || !cell)) return SO_ERR_BAD_ARG;
     const int chunks = hist_chunks(n_seg);
     SoArena a(workspace, workspace_bytes);
     double* partial = a.take<double>((int64_t)n_seg * chunks * 2 * ncell);

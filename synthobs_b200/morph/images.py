@@ -76,28 +76,33 @@ def convolve_fft_device(img, kernel):
     """astropy.convolution.convolve_fft with its defaults (zero fill, kernel
     normalised to unit sum and centred on element n//2, output cropped to the
     image; see oracle/ref_loader.py for the restated identity) as a batched
-    cuFFT step (K10).  img: [..., n, n] float32 CUDA; kernel: [nk, nk] host
-    float64 array (normalised in float64) or CUDA tensor."""
+    cuFFT step (K10).  img: [..., n, n] float32 CUDA; kernel: [nk, nk] (shared by
+    all images) or [C, nk, nk] (one per image), host float64 array (normalised
+    in float64) or CUDA tensor."""
     import scipy.fft as sfft
     _cabi.require_device()
     if isinstance(kernel, torch.Tensor):
         k = kernel.to(img.device, torch.float64)
-        k = (k / k.sum()).to(torch.float32)
+        k = (k / k.sum(dim=(-2, -1), keepdim=True)).to(torch.float32)
     else:
         kh = np.asarray(kernel, dtype=np.float64)
-        k = dv.to_dev((kh / kh.sum()).astype(np.float32), torch.float32)
+        k = dv.to_dev((kh / kh.sum(axis=(-2, -1), keepdims=True)).astype(np.float32), torch.float32)
     n_y, n_x = img.shape[-2], img.shape[-1]
-    py = sfft.next_fast_len(n_y + k.shape[0] - 1, real=True)
-    px = sfft.next_fast_len(n_x + k.shape[1] - 1, real=True)
+    py = sfft.next_fast_len(n_y + k.shape[-2] - 1, real=True)
+    px = sfft.next_fast_len(n_x + k.shape[-1] - 1, real=True)
     x = img.reshape(-1, n_y, n_x)
-    A = torch.fft.rfft2(x, s=(py, px))
-    K = torch.fft.rfft2(k, s=(py, px))
+    per_image = k.dim() == 3
+    if per_image and k.shape[0] != x.shape[0]:
+        raise ValueError('one kernel per image expected')
+    A = torch.fft.rfft2(x, s=(py, px)).contiguous()
+    K = torch.fft.rfft2(k, s=(py, px)).contiguous()     # 2-D rfft2 returns a transposed-stride view
     prod = torch.empty_like(A)
     _cabi.check(_cabi.lib.so_complex_mul_bcast(_cabi.ptr(torch.view_as_real(A)), _cabi.ptr(torch.view_as_real(K)),
                                                _cabi.ptr(torch.view_as_real(prod)), A.shape[-2] * A.shape[-1],
-                                               A.shape[0], _cabi.stream()), 'so_complex_mul_bcast')
+                                               A.shape[0], 1 if per_image else 0, _cabi.stream()),
+                'so_complex_mul_bcast')
     full = torch.fft.irfft2(prod, s=(py, px))
-    oy, ox = k.shape[0] // 2, k.shape[1] // 2
+    oy, ox = k.shape[-2] // 2, k.shape[-1] // 2
     out = full[:, oy:oy + n_y, ox:ox + n_x].contiguous()
     return out.reshape(img.shape)
 
@@ -229,13 +234,43 @@ def core(X, Y, L, resolution=0.1, ndim=100, smoothing=False, verbose=False):
     return img
 
 
+def median_device(x):
+    """np.median semantics (mean of the two middle values for even n) on a CUDA tensor."""
+    srt = torch.sort(x.reshape(-1)).values
+    m = srt.numel()
+    return srt[m // 2] if m % 2 else 0.5 * (srt[m // 2 - 1] + srt[m // 2])
+
+
+def particle_device_multi(obs_list, Xd, Yd, Ld):
+    """Several observed() set-ups that share one geometry (same pixel scale, width,
+    super-sampling, offsets, smoothing) imaged in one pass: one k-NN, one tile
+    binning, a C-channel deposit, one batched FFT with a PSF per channel, one
+    rebin.  Xd, Yd already recentred; Ld: [C, n].  The reference repeats the k-NN
+    and the deposit per filter on identical positions (images.py:277-284)."""
+    o0 = obs_list[0]
+    for o in obs_list[1:]:
+        same = (o.ndim_super == o0.ndim_super and o.resolution == o0.resolution and o.xoffset == o0.xoffset
+                and o.yoffset == o0.yoffset and o.smoothing == o0.smoothing and o.ndim == o0.ndim)
+        if not same:
+            raise ValueError('particle_device_multi needs identical geometry; group the filters by pixel scale')
+    method, scale = _parse_smoothing(o0.smoothing)
+    X = Xd + o0.xoffset if o0.xoffset else Xd
+    Y = Yd + o0.yoffset if o0.yoffset else Yd
+    if method == 'adaptive':
+        r = deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=int(scale), want_ngp=False)
+        no_psf = r['data']
+    else:
+        no_psf, _, _, r = core_device(X, Y, Ld, o0.resolution, o0.ndim_super, o0.smoothing)
+    kernels = np.stack([o.psf_kernel() for o in obs_list])
+    conv = convolve_fft_device(no_psf, kernels)
+    return {'super_no_PSF': no_psf, 'super_data': conv, 'no_PSF': rebin_device(no_psf, o0.ndim),
+            'data': rebin_device(conv, o0.ndim), 'stats': r['stats']}
+
+
 def _median_inplace_shift(A, offset):
     """A -= median(A); A += offset, in place on the caller's array (images.py:183-187)."""
     if isinstance(A, torch.Tensor):
-        srt = torch.sort(A.reshape(-1)).values
-        m = A.numel()
-        med = srt[m // 2] if m % 2 else 0.5 * (srt[m // 2 - 1] + srt[m // 2])   # np.median semantics
-        A -= med
+        A -= median_device(A)
         A += offset
     else:
         A -= np.median(A)

@@ -316,9 +316,14 @@ def _broadband(model, kind, F, filters, Masses, Ages, Metallicities, tauVs_ISM, 
     thr = model._thresholds()
     tab_inc, tab_tn = _tables(model, kind, filters)
     zshift = (1. + model.Fnu['z']) if kind == 'Fnu' else 1.0                    # models.py:163,167
-    piv = [F[f].pivwv() / zshift for f in filters]
-    kI = None if not model.dust_ISM else [float(_dust_k(model, 'ISM', p)) for p in piv]
-    kB = None if not model.dust_BC else [float(_dust_k(model, 'BC', p)) for p in piv]
+    ckey = (kind, id(F), tuple(filters), repr(model.dust_ISM), repr(model.dust_BC), zshift)
+    kcache = model._dev.setdefault('dustk', {})
+    if ckey not in kcache:     # pivot wavelengths cost two trapz per filter: do them once per (F, dust) setup
+        piv = [F[f].pivwv() / zshift for f in filters]
+        kcache.clear()
+        kcache[ckey] = (None if not model.dust_ISM else [float(_dust_k(model, 'ISM', p)) for p in piv],
+                        None if not model.dust_BC else [float(_dust_k(model, 'BC', p)) for p in piv])
+    kI, kB = kcache[ckey]
     if offsets is not None:
         off = dv.to_dev(offsets, torch.int64)
         nseg = off.numel() - 1
