@@ -56,59 +56,65 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, 20 ms period;
+    same fields as the nvidia-smi clocks line of B200_PROFILING.md)."""
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = 0.0
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:   # noqa: BLE001
+            self.nv = None
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+    def _run(self):
+        nv = self.nv
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = get_reasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.time(), float(clk), int(r), pw))
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
 
     def summary(self, t0, t1):
-        sm, smax, reasons = [], [], set()
-        for t, line in self.lines:
-            f = [x.strip() for x in line.split(',')]
-            if len(f) < 9:
-                continue
-            try:
-                clk, mx = float(f[1]), float(f[2])
-            except ValueError:
-                continue
-            smax.append(mx)
-            if t0 - 0.05 <= t <= t1 + 0.05:
-                sm.append(clk)
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-        if not sm:
-            sm = [float(x[1].split(',')[1]) for x in self.lines[-3:]] if self.lines else [0.0]
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)) if smax else 0.0,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        if self.nv is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + getattr(self, 'err', '')]}
+        # reason bit masks (nvml.h): sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40
+        names = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown'}
+        sel = [x for x in self.samples if t0 <= x[0] <= t1] or self.samples[-3:]
+        reasons = set()
+        for _, _, r, _ in sel:
+            for bit, name in names.items():
+                if r & bit:
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median([x[1] for x in sel])) if sel else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(reasons), 'samples': len(sel),
+                'power_w_max': max([x[3] for x in sel]) if sel else None}
 
 
 def setup_model(n_lam=N_LAM, n_filters=N_FILTERS):
@@ -447,6 +453,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-imaging', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-sed-e2e', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -64,11 +64,9 @@ int so_device_ok(void);
  *   tau_ism, tau_bc      : [n] float64 or NULL (= zeros, :92-93)
  *   seg_offsets          : [n_seg+1] int64 CSR offsets of the galaxies, or NULL
  *                          with n_seg = 1 (one galaxy = all particles)
- *   age_thr [na-1], z_thr [nz-1] : float64 thresholds (device)
- *   age_guess_a, age_guess_b     : optional closed-form first guess of the age
- *                          node, floor(log2f(Age)*a + b), for log-uniform age grids;
- *                          it is always corrected against age_thr, so it affects
- *                          speed only.  a = 0 selects a binary search.
+ *   age_thr [na-1], z_thr [nz-1] : HOST float64 thresholds (na, nz <= 128); they
+ *                          travel to the kernel as launch parameters together with
+ *                          a log2-spaced first-guess table built from them
  *   tab_inc, tab_tn      : [n_filters, na*nz] float32: stellar_incident and
  *                          (stellar_transmitted + nebular) per filter (:131-133)
  *   k_ism, k_bc          : HOST [n_filters] float64 dust-curve value at the filter
@@ -84,7 +82,6 @@ int so_sed_broadband(const double* masses, const double* ages, const double* met
                      const double* tau_ism, const double* tau_bc, int64_t n,
                      const int64_t* seg_offsets, int64_t n_seg,
                      const double* age_thr, int32_t na, const double* z_thr, int32_t nz, double young_thr,
-                     double age_guess_a, double age_guess_b,
                      const float* tab_inc, const float* tab_tn, int32_t n_filters,
                      const double* k_ism, const double* k_bc, double fesc,
                      float* out_pf, double* out_sums, int32_t* out_cell,

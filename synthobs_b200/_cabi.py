@@ -30,7 +30,7 @@ SIGNATURES = {
     'so_version': (c_char_p, []),
     'so_device_ok': (c_int, []),
     'so_sed_broadband_workspace_bytes': (I64, [I64, I64, I32]),
-    'so_sed_broadband': (c_int, [P, P, P, P, P, I64, P, I64, P, I32, P, I32, D, D, D, P, P, I32,
+    'so_sed_broadband': (c_int, [P, P, P, P, P, I64, P, I64, POINTER(c_double), I32, POINTER(c_double), I32, D, P, P, I32,
                                  POINTER(c_double), POINTER(c_double), D, P, P, P, P, I64, P]),
     'so_sed_hist_workspace_bytes': (I64, [I64, I32]),
     'so_sed_hist': (c_int, [P, P, I64, P, I64, I32, P, P, I64, P, I64, P]),

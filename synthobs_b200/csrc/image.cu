@@ -556,7 +556,7 @@ extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64
     cudaStream_t st = (cudaStream_t)stream;
     if (n < 0 || ndim < 1 || n_chan < 1 || n_pairs < 0 || !plan_workspace) return SO_ERR_BAD_ARG;
     if (n_pairs >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
-    if ((data || simple) && !L) return SO_ERR_BAD_ARG;
+    if (n > 0 && (data || simple) && !L) return SO_ERR_BAD_ARG;
     bool ok = false;
     PlanView pv = carve_plan(const_cast<void*>(plan_workspace), (int64_t)1 << 60, n, &ok);
     DepositLayout d = carve_deposit(workspace, workspace_bytes, n_pairs, ndim, n_chan, &ok);

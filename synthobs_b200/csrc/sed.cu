@@ -13,10 +13,19 @@
 
 namespace {
 
-constexpr int kThreads = 512;           // threads per persistent CTA
-constexpr int kPerThread = 4;           // particles per thread per work item
+constexpr int kThreads = 512;                 // threads per persistent CTA, 2 CTAs per SM
+constexpr int kPerThread = 2;                 // particles per thread per work item
 constexpr int kItem = kThreads * kPerThread;  // particles per work item
-constexpr int kMaxThr = 512;            // max thresholds per axis held in smem
+constexpr int kMaxThr = 127;                  // max thresholds per axis (kernel-parameter resident)
+constexpr int kLut = 256;                     // first-guess table entries per axis
+
+// One NGP axis: ascending float64 thresholds + a log2-spaced first-guess table.
+struct Axis {
+    double thr[kMaxThr + 1];
+    unsigned char lut[kLut];   // lut[b] = #{thr <= lower edge of log2-bin b}
+    float lo, inv_w;           // bin = (log2f(v) - lo) * inv_w
+    int n;                     // number of thresholds
+};
 
 struct BroadbandParams {
     const double* masses;
@@ -25,65 +34,65 @@ struct BroadbandParams {
     const double* tau_ism;
     const double* tau_bc;
     int64_t n;
-    const int64_t* seg_offsets;   // device, may be null (single segment)
+    const int64_t* seg_offsets;   // device, null = single segment
     int64_t n_seg;
     const int64_t* item_start;    // [n_seg+1] device (null when single segment)
     const int32_t* item_gal;      // [n_items] device (null when single segment)
-    int64_t n_items;
-    const double* age_thr;
-    const double* z_thr;
+    int64_t n_items;              // exact when single segment, else read from item_start[n_seg]
     int32_t na, nz;
     double young_thr;
-    float age_guess_a, age_guess_b;  // guess = floor(log2f(age)*a + b); a == 0 -> binary search
-    const float* tab_inc;            // [F, ncell]
+    const float* tab_inc;         // [F_total, ncell]
     const float* tab_tn;
     int32_t n_filters;
-    int32_t f0;                      // first filter of this launch (for out indexing)
+    int32_t f0;                   // first filter of this launch
     int32_t n_filters_total;
-    float k_ism[SO_MAX_FILTERS];     // dust k * log2(e), 0 when no dust
+    float k_ism[SO_MAX_FILTERS];  // -k * log2(e), 0 when no dust
     float k_bc[SO_MAX_FILTERS];
     float fesc;
-    float* out_pf;                   // [F_total, n]
-    double* partial;                 // [n_items, F_total]
+    float* out_pf;                // [F_total, n]
+    double* partial;              // [n_items, F_total]
     int32_t* out_cell;
+    Axis age, z;
 };
 
-// index = number of thresholds <= v, thresholds ascending; NaN -> 0
-__device__ __forceinline__ int locate_from_guess(const double* thr, int nthr, double v, int g) {
-    g = max(0, min(g, nthr));
-    while (g > 0 && !(v >= thr[g - 1])) --g;
-    while (g < nthr && v >= thr[g]) ++g;
-    return g;
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ int locate_bsearch(const double* thr, int nthr, double v) {
-    int lo = 0, hi = nthr;  // first index with thr > v
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (v >= thr[mid]) lo = mid + 1; else hi = mid;
-    }
-    return lo;
+
+// index = #{thr <= v} (ascending thresholds); NaN / +inf -> 0 like np.argmin over all-NaN/inf distances
+__device__ __forceinline__ int locate(const double* __restrict__ thr, const unsigned char* __restrict__ lut, int n,
+                                      float lo, float inv_w, double v) {
+    if (!(v < __longlong_as_double(0x7ff0000000000000LL))) return 0;
+    int b = (int)((__log2f((float)v) - lo) * inv_w);
+    b = max(0, min(kLut - 1, b));
+    int g = lut[b];
+    while (g > 0 && !(v >= thr[g - 1])) --g;
+    while (g < n && v >= thr[g]) ++g;
+    return g;
 }
 
 template <int FP>
-__global__ void __launch_bounds__(kThreads, 1) sed_broadband_kernel(const BroadbandParams p) {
+__global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid_constant__ BroadbandParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // row stride in float4 units is odd so random cells spread over all bank groups
-    constexpr int kStride4 = (FP / 4) | 1;
-    constexpr int kStride = kStride4 * 4;
+    constexpr int kStride = ((FP / 4) | 1) * 4;
     const int ncell = p.na * p.nz;
     float* s_inc = reinterpret_cast<float*>(smem_raw);
     float* s_tn = s_inc + (size_t)ncell * kStride;
     double* s_age_thr = reinterpret_cast<double*>(s_tn + (size_t)ncell * kStride);
-    double* s_z_thr = s_age_thr + (p.na - 1);
-    double* s_red = s_z_thr + (p.nz - 1);      // [kThreads/32][FP]
+    double* s_z_thr = s_age_thr + (kMaxThr + 1);
+    double* s_red = s_z_thr + (kMaxThr + 1);                       // [kThreads/32][FP]
+    unsigned char* s_age_lut = reinterpret_cast<unsigned char*>(s_red + (kThreads / 32) * FP);
+    unsigned char* s_z_lut = s_age_lut + kLut;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nthr_a = p.na - 1, nthr_z = p.nz - 1;
 
     // stage the per-filter tables as [cell][filter] (transposed from [filter][cell])
     for (int idx = tid; idx < ncell * FP; idx += kThreads) {
-        int f = idx / ncell, c = idx - f * ncell;   // consecutive threads -> consecutive cells: coalesced
+        const int f = idx / ncell, c = idx - f * ncell;   // consecutive threads -> consecutive cells: coalesced
         float a = 0.f, b = 0.f;
         if (f < p.n_filters) {
             a = p.tab_inc[(size_t)(p.f0 + f) * ncell + c];
@@ -92,107 +101,98 @@ __global__ void __launch_bounds__(kThreads, 1) sed_broadband_kernel(const Broadb
         s_inc[c * kStride + f] = a;
         s_tn[c * kStride + f] = b;
     }
-    for (int i = tid; i < nthr_a; i += kThreads) s_age_thr[i] = p.age_thr[i];
-    for (int i = tid; i < nthr_z; i += kThreads) s_z_thr[i] = p.z_thr[i];
+    for (int i = tid; i <= kMaxThr; i += kThreads) { s_age_thr[i] = p.age.thr[i]; s_z_thr[i] = p.z.thr[i]; }
+    for (int i = tid; i < kLut; i += kThreads) { s_age_lut[i] = p.age.lut[i]; s_z_lut[i] = p.z.lut[i]; }
     __syncthreads();
 
     // contiguous range of work items per CTA so consecutive items share a galaxy
-    const int64_t n_items = p.item_start ? p.item_start[p.n_seg] : p.n_items;
+    const bool segmented = p.item_start != nullptr;
+    const int64_t n_items = segmented ? p.item_start[p.n_seg] : p.n_items;
     const int64_t per = (n_items + gridDim.x - 1) / gridDim.x;
     const int64_t item_lo = (int64_t)blockIdx.x * per;
     const int64_t item_hi = min(n_items, item_lo + per);
+    if (item_lo >= item_hi) return;
+
+    // running (galaxy, segment end, chunk start): advanced incrementally, no per-item lookups
+    int64_t gal = 0, s1 = p.n, begin = item_lo * kItem;
+    if (segmented) {
+        gal = p.item_gal[item_lo];
+        const int64_t s0 = p.seg_offsets[gal];
+        s1 = p.seg_offsets[gal + 1];
+        begin = s0 + (item_lo - p.item_start[gal]) * kItem;
+    }
 
     float acc[FP];
 #pragma unroll
     for (int f = 0; f < FP; ++f) acc[f] = 0.f;
     const float fesc = p.fesc, ofe = 1.0f - p.fesc;
+    const int nf = p.n_filters;
 
     for (int64_t item = item_lo; item < item_hi; ++item) {
-        int64_t begin, count;
-        int32_t gal = 0;
-        bool last_of_run;
-        if (p.item_gal) {
-            gal = p.item_gal[item];
-            const int64_t s0 = p.seg_offsets[gal], s1 = p.seg_offsets[gal + 1];
-            begin = s0 + (item - p.item_start[gal]) * kItem;
-            count = min((int64_t)kItem, s1 - begin);
-            last_of_run = (item + 1 == item_hi) || (p.item_gal[item + 1] != gal);
-        } else {
-            begin = item * kItem;
-            count = min((int64_t)kItem, p.n - begin);
-            last_of_run = (item + 1 == item_hi);
-        }
+        const int count = (int)min((int64_t)kItem, s1 - begin);
 
-        double age[kPerThread], zz[kPerThread], mm[kPerThread], ti[kPerThread], tb[kPerThread];
+        double age[kPerThread], zz[kPerThread];
+        float mm[kPerThread], ti[kPerThread], tb[kPerThread];
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
             const int64_t i = begin + j * kThreads + tid;
             const bool on = (j * kThreads + tid) < count;
             age[j] = on ? ldg_stream(p.ages + i) : 1.0;
             zz[j] = on ? ldg_stream(p.metals + i) : 1.0;
-            mm[j] = on ? ldg_stream(p.masses + i) : 0.0;
-            ti[j] = (on && p.tau_ism) ? ldg_stream(p.tau_ism + i) : 0.0;
-            tb[j] = (on && p.tau_bc) ? ldg_stream(p.tau_bc + i) : 0.0;
+            mm[j] = on ? (float)ldg_stream(p.masses + i) : 0.f;
+            ti[j] = (on && p.tau_ism) ? (float)ldg_stream(p.tau_ism + i) : 0.f;
+            tb[j] = (on && p.tau_bc) ? (float)ldg_stream(p.tau_bc + i) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
             const int64_t i = begin + j * kThreads + tid;
             const bool on = (j * kThreads + tid) < count;
-            // --- NGP cell (float64 compares only)
-            int ia, iz;
-            if (!(age[j] < __longlong_as_double(0x7ff0000000000000LL))) {
-                ia = 0;  // +inf or NaN: every |grid - v| is inf/NaN -> argmin 0
-            } else if (p.age_guess_a != 0.f) {
-                int g = (int)floorf(fmaf(__log2f((float)age[j]), p.age_guess_a, p.age_guess_b));
-                ia = locate_from_guess(s_age_thr, nthr_a, age[j], g);
-            } else {
-                ia = locate_from_guess(s_age_thr, nthr_a, age[j], locate_bsearch(s_age_thr, nthr_a, age[j]));
-            }
-            if (!(zz[j] < __longlong_as_double(0x7ff0000000000000LL))) {
-                iz = 0;
-            } else if (nthr_z <= 16) {
-                iz = 0;
-                for (int k = 0; k < nthr_z; ++k) iz += (zz[j] >= s_z_thr[k]) ? 1 : 0;
-            } else {
-                iz = locate_bsearch(s_z_thr, nthr_z, zz[j]);
-            }
+            // --- NGP cell: float64 compares against the host-built thresholds
+            const int ia = locate(s_age_thr, s_age_lut, p.age.n, p.age.lo, p.age.inv_w, age[j]);
+            const int iz = locate(s_z_thr, s_z_lut, p.z.n, p.z.lo, p.z.inv_w, zz[j]);
             const bool young = (age[j] < p.young_thr) && (age[j] >= 0.0);
             const int cell = ia * p.nz + iz;
             if (on && p.out_cell) p.out_cell[i] = cell + (young ? 65536 : 0);
 
-            const float m = (float)mm[j];
-            const float tI = (float)ti[j], tB = (float)tb[j];
+            const float m = mm[j], tI = ti[j], tB = tb[j];     // m == 0 for lanes past the end
             const float4* rinc = reinterpret_cast<const float4*>(s_inc + cell * kStride);
             const float4* rtn = reinterpret_cast<const float4*>(s_tn + cell * kStride);
+            float* po = p.out_pf ? p.out_pf + (size_t)p.f0 * p.n + i : nullptr;
 #pragma unroll
             for (int q = 0; q < FP / 4; ++q) {
-                const float4 vi = rinc[q];
-                float4 vt = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (young) vt = rtn[q];
-                const float inc4[4] = {vi.x, vi.y, vi.z, vi.w};
-                const float tn4[4] = {vt.x, vt.y, vt.z, vt.w};
+                if (q * 4 < nf) {
+                    const float4 vi = rinc[q];
+                    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (young) vt = rtn[q];
+                    const float inc4[4] = {vi.x, vi.y, vi.z, vi.w};
+                    const float tn4[4] = {vt.x, vt.y, vt.z, vt.w};
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int f = q * 4 + r;
-                    const float TI = exp2f(-tI * p.k_ism[f]);
-                    float l;
-                    if (young) {
-                        const float TB = exp2f(-tB * p.k_bc[f]);
-                        l = m * (TI * fesc * inc4[r] + (TI * TB) * ofe * tn4[r]);
-                    } else {
-                        l = m * TI * inc4[r];
-                    }
-                    if (on) {
+                    for (int r = 0; r < 4; ++r) {
+                        const int f = q * 4 + r;
+                        const float TI = ex2_approx(tI * p.k_ism[f]);
+                        float x = inc4[r];
+                        if (young) x = fesc * x + ex2_approx(tB * p.k_bc[f]) * (ofe * tn4[r]);
+                        const float l = m * (TI * x);
                         acc[f] += l;
-                        if (p.out_pf && f < p.n_filters)
-                            p.out_pf[(size_t)(p.f0 + f) * p.n + i] = l;
+                        if (po && on && f < nf) po[(size_t)f * p.n] = l;
                     }
                 }
             }
         }
 
+        // advance to the next work item; a run ends with the galaxy (or with this CTA's range)
+        int64_t next_begin = begin + kItem;
+        bool run_end = (item + 1 == item_hi);
+        if (segmented && !run_end && next_begin >= s1) {
+            int64_t s0n;
+            do { ++gal; s0n = p.seg_offsets[gal]; s1 = p.seg_offsets[gal + 1]; } while (s1 == s0n);
+            next_begin = s0n;
+            run_end = true;
+        }
+        begin = next_begin;
+
         if (p.partial) {
-            if (last_of_run) {
+            if (run_end) {
                 // block reduction of the per-thread sums of this run of items
 #pragma unroll
                 for (int f = 0; f < FP; ++f) {
@@ -201,13 +201,13 @@ __global__ void __launch_bounds__(kThreads, 1) sed_broadband_kernel(const Broadb
                     acc[f] = 0.f;
                 }
                 __syncthreads();
-                if (tid < p.n_filters) {
+                if (tid < nf) {
                     double s = 0.0;
                     for (int w = 0; w < kThreads / 32; ++w) s += s_red[w * FP + tid];
                     p.partial[item * p.n_filters_total + p.f0 + tid] = s;
                 }
                 __syncthreads();
-            } else if (tid < p.n_filters) {
+            } else if (tid < nf) {
                 p.partial[item * p.n_filters_total + p.f0 + tid] = 0.0;
             }
         }
@@ -295,16 +295,43 @@ template <int FP>
 int launch_broadband(const BroadbandParams& p, cudaStream_t st) {
     constexpr int kStride = ((FP / 4) | 1) * 4;
     const size_t ncell = (size_t)p.na * p.nz;
-    size_t smem = 2 * ncell * kStride * sizeof(float) + (size_t)(p.na - 1 + p.nz - 1) * sizeof(double) +
-                  (size_t)(kThreads / 32) * FP * sizeof(double) + 64;
+    size_t smem = 2 * ncell * kStride * sizeof(float) + 2 * (size_t)(kMaxThr + 1) * sizeof(double) +
+                  (size_t)(kThreads / 32) * FP * sizeof(double) + 2 * kLut + 64;
     if (smem > 227 * 1024) return SO_ERR_TOO_LARGE;
     SO_CUDA(cudaFuncSetAttribute(sed_broadband_kernel<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = so_num_sms();
-    if ((int64_t)grid > p.n_items) grid = (int)p.n_items;
+    int per_sm = (smem <= 110 * 1024) ? 2 : 1;
+    int64_t grid = (int64_t)so_num_sms() * per_sm;
+    if (grid > p.n_items) grid = p.n_items;
     if (grid < 1) grid = 1;
-    sed_broadband_kernel<FP><<<grid, kThreads, smem, st>>>(p);
+    sed_broadband_kernel<FP><<<(unsigned)grid, kThreads, smem, st>>>(p);
     SO_LAUNCH_CHECK();
     return SO_OK;
+}
+
+// host: thresholds (ascending, may end with +inf) -> Axis with its log2-spaced first-guess table
+static void fill_axis(Axis& ax, const double* thr, int n) {
+    ax.n = n;
+    for (int i = 0; i <= kMaxThr; ++i) ax.thr[i] = (i < n) ? thr[i] : __builtin_inf();
+    double lo = 0.0, hi = 1.0;
+    bool any = false;
+    for (int i = 0; i < n; ++i) {
+        if (thr[i] > 0 && thr[i] < __builtin_inf()) {
+            const double l = log2(thr[i]);
+            if (!any) { lo = hi = l; any = true; }
+            if (l < lo) lo = l;
+            if (l > hi) hi = l;
+        }
+    }
+    lo -= 1.0; hi += 1.0;
+    const double w = (hi - lo) / kLut;
+    ax.lo = (float)lo;
+    ax.inv_w = (float)(1.0 / w);
+    for (int b = 0; b < kLut; ++b) {
+        const double edge = exp2(lo + b * w);
+        int g = 0;
+        while (g < n && edge >= thr[g]) ++g;
+        ax.lut[b] = (unsigned char)g;
+    }
 }
 
 __global__ void hist_kernel(const double* __restrict__ masses, const int32_t* __restrict__ cell,
@@ -374,7 +401,6 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
                                 const double* tau_ism, const double* tau_bc, int64_t n,
                                 const int64_t* seg_offsets, int64_t n_seg,
                                 const double* age_thr, int32_t na, const double* z_thr, int32_t nz, double young_thr,
-                                double age_guess_a, double age_guess_b,
                                 const float* tab_inc, const float* tab_tn, int32_t n_filters,
                                 const double* k_ism, const double* k_bc, double fesc,
                                 float* out_pf, double* out_sums, int32_t* out_cell,
@@ -400,10 +426,11 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
     BroadbandParams p{};
     p.masses = masses; p.ages = ages; p.metals = metals; p.tau_ism = tau_ism; p.tau_bc = tau_bc; p.n = n;
     p.seg_offsets = seg_offsets; p.n_seg = n_seg;
-    p.age_thr = age_thr; p.z_thr = z_thr; p.na = na; p.nz = nz; p.young_thr = young_thr;
+    p.na = na; p.nz = nz; p.young_thr = young_thr;
+    fill_axis(p.age, age_thr, na - 1);
+    fill_axis(p.z, z_thr, nz - 1);
     p.tab_inc = tab_inc; p.tab_tn = tab_tn; p.n_filters_total = n_filters;
     p.fesc = (float)fesc; p.out_pf = out_pf; p.partial = out_sums ? partial : nullptr; p.out_cell = out_cell;
-    p.age_guess_a = (float)age_guess_a; p.age_guess_b = (float)age_guess_b;
 
     if (segmented) {
         item_scan_kernel<<<1, 1024, 0, st>>>(seg_offsets, n_seg, item_start);
@@ -422,8 +449,8 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
         p.f0 = f0; p.n_filters = nf;
         const double log2e = 1.4426950408889634;
         for (int f = 0; f < SO_MAX_FILTERS; ++f) {
-            p.k_ism[f] = (f < nf && k_ism) ? (float)(k_ism[f0 + f] * log2e) : 0.f;
-            p.k_bc[f] = (f < nf && k_bc) ? (float)(k_bc[f0 + f] * log2e) : 0.f;
+            p.k_ism[f] = (f < nf && k_ism) ? (float)(-k_ism[f0 + f] * log2e) : 0.f;
+            p.k_bc[f] = (f < nf && k_bc) ? (float)(-k_bc[f0 + f] * log2e) : 0.f;
         }
         // only the first chunk writes the cell ids
         if (f0 > 0) p.out_cell = nullptr;

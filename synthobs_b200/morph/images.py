@@ -72,38 +72,51 @@ def rebin(arr, new_shape):
     return dv.to_host(rebin_device(dv.to_dev(arr, torch.float32), new_shape[0]))
 
 
+class KernelSpectrum:
+    """A convolution kernel prepared for an image size: normalised (float64), zero-padded,
+    transformed once.  Re-usable across calls (the PSF image of an observed() set-up only
+    depends on its geometry)."""
+
+    def __init__(self, kernel, n_y, n_x):
+        import scipy.fft as sfft
+        dev = dv.device()
+        if isinstance(kernel, torch.Tensor):
+            k = kernel.to(dev, torch.float64)
+            k = (k / k.sum(dim=(-2, -1), keepdim=True)).to(torch.float32)
+        else:
+            kh = np.asarray(kernel, dtype=np.float64)
+            k = dv.to_dev((kh / kh.sum(axis=(-2, -1), keepdims=True)).astype(np.float32), torch.float32)
+        self.per_image = k.dim() == 3
+        self.n_kernels = k.shape[0] if self.per_image else 1
+        self.n_y, self.n_x = n_y, n_x
+        self.py = sfft.next_fast_len(n_y + k.shape[-2] - 1, real=True)
+        self.px = sfft.next_fast_len(n_x + k.shape[-1] - 1, real=True)
+        self.oy, self.ox = k.shape[-2] // 2, k.shape[-1] // 2     # astropy centres the kernel on element n//2
+        self.K = torch.fft.rfft2(k, s=(self.py, self.px)).contiguous()   # 2-D rfft2 returns a strided view
+
+
 def convolve_fft_device(img, kernel):
     """astropy.convolution.convolve_fft with its defaults (zero fill, kernel
     normalised to unit sum and centred on element n//2, output cropped to the
     image; see oracle/ref_loader.py for the restated identity) as a batched
     cuFFT step (K10).  img: [..., n, n] float32 CUDA; kernel: [nk, nk] (shared by
-    all images) or [C, nk, nk] (one per image), host float64 array (normalised
-    in float64) or CUDA tensor."""
-    import scipy.fft as sfft
+    all images) or [C, nk, nk] (one per image) as host float64 array or CUDA
+    tensor, or a prepared KernelSpectrum."""
     _cabi.require_device()
-    if isinstance(kernel, torch.Tensor):
-        k = kernel.to(img.device, torch.float64)
-        k = (k / k.sum(dim=(-2, -1), keepdim=True)).to(torch.float32)
-    else:
-        kh = np.asarray(kernel, dtype=np.float64)
-        k = dv.to_dev((kh / kh.sum(axis=(-2, -1), keepdims=True)).astype(np.float32), torch.float32)
     n_y, n_x = img.shape[-2], img.shape[-1]
-    py = sfft.next_fast_len(n_y + k.shape[-2] - 1, real=True)
-    px = sfft.next_fast_len(n_x + k.shape[-1] - 1, real=True)
+    ks = kernel if isinstance(kernel, KernelSpectrum) else KernelSpectrum(kernel, n_y, n_x)
+    if (ks.n_y, ks.n_x) != (n_y, n_x):
+        raise ValueError('kernel spectrum prepared for another image size')
     x = img.reshape(-1, n_y, n_x)
-    per_image = k.dim() == 3
-    if per_image and k.shape[0] != x.shape[0]:
+    if ks.per_image and ks.n_kernels != x.shape[0]:
         raise ValueError('one kernel per image expected')
-    A = torch.fft.rfft2(x, s=(py, px)).contiguous()
-    K = torch.fft.rfft2(k, s=(py, px)).contiguous()     # 2-D rfft2 returns a transposed-stride view
-    prod = torch.empty_like(A)
-    _cabi.check(_cabi.lib.so_complex_mul_bcast(_cabi.ptr(torch.view_as_real(A)), _cabi.ptr(torch.view_as_real(K)),
-                                               _cabi.ptr(torch.view_as_real(prod)), A.shape[-2] * A.shape[-1],
-                                               A.shape[0], 1 if per_image else 0, _cabi.stream()),
+    A = torch.fft.rfft2(x, s=(ks.py, ks.px)).contiguous()
+    _cabi.check(_cabi.lib.so_complex_mul_bcast(_cabi.ptr(torch.view_as_real(A)), _cabi.ptr(torch.view_as_real(ks.K)),
+                                               _cabi.ptr(torch.view_as_real(A)), A.shape[-2] * A.shape[-1],
+                                               A.shape[0], 1 if ks.per_image else 0, _cabi.stream()),
                 'so_complex_mul_bcast')
-    full = torch.fft.irfft2(prod, s=(py, px))
-    oy, ox = k.shape[-2] // 2, k.shape[-1] // 2
-    out = full[:, oy:oy + n_y, ox:ox + n_x].contiguous()
+    full = torch.fft.irfft2(A, s=(ks.py, ks.px))
+    out = full[:, ks.oy:ks.oy + n_y, ks.ox:ks.ox + n_x].contiguous()
     return out.reshape(img.shape)
 
 
@@ -261,8 +274,11 @@ def particle_device_multi(obs_list, Xd, Yd, Ld):
         no_psf = r['data']
     else:
         no_psf, _, _, r = core_device(X, Y, Ld, o0.resolution, o0.ndim_super, o0.smoothing)
-    kernels = np.stack([o.psf_kernel() for o in obs_list])
-    conv = convolve_fft_device(no_psf, kernels)
+    key = tuple(id(o) for o in obs_list)
+    if getattr(o0, '_multi_spec', (None, None))[0] != key:
+        o0._multi_spec = (key, KernelSpectrum(np.stack([o.psf_kernel() for o in obs_list]), o0.ndim_super,
+                                              o0.ndim_super))
+    conv = convolve_fft_device(no_psf, o0._multi_spec[1])
     return {'super_no_PSF': no_psf, 'super_data': conv, 'no_PSF': rebin_device(no_psf, o0.ndim),
             'data': rebin_device(conv, o0.ndim), 'stats': r['stats']}
 
@@ -330,9 +346,18 @@ class observed():
             print('-' * 10)
 
     def psf_kernel(self):
-        xx = yy = np.linspace(-(self.width_arcsec / self.native_pixel_scale / 2.),
-                              (self.width_arcsec / self.native_pixel_scale / 2.), self.ndim_super)   # images.py:198
-        return self.PSF.f(xx, yy)                                                                   # images.py:200
+        """PSF image on the super-sampled grid; depends only on the geometry fixed at
+        construction, so it is evaluated once per observed() object."""
+        if getattr(self, '_psf_image', None) is None:
+            xx = yy = np.linspace(-(self.width_arcsec / self.native_pixel_scale / 2.),
+                                  (self.width_arcsec / self.native_pixel_scale / 2.), self.ndim_super)   # images.py:198
+            self._psf_image = self.PSF.f(xx, yy)                                                        # images.py:200
+        return self._psf_image
+
+    def psf_spectrum(self):
+        if getattr(self, '_psf_spec', None) is None:
+            self._psf_spec = KernelSpectrum(self.psf_kernel(), self.ndim_super, self.ndim_super)
+        return self._psf_spec
 
     def particle_device(self, Xd, Yd, Ld, dk=None):
         """Device pipeline after recentring: deposit -> PSF FFT convolution -> rebin.
@@ -344,7 +369,7 @@ class observed():
             no_psf = r['data']
         else:
             no_psf, _, _, r = core_device(Xd, Yd, Ld, self.resolution, self.ndim_super, self.smoothing)
-        conv = convolve_fft_device(no_psf, self.psf_kernel())                                       # images.py:202
+        conv = convolve_fft_device(no_psf, self.psf_spectrum())                                     # images.py:202
         return {'super_no_PSF': no_psf, 'super_data': conv,
                 'no_PSF': rebin_device(no_psf, self.ndim), 'data': rebin_device(conv, self.ndim),  # images.py:210-211
                 'info': r}

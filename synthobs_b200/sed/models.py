@@ -147,13 +147,7 @@ class define_model():
             la = np.asarray(self.grid['log10age'], dtype=np.float64)
             age_thr = ngp_thresholds(la, 6.0)
             z_thr = ngp_thresholds(self.grid['log10Z'], 0.0)
-            ga = gb = 0.0
-            if la.size > 2:
-                step = (la[-1] - la[0]) / (la.size - 1)
-                if step > 0 and np.allclose(np.diff(la), step, rtol=1e-9, atol=1e-12):
-                    ga = np.log10(2.0) / step
-                    gb = (6.0 - la[0]) / step + 0.5
-            c = {'age': dv.to_dev(age_thr), 'z': dv.to_dev(z_thr), 'ga': ga, 'gb': gb,
+            c = {'age': _cabi.host_doubles(age_thr), 'z': _cabi.host_doubles(z_thr),
                  'age_host': age_thr, 'z_host': z_thr, 'young': {}}
             self._dev['thr'] = c
         return c
@@ -338,8 +332,7 @@ def _broadband(model, kind, F, filters, Masses, Ages, Metallicities, tauVs_ISM, 
     rc = _cabi.lib.so_sed_broadband(
         _cabi.ptr(M), _cabi.ptr(A), _cabi.ptr(Z), _cabi.ptr(tI), _cabi.ptr(tB), n,
         _cabi.ptr(off), nseg,
-        _cabi.ptr(thr['age']), model.na, _cabi.ptr(thr['z']), model.nz, model._young_thr(log10t_BC),
-        thr['ga'], thr['gb'],
+        thr['age'], model.na, thr['z'], model.nz, model._young_thr(log10t_BC),
         _cabi.ptr(tab_inc), _cabi.ptr(tab_tn), nf,
         _cabi.host_doubles(kI), _cabi.host_doubles(kB), float(fesc),
         _cabi.ptr(out_pf), _cabi.ptr(out_sums), _cabi.ptr(out_cell),
@@ -428,8 +421,8 @@ def ngp_cells(model, Ages, Metallicities, log10t_BC=7.):
     ws = dv.workspace(wsb)
     rc = _cabi.lib.so_sed_broadband(
         _cabi.ptr(ones), _cabi.ptr(A), _cabi.ptr(Z), None, None, n, None, 1,
-        _cabi.ptr(thr['age']), model.na, _cabi.ptr(thr['z']), model.nz, model._young_thr(log10t_BC),
-        thr['ga'], thr['gb'], _cabi.ptr(dummy), _cabi.ptr(dummy), 1, None, None, 0.0,
+        thr['age'], model.na, thr['z'], model.nz, model._young_thr(log10t_BC),
+        _cabi.ptr(dummy), _cabi.ptr(dummy), 1, None, None, 0.0,
         None, None, _cabi.ptr(cell), _cabi.ptr(ws), wsb, _cabi.stream())
     _cabi.check(rc, 'so_sed_broadband')
     c = cell.cpu().numpy()
@@ -460,8 +453,8 @@ def _cells_and_hist(model, Masses, Ages, Metallicities, log10t_BC, offsets=None,
     ws = dv.workspace(wsb)
     rc = _cabi.lib.so_sed_broadband(
         _cabi.ptr(M), _cabi.ptr(A), _cabi.ptr(Z), None, None, n, _cabi.ptr(off), nseg,
-        _cabi.ptr(thr['age']), model.na, _cabi.ptr(thr['z']), model.nz, model._young_thr(log10t_BC),
-        thr['ga'], thr['gb'], _cabi.ptr(dummy), _cabi.ptr(dummy), 1, None, None, 0.0,
+        thr['age'], model.na, thr['z'], model.nz, model._young_thr(log10t_BC),
+        _cabi.ptr(dummy), _cabi.ptr(dummy), 1, None, None, 0.0,
         None, None, _cabi.ptr(cell), _cabi.ptr(ws), wsb, _cabi.stream())
     _cabi.check(rc, 'so_sed_broadband')
     ld = (2 * ncell + 3) // 4 * 4
