@@ -94,7 +94,7 @@ class ClockSampler:
                 self.samples.append((time.time(), float(clk), int(r), pw))
             except Exception:   # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         self.stop_flag = True
@@ -188,26 +188,27 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    sed_steps = 1 if args.no_sed else args.steps
+    for _ in range(1 if args.no_sed else max(args.warmup, 3)):
         out = sed_step_device()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(sed_steps):
         out = sed_step_device()
     e1.record()
     barrier()
     t_wall1 = time.time()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / sed_steps)
     sed_value = world * G * N_FILTERS / (ms_step * 1e-3)
     algo_bytes = 40.0 * n_part                     # 5 float64 arrays read once
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
     clocks = sampler.summary(t_wall0, t_wall1)
 
     # e2e
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = 1 if args.no_sed else max(3, min(args.steps, 10))
+    for _ in range(0 if args.no_sed else 2):
         sed_step_e2e()
     barrier()
     t0 = time.time()
@@ -452,6 +453,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-imaging', action='store_true')
+    ap.add_argument('--no-sed', action='store_true', help='profiling aid: skip the SED timed loops')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-sed-e2e', action='store_true')
     args = ap.parse_args()

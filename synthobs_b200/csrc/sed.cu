@@ -65,7 +65,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ int locate(const double* __restrict__ thr, const unsigned char* __restrict__ lut, int n,
                                       float lo, float inv_w, double v) {
     if (!(v < __longlong_as_double(0x7ff0000000000000LL))) return 0;
-    int b = (int)((__log2f((float)v) - lo) * inv_w);
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)v));
+    int b = (int)((lg - lo) * inv_w);
     b = max(0, min(kLut - 1, b));
     int g = lut[b];
     while (g > 0 && !(v >= thr[g - 1])) --g;
@@ -73,7 +75,13 @@ __device__ __forceinline__ int locate(const double* __restrict__ thr, const unsi
     return g;
 }
 
-template <int FP>
+__device__ __forceinline__ float2 ex2_approx2(float2 x) { return make_float2(ex2_approx(x.x), ex2_approx(x.y)); }
+
+// Persistent streaming kernel: each CTA walks a contiguous range of work items (kItem particles of
+// one galaxy).  The per-filter arithmetic runs on pairs of filters with the sm_100 packed FP32
+// instructions (FMUL2 / FFMA2): the kernel is issue-bound, not FLOP-bound, so halving the FP
+// instruction count is what moves it towards the HBM roofline.
+template <int FP, bool WRITE_PF>
 __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid_constant__ BroadbandParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // row stride in float4 units is odd so random cells spread over all bank groups
@@ -84,7 +92,8 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
     double* s_age_thr = reinterpret_cast<double*>(s_tn + (size_t)ncell * kStride);
     double* s_z_thr = s_age_thr + (kMaxThr + 1);
     double* s_red = s_z_thr + (kMaxThr + 1);                       // [kThreads/32][FP]
-    unsigned char* s_age_lut = reinterpret_cast<unsigned char*>(s_red + (kThreads / 32) * FP);
+    float2* s_k = reinterpret_cast<float2*>(s_red + (kThreads / 32) * FP);   // [2][FP/2]: -k log2e pairs (ISM, BC)
+    unsigned char* s_age_lut = reinterpret_cast<unsigned char*>(s_k + FP);
     unsigned char* s_z_lut = s_age_lut + kLut;
 
     const int tid = threadIdx.x;
@@ -103,6 +112,10 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
     }
     for (int i = tid; i <= kMaxThr; i += kThreads) { s_age_thr[i] = p.age.thr[i]; s_z_thr[i] = p.z.thr[i]; }
     for (int i = tid; i < kLut; i += kThreads) { s_age_lut[i] = p.age.lut[i]; s_z_lut[i] = p.z.lut[i]; }
+    for (int i = tid; i < FP; i += kThreads) {
+        reinterpret_cast<float*>(s_k)[i] = p.k_ism[i];
+        reinterpret_cast<float*>(s_k)[FP + i] = p.k_bc[i];
+    }
     __syncthreads();
 
     // contiguous range of work items per CTA so consecutive items share a galaxy
@@ -122,9 +135,9 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
         begin = s0 + (item_lo - p.item_start[gal]) * kItem;
     }
 
-    float acc[FP];
+    float2 acc[FP / 2];
 #pragma unroll
-    for (int f = 0; f < FP; ++f) acc[f] = 0.f;
+    for (int f = 0; f < FP / 2; ++f) acc[f] = make_float2(0.f, 0.f);
     const float fesc = p.fesc, ofe = 1.0f - p.fesc;
     const int nf = p.n_filters;
 
@@ -146,35 +159,55 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
             const int64_t i = begin + j * kThreads + tid;
-            const bool on = (j * kThreads + tid) < count;
+            [[maybe_unused]] const bool on = (j * kThreads + tid) < count;
             // --- NGP cell: float64 compares against the host-built thresholds
             const int ia = locate(s_age_thr, s_age_lut, p.age.n, p.age.lo, p.age.inv_w, age[j]);
             const int iz = locate(s_z_thr, s_z_lut, p.z.n, p.z.lo, p.z.inv_w, zz[j]);
             const bool young = (age[j] < p.young_thr) && (age[j] >= 0.0);
             const int cell = ia * p.nz + iz;
-            if (on && p.out_cell) p.out_cell[i] = cell + (young ? 65536 : 0);
+            if (p.out_cell && on) p.out_cell[i] = cell + (young ? 65536 : 0);
 
-            const float m = mm[j], tI = ti[j], tB = tb[j];     // m == 0 for lanes past the end
+            // l = m T_ISM inc                                       (old,   models.py:133)
+            // l = m T_ISM (fesc inc + T_BC (1-fesc)(tra+neb))       (young, models.py:131)
+            //   = w T_ISM inc + [young] m (1-fesc) 2^(argI+argB) tn,   w = young ? m fesc : m
+            const float m = mm[j];                             // m == 0 for lanes past the end
+            const float wv = young ? m * fesc : m;
+            const float2 w2 = make_float2(wv, wv), mo2 = make_float2(m * ofe, m * ofe);
+            const float2 tI2 = make_float2(ti[j], ti[j]), tB2 = make_float2(tb[j], tb[j]);
             const float4* rinc = reinterpret_cast<const float4*>(s_inc + cell * kStride);
             const float4* rtn = reinterpret_cast<const float4*>(s_tn + cell * kStride);
-            float* po = p.out_pf ? p.out_pf + (size_t)p.f0 * p.n + i : nullptr;
+            [[maybe_unused]] float* po = nullptr;
+            if constexpr (WRITE_PF) po = p.out_pf + (size_t)p.f0 * p.n + i;
+            // FP = n_filters rounded up to 4: every quad but the last is full
 #pragma unroll
             for (int q = 0; q < FP / 4; ++q) {
-                if (q * 4 < nf) {
-                    const float4 vi = rinc[q];
-                    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (young) vt = rtn[q];
-                    const float inc4[4] = {vi.x, vi.y, vi.z, vi.w};
-                    const float tn4[4] = {vt.x, vt.y, vt.z, vt.w};
+                const float4 vi = rinc[q];
+                float4 vt = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (young) vt = rtn[q];
+                const float2 inc2[2] = {make_float2(vi.x, vi.y), make_float2(vi.z, vi.w)};
+                const float2 tn2[2] = {make_float2(vt.x, vt.y), make_float2(vt.z, vt.w)};
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int f = q * 4 + r;
-                        const float TI = ex2_approx(tI * p.k_ism[f]);
-                        float x = inc4[r];
-                        if (young) x = fesc * x + ex2_approx(tB * p.k_bc[f]) * (ofe * tn4[r]);
-                        const float l = m * (TI * x);
-                        acc[f] += l;
-                        if (po && on && f < nf) po[(size_t)f * p.n] = l;
+                for (int h = 0; h < 2; ++h) {
+                    const int pr = q * 2 + h;                       // filter pair (2 pr, 2 pr + 1)
+                    if (q < FP / 4 - 1 || h == 0 || 2 * pr < nf) {  // uniform; only the last quad can be partial
+                        const float2 argI = __fmul2_rn(tI2, s_k[pr]);
+                        const float2 t = __fmul2_rn(w2, ex2_approx2(argI));
+                        if constexpr (WRITE_PF) {
+                            float2 l = __fmul2_rn(t, inc2[h]);
+                            if (young)
+                                l = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(__ffma2_rn(tB2, s_k[FP / 2 + pr], argI))),
+                                               tn2[h], l);
+                            acc[pr] = __fadd2_rn(acc[pr], l);
+                            if (on) {
+                                po[(size_t)(2 * pr) * p.n] = l.x;
+                                if (2 * pr + 1 < nf) po[(size_t)(2 * pr + 1) * p.n] = l.y;
+                            }
+                        } else {
+                            acc[pr] = __ffma2_rn(t, inc2[h], acc[pr]);
+                            if (young)
+                                acc[pr] = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(__ffma2_rn(tB2, s_k[FP / 2 + pr], argI))),
+                                                     tn2[h], acc[pr]);
+                        }
                     }
                 }
             }
@@ -196,15 +229,17 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
                 // block reduction of the per-thread sums of this run of items
 #pragma unroll
                 for (int f = 0; f < FP; ++f) {
-                    const float w = warp_sum(acc[f]);
-                    if (lane == 0) s_red[warp * FP + f] = (double)w;
-                    acc[f] = 0.f;
+                    const float v = (f & 1) ? acc[f / 2].y : acc[f / 2].x;
+                    const float ws = warp_sum(v);
+                    if (lane == 0) s_red[warp * FP + f] = (double)ws;
                 }
+#pragma unroll
+                for (int f = 0; f < FP / 2; ++f) acc[f] = make_float2(0.f, 0.f);
                 __syncthreads();
                 if (tid < nf) {
-                    double s = 0.0;
-                    for (int w = 0; w < kThreads / 32; ++w) s += s_red[w * FP + tid];
-                    p.partial[item * p.n_filters_total + p.f0 + tid] = s;
+                    double sum = 0.0;
+                    for (int ww = 0; ww < kThreads / 32; ++ww) sum += s_red[ww * FP + tid];
+                    p.partial[item * p.n_filters_total + p.f0 + tid] = sum;
                 }
                 __syncthreads();
             } else if (tid < nf) {
@@ -291,21 +326,27 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const double* __restric
     }
 }
 
-template <int FP>
-int launch_broadband(const BroadbandParams& p, cudaStream_t st) {
+template <int FP, bool WRITE_PF>
+int launch_broadband_impl(const BroadbandParams& p, cudaStream_t st) {
     constexpr int kStride = ((FP / 4) | 1) * 4;
     const size_t ncell = (size_t)p.na * p.nz;
     size_t smem = 2 * ncell * kStride * sizeof(float) + 2 * (size_t)(kMaxThr + 1) * sizeof(double) +
-                  (size_t)(kThreads / 32) * FP * sizeof(double) + 2 * kLut + 64;
+                  (size_t)(kThreads / 32) * FP * sizeof(double) + 2 * FP * sizeof(float) + 2 * kLut + 64;
     if (smem > 227 * 1024) return SO_ERR_TOO_LARGE;
-    SO_CUDA(cudaFuncSetAttribute(sed_broadband_kernel<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (smem <= 110 * 1024) ? 2 : 1;
+    SO_CUDA(cudaFuncSetAttribute(sed_broadband_kernel<FP, WRITE_PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    int per_sm = (smem <= 113 * 1024) ? 2 : 1;
     int64_t grid = (int64_t)so_num_sms() * per_sm;
     if (grid > p.n_items) grid = p.n_items;
     if (grid < 1) grid = 1;
-    sed_broadband_kernel<FP><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    sed_broadband_kernel<FP, WRITE_PF><<<(unsigned)grid, kThreads, smem, st>>>(p);
     SO_LAUNCH_CHECK();
     return SO_OK;
+}
+
+template <int FP>
+int launch_broadband(const BroadbandParams& p, cudaStream_t st) {
+    return p.out_pf ? launch_broadband_impl<FP, true>(p, st) : launch_broadband_impl<FP, false>(p, st);
 }
 
 // host: thresholds (ascending, may end with +inf) -> Axis with its log2-spaced first-guess table
