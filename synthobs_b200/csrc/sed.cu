@@ -9,6 +9,8 @@
 //   synthobs/sed/models.py:88-135, :153-200  per-particle loop of generate_{L,F}nu_array
 //   synthobs/sed/models.py:74-85, :139-150   np.sum of generate_{L,F}nu
 //   synthobs/sed/models.py:108-114           NGP argmin (via float64 thresholds, see header)
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -17,13 +19,17 @@ constexpr int kThreads = 512;                 // threads per persistent CTA, 2 C
 constexpr int kPerThread = 2;                 // particles per thread per work item
 constexpr int kItem = kThreads * kPerThread;  // particles per work item
 constexpr int kMaxThr = 127;                  // max thresholds per axis (kernel-parameter resident)
-constexpr int kLut = 256;                     // first-guess table entries per axis
+constexpr int kLut = 12288;                   // index table entries per axis (512 per octave, 24 octaves)
+constexpr int kLutShift = 11;                 // bin = (high 32 bits of the double >> 11): exponent + 9 mantissa bits
 
-// One NGP axis: ascending float64 thresholds + a log2-spaced first-guess table.
+// One NGP axis: ascending float64 thresholds + an index table over bins of the double's own bit
+// pattern (sign/exponent/top 9 mantissa bits: 512 bins per octave, exact edges, integer ALU only).
+// lut[b] & 127 = #{thr <= lower edge of bin b}; bit 7 is set when a threshold lies inside the bin:
+// only then (< 1 % of the particles) are exact float64 compares against thr[] needed.
 struct Axis {
     double thr[kMaxThr + 1];
-    unsigned char lut[kLut];   // lut[b] = #{thr <= lower edge of log2-bin b}
-    float lo, inv_w;           // bin = (log2f(v) - lo) * inv_w
+    unsigned char lut[kLut];
+    int base;                  // bin = (hi32(v) >> kLutShift) - base, clamped to [0, kLut)
     int n;                     // number of thresholds
 };
 
@@ -63,15 +69,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // index = #{thr <= v} (ascending thresholds); NaN / +inf -> 0 like np.argmin over all-NaN/inf distances
 __device__ __forceinline__ int locate(const double* __restrict__ thr, const unsigned char* __restrict__ lut, int n,
-                                      float lo, float inv_w, double v) {
+                                      int base, double v) {
     if (!(v < __longlong_as_double(0x7ff0000000000000LL))) return 0;
-    float lg;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)v));
-    int b = (int)((lg - lo) * inv_w);
+    int b = (__double2hiint(v) >> kLutShift) - base;     // negative v -> negative -> bin 0
     b = max(0, min(kLut - 1, b));
-    int g = lut[b];
-    while (g > 0 && !(v >= thr[g - 1])) --g;
-    while (g < n && v >= thr[g]) ++g;
+    const int e = lut[b];
+    int g = e & 127;
+    if (e & 128) {      // a threshold lies inside this bin: decide with the exact float64 values
+        while (g > 0 && !(v >= thr[g - 1])) --g;
+        while (g < n && v >= thr[g]) ++g;
+    }
     return g;
 }
 
@@ -92,8 +99,7 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
     double* s_age_thr = reinterpret_cast<double*>(s_tn + (size_t)ncell * kStride);
     double* s_z_thr = s_age_thr + (kMaxThr + 1);
     double* s_red = s_z_thr + (kMaxThr + 1);                       // [kThreads/32][FP]
-    float2* s_k = reinterpret_cast<float2*>(s_red + (kThreads / 32) * FP);   // [2][FP/2]: -k log2e pairs (ISM, BC)
-    unsigned char* s_age_lut = reinterpret_cast<unsigned char*>(s_k + FP);
+    unsigned char* s_age_lut = reinterpret_cast<unsigned char*>(s_red + (kThreads / 32) * FP);
     unsigned char* s_z_lut = s_age_lut + kLut;
 
     const int tid = threadIdx.x;
@@ -111,10 +117,9 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
         s_tn[c * kStride + f] = b;
     }
     for (int i = tid; i <= kMaxThr; i += kThreads) { s_age_thr[i] = p.age.thr[i]; s_z_thr[i] = p.z.thr[i]; }
-    for (int i = tid; i < kLut; i += kThreads) { s_age_lut[i] = p.age.lut[i]; s_z_lut[i] = p.z.lut[i]; }
-    for (int i = tid; i < FP; i += kThreads) {
-        reinterpret_cast<float*>(s_k)[i] = p.k_ism[i];
-        reinterpret_cast<float*>(s_k)[FP + i] = p.k_bc[i];
+    for (int i = tid; i < kLut / 4; i += kThreads) {
+        reinterpret_cast<unsigned*>(s_age_lut)[i] = reinterpret_cast<const unsigned*>(p.age.lut)[i];
+        reinterpret_cast<unsigned*>(s_z_lut)[i] = reinterpret_cast<const unsigned*>(p.z.lut)[i];
     }
     __syncthreads();
 
@@ -161,8 +166,8 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
             const int64_t i = begin + j * kThreads + tid;
             [[maybe_unused]] const bool on = (j * kThreads + tid) < count;
             // --- NGP cell: float64 compares against the host-built thresholds
-            const int ia = locate(s_age_thr, s_age_lut, p.age.n, p.age.lo, p.age.inv_w, age[j]);
-            const int iz = locate(s_z_thr, s_z_lut, p.z.n, p.z.lo, p.z.inv_w, zz[j]);
+            const int ia = locate(s_age_thr, s_age_lut, p.age.n, p.age.base, age[j]);
+            const int iz = locate(s_z_thr, s_z_lut, p.z.n, p.z.base, zz[j]);
             const bool young = (age[j] < p.young_thr) && (age[j] >= 0.0);
             const int cell = ia * p.nz + iz;
             if (p.out_cell && on) p.out_cell[i] = cell + (young ? 65536 : 0);
@@ -190,12 +195,12 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
                 for (int h = 0; h < 2; ++h) {
                     const int pr = q * 2 + h;                       // filter pair (2 pr, 2 pr + 1)
                     if (q < FP / 4 - 1 || h == 0 || 2 * pr < nf) {  // uniform; only the last quad can be partial
-                        const float2 argI = __fmul2_rn(tI2, s_k[pr]);
+                        const float2 argI = __fmul2_rn(tI2, make_float2(p.k_ism[2 * pr], p.k_ism[2 * pr + 1]));
                         const float2 t = __fmul2_rn(w2, ex2_approx2(argI));
                         if constexpr (WRITE_PF) {
                             float2 l = __fmul2_rn(t, inc2[h]);
                             if (young)
-                                l = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(__ffma2_rn(tB2, s_k[FP / 2 + pr], argI))),
+                                l = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(__ffma2_rn(tB2, make_float2(p.k_bc[2 * pr], p.k_bc[2 * pr + 1]), argI))),
                                                tn2[h], l);
                             acc[pr] = __fadd2_rn(acc[pr], l);
                             if (on) {
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
                         } else {
                             acc[pr] = __ffma2_rn(t, inc2[h], acc[pr]);
                             if (young)
-                                acc[pr] = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(__ffma2_rn(tB2, s_k[FP / 2 + pr], argI))),
+                                acc[pr] = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(__ffma2_rn(tB2, make_float2(p.k_bc[2 * pr], p.k_bc[2 * pr + 1]), argI))),
                                                      tn2[h], acc[pr]);
                         }
                     }
@@ -331,7 +336,7 @@ int launch_broadband_impl(const BroadbandParams& p, cudaStream_t st) {
     constexpr int kStride = ((FP / 4) | 1) * 4;
     const size_t ncell = (size_t)p.na * p.nz;
     size_t smem = 2 * ncell * kStride * sizeof(float) + 2 * (size_t)(kMaxThr + 1) * sizeof(double) +
-                  (size_t)(kThreads / 32) * FP * sizeof(double) + 2 * FP * sizeof(float) + 2 * kLut + 64;
+                  (size_t)(kThreads / 32) * FP * sizeof(double) + 2 * kLut + 64;
     if (smem > 227 * 1024) return SO_ERR_TOO_LARGE;
     SO_CUDA(cudaFuncSetAttribute(sed_broadband_kernel<FP, WRITE_PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
@@ -349,29 +354,43 @@ int launch_broadband(const BroadbandParams& p, cudaStream_t st) {
     return p.out_pf ? launch_broadband_impl<FP, true>(p, st) : launch_broadband_impl<FP, false>(p, st);
 }
 
-// host: thresholds (ascending, may end with +inf) -> Axis with its log2-spaced first-guess table
+// host: thresholds (ascending, may end with +inf) -> Axis with its bit-pattern index table
 static void fill_axis(Axis& ax, const double* thr, int n) {
     ax.n = n;
     for (int i = 0; i <= kMaxThr; ++i) ax.thr[i] = (i < n) ? thr[i] : __builtin_inf();
-    double lo = 0.0, hi = 1.0;
+    auto hi_bin = [](double v) -> int64_t {
+        int64_t bits;
+        memcpy(&bits, &v, sizeof(bits));
+        return (int64_t)((int32_t)(bits >> 32) >> kLutShift);
+    };
+    // centre the table on the finite positive thresholds
+    double tmin = 0.0, tmax = 0.0;
     bool any = false;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i)
         if (thr[i] > 0 && thr[i] < __builtin_inf()) {
-            const double l = log2(thr[i]);
-            if (!any) { lo = hi = l; any = true; }
-            if (l < lo) lo = l;
-            if (l > hi) hi = l;
+            if (!any) { tmin = tmax = thr[i]; any = true; }
+            if (thr[i] < tmin) tmin = thr[i];
+            if (thr[i] > tmax) tmax = thr[i];
         }
-    }
-    lo -= 1.0; hi += 1.0;
-    const double w = (hi - lo) / kLut;
-    ax.lo = (float)lo;
-    ax.inv_w = (float)(1.0 / w);
+    if (!any) { tmin = tmax = 1.0; }
+    const int64_t b_lo = hi_bin(tmin), b_hi = hi_bin(tmax);
+    int64_t base = b_lo - 16;
+    if (b_hi - base + 16 >= kLut) base = b_lo - 1;   // very wide grids: bins above the table share the last entry
+    ax.base = (int)base;
+    int g = 0;
     for (int b = 0; b < kLut; ++b) {
-        const double edge = exp2(lo + b * w);
-        int g = 0;
-        while (g < n && edge >= thr[g]) ++g;
-        ax.lut[b] = (unsigned char)g;
+        // lower edge of bin b = the double whose high word is (base + b) << kLutShift, low word 0
+        const int64_t hb = (base + b) << kLutShift;
+        double e0, e1;
+        int64_t bits0 = hb << 32, bits1 = ((base + b + 1) << kLutShift) << 32;
+        memcpy(&e0, &bits0, sizeof(e0));
+        memcpy(&e1, &bits1, sizeof(e1));
+        while (g < n && e0 >= thr[g]) ++g;                   // #{thr <= lower edge}
+        int g1 = g;
+        while (g1 < n && e1 > thr[g1]) ++g1;                 // thresholds in [e0, e1)
+        bool check = (g1 != g);
+        if (b == 0 || b == kLut - 1 || hb <= 0) check = true;    // clamped bins cover half-lines; zero/denormal edge
+        ax.lut[b] = (unsigned char)(g | (check ? 128 : 0));
     }
 }
 
