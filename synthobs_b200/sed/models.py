@@ -230,36 +230,46 @@ class define_model():
 GEMM_ALGO = 'auto'   # 'auto' | '3xtf32' | 'f32'
 
 
-def gemm(A, B):
+def gemm(A, B, algo=None):
     """C[M,N] = A[M,K] @ B[N,K]^T on the device (float32 in/out).  '3xtf32' is the
-    tcgen05 tensor-core kernel with error compensation; 'f32' the FMA-pipe kernel."""
+    tcgen05 tensor-core kernel with error compensation (default); 'f32' the
+    FMA-pipe kernel kept for on-device validation."""
     _cabi.require_device()
     M, K = A.shape
     N = B.shape[0]
-    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
-    algo = GEMM_ALGO
+    algo = algo or GEMM_ALGO
     if algo == 'auto':
-        algo = '3xtf32' if _HAVE_TC[0] else 'f32'
+        algo = '3xtf32'
+    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
     if algo == '3xtf32':
+        Kp = (K + 3) // 4 * 4       # TMA needs 16-byte row strides
+
+        def prep(X):
+            if X.stride(1) == 1 and X.stride(0) % 4 == 0 and X.stride(0) >= K and X.data_ptr() % 16 == 0:
+                return X
+            Y = torch.zeros((X.shape[0], Kp), dtype=torch.float32, device=X.device)
+            Y[:, :K] = X
+            return Y
+        A, B = prep(A), prep(B)
         Ah, Al = split_tf32(A)
         Bh, Bl = split_tf32(B)
         rc = _cabi.lib.so_gemm_3xtf32(_cabi.ptr(Ah), _cabi.ptr(Al), A.stride(0), _cabi.ptr(Bh), _cabi.ptr(Bl),
                                       B.stride(0), _cabi.ptr(C), C.stride(0), M, N, K, _cabi.stream())
         _cabi.check(rc, 'so_gemm_3xtf32')
     else:
+        A, B = A.contiguous(), B.contiguous()
         rc = _cabi.lib.so_gemm_f32(_cabi.ptr(A), A.stride(0), _cabi.ptr(B), B.stride(0), _cabi.ptr(C), C.stride(0),
                                    M, N, K, _cabi.stream())
         _cabi.check(rc, 'so_gemm_f32')
     return C
 
 
-_HAVE_TC = [False]   # flipped on once the tcgen05 kernel is in the library
-
-
 def split_tf32(x):
-    hi = torch.empty_like(x)
-    lo = torch.empty_like(x)
-    _cabi.check(_cabi.lib.so_split_tf32(_cabi.ptr(x), _cabi.ptr(hi), _cabi.ptr(lo), x.numel(), _cabi.stream()),
+    """x (dense rows, possibly with a padded row stride) -> TF32-exact hi and lo parts"""
+    n = x.stride(0) * (x.shape[0] - 1) + x.shape[1] if x.dim() == 2 else x.numel()
+    hi = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
+    lo = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
+    _cabi.check(_cabi.lib.so_split_tf32(_cabi.ptr(x), _cabi.ptr(hi), _cabi.ptr(lo), n, _cabi.stream()),
                 'so_split_tf32')
     return hi, lo
 

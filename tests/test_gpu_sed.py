@@ -190,3 +190,28 @@ def test_empty_and_tiny_inputs():
     ref = sed_oracle.broadband_array(tab, grid['log10age'], grid['log10Z'], np.array([1e6]), np.array([5.0]),
                                      np.array([0.01]))
     np.testing.assert_allclose(one, ref, rtol=RTOL_PARTICLE)
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 32), (2, 9000, 1326), (300, 500, 100), (1989, 10, 9000), (129, 257, 7),
+                                   (1, 8, 4)])
+def test_gemm_3xtf32_tensor_core_vs_float64(M, N, K):
+    """K4/K5: tcgen05 3xTF32 contraction against float64 (target 1e-5 relative, north_star);
+    the FMA-pipe kernel is checked alongside as the on-device cross-check."""
+    import torch
+    from synthobs_b200.sed import models
+    rng = np.random.default_rng(M * 7 + N)
+    A = (10.0 ** rng.uniform(-3, 3, (M, K))) * rng.choice([1.0, 1.0, 1.0, -1.0], (M, K))
+    B = 10.0 ** rng.uniform(-2, 2, (N, K))
+    ref = A @ B.T
+    scale = np.abs(A) @ np.abs(B).T
+    Ad = torch.from_numpy(A.astype(np.float32)).cuda()
+    Bd = torch.from_numpy(B.astype(np.float32)).cuda()
+    ref32 = Ad.double().cpu().numpy() @ Bd.double().cpu().numpy().T     # exact product of the float32 inputs
+    # measured on B200: the tensor core aligns every product to the running accumulator and truncates, a
+    # bias of about -1.3e-6 of sum|a||b| per 64-product chunk (DESIGN.md, GEMM accuracy); the FMA-pipe
+    # kernel sums K terms sequentially in FP32 and is LESS accurate at large K
+    for algo, tol in (('3xtf32', 5e-6), ('f32', 2e-5)):
+        C = models.gemm(Ad, Bd, algo=algo).double().cpu().numpy()
+        err = np.abs(C - ref32) / scale
+        assert err.max() < tol, (algo, err.max())
+    assert np.abs(ref - ref32).max() / scale.max() < 1e-6
