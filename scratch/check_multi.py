@@ -1,0 +1,28 @@
+"""torchrun --nproc-per-node N scratch/check_multi.py : sharded paths vs the single-rank result."""
+import contextlib, io, os, sys
+sys.path.insert(0, '.')
+import numpy as np, torch, torch.distributed as dist
+from synthobs_b200 import dist as sdist, synthetic
+from synthobs_b200.sed import models
+from synthobs_b200.morph import images
+rank, ws = sdist.init_from_env('nccl')
+grid = synthetic.ssp_grid(n_lam=200)
+with contextlib.redirect_stdout(io.StringIO()):
+    model = models.define_model(grid)
+model.dust_ISM = model.dust_BC = ('simple', {'slope': -1.0})
+F = synthetic.filter_set(grid['lam'], n_filters=10)
+model.create_Lnu_grid(F)
+b = synthetic.galaxy_batch(64, n_min=1000, n_max=100000, seed=3)
+full = sdist.generate_Fnu_sharded(model, F, b, kind='Lnu').cpu().numpy()
+ref = models.generate_Lnu_batch(model, F, b['Masses'], b['Ages'], b['Metallicities'], b['offsets'], tauVs_ISM=b['tauVs_ISM'], tauVs_BC=b['tauVs_BC'])
+e1 = np.abs(full / ref - 1).max()
+p = synthetic.particles(400000, seed=12)
+torch.cuda.synchronize(); dist.barrier()
+import time; t = time.time()
+img = sdist.image_huge(p['X'], p['Y'], p['Masses'], 0.01, 2048, 8)
+torch.cuda.synchronize(); dt = time.time() - t
+one = images.core(p['X'], p['Y'], p['Masses'], resolution=0.01, ndim=2048, smoothing=('adaptive', 8)).data
+e2 = np.abs(img.cpu().numpy() - one).max() / one.max()
+print('rank %d/%d: sharded SED max rel diff %.2e ; huge image vs single-rank max diff/peak %.2e ; image_huge %.1f ms' % (rank, ws, e1, e2, dt * 1e3))
+assert e1 < 1e-12 and e2 < 2e-6
+dist.destroy_process_group()

@@ -1,0 +1,160 @@
+"""Multi-GPU partitioning of the two hot paths (one process per GPU, torch.distributed).
+
+SURVEY.md §8e: (i) batches of galaxies are independent units -> shard galaxies over ranks,
+balanced by particle count, NO collective on the compute path, one gather of the small
+[G, F] result; (ii) a single huge image -> particle blocks per rank, each rank deposits onto
+a private full image, one sum all-reduce of the image over NVLink (NCCL).
+
+The partitioning / gather logic is backend-agnostic (it is exercised with gloo on CPU in
+tests/test_dist_gloo.py); the compute callbacks are the CUDA paths.
+"""
+
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend=None):
+    """torchrun-style initialisation (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*)."""
+    ws = int(os.environ.get('WORLD_SIZE', '1'))
+    if ws <= 1 or dist.is_initialized():
+        return world()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if backend is None:
+        backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if backend == 'nccl':
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        dist.init_process_group(backend)
+    return world()
+
+
+def shard_galaxies(sizes, n_ranks):
+    """Longest-processing-time-first assignment of galaxies to ranks, balanced by particle
+    count.  Returns a list (per rank) of ascending galaxy indices; deterministic."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    order = np.argsort(-sizes, kind='stable')
+    load = np.zeros(n_ranks, dtype=np.int64)
+    out = [[] for _ in range(n_ranks)]
+    for g in order:
+        r = int(np.argmin(load))          # first minimum: deterministic tie-break
+        out[r].append(int(g))
+        load[r] += sizes[g]
+    return [sorted(o) for o in out]
+
+
+def gather_rows(local_rows, local_index, n_total, device=None):
+    """Every rank holds rows for the galaxy indices `local_index`; returns the full
+    [n_total, F] array on every rank (all_gather of padded blocks; the only collective of
+    the galaxy-sharded path, a few MB at most)."""
+    rank, ws = world()
+    rows = torch.as_tensor(local_rows)
+    if ws == 1:
+        out = torch.empty((n_total,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        out[torch.as_tensor(local_index, dtype=torch.long, device=rows.device)] = rows
+        return out
+    dev = rows.device if device is None else device
+    counts = torch.zeros(ws, dtype=torch.long, device=dev)
+    counts[rank] = len(local_index)
+    dist.all_reduce(counts)
+    cmax = int(counts.max().item())
+    F = tuple(rows.shape[1:])
+    pad_rows = torch.zeros((cmax,) + F, dtype=rows.dtype, device=dev)
+    pad_rows[:len(local_index)] = rows.to(dev)
+    pad_idx = torch.full((cmax,), -1, dtype=torch.long, device=dev)
+    pad_idx[:len(local_index)] = torch.as_tensor(local_index, dtype=torch.long, device=dev)
+    all_rows = [torch.empty_like(pad_rows) for _ in range(ws)]
+    all_idx = [torch.empty_like(pad_idx) for _ in range(ws)]
+    dist.all_gather(all_rows, pad_rows)
+    dist.all_gather(all_idx, pad_idx)
+    out = torch.zeros((n_total,) + F, dtype=rows.dtype, device=dev)
+    for r in range(ws):
+        c = int(counts[r].item())
+        out[all_idx[r][:c]] = all_rows[r][:c]
+    return out
+
+
+def sharded_galaxy_map(compute, offsets, n_filters_hint=None):
+    """Run `compute(galaxy_indices) -> [len(indices), F] tensor` on this rank's share of the
+    galaxies described by CSR `offsets` and return the full [G, F] result on every rank."""
+    rank, ws = world()
+    offsets = np.asarray(offsets, dtype=np.int64)
+    sizes = np.diff(offsets)
+    mine = shard_galaxies(sizes, ws)[rank]
+    rows = compute(mine)
+    return gather_rows(rows, mine, sizes.size)
+
+
+def subset_csr(arrays, offsets, indices):
+    """Concatenate the particle ranges of the chosen galaxies: (dict of arrays, new offsets)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    idx = np.asarray(indices, dtype=np.int64)
+    lens = offsets[idx + 1] - offsets[idx]
+    new_off = np.zeros(idx.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    sel = np.concatenate([np.arange(offsets[g], offsets[g + 1]) for g in idx]) if idx.size else np.zeros(0, np.int64)
+    return {k: v[sel] for k, v in arrays.items()}, new_off
+
+
+def particle_block(n, rank=None, n_ranks=None):
+    """Contiguous block [begin, end) of n particles owned by a rank."""
+    r, ws = world()
+    rank = r if rank is None else rank
+    n_ranks = ws if n_ranks is None else n_ranks
+    per = (n + n_ranks - 1) // n_ranks
+    b = min(n, rank * per)
+    return b, min(n, b + per)
+
+
+def reduce_image(img):
+    """Sum the ranks' partial images in place (NCCL all-reduce over NVLink on GPUs).  FP32
+    summation order differs between rank counts (~1e-7 relative), inside the tolerance."""
+    rank, ws = world()
+    if ws > 1:
+        dist.all_reduce(img, op=dist.ReduceOp.SUM)
+    return img
+
+
+def generate_Fnu_sharded(model, F, batch, kind='Fnu', **kw):
+    """Broadband fluxes of a batch of galaxies, sharded by galaxy over the ranks.  `batch` is a
+    dict with Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, offsets (host arrays)."""
+    from .sed import models
+    keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
+
+    def compute(indices):
+        sub, off = subset_csr({k: batch[k] for k in keys if k in batch}, batch['offsets'], indices)
+        out = models.generate_Lnu_batch(model, F, sub['Masses'], sub['Ages'], sub['Metallicities'], off,
+                                        tauVs_ISM=sub.get('tauVs_ISM', False), tauVs_BC=sub.get('tauVs_BC', False),
+                                        kind=kind, **kw)
+        return torch.as_tensor(out).cuda()
+
+    return sharded_galaxy_map(compute, batch['offsets'])
+
+
+def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None):
+    """One huge adaptive-smoothed image, particle-block sharded (BASELINE config 5).
+    Every rank holds all positions (the k-NN needs neighbours across blocks), computes the
+    k-th neighbour distance and the deposit only for its own block of particles onto a private
+    full image, then the partial images are summed with one all-reduce.  Returns the full
+    [ndim, ndim] float32 CUDA image on every rank."""
+    from . import device as dv
+    from .morph import images
+    rank, ws = world()
+    Xd, Yd, Ld = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L)
+    width, G = images.pixel_grid(resolution, ndim)
+    ix, iy = images.ngp_index_device(Xd, Yd, dv.to_dev(G), ndim, width / 2.)
+    dk = images.knn_device(Xd, Yd, ix, int(k), width / 2.)       # all points; queries are cheap to replicate
+    b, e = particle_block(Xd.numel(), rank, ws)
+    r = images.deposit_device(Xd[b:e], Yd[b:e], Ld[..., b:e], resolution, ndim, adaptive_k=int(k), want_ngp=False,
+                              support_sigmas=support_sigmas, dk=dk[b:e])
+    img = r['data'][0]
+    return reduce_image(img)

@@ -200,3 +200,13 @@ def test_observed_matches_reference():
     for i, f in enumerate(filters):
         assert_image_close(IMGs[f].data, g['multi_%d_data' % i])
         assert_image_close(IMGs[f].no_PSF, g['multi_%d_no_PSF' % i])
+
+
+def test_image_huge_single_rank_equals_core():
+    """particle-block path (BASELINE config 5) on one rank == images.core adaptive"""
+    from synthobs_b200 import dist as sdist
+    from synthobs_b200.morph import images
+    p = synthetic.particles(30000, seed=12)
+    img = sdist.image_huge(p['X'], p['Y'], p['Masses'], 0.02, 400, 8).cpu().numpy().astype(np.float64)
+    o = image_oracle.core(p['X'], p['Y'], p['Masses'], resolution=0.02, ndim=400, smoothing=('adaptive', 8))
+    assert_image_close(img, o['data'])

@@ -215,3 +215,18 @@ def test_gemm_3xtf32_tensor_core_vs_float64(M, N, K):
         err = np.abs(C - ref32) / scale
         assert err.max() < tol, (algo, err.max())
     assert np.abs(ref - ref32).max() / scale.max() < 1e-6
+
+
+def test_sharded_batch_single_rank_equals_batch():
+    from synthobs_b200 import dist as sdist
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=200)
+    simple = ('simple', {'slope': -1.0})
+    model = make_model(grid, simple, simple)
+    F = synthetic.filter_set(grid['lam'], n_filters=5)
+    model.create_Lnu_grid(F)
+    b = synthetic.galaxy_batch(11, n_min=10, n_max=3000, seed=3)
+    full = sdist.generate_Fnu_sharded(model, F, b, kind='Lnu', fesc=0.1).cpu().numpy()
+    ref = models.generate_Lnu_batch(model, F, b['Masses'], b['Ages'], b['Metallicities'], b['offsets'],
+                                    tauVs_ISM=b['tauVs_ISM'], tauVs_BC=b['tauVs_BC'], fesc=0.1)
+    np.testing.assert_allclose(full, ref, rtol=1e-12)
