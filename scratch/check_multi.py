@@ -24,5 +24,5 @@ torch.cuda.synchronize(); dt = time.time() - t
 one = images.core(p['X'], p['Y'], p['Masses'], resolution=0.01, ndim=2048, smoothing=('adaptive', 8)).data
 e2 = np.abs(img.cpu().numpy() - one).max() / one.max()
 print('rank %d/%d: sharded SED max rel diff %.2e ; huge image vs single-rank max diff/peak %.2e ; image_huge %.1f ms' % (rank, ws, e1, e2, dt * 1e3))
-assert e1 < 1e-12 and e2 < 2e-6
+assert e1 < 1e-6 and e2 < 2e-6   # per-rank sub-batches group the FP32 partial sums differently
 dist.destroy_process_group()
