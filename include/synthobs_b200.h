@@ -37,7 +37,7 @@ extern "C" {
 #define SO_ERR_UNSUPPORTED (-4)
 
 #define SO_MAX_FILTERS 32 /* filters per so_sed_broadband launch (smem tables) */
-#define SO_TILE 64        /* image tile edge in pixels (so_img_*) */
+#define SO_TILE 16        /* image sub-tile edge in pixels (so_img_*) */
 
 /* library / build identification; returns a static string */
 const char* so_version(void);
@@ -173,10 +173,9 @@ int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int
  * Two phases because the number of (particle, tile) pairs is data dependent:
  *   so_img_plan      computes per-particle records + pair counts; synchronises
  *                    and returns the pair count in *n_pairs (host).
- *   so_img_deposit   bins the pairs per 64x64 tile (stable radix sort: bit-exact,
- *                    order-deterministic tile lists), accumulates each tile in
- *                    shared memory/registers (no global atomics) and writes every
- *                    pixel once.
+ *   so_img_deposit   bins the pairs per 16x16 sub-tile (stable radix sort: bit-exact,
+ *                    order-deterministic lists), accumulates each sub-tile in one
+ *                    warp's registers (no global atomics) and writes every pixel once.
  *
  *   L        : [n_chan, n] float64 weights (n_chan images share positions/sigma)
  *   dk       : [n] float64 k-th neighbour distance, or NULL for NGP only

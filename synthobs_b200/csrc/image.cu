@@ -8,21 +8,35 @@
 //   synthobs/morph/images.py:19-22   rebin (block sum)
 //
 // Design: the Gaussian is separable, so one particle's contribution to a
-// 64x64 tile is a rank-1 update  tile += (w * ey) (x) ex.  Particles are binned per tile with a
-// stable radix sort (deterministic lists), each work item (tile, chunk of the tile's list) keeps
-// its 64x64 accumulator in registers (8x4 per thread, 128 threads), stages the per-particle
-// factor vectors in shared memory, and writes its tile exactly once with plain stores; tiles
-// split over several items are summed by a second kernel in fixed order.  No global atomics
-// touch pixels.
+// block of pixels is a rank-1 update  block += (w * ey) (x) ex.  Particles are binned per 16x16
+// sub-tile with a stable radix sort (deterministic lists).  One WARP owns one work item (sub-tile,
+// slice of its list): lane l owns row l/2, columns 8*(l%2)..+7 for all C channels in registers;
+// per particle the 16 column factors and 16 row factors are evaluated once (one ex2 per lane),
+// exchanged with warp shuffles, and every lane does 8*C FMAs.  Each sub-tile is written exactly
+// once with plain stores; sub-tiles split over several items are summed by a second kernel in
+// fixed order.  No global atomics touch pixels; results are bitwise reproducible.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kT = SO_TILE;          // tile edge
-constexpr int kDepThreads = 128;     // deposit CTA
-constexpr int kP = 32;               // particles staged per phase
+constexpr int kT = SO_TILE;          // sub-tile edge (16)
+constexpr int kDepWarps = 4;         // warps (= work items) per deposit CTA
+constexpr int kP = 32;               // particles staged per phase (one per lane)
+constexpr int kWideW = 48;           // supports wider than this get a warp for their normalisation sums
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Gaussian factor of pixel offset k from the nearest pixel, relative to the nearest-pixel term
+// (exponent shifted so narrow particles survive FP32): exp(-((k - u)^2 - u^2) / 2 sigma^2 * pitch^2)
+__device__ __forceinline__ float gauss_factor(float cpx, int k, float u) {
+    const float fk = (float)k;
+    return ex2_ftz(-cpx * fk * (fk - 2.f * u));
+}
 
 struct PlanView {
     float* ux;        // (x - G[ix]) / pitch
@@ -95,14 +109,14 @@ __global__ void ngp_index_kernel(const double* __restrict__ X, const double* __r
     ix[i] = rx; iy[i] = ry;
 }
 
-// one warp per particle: support box, normalisation sums, tile count
+// one thread per particle: support box, normalisation sums, sub-tile count.  Particles whose support is
+// wider than kWideW pixels only get their box here; plan_wide_kernel sums their factors with a warp.
 __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ ix_in, const int32_t* __restrict__ iy_in,
                                                    const double* __restrict__ X, const double* __restrict__ Y,
                                                    const double* __restrict__ dk, int64_t n,
                                                    const double* __restrict__ G, int ndim, double R,
                                                    PlanView pv) {
-    const int lane = threadIdx.x & 31;
-    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_dep = 0, my_sel = 0, my_drop = 0, my_pairs = 0;
     if (p < n) {
         const int ip = ix_in[p], jp = iy_in[p];
@@ -132,22 +146,18 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ i
             }
             ux = (float)(dx0 / pitch);
             uy = (float)(dy0 / pitch);
-            if (dropped || !dk) W = dk ? 0 : 0;
+            if (dropped || !dk) W = 0;
             const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
             const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
             if (dk && !dropped) {
-                float sx = 0.f, sy = 0.f;
-                for (int k = kx0 + lane; k <= kx1; k += 32) {
-                    const float fk = (float)k;
-                    sx += exp2f(-cpx * fk * (fk - 2.f * ux));
+                if (W <= kWideW) {
+                    float sx = 0.f, sy = 0.f;
+                    for (int k = kx0; k <= kx1; ++k) sx += gauss_factor(cpx, k, ux);
+                    for (int k = ky0; k <= ky1; ++k) sy += gauss_factor(cpx, k, uy);
+                    wn = 1.0f / (sx * sy);
+                } else {
+                    wn = -1.0f;     // marker: plan_wide_kernel fills it in
                 }
-                for (int k = ky0 + lane; k <= ky1; k += 32) {
-                    const float fk = (float)k;
-                    sy += exp2f(-cpx * fk * (fk - 2.f * uy));
-                }
-                sx = warp_sum(sx);
-                sy = warp_sum(sy);
-                wn = 1.0f / (sx * sy);
                 my_dep = (unsigned long long)(kx1 - kx0 + 1) * (unsigned long long)(ky1 - ky0 + 1);
             }
             const int tx0 = (ip + kx0) / kT, tx1 = (ip + kx1) / kT;
@@ -157,23 +167,42 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ i
             my_drop = dropped ? 1 : 0;
             my_pairs = (unsigned long long)count;
         }
-        if (lane == 0) {
-            pv.ux[p] = ux; pv.uy[p] = uy; pv.cpx[p] = cpx; pv.wnorm[p] = wn;
-            pv.ix[p] = ip; pv.iy[p] = jp; pv.W[p] = W;
-            pv.offs[p] = count;
-            if (p == n - 1) pv.offs[n] = 0;
-        }
+        pv.ux[p] = ux; pv.uy[p] = uy; pv.cpx[p] = cpx; pv.wnorm[p] = wn;
+        pv.ix[p] = ip; pv.iy[p] = jp; pv.W[p] = W;
+        pv.offs[p] = count;
+        if (p == n - 1) pv.offs[n] = 0;
     }
     // statistics (integer atomics on 4 counters; never on pixels)
-    if (lane != 0) { my_dep = 0; my_sel = 0; my_drop = 0; my_pairs = 0; }
-    __shared__ unsigned long long s[4];
-    if (threadIdx.x < 4) s[threadIdx.x] = 0;
-    __syncthreads();
-    if (my_sel) {
-        atomicAdd(&s[0], my_pairs); atomicAdd(&s[1], my_dep); atomicAdd(&s[2], my_sel); atomicAdd(&s[3], my_drop);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_dep += __shfl_xor_sync(0xffffffffu, my_dep, o);
+        my_sel += __shfl_xor_sync(0xffffffffu, my_sel, o);
+        my_drop += __shfl_xor_sync(0xffffffffu, my_drop, o);
+        my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
     }
-    __syncthreads();
-    if (threadIdx.x < 4 && s[threadIdx.x]) atomicAdd(&pv.stats[threadIdx.x], s[threadIdx.x]);
+    if ((threadIdx.x & 31) == 0 && my_sel) {
+        atomicAdd(&pv.stats[0], my_pairs); atomicAdd(&pv.stats[1], my_dep);
+        atomicAdd(&pv.stats[2], my_sel); atomicAdd(&pv.stats[3], my_drop);
+    }
+}
+
+// one warp per particle, only for supports wider than kWideW (marked wnorm < 0)
+__global__ void __launch_bounds__(256) plan_wide_kernel(int64_t n, int ndim, PlanView pv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= n) return;
+    if (!(pv.wnorm[p] < 0.f)) return;
+    const int ip = pv.ix[p], jp = pv.iy[p], W = pv.W[p];
+    const float cpx = pv.cpx[p], ux = pv.ux[p], uy = pv.uy[p];
+    const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
+    const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
+    float sx = 0.f, sy = 0.f;
+    for (int k = kx0 + lane; k <= kx1; k += 32) sx += gauss_factor(cpx, k, ux);
+    for (int k = ky0 + lane; k <= ky1; k += 32) sy += gauss_factor(cpx, k, uy);
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    __syncwarp();
+    if (lane == 0) pv.wnorm[p] = 1.0f / (sx * sy);
 }
 
 // one warp per particle: write its (tile, pid) pairs at offs[p].. (row-major over the tile box)
@@ -265,7 +294,7 @@ __global__ void item_tile_kernel(const int64_t* __restrict__ item_start, int nti
 
 struct DepositParams {
     PlanView pv;
-    const double* L;          // [C, n]
+    const double* L;          // [C_total, n]
     int64_t n;
     int ndim, ntx, ntiles;
     const int32_t* pids;      // sorted pair list
@@ -273,13 +302,17 @@ struct DepositParams {
     const int64_t* item_start;
     const int32_t* item_tile;
     int64_t chunk;
-    float* data;              // [C, ndim, ndim]
-    float* partial;           // [max_items, C, kT*kT]
+    float* data;              // [C_total, ndim, ndim]
+    float* partial;           // [max_items, C_total, kT*kT]
+    int n_chan;               // C_total
+    int chan0;                // first channel of this launch
 };
 
-__global__ void __launch_bounds__(kDepThreads) deposit_kernel(const DepositParams p) {
-    const int64_t item = blockIdx.x;
-    const int chan = blockIdx.y;
+// One warp = one work item (sub-tile, slice of its particle list), C channels in registers.
+template <int C>
+__global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * kDepWarps + warp;
     if (item >= p.item_start[p.ntiles]) return;
     const int tile = p.item_tile[item];
     const int64_t t0 = p.tile_start[tile], t1 = p.tile_start[tile + 1];
@@ -288,126 +321,112 @@ __global__ void __launch_bounds__(kDepThreads) deposit_kernel(const DepositParam
     const bool single = (p.item_start[tile + 1] - p.item_start[tile]) == 1;
     const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
 
-    __shared__ __align__(16) float sA[kP][kT];   // w * ey over the tile rows
-    __shared__ __align__(16) float sB[kP][kT];   // ex over the tile columns
-    __shared__ float s_u[2][kP], s_c[kP], s_w[kP];
-    __shared__ int s_i[2][kP], s_W[kP];
+    __shared__ float s_u[kDepWarps][2][kP], s_c[kDepWarps][kP], s_w[kDepWarps][C][kP];
+    __shared__ int s_i[kDepWarps][2][kP], s_W[kDepWarps][kP];
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int tyi = tid >> 4, txi = tid & 15;     // 8 x 16 threads, 8 rows x 4 cols each
-    float acc[8][4];
+    // lane -> one factor to evaluate (lanes 0-15: column px0+lane, lanes 16-31: row py0+lane-16) and
+    // 8 owned pixels (row lane/2, columns 8*(lane%2) ..)
+    const int axis = lane >> 4;                  // 0: x (columns), 1: y (rows)
+    const int fpix = (axis ? py0 : px0) + (lane & 15);
+    const int row = lane >> 1, col0 = (lane & 1) * 8;
+    float acc[C][8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
 
-    const double* Lc = p.L + (size_t)chan * p.n;
     for (int64_t base = start; base < end; base += kP) {
         const int np = (int)min((int64_t)kP, end - base);
-        if (tid < np) {
-            const int pid = p.pids[base + tid];
-            s_u[0][tid] = p.pv.ux[pid];
-            s_u[1][tid] = p.pv.uy[pid];
-            s_c[tid] = p.pv.cpx[pid];
-            s_w[tid] = (float)(Lc[pid] * (double)p.pv.wnorm[pid]);
-            s_i[0][tid] = p.pv.ix[pid];
-            s_i[1][tid] = p.pv.iy[pid];
-            s_W[tid] = p.pv.W[pid];
+        __syncwarp();
+        if (lane < np) {
+            const int pid = p.pids[base + lane];
+            s_u[warp][0][lane] = p.pv.ux[pid];
+            s_u[warp][1][lane] = p.pv.uy[pid];
+            s_c[warp][lane] = p.pv.cpx[pid];
+            s_i[warp][0][lane] = p.pv.ix[pid];
+            s_i[warp][1][lane] = p.pv.iy[pid];
+            s_W[warp][lane] = p.pv.W[pid];
+            const double wn = (double)p.pv.wnorm[pid];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                s_w[warp][c][lane] = (float)(p.L[(size_t)(p.chan0 + c) * p.n + pid] * wn);
         }
-        __syncthreads();
-        // phase A: factor vectors. thread t < 64 -> row t (y axis, weighted); t >= 64 -> column t-64
-        {
-            const int axis = (tid < kT) ? 1 : 0;
-            const int t = tid & (kT - 1);
-            const int pix = (axis ? py0 : px0) + t;
-            for (int q = 0; q < np; ++q) {
-                const int k = pix - s_i[axis][q];
-                float v = 0.f;
-                if (abs(k) <= s_W[q] && pix < p.ndim) {
-                    const float fk = (float)k;
-                    v = exp2f(-s_c[q] * fk * (fk - 2.f * s_u[axis][q]));
-                    if (axis) v *= s_w[q];
-                }
-                if (axis) sA[q][t] = v; else sB[q][t] = v;
+        __syncwarp();
+        for (int q = 0; q < np; ++q) {
+            const int k = fpix - s_i[warp][axis][q];
+            float f = 0.f;
+            if (abs(k) <= s_W[warp][q] && fpix < p.ndim) f = gauss_factor(s_c[warp][q], k, s_u[warp][axis][q]);
+            const float ey = __shfl_sync(0xffffffffu, f, 16 + row);
+            float g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = ey * __shfl_sync(0xffffffffu, f, col0 + j);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float w = s_w[warp][c][q];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(w, g[j], acc[c][j]);
             }
         }
-        __syncthreads();
-        // phase B: rank-1 updates; a warp skips particles whose rows miss its 16-row band
-        const int band0 = py0 + warp * 16, band1 = band0 + 15;
-        for (int q = 0; q < np; ++q) {
-            const int jp = s_i[1][q], W = s_W[q];
-            if (jp + W < band0 || jp - W > band1) continue;
-            const float4 a0 = *reinterpret_cast<const float4*>(&sA[q][tyi * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&sA[q][tyi * 8 + 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&sB[q][txi * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], bb[c], acc[r][c]);
-        }
-        __syncthreads();
     }
 
-    if (single) {
-        float* img = p.data + (size_t)chan * p.ndim * p.ndim;
+    const int r = py0 + row;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int row = py0 + tyi * 8 + r;
-            if (row >= p.ndim) continue;
+    for (int c = 0; c < C; ++c) {
+        if (single) {
+            if (r < p.ndim) {
+                float* out = p.data + ((size_t)(p.chan0 + c) * p.ndim + r) * p.ndim + px0 + col0;
+                if (px0 + col0 + 8 <= p.ndim && (p.ndim & 3) == 0) {
+                    *reinterpret_cast<float4*>(out) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                    *reinterpret_cast<float4*>(out + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+                } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int col = px0 + txi * 4 + c;
-                if (col < p.ndim) img[(size_t)row * p.ndim + col] = acc[r][c];
+                    for (int j = 0; j < 8; ++j)
+                        if (px0 + col0 + j < p.ndim) out[j] = acc[c][j];
+                }
             }
+        } else {
+            float* out = p.partial + ((size_t)item * p.n_chan + p.chan0 + c) * (kT * kT) + row * kT + col0;
+            *reinterpret_cast<float4*>(out) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+            *reinterpret_cast<float4*>(out + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
         }
-    } else {
-        float* out = p.partial + ((size_t)item * gridDim.y + chan) * (kT * kT);
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            *reinterpret_cast<float4*>(&out[(tyi * 8 + r) * kT + txi * 4]) =
-                make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
 }
 
-// tiles with 0 items -> zeros, 1 item -> already written, >1 -> ordered sum of the partial tiles
-__global__ void __launch_bounds__(256) tile_reduce_kernel(const DepositParams p, int n_chan) {
+// sub-tiles with 0 items -> zeros, 1 item -> already written, >1 -> ordered sum of the partial sub-tiles
+__global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParams p, int n_chan) {
     const int tile = blockIdx.x, chan = blockIdx.y;
     const int64_t i0 = p.item_start[tile], i1 = p.item_start[tile + 1];
     if (i1 - i0 == 1) return;
     const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
-    float* img = p.data + (size_t)chan * p.ndim * p.ndim;
-    for (int e = threadIdx.x; e < kT * kT; e += 256) {
-        float s = 0.f;
-        for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
-        const int row = py0 + e / kT, col = px0 + e % kT;
-        if (row < p.ndim && col < p.ndim) img[(size_t)row * p.ndim + col] = s;
-    }
+    const int e = threadIdx.x;
+    float s = 0.f;
+    for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
+    const int row = py0 + e / kT, col = px0 + e % kT;
+    if (row < p.ndim && col < p.ndim) p.data[((size_t)chan * p.ndim + row) * p.ndim + col] = s;
 }
 
-// NGP products: one CTA per tile; shared-memory accumulation (float64 sums, integer counts)
-__global__ void __launch_bounds__(256) ngp_tile_kernel(const DepositParams p, int n_chan, float* __restrict__ simple,
-                                                       float* __restrict__ hist) {
+// NGP products: one CTA per sub-tile; shared-memory accumulation (float64 sums, integer counts)
+__global__ void __launch_bounds__(64) ngp_tile_kernel(const DepositParams p, int n_chan, float* __restrict__ simple,
+                                                      float* __restrict__ hist) {
     __shared__ double s_sum[kT * kT];
     __shared__ unsigned int s_cnt[kT * kT];
     const int tile = blockIdx.x;
     const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
     const int64_t t0 = p.tile_start[tile], t1 = p.tile_start[tile + 1];
     for (int chan = 0; chan < (simple ? n_chan : 1); ++chan) {
-        for (int e = threadIdx.x; e < kT * kT; e += 256) { s_sum[e] = 0.0; s_cnt[e] = 0; }
+        for (int e = threadIdx.x; e < kT * kT; e += 64) { s_sum[e] = 0.0; s_cnt[e] = 0; }
         __syncthreads();
         const double* Lc = p.L ? p.L + (size_t)chan * p.n : nullptr;
-        for (int64_t q = t0 + threadIdx.x; q < t1; q += 256) {
+        for (int64_t q = t0 + threadIdx.x; q < t1; q += 64) {
             const int pid = p.pids[q];
             const int lx = p.pv.ix[pid] - px0, ly = p.pv.iy[pid] - py0;
-            if (lx >= 0 && lx < kT && ly >= 0 && ly < kT) {   // the particle's own tile only
+            if (lx >= 0 && lx < kT && ly >= 0 && ly < kT) {   // the particle's own sub-tile only
                 if (simple) atomicAdd(&s_sum[ly * kT + lx], Lc[pid]);
                 atomicAdd(&s_cnt[ly * kT + lx], 1u);
             }
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < kT * kT; e += 256) {
+        for (int e = threadIdx.x; e < kT * kT; e += 64) {
             const int row = py0 + e / kT, col = px0 + e % kT;
             if (row < p.ndim && col < p.ndim) {
                 if (simple) simple[((size_t)chan * p.ndim + row) * p.ndim + col] = (float)s_sum[e];
@@ -464,11 +483,11 @@ static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n_pairs, int
     DepositLayout d;
     d.ntx = (ndim + kT - 1) / kT;
     d.ntiles = d.ntx * d.ntx;
-    // aim for ~16 work items per SM (but never below one staging phase worth of particles)
-    const int64_t target = 16 * 148;
+    // one warp per work item: aim for ~32 items (warps) per SM, never below two staging phases
+    const int64_t target = 32 * 148;
     int64_t chunk = (n_pairs + target - 1) / target;
     chunk = (chunk + kP - 1) / kP * kP;
-    if (chunk < 4 * kP) chunk = 4 * kP;
+    if (chunk < 2 * kP) chunk = 2 * kP;
     d.chunk = chunk;
     d.max_items = n_pairs / chunk + d.ntiles + 1;
     SoArena a(ws, bytes);
@@ -527,9 +546,12 @@ extern "C" int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X
         if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0.0;
         return SO_OK;
     }
-    const int64_t threads = n * 32;
-    plan_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ix, iy, X, Y, dk, n, G, ndim, support_sigmas, pv);
+    plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix, iy, X, Y, dk, n, G, ndim, support_sigmas, pv);
     SO_LAUNCH_CHECK();
+    if (dk) {
+        plan_wide_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(n, ndim, pv);
+        SO_LAUNCH_CHECK();
+    }
     size_t tmp = (size_t)pv.cub_tmp_bytes;
     SO_CUDA(cub::DeviceScan::ExclusiveSum(pv.cub_tmp, tmp, pv.offs, pv.offs, (int)(n + 1), st));
     unsigned long long h[4];
@@ -583,22 +605,29 @@ extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64
     DepositParams p{};
     p.pv = pv; p.L = L; p.n = n; p.ndim = ndim; p.ntx = d.ntx; p.ntiles = d.ntiles;
     p.pids = d.vals1; p.tile_start = d.tile_start; p.item_start = d.item_start; p.item_tile = d.item_tile;
-    p.chunk = d.chunk; p.data = data; p.partial = d.partial;
+    p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0;
     if (data) {
         tile_item_scan_kernel<<<1, 1024, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start);
         SO_LAUNCH_CHECK();
         item_tile_kernel<<<(unsigned)((d.max_items + 255) / 256), 256, 0, st>>>(d.item_start, d.ntiles, d.max_items,
                                                                               d.item_tile);
         SO_LAUNCH_CHECK();
-        dim3 grid((unsigned)d.max_items, (unsigned)n_chan);
-        deposit_kernel<<<grid, kDepThreads, 0, st>>>(p);
-        SO_LAUNCH_CHECK();
+        const unsigned grid = (unsigned)((d.max_items + kDepWarps - 1) / kDepWarps);
+        for (int c0 = 0; c0 < n_chan;) {       // channel groups of 8 / 4 / 2 / 1 share one pass over the lists
+            p.chan0 = c0;
+            const int left = n_chan - c0;
+            if (left >= 8) { deposit_kernel<8><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 8; }
+            else if (left >= 4) { deposit_kernel<4><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 4; }
+            else if (left >= 2) { deposit_kernel<2><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 2; }
+            else { deposit_kernel<1><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 1; }
+            SO_LAUNCH_CHECK();
+        }
         dim3 rgrid((unsigned)d.ntiles, (unsigned)n_chan);
-        tile_reduce_kernel<<<rgrid, 256, 0, st>>>(p, n_chan);
+        tile_reduce_kernel<<<rgrid, kT * kT, 0, st>>>(p, n_chan);
         SO_LAUNCH_CHECK();
     }
     if (simple || hist) {
-        ngp_tile_kernel<<<(unsigned)d.ntiles, 256, 0, st>>>(p, n_chan, simple, hist);
+        ngp_tile_kernel<<<(unsigned)d.ntiles, 64, 0, st>>>(p, n_chan, simple, hist);
         SO_LAUNCH_CHECK();
     }
     return SO_OK;

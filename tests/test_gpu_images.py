@@ -119,7 +119,7 @@ def test_tile_assignment_bit_exact():
     dk = r['dk'].cpu().numpy()[sel]
     np.testing.assert_allclose(dk, o['aux']['dk'], rtol=4e-16)
     W = image_oracle.support_halfwidth(dk, pitch, images.SUPPORT_SIGMAS)
-    tiles, pids = image_oracle.tile_pairs(o['aux']['i'], o['aux']['j'], W, ndim, 64)
+    tiles, pids = image_oracle.tile_pairs(o["aux"]["i"], o["aux"]["j"], W, ndim, 16)
     gid = np.nonzero(sel)[0]
     assert np.array_equal(r['tiles'].cpu().numpy(), tiles)
     assert np.array_equal(r['pids'].cpu().numpy(), gid[pids])
