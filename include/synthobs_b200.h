@@ -121,13 +121,17 @@ int so_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb,
 /* K6 — dust-attenuated spectra of generate_SED (synthobs/sed/models.py:285-310):
  * BC, total and no_HII_no_BC need T_i(lambda) = exp(-tauV_i * k(lambda)) per
  * particle and wavelength, which does not factor through the histogram.
- * Particles must be sorted by cell (`order` = permutation, `cell_sorted` the
- * sorted keys).  grid_inc / grid_tn: [2? no: ncell, n_lam] float32 rows
- * (stellar_incident, transmitted+nebular).  k_ism_lam / k_bc_lam: [n_lam] float32
- * or NULL.  Outputs [n_lam] float32 each (NULL = not wanted). */
-int64_t so_sed_dust_spectra_workspace_bytes(int64_t n, int32_t n_lam);
+ * Particles are given in an order sorted by (galaxy, young, cell): `order` =
+ * sorted position -> particle index, `cell_sorted` = the cell codes
+ * (so_sed_broadband's out_cell) in that order, `seg_offsets` = CSR offsets of the
+ * galaxies in the sorted order (NULL with n_seg = 1 for one galaxy).
+ * grid_inc / grid_tn: [ncell, n_lam] float32 rows (stellar_incident,
+ * transmitted+nebular).  k_ism_lam / k_bc_lam: [n_lam] float32 or NULL (T = 1).
+ * Outputs [n_seg, n_lam] float32 each (NULL = not wanted). */
+int64_t so_sed_dust_spectra_workspace_bytes(int64_t n, int64_t n_seg, int32_t n_lam);
 int so_sed_dust_spectra(const double* masses, const double* tau_ism, const double* tau_bc,
                         const int32_t* cell_sorted, const int32_t* order, int64_t n,
+                        const int64_t* seg_offsets, int64_t n_seg,
                         const float* grid_inc, const float* grid_tn, int32_t ncell, int32_t n_lam,
                         const float* k_ism_lam, const float* k_bc_lam, double fesc,
                         float* out_bc, float* out_total, float* out_nohii,

@@ -37,8 +37,8 @@ SIGNATURES = {
     'so_split_tf32': (c_int, [P, P, P, I64, P]),
     'so_gemm_3xtf32': (c_int, [P, P, I64, P, P, I64, P, I64, I64, I64, I64, P]),
     'so_gemm_f32': (c_int, [P, I64, P, I64, P, I64, I64, I64, I64, P]),
-    'so_sed_dust_spectra_workspace_bytes': (I64, [I64, I32]),
-    'so_sed_dust_spectra': (c_int, [P, P, P, P, P, I64, P, P, I32, I32, P, P, D, P, P, P, P, I64, P]),
+    'so_sed_dust_spectra_workspace_bytes': (I64, [I64, I64, I32]),
+    'so_sed_dust_spectra': (c_int, [P, P, P, P, P, I64, P, I64, P, P, I32, I32, P, P, D, P, P, P, P, I64, P]),
     'so_img_ngp_index': (c_int, [P, P, I64, P, I32, D, P, P, P]),
     'so_knn_workspace_bytes': (I64, [I64, I32]),
     'so_knn_kth_distance': (c_int, [P, P, P, I64, I32, D, P, P, I64, P]),

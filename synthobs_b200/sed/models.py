@@ -230,7 +230,7 @@ class define_model():
 GEMM_ALGO = 'auto'   # 'auto' | '3xtf32' | 'f32'
 
 
-def gemm(A, B, algo=None):
+def gemm(A, B, algo=None, B_split=None):
     """C[M,N] = A[M,K] @ B[N,K]^T on the device (float32 in/out).  '3xtf32' is the
     tcgen05 tensor-core kernel with error compensation (default); 'f32' the
     FMA-pipe kernel kept for on-device validation."""
@@ -250,9 +250,14 @@ def gemm(A, B, algo=None):
             Y = torch.zeros((X.shape[0], Kp), dtype=torch.float32, device=X.device)
             Y[:, :K] = X
             return Y
-        A, B = prep(A), prep(B)
+        A = prep(A)
         Ah, Al = split_tf32(A)
-        Bh, Bl = split_tf32(B)
+        if B_split is not None:      # static operand (the SSP grid): split once per model
+            Bh, Bl = B_split
+            B = Bh
+        else:
+            B = prep(B)
+            Bh, Bl = split_tf32(B)
         rc = _cabi.lib.so_gemm_3xtf32(_cabi.ptr(Ah), _cabi.ptr(Al), A.stride(0), _cabi.ptr(Bh), _cabi.ptr(Bl),
                                       B.stride(0), _cabi.ptr(C), C.stride(0), M, N, K, _cabi.stream())
         _cabi.check(rc, 'so_gemm_3xtf32')
@@ -535,30 +540,34 @@ def _spectral_operands(model):
         c = {'BT': dv.to_dev(BT, torch.float32),
              'inc': dv.to_dev(inc.astype(np.float32), torch.float32),
              'tn': dv.to_dev(tn.astype(np.float32), torch.float32), 'ld': ld}
+        c['BT_split'] = split_tf32(c['BT'])
         model._dev['BT'] = c
     return c
 
 
 def sed_spectra_device(model, Masses, Ages, Metallicities, tauVs_ISM=False, tauVs_BC=False, fesc=0.0,
-                       log10t_BC=7.):
-    """The five spectra of generate_SED as float32 CUDA tensors [n_lam]."""
-    M, cell, H, _, ncell = _cells_and_hist(model, Masses, Ages, Metallicities, log10t_BC)
+                       log10t_BC=7., offsets=None):
+    """The five spectra of generate_SED as float32 CUDA tensors: [n_lam] for one
+    galaxy, [G, n_lam] when CSR `offsets` are given (batch of galaxies)."""
+    M, cell, H, Hlo_unused, ncell = _cells_and_hist(model, Masses, Ages, Metallicities, log10t_BC, offsets=offsets)
     ops = _spectral_operands(model)
     ld = ops['ld']
-    Hold = H[0, :ncell]
-    Hyng = H[0, ncell:2 * ncell]
-    A = torch.zeros((2, ld), dtype=torch.float32, device=H.device)
-    A[0, :ncell] = Hold + Hyng                        # stellar = sum_i M_i inc               (models.py:277,306)
-    A[1, :ncell] = Hold + float(fesc) * Hyng          # intrinsic, incident part              (models.py:281,295)
-    A[1, ncell:2 * ncell] = (1.0 - float(fesc)) * Hyng   # intrinsic, transmitted+nebular part
-    C = gemm(A, ops['BT'])                            # [2, n_lam]
-    out = {'stellar': C[0], 'intrinsic': C[1]}
+    G = H.shape[0]
+    Hold = H[:, :ncell]
+    Hyng = H[:, ncell:2 * ncell]
+    A = torch.zeros((2 * G, ld), dtype=torch.float32, device=H.device)
+    A[:G, :ncell] = Hold + Hyng                           # stellar = sum_i M_i inc            (models.py:277,306)
+    A[G:, :ncell] = Hold + float(fesc) * Hyng             # intrinsic, incident part           (models.py:281,295)
+    A[G:, ncell:2 * ncell] = (1.0 - float(fesc)) * Hyng   # intrinsic, transmitted+nebular part
+    C = gemm(A, ops['BT'], B_split=ops.get('BT_split'))   # [2G, n_lam] on the tensor cores
+    squeeze = (lambda t: t[0]) if offsets is None else (lambda t: t)
+    out = {'stellar': squeeze(C[:G]), 'intrinsic': squeeze(C[G:])}
     have_ism = bool(model.dust_ISM)
     have_bc = bool(model.dust_BC)
     if not have_ism and not have_bc:
-        out['BC'] = C[1].clone()                      # T = 1 everywhere                       (models.py:285-304)
-        out['total'] = C[1].clone()
-        out['no_HII_no_BC'] = C[0].clone()
+        out['BC'] = out['intrinsic'].clone()              # T = 1 everywhere                   (models.py:285-304)
+        out['total'] = out['intrinsic'].clone()
+        out['no_HII_no_BC'] = out['stellar'].clone()
         return out
     n = M.numel()
     nl = model.lam.size
@@ -566,17 +575,36 @@ def sed_spectra_device(model, Masses, Ages, Metallicities, tauVs_ISM=False, tauV
     tB = _opt(tauVs_BC, M) if have_bc else None
     kI = dv.to_dev(np.asarray(_dust_k(model, 'ISM', model.lam), dtype=np.float32), torch.float32) if have_ism else None
     kB = dv.to_dev(np.asarray(_dust_k(model, 'BC', model.lam), dtype=np.float32), torch.float32) if have_bc else None
-    key, order = torch.sort(cell, stable=True)
+    if offsets is None:
+        off = None
+        key, order = torch.sort(cell, stable=True)
+    else:
+        off = dv.to_dev(offsets, torch.int64)
+        gal = torch.repeat_interleave(torch.arange(G, device=M.device, dtype=torch.int64), off[1:] - off[:-1])
+        _, order = torch.sort(gal * (1 << 17) + cell.to(torch.int64), stable=True)     # (galaxy, young, cell)
+        key = cell[order]
     order = order.to(torch.int32)
-    bc = torch.empty(nl, dtype=torch.float32, device=M.device)
+    bc = torch.empty((G, nl), dtype=torch.float32, device=M.device)
     tot = torch.empty_like(bc)
     noh = torch.empty_like(bc)
-    wsb = _cabi.lib.so_sed_dust_spectra_workspace_bytes(n, nl)
+    wsb = _cabi.lib.so_sed_dust_spectra_workspace_bytes(n, G, nl)
     ws = dv.workspace(wsb)
     rc = _cabi.lib.so_sed_dust_spectra(_cabi.ptr(M), _cabi.ptr(tI), _cabi.ptr(tB), _cabi.ptr(key), _cabi.ptr(order), n,
+                                       _cabi.ptr(off), G,
                                        _cabi.ptr(ops['inc']), _cabi.ptr(ops['tn']), ncell, nl,
                                        _cabi.ptr(kI), _cabi.ptr(kB), float(fesc),
                                        _cabi.ptr(bc), _cabi.ptr(tot), _cabi.ptr(noh), _cabi.ptr(ws), wsb, _cabi.stream())
     _cabi.check(rc, 'so_sed_dust_spectra')
-    out['BC'], out['total'], out['no_HII_no_BC'] = bc, tot, noh
+    out['BC'], out['total'], out['no_HII_no_BC'] = squeeze(bc), squeeze(tot), squeeze(noh)
+    return out
+
+
+def generate_SED_batch(model, Masses, Ages, Metallicities, offsets, tauVs_ISM=False, tauVs_BC=False, fesc=0.0,
+                       log10t_BC=7.):
+    """generate_SED for many galaxies in one call (no upstream equivalent):
+    dict of [G, n_lam] arrays (NumPy float64 for host inputs, CUDA float32 tensors otherwise)
+    equal to a Python loop of generate_SED over the galaxies."""
+    out = sed_spectra_device(model, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC, offsets=offsets)
+    if _host_like(Masses):
+        return {k: dv.to_host(v) for k, v in out.items()}
     return out
