@@ -220,6 +220,11 @@ def run_ours(args):
     h2d = int(sum(host[k].numel() * 8 for k in keys) + offsets.numel() * 8)
     d2h = int(G * N_FILTERS * 8)
 
+    # ---------------- full spectra (generate_SED) + the two tensor-core contractions (secondary)
+    spectra = None
+    if not args.no_spectra:
+        spectra = run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks)
+
     # ---------------- imaging workload (secondary, config[2])
     imaging = None
     if not args.no_imaging:
@@ -252,14 +257,103 @@ def run_ours(args):
                                  'reduce), so the fraction is a lower bound for the streaming kernel'},
             'e2e': {'value': e2e_value, 'unit': 'galaxy_SEDs_x_filters/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
-            'gpu_launches': 4 * args.steps,
+            'gpu_launches': 4 * sed_steps,
             'clocks': clocks,
             'cpu_baseline': cpu,
+            'spectra': spectra,
             'imaging': imaging,
         }
         print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
+    """generate_SED for a batch of galaxies (five spectra over 9000 wavelengths each: segmented
+    histogram -> 3xTF32 tcgen05 GEMM against the SSP grid, per-particle dust kernel) followed by the
+    second contraction spectra x filter weights; plus the histogram x grid GEMM alone at FLARES batch
+    size (1e4 galaxies -> M = 2e4 rows) with its tensor-pipe roofline."""
+    import torch
+    from synthobs_b200 import _cabi, synthetic
+    from synthobs_b200.sed import models
+    G = 32
+    batch = synthetic.galaxy_batch(G, fixed_n=N_PER_GALAXY, seed=300 + rank)
+    keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
+    d = {k: torch.from_numpy(batch[k]).to(dev) for k in keys}
+    off = torch.from_numpy(batch['offsets']).to(dev)
+    # filter weights for the spectra -> flux contraction (trapz weights * T / norm, folded on the host)
+    Wt = np.stack([models.trapz_weights(F[f].lam) * F[f].T / np.trapezoid(F[f].T, x=F[f].lam) for f in F['filters']])
+    Wt = Wt / np.abs(Wt).max(axis=1, keepdims=True)
+    nlp = (Wt.shape[1] + 3) // 4 * 4
+    Wp = np.zeros((Wt.shape[0], nlp), dtype=np.float32)
+    Wp[:, :Wt.shape[1]] = Wt
+    Wd = torch.from_numpy(Wp).to(dev)
+    W_split = models.split_tf32(Wd)
+
+    def step():
+        o = models.sed_spectra_device(model, d['Masses'], d['Ages'], d['Metallicities'], d['tauVs_ISM'], d['tauVs_BC'],
+                                      0.0, 7.0, offsets=off)
+        tot = o['total']
+        if tot.shape[1] != nlp:
+            tot = torch.nn.functional.pad(tot, (0, nlp - tot.shape[1]))
+        return models.gemm(tot, Wd, B_split=W_split)            # [G, F] band fluxes from the spectra
+
+    for _ in range(2):
+        step()
+    barrier()
+    steps = max(3, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    n_lam = model.lam.size
+    n_part = G * N_PER_GALAXY
+    # the hist x grid GEMM alone, FLARES batch size
+    ops = models._spectral_operands(model)
+    M = 20000
+    A = torch.rand((M, ops['ld']), device=dev)
+    Ah, Al = models.split_tf32(A)
+    Bh, Bl = ops['BT_split']
+    C = torch.empty((M, n_lam), dtype=torch.float32, device=dev)
+    K = 2 * model.na * model.nz
+
+    def gemm_only():
+        _cabi.check(_cabi.lib.so_gemm_3xtf32(_cabi.ptr(Ah), _cabi.ptr(Al), A.stride(0), _cabi.ptr(Bh), _cabi.ptr(Bl),
+                                             Bh.stride(0), _cabi.ptr(C), C.stride(0), M, n_lam, K, _cabi.stream()),
+                    'so_gemm_3xtf32')
+    for _ in range(3):
+        gemm_only()
+    barrier()
+    e0.record()
+    for _ in range(10):
+        gemm_only()
+    e1.record()
+    barrier()
+    gms = max_over_ranks(e0.elapsed_time(e1) / 10)
+    flops = 2.0 * M * n_lam * K
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops'])
+        src = 'measured bf16 burst / 2 (no TF32 entry in MEASURED_PEAKS.json)'
+    except Exception:
+        bf16_peak, src = 1590.0, 'fallback bf16 / 2'
+    tf32_peak = bf16_peak / 2
+    return {
+        'metric': 'galaxy SEDs/sec (5 spectra x %d wavelengths, ISM+BC dust) + %d band fluxes' % (n_lam, len(F['filters'])),
+        'value': world * G / (ms * 1e-3), 'unit': 'galaxy_SEDs/s', 'ms_per_step': ms,
+        'galaxy_SEDs_x_filters_per_s': world * G * len(F['filters']) / (ms * 1e-3),
+        'particle_wavelengths_per_s': world * n_part * n_lam / (ms * 1e-3),
+        'config': {'workload': '%d galaxies x 1e5 particles per GPU, generate_SED_batch + spectra x filters' % G},
+        'gemm_hist_x_grid': {'M': M, 'N': n_lam, 'K': K, 'ms': gms, 'algorithmic_tflops': flops / gms / 1e9,
+                             'executed_tf32_tflops': 3 * flops / gms / 1e9,
+                             'roofline': {'bound': 'tensor', 'achieved': 3 * flops / gms / 1e9, 'peak': tf32_peak,
+                                          'unit': 'TFLOP/s', 'frac': 3 * flops / gms / 1e9 / tf32_peak, 'traffic': None,
+                                          'peak_source': src,
+                                          'note': 'achieved counts the three TF32 MMAs actually executed per '
+                                                  'algorithmic product (3xTF32); algorithmic fraction is a third'}},
+    }
 
 
 def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
@@ -453,6 +547,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-imaging', action='store_true')
+    ap.add_argument('--no-spectra', action='store_true')
     ap.add_argument('--no-sed', action='store_true', help='profiling aid: skip the SED timed loops')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-sed-e2e', action='store_true')

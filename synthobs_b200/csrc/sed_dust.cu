@@ -36,37 +36,72 @@ struct DustParams {
     const int64_t* seg;      // CSR offsets of the galaxies in the sorted order, or null (one galaxy)
 };
 
+__device__ __forceinline__ float ex2a(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// kLamPerThread wavelengths per thread (strided by the CTA width, so grid rows are read coalesced):
+// the particle record is fetched from shared memory once per 4 wavelengths and the arithmetic runs
+// on wavelength pairs with the packed FMUL2/FFMA2 instructions; what remains per particle and
+// wavelength is essentially the ex2 itself (MUFU-bound).
+constexpr int kLamPerThread = 4;
+
 __global__ void __launch_bounds__(kDustThreads) dust_spectra_kernel(const DustParams p) {
     __shared__ float s_m[kStage], s_ti[kStage], s_tb[kStage];
     __shared__ int s_key[kStage];
-    const int lam = blockIdx.x * kDustThreads + threadIdx.x;
-    const bool lam_ok = lam < p.n_lam;
+    const int lam0 = blockIdx.x * (kDustThreads * kLamPerThread) + threadIdx.x;
     const int gal = blockIdx.y / p.pblocks, pb = blockIdx.y % p.pblocks;
     const int64_t g0 = p.seg ? p.seg[gal] : 0, g1 = p.seg ? p.seg[gal + 1] : p.n;
     const int64_t per = (g1 - g0 + p.pblocks - 1) / p.pblocks;
     const int64_t p0 = min(g1, g0 + (int64_t)pb * per), p1 = min(g1, p0 + per);
     const float log2e = 1.4426950408889634f;
-    const float kI = (p.k_ism && lam_ok) ? p.k_ism[lam] * log2e : 0.f;
-    const float kB = (p.k_bc && lam_ok) ? p.k_bc[lam] * log2e : 0.f;
+    // -k log2(e) per owned wavelength, as pairs (0 where the wavelength is out of range or no dust)
+    float2 kI[kLamPerThread / 2], kB[kLamPerThread / 2];
+    bool ok[kLamPerThread];
+#pragma unroll
+    for (int j = 0; j < kLamPerThread; ++j) {
+        const int lam = lam0 + j * kDustThreads;
+        ok[j] = lam < p.n_lam;
+        const float a = (p.k_ism && ok[j]) ? -p.k_ism[lam] * log2e : 0.f;
+        const float b = (p.k_bc && ok[j]) ? -p.k_bc[lam] * log2e : 0.f;
+        if (j & 1) { kI[j / 2].y = a; kB[j / 2].y = b; } else { kI[j / 2].x = a; kB[j / 2].x = b; }
+    }
     const float fesc = p.fesc, ofe = 1.f - p.fesc;
 
-    float bc = 0.f, tot = 0.f, noh = 0.f;
-    float d1 = 0.f, d2 = 0.f, d3 = 0.f, ms = 0.f;
+    float2 bc[kLamPerThread / 2], tot[kLamPerThread / 2], noh[kLamPerThread / 2];
+    float2 d1[kLamPerThread / 2], d2[kLamPerThread / 2], d3[kLamPerThread / 2];
+    const float2 z2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < kLamPerThread / 2; ++h) { bc[h] = tot[h] = noh[h] = d1[h] = d2[h] = d3[h] = z2; }
+    float ms = 0.f;
     int cur = -1;
 
     auto flush = [&]() {
-        if (cur < 0 || !lam_ok) return;
+        if (cur < 0) return;
         const int cell = cur & 65535;
         const bool young = (cur >> 16) != 0;
-        const float inc = p.inc[(size_t)cell * p.n_lam + lam];
-        noh = fmaf(d1, inc, noh);
-        if (young) {
-            const float tn = p.tn[(size_t)cell * p.n_lam + lam];
-            bc += fesc * ms * inc + ofe * d3 * tn;
-            tot += fesc * d1 * inc + ofe * d2 * tn;
-        } else {
-            bc = fmaf(ms, inc, bc);
-            tot = fmaf(d1, inc, tot);
+#pragma unroll
+        for (int j = 0; j < kLamPerThread; ++j) {
+            if (!ok[j]) continue;
+            const int lam = lam0 + j * kDustThreads;
+            const float inc = p.inc[(size_t)cell * p.n_lam + lam];
+            float& rbc = (j & 1) ? bc[j / 2].y : bc[j / 2].x;
+            float& rtot = (j & 1) ? tot[j / 2].y : tot[j / 2].x;
+            float& rnoh = (j & 1) ? noh[j / 2].y : noh[j / 2].x;
+            const float v1 = (j & 1) ? d1[j / 2].y : d1[j / 2].x;
+            const float v2 = (j & 1) ? d2[j / 2].y : d2[j / 2].x;
+            const float v3 = (j & 1) ? d3[j / 2].y : d3[j / 2].x;
+            rnoh = fmaf(v1, inc, rnoh);
+            if (young) {
+                const float tn = p.tn[(size_t)cell * p.n_lam + lam];
+                rbc += fesc * ms * inc + ofe * v3 * tn;
+                rtot += fesc * v1 * inc + ofe * v2 * tn;
+            } else {
+                rbc = fmaf(ms, inc, rbc);
+                rtot = fmaf(v1, inc, rtot);
+            }
         }
     };
 
@@ -86,26 +121,43 @@ __global__ void __launch_bounds__(kDustThreads) dust_spectra_kernel(const DustPa
             const int key = s_key[q];
             if (key != cur) {           // uniform across the CTA
                 flush();
-                cur = key; d1 = d2 = d3 = ms = 0.f;
+                cur = key; ms = 0.f;
+#pragma unroll
+                for (int h = 0; h < kLamPerThread / 2; ++h) { d1[h] = d2[h] = d3[h] = z2; }
             }
             const float m = s_m[q];
-            const float TI = exp2f(-s_ti[q] * kI);
-            d1 = fmaf(m, TI, d1);
+            const float2 m2 = make_float2(m, m), ti2 = make_float2(s_ti[q], s_ti[q]);
             ms += m;
             if (key >> 16) {
-                const float TB = exp2f(-s_tb[q] * kB);
-                const float mTB = m * TB;
-                d3 += mTB;
-                d2 = fmaf(mTB, TI, d2);
+                const float2 tb2 = make_float2(s_tb[q], s_tb[q]);
+#pragma unroll
+                for (int h = 0; h < kLamPerThread / 2; ++h) {
+                    const float2 aI = __fmul2_rn(ti2, kI[h]);
+                    const float2 TI = make_float2(ex2a(aI.x), ex2a(aI.y));
+                    d1[h] = __ffma2_rn(m2, TI, d1[h]);
+                    const float2 aB = __fmul2_rn(tb2, kB[h]);
+                    const float2 mTB = __fmul2_rn(m2, make_float2(ex2a(aB.x), ex2a(aB.y)));
+                    d3[h] = __fadd2_rn(d3[h], mTB);
+                    d2[h] = __ffma2_rn(mTB, TI, d2[h]);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < kLamPerThread / 2; ++h) {
+                    const float2 aI = __fmul2_rn(ti2, kI[h]);
+                    d1[h] = __ffma2_rn(m2, make_float2(ex2a(aI.x), ex2a(aI.y)), d1[h]);
+                }
             }
         }
     }
     flush();
-    if (lam_ok) {
-        float* out = p.partial + (size_t)blockIdx.y * 3 * p.n_lam;
-        out[lam] = bc;
-        out[p.n_lam + lam] = tot;
-        out[2 * p.n_lam + lam] = noh;
+    float* out = p.partial + (size_t)blockIdx.y * 3 * p.n_lam;
+#pragma unroll
+    for (int j = 0; j < kLamPerThread; ++j) {
+        if (!ok[j]) continue;
+        const int lam = lam0 + j * kDustThreads;
+        out[lam] = (j & 1) ? bc[j / 2].y : bc[j / 2].x;
+        out[p.n_lam + lam] = (j & 1) ? tot[j / 2].y : tot[j / 2].x;
+        out[2 * p.n_lam + lam] = (j & 1) ? noh[j / 2].y : noh[j / 2].x;
     }
 }
 
@@ -126,7 +178,7 @@ __global__ void dust_reduce_kernel(const float* __restrict__ partial, int pblock
 }
 
 static int dust_pblocks(int64_t n, int64_t n_seg, int n_lam) {
-    const int64_t lam_blocks = (n_lam + kDustThreads - 1) / kDustThreads;
+    const int64_t lam_blocks = (n_lam + kDustThreads * 4 - 1) / (kDustThreads * 4);
     int64_t pb = (4 * 148 + lam_blocks * n_seg - 1) / (lam_blocks * n_seg);
     const int64_t max_pb = (n / (n_seg > 0 ? n_seg : 1) + 63) / 64;
     if (pb > max_pb) pb = (int)max_pb;
@@ -165,7 +217,7 @@ extern "C" int so_sed_dust_spectra(const double* masses, const double* tau_ism, 
     p.masses = masses; p.tau_ism = tau_ism; p.tau_bc = tau_bc; p.key = cell_sorted; p.order = order; p.n = n;
     p.inc = grid_inc; p.tn = grid_tn; p.ncell = ncell; p.n_lam = n_lam; p.k_ism = k_ism_lam; p.k_bc = k_bc_lam;
     p.fesc = (float)fesc; p.partial = partial; p.pblocks = pb; p.seg = seg_offsets;
-    dim3 grid((n_lam + kDustThreads - 1) / kDustThreads, (unsigned)(n_seg * pb));
+    dim3 grid((n_lam + kDustThreads * kLamPerThread - 1) / (kDustThreads * kLamPerThread), (unsigned)(n_seg * pb));
     dust_spectra_kernel<<<grid, kDustThreads, 0, st>>>(p);
     SO_LAUNCH_CHECK();
     dim3 rgrid((n_lam + 255) / 256, (unsigned)n_seg);
