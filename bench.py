@@ -253,8 +253,11 @@ def run_ours(args):
                        'parallelism': 'galaxies sharded by rank, no collective'},
             'particles_per_s': world * n_part / (ms_step * 1e-3),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                         'kernel': 'sed_broadband_kernel<12>', 'algorithmic_bytes_per_particle': 40,
+                         'frac': achieved / hbm_peak, 'traffic': 1.031e9 if n_part == 25600000 else None,
+                         'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
+                                           '(profiles/r01_ncu_kernels.md): 1.024 GB + 6.8 MB vs 1.024 GB algorithmic',
+                         'peak_source': peak_src,
+                         'kernel': 'sed_broadband_kernel<12,0>', 'algorithmic_bytes_per_particle': 40,
                          'note': 'duration = whole step (4 launches: item scan, item map, broadband, per-galaxy '
                                  'reduce), so the fraction is a lower bound for the streaming kernel'},
             'e2e': {'value': e2e_value, 'unit': 'galaxy_SEDs_x_filters/s', 'h2d_bytes_per_step': h2d,

@@ -1,0 +1,139 @@
+"""GPU: BASELINE.json's full sizes through size-independent properties (the oracle would take
+minutes to hours there): linearity, permutation invariance, batch == concatenation, flux
+conservation, count conservation, determinism, rebin sum preservation."""
+
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from synthobs_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def model_full():
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=9000, seed=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = models.define_model(grid)
+    m.dust_ISM = ('simple', {'slope': -1.0})
+    m.dust_BC = ('simple', {'slope': -1.0})
+    F = synthetic.filter_set(m.lam * 9.0, n_filters=10, kind='gauss', lo=12000., hi=50000., prefix='J.')
+    m.create_Fnu_grid(F, 8.0, synthetic.FixedCosmology())
+    return m, F
+
+
+def test_config2_sed_properties(model_full):
+    """config[1]: 1e5 particles, 51x13x9000 grid, ISM+BC dust, 10 filters"""
+    from synthobs_b200.sed import models
+    model, F = model_full
+    p = synthetic.particles(100000, seed=41, lognormal_mass=True)
+    args = (p['Masses'], p['Ages'], p['Metallicities'])
+    kw = dict(tauVs_ISM=p['tauVs_ISM'], tauVs_BC=p['tauVs_BC'], fesc=0.1)
+    f = models.generate_Fnu(model, F, *args, **kw)
+    base = np.array([f[k] for k in F['filters']])
+    assert np.all(np.isfinite(base)) and np.all(base > 0)
+    # linearity in mass
+    f2 = models.generate_Fnu(model, F, 2.0 * p['Masses'], p['Ages'], p['Metallicities'], **kw)
+    np.testing.assert_allclose([f2[k] for k in F['filters']], 2 * base, rtol=2e-6)
+    # permutation invariance
+    perm = np.random.default_rng(0).permutation(100000)
+    fp = models.generate_Fnu(model, F, p['Masses'][perm], p['Ages'][perm], p['Metallicities'][perm],
+                             tauVs_ISM=p['tauVs_ISM'][perm], tauVs_BC=p['tauVs_BC'][perm], fesc=0.1)
+    np.testing.assert_allclose([fp[k] for k in F['filters']], base, rtol=2e-6)
+    # split into 7 "galaxies": batch rows add up to the whole
+    off = np.array([0, 1, 1, 5000, 33333, 33334, 99999, 100000])
+    rows = models.generate_Fnu_batch(model, F, *args, off, **kw)
+    np.testing.assert_allclose(rows.sum(axis=0), base, rtol=2e-6)
+    assert np.all(rows[1] == 0)          # empty galaxy
+    # sum of the per-particle arrays == totals (models.py:83)
+    arrs = models.generate_Fnu_arrays(model, F, *args, **kw)
+    np.testing.assert_allclose([arrs[k].sum() for k in F['filters']], base, rtol=2e-6)
+    # more dust -> less flux, no dust -> upper bound
+    fd = models.generate_Fnu(model, F, *args, tauVs_ISM=3 * p['tauVs_ISM'], tauVs_BC=p['tauVs_BC'], fesc=0.1)
+    f0 = models.generate_Fnu(model, F, *args, fesc=0.1)
+    assert all(fd[k] < f[k] < f0[k] for k in F['filters'])
+
+
+def test_config2_spectra_properties(model_full):
+    from synthobs_b200.sed import models
+    model, F = model_full
+    p = synthetic.particles(100000, seed=42)
+    args = (p['Masses'], p['Ages'], p['Metallicities'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        o = models.generate_SED(model, *args, tauVs_ISM=p['tauVs_ISM'], tauVs_BC=p['tauVs_BC'], fesc=0.0)
+        nod = models.generate_SED(model, *args, fesc=0.0)      # tau arrays absent -> exp(-0) = 1
+    assert o.total.lnu.shape == (9000,)
+    # attenuation ordering: total <= BC <= intrinsic ; no_HII_no_BC <= stellar
+    tol = 1e-5 * o.intrinsic.lnu.max()
+    assert np.all(o.total.lnu <= o.BC.lnu + tol) and np.all(o.BC.lnu <= o.intrinsic.lnu + tol)
+    assert np.all(o.no_HII_no_BC.lnu <= o.stellar.lnu + tol)
+    # dust-free limits reduce to the tensor-core contractions
+    np.testing.assert_allclose(nod.total.lnu, nod.intrinsic.lnu, rtol=2e-5, atol=tol)
+    np.testing.assert_allclose(nod.no_HII_no_BC.lnu, nod.stellar.lnu, rtol=2e-5, atol=tol)
+    np.testing.assert_allclose(o.stellar.lnu, nod.stellar.lnu, rtol=1e-6)
+    # the Lnu-grid path and the spectrum path agree in the dust-free case (examples/SED_luminosities.py:18)
+    Fr = synthetic.filter_set(model.lam, n_filters=6)
+    model.create_Lnu_grid(Fr)
+    keep_I, keep_B = model.dust_ISM, model.dust_BC
+    model.dust_ISM = model.dust_BC = False
+    try:
+        L = models.generate_Lnu(model, Fr, *args)
+    finally:
+        model.dust_ISM, model.dust_BC = keep_I, keep_B
+    for f in Fr['filters']:
+        band = np.trapezoid(nod.intrinsic.lnu * Fr[f].T, x=Fr[f].lam) / np.trapezoid(Fr[f].T, x=Fr[f].lam)
+        assert band == pytest.approx(L[f], rel=1e-4)
+
+
+def test_config3_imaging_properties():
+    """config[2]: 1e6 particles, 512x512 observed frame, super-sampling 2, adaptive k=8, PSF"""
+    import torch
+    from synthobs_b200.morph import images
+    p = synthetic.particles(1000000, seed=43, scale_kpc=3.0)
+    filters = ['P.A', 'P.B']
+    for f in filters:
+        images.filter_info[f] = {'pixel_scale': 0.031}
+    cosmo = synthetic.FixedCosmology()
+    obs = [images.observed(f, cosmo, 8.0, 512 * 0.031 + 1e-9, smoothing=('adaptive', 8.), PSF=synthetic.GaussianPSF(2.0),
+                           super_sampling=2) for f in filters]
+    assert obs[0].ndim == 512 and obs[0].ndim_super == 1024
+    X = torch.from_numpy(p['X'] - np.median(p['X'])).cuda()
+    Y = torch.from_numpy(p['Y'] - np.median(p['Y'])).cuda()
+    w = np.stack([p['Masses'], p['Masses'] * np.random.default_rng(1).random(1000000)])
+    L = torch.from_numpy(w).cuda()
+    r1 = images.particle_device_multi(obs, X, Y, L)
+    r2 = images.particle_device_multi(obs, X, Y, L)
+    assert torch.equal(r1['data'], r2['data']) and torch.equal(r1['super_no_PSF'], r2['super_no_PSF'])   # deterministic
+    sel = r1['stats']['selected']
+    assert sel == 1000000 and r1['stats']['dropped'] == 0
+    for c in range(2):
+        tot = w[c].sum()
+        assert float(r1['super_no_PSF'][c].double().sum()) == pytest.approx(tot, rel=5e-6)     # flux conservation
+        assert float(r1['no_PSF'][c].double().sum()) == pytest.approx(tot, rel=5e-6)           # rebin keeps sums
+        assert float(r1['data'][c].double().sum()) == pytest.approx(tot, rel=2e-3)             # PSF wings leave the frame
+        assert float(r1['super_no_PSF'][c].min()) >= 0.0
+    # NGP products: counts conserve the particle number
+    h = images.deposit_device(X, Y, L[:1], obs[0].resolution, 1024, adaptive_k=None)
+    assert float(h['hist'].double().sum()) == 1000000
+    assert float(h['simple'][0].double().sum()) == pytest.approx(w[0].sum(), rel=1e-6)
+    # linearity in the weights
+    r3 = images.particle_device_multi(obs, X, Y, 3.0 * L)
+    assert torch.allclose(r3['no_PSF'], 3.0 * r1['no_PSF'], rtol=1e-5, atol=1e-7 * float(r1['no_PSF'].max()))
+
+
+def test_large_image_flux_and_odd_sizes():
+    """a 4099x4099 image (not a multiple of the 16-pixel sub-tile) from 2e6 particles"""
+    import torch
+    from synthobs_b200 import device as dv
+    from synthobs_b200.morph import images
+    p = synthetic.particles(2000000, seed=44, scale_kpc=6.0)
+    r = images.deposit_device(dv.to_dev(p['X']), dv.to_dev(p['Y']), dv.to_dev(p['Masses']), 0.01, 4099, adaptive_k=5,
+                              want_ngp=False)
+    width = 4099 * 0.01
+    sel = (np.abs(p['X']) < width / 2) & (np.abs(p['Y']) < width / 2)
+    assert r['stats']['selected'] == sel.sum()
+    assert float(r['data'].double().sum()) == pytest.approx(p['Masses'][sel].sum(), rel=5e-6)
