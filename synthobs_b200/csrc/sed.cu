@@ -19,11 +19,11 @@ constexpr int kThreads = 512;                 // threads per persistent CTA, 2 C
 constexpr int kPerThread = 2;                 // particles per thread per work item
 constexpr int kItem = kThreads * kPerThread;  // particles per work item
 constexpr int kMaxThr = 127;                  // max thresholds per axis (kernel-parameter resident)
-constexpr int kLut = 12288;                   // index table entries per axis (512 per octave, 24 octaves)
-constexpr int kLutShift = 11;                 // bin = (high 32 bits of the double >> 11): exponent + 9 mantissa bits
+constexpr int kLut = 6144;                    // index table entries per axis (256 per octave, 24 octaves)
+constexpr int kLutShift = 12;                 // bin = (high 32 bits of the double >> 12): exponent + 8 mantissa bits
 
 // One NGP axis: ascending float64 thresholds + an index table over bins of the double's own bit
-// pattern (sign/exponent/top 9 mantissa bits: 512 bins per octave, exact edges, integer ALU only).
+// pattern (sign/exponent/top 8 mantissa bits: 256 bins per octave, exact edges, integer ALU only).
 // lut[b] & 127 = #{thr <= lower edge of bin b}; bit 7 is set when a threshold lies inside the bin:
 // only then (< 1 % of the particles) are exact float64 compares against thr[] needed.
 struct Axis {
