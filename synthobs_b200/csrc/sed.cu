@@ -21,6 +21,7 @@ constexpr int kItem = kThreads * kPerThread;  // particles per work item
 constexpr int kMaxThr = 127;                  // max thresholds per axis (kernel-parameter resident)
 constexpr int kLut = 6144;                    // index table entries per axis (256 per octave, 24 octaves)
 constexpr int kLutShift = 12;                 // bin = (high 32 bits of the double >> 12): exponent + 8 mantissa bits
+constexpr int kYWarp = 32 * (kPerThread + 1); // per-warp ring of compacted young particles
 
 // One NGP axis: ascending float64 thresholds + an index table over bins of the double's own bit
 // pattern (sign/exponent/top 8 mantissa bits: 256 bins per octave, exact edges, integer ALU only).
@@ -86,8 +87,11 @@ __device__ __forceinline__ float2 ex2_approx2(float2 x) { return make_float2(ex2
 
 // Persistent streaming kernel: each CTA walks a contiguous range of work items (kItem particles of
 // one galaxy).  The per-filter arithmetic runs on pairs of filters with the sm_100 packed FP32
-// instructions (FMUL2 / FFMA2): the kernel is issue-bound, not FLOP-bound, so halving the FP
-// instruction count is what moves it towards the HBM roofline.
+// instructions (FMUL2 / FFMA2): the kernel is issue/XU-bound, not FLOP-bound.
+// Sums-only variant (WRITE_PF = false): only ~1/4 of the particles are young, so their extra
+// birth-cloud term (a second ex2 per filter) is not evaluated under a predicate by every warp:
+// each warp compacts its young particles (ballot/popc, fixed order, no block barrier) into a small
+// private shared-memory ring and evaluates the term 32 particles at a time with all lanes active.
 template <int FP, bool WRITE_PF>
 __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid_constant__ BroadbandParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -101,9 +105,12 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
     double* s_red = s_z_thr + (kMaxThr + 1);                       // [kThreads/32][FP]
     unsigned char* s_age_lut = reinterpret_cast<unsigned char*>(s_red + (kThreads / 32) * FP);
     unsigned char* s_z_lut = s_age_lut + kLut;
+    float4* s_y = reinterpret_cast<float4*>(s_z_lut + kLut);       // [warps][kYWarp] {m(1-fesc), tauI, tauB, cell}
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    float4* my_y = s_y + warp * kYWarp;
+    int ytail = 0, yhead = 0;      // this warp's ring positions (warp-uniform)
 
     // stage the per-filter tables as [cell][filter] (transposed from [filter][cell])
     for (int idx = tid; idx < ncell * FP; idx += kThreads) {
@@ -171,6 +178,17 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
             const bool young = (age[j] < p.young_thr) && (age[j] >= 0.0);
             const int cell = ia * p.nz + iz;
             if (p.out_cell && on) p.out_cell[i] = cell + (young ? 65536 : 0);
+            if constexpr (!WRITE_PF) {
+                // warp-level compaction of the young particles (fixed order: slot, lane)
+                const bool isy = young && on;
+                const unsigned bal = __ballot_sync(0xffffffffu, isy);
+                if (isy) {
+                    int pos = ytail + __popc(bal & ((1u << lane) - 1u));
+                    pos = pos >= kYWarp ? pos - kYWarp : pos;
+                    my_y[pos] = make_float4(mm[j] * ofe, ti[j], tb[j], __int_as_float(cell));
+                }
+                ytail += __popc(bal);
+            }
 
             // l = m T_ISM inc                                       (old,   models.py:133)
             // l = m T_ISM (fesc inc + T_BC (1-fesc)(tra+neb))       (young, models.py:131)
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
             for (int q = 0; q < FP / 4; ++q) {
                 const float4 vi = rinc[q];
                 float4 vt = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (young) vt = rtn[q];
+                if constexpr (WRITE_PF) { if (young) vt = rtn[q]; }
                 const float2 inc2[2] = {make_float2(vi.x, vi.y), make_float2(vi.z, vi.w)};
                 const float2 tn2[2] = {make_float2(vt.x, vt.y), make_float2(vt.z, vt.w)};
 #pragma unroll
@@ -208,10 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
                                 if (2 * pr + 1 < nf) po[(size_t)(2 * pr + 1) * p.n] = l.y;
                             }
                         } else {
-                            acc[pr] = __ffma2_rn(t, inc2[h], acc[pr]);
-                            if (young)
-                                acc[pr] = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(__ffma2_rn(tB2, make_float2(p.k_bc[2 * pr], p.k_bc[2 * pr + 1]), argI))),
-                                                     tn2[h], acc[pr]);
+                            acc[pr] = __ffma2_rn(t, inc2[h], acc[pr]);     // young term: dense pass below
                         }
                     }
                 }
@@ -228,6 +243,39 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
             run_end = true;
         }
         begin = next_begin;
+
+        if constexpr (!WRITE_PF) {
+            // dense evaluation of the birth-cloud term  m (1-fesc) 2^(tI kI + tB kB) (tra+neb)
+            __syncwarp();
+            while (ytail - yhead >= 32 || (run_end && ytail > yhead)) {
+                const int cnt = min(32, ytail - yhead);
+                if (lane < cnt) {
+                    int pos = yhead + lane;
+                    pos = pos >= kYWarp ? pos - kYWarp : pos;
+                    const float4 rec = my_y[pos];
+                    const float2 mo2 = make_float2(rec.x, rec.x), tI2 = make_float2(rec.y, rec.y);
+                    const float2 tB2 = make_float2(rec.z, rec.z);
+                    const float4* rtn = reinterpret_cast<const float4*>(s_tn + __float_as_int(rec.w) * kStride);
+#pragma unroll
+                    for (int q = 0; q < FP / 4; ++q) {
+                        const float4 vt = rtn[q];
+                        const float2 tn2[2] = {make_float2(vt.x, vt.y), make_float2(vt.z, vt.w)};
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int pr = q * 2 + h;
+                            if (q < FP / 4 - 1 || h == 0 || 2 * pr < nf) {
+                                const float2 arg = __ffma2_rn(tB2, make_float2(p.k_bc[2 * pr], p.k_bc[2 * pr + 1]),
+                                                              __fmul2_rn(tI2, make_float2(p.k_ism[2 * pr], p.k_ism[2 * pr + 1])));
+                                acc[pr] = __ffma2_rn(__fmul2_rn(mo2, ex2_approx2(arg)), tn2[h], acc[pr]);
+                            }
+                        }
+                    }
+                }
+                yhead += cnt;
+            }
+            if (yhead >= kYWarp) { ytail -= kYWarp; yhead -= kYWarp; }
+            __syncwarp();
+        }
 
         if (p.partial) {
             if (run_end) {
@@ -336,7 +384,8 @@ int launch_broadband_impl(const BroadbandParams& p, cudaStream_t st) {
     constexpr int kStride = ((FP / 4) | 1) * 4;
     const size_t ncell = (size_t)p.na * p.nz;
     size_t smem = 2 * ncell * kStride * sizeof(float) + 2 * (size_t)(kMaxThr + 1) * sizeof(double) +
-                  (size_t)(kThreads / 32) * FP * sizeof(double) + 2 * kLut + 64;
+                  (size_t)(kThreads / 32) * FP * sizeof(double) + 2 * kLut + 64 +
+                  (WRITE_PF ? 0 : (size_t)(kThreads / 32) * kYWarp * sizeof(float4));
     if (smem > 227 * 1024) return SO_ERR_TOO_LARGE;
     SO_CUDA(cudaFuncSetAttribute(sed_broadband_kernel<FP, WRITE_PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
@@ -504,8 +553,18 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
         p.n_items = (n + kItem - 1) / kItem;
     }
 
-    for (int f0 = 0; f0 < n_filters; f0 += SO_MAX_FILTERS) {
-        const int nf = (n_filters - f0 < SO_MAX_FILTERS) ? (n_filters - f0) : SO_MAX_FILTERS;
+    // filters per launch: as many as fit the shared-memory tables (<= SO_MAX_FILTERS)
+    int fmax = SO_MAX_FILTERS;
+    while (fmax > 4) {
+        const size_t stride = (size_t)(((fmax / 4) | 1) * 4);
+        const size_t smem = 2 * (size_t)na * nz * stride * sizeof(float) + 2 * (size_t)(kMaxThr + 1) * sizeof(double) +
+                            (size_t)(kThreads / 32) * fmax * sizeof(double) + 2 * kLut + 64 +
+                            (size_t)(kThreads / 32) * kYWarp * sizeof(float4);
+        if (smem <= 227 * 1024) break;
+        fmax -= 4;
+    }
+    for (int f0 = 0; f0 < n_filters; f0 += fmax) {
+        const int nf = (n_filters - f0 < fmax) ? (n_filters - f0) : fmax;
         p.f0 = f0; p.n_filters = nf;
         const double log2e = 1.4426950408889634;
         for (int f = 0; f < SO_MAX_FILTERS; ++f) {
