@@ -11,12 +11,14 @@
 // thread keeps D1 = sum M T_ISM, D2 = sum M T_ISM T_BC, D3 = sum M T_BC, Ms = sum M for its
 // wavelengths in registers and folds them into the grid rows once per run, so each SSP row is
 // read once per (run, particle block) instead of once per particle.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int kDustThreads = 256;
-constexpr int kStage = 256;
+constexpr int kStage = 512;
 
 struct DustParams {
     const double* masses;
@@ -41,16 +43,44 @@ __device__ __forceinline__ float ex2a(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float2 ex2_mufu2(float2 x) { return make_float2(ex2a(x.x), ex2a(x.y)); }
 
-// kLamPerThread wavelengths per thread (strided by the CTA width, so grid rows are read coalesced):
-// the particle record is fetched from shared memory once per 4 wavelengths and the arithmetic runs
-// on wavelength pairs with the packed FMUL2/FFMA2 instructions; what remains per particle and
-// wavelength is essentially the ex2 itself (MUFU-bound).
+// 2^x for x <= 0 on the FMA/ALU pipes (packed FP32): the XU pipe (16 ex2/clk/SM) is this kernel's
+// roof, so half of the exponentials are evaluated here instead.  Round-to-nearest split x = n + f
+// via the 1.5*2^23 magic constant, degree-5 minimax polynomial of 2^f on [-0.5, 0.5] (max relative
+// error 2.3e-7 in FP32 Horner form, the same order as ex2.approx), exponent add on the bit pattern.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    const float kMagic = 12582912.f;
+    x.x = fmaxf(x.x, -125.f);
+    x.y = fmaxf(x.y, -125.f);
+    const float2 r = __fadd2_rn(x, make_float2(kMagic, kMagic));
+    const float2 rn = __fadd2_rn(r, make_float2(-kMagic, -kMagic));
+    const float2 f = __ffma2_rn(rn, make_float2(-1.f, -1.f), x);
+    float2 q = make_float2(0.0013276471518578379f, 0.0013276471518578379f);
+    q = __ffma2_rn(q, f, make_float2(0.009675541330665999f, 0.009675541330665999f));
+    q = __ffma2_rn(q, f, make_float2(0.05550713274963921f, 0.05550713274963921f));
+    q = __ffma2_rn(q, f, make_float2(0.24022119723934243f, 0.24022119723934243f));
+    q = __ffma2_rn(q, f, make_float2(0.6931469670638628f, 0.6931469670638628f));
+    q = __ffma2_rn(q, f, make_float2(1.0000000716546567f, 1.0000000716546567f));
+    q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
+    q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
+    return q;
+}
+
+// kLamPerThread wavelengths per thread (strided by the CTA width, so grid rows are read coalesced).
+// Particles are staged in shared memory as 16-byte records {M, tauV_ISM, tauV_BC, key} (one
+// broadcast LDS.128 per particle) together with a bit mask of the run ends (ballot), so the CTA
+// walks the sorted list run by run: the inner loops carry no key test, the fold into the grid rows
+// sits between runs, and what remains per particle and wavelength is the exponential itself plus
+// half a packed FMUL2/FFMA2.
+// HYBRID: every fourth particle of a run evaluates its exponentials with the FMA-pipe polynomial
+// instead of MUFU.EX2 (the XU pipe is the roof; the two pipes overlap).
 constexpr int kLamPerThread = 4;
 
+template <bool HYBRID>
 __global__ void __launch_bounds__(kDustThreads) dust_spectra_kernel(const DustParams p) {
-    __shared__ float s_m[kStage], s_ti[kStage], s_tb[kStage];
-    __shared__ int s_key[kStage];
+    __shared__ float4 s_rec[kStage];
+    __shared__ unsigned s_end[kStage / 32];
     const int lam0 = blockIdx.x * (kDustThreads * kLamPerThread) + threadIdx.x;
     const int gal = blockIdx.y / p.pblocks, pb = blockIdx.y % p.pblocks;
     const int64_t g0 = p.seg ? p.seg[gal] : 0, g1 = p.seg ? p.seg[gal + 1] : p.n;
@@ -78,74 +108,104 @@ __global__ void __launch_bounds__(kDustThreads) dust_spectra_kernel(const DustPa
     float ms = 0.f;
     int cur = -1;
 
+    // fold the run's sums into the grid rows:  D1 = sum M T_ISM, D2 = sum M T_ISM T_BC, D3 = sum M T_BC
     auto flush = [&]() {
-        if (cur < 0) return;
-        const int cell = cur & 65535;
-        const bool young = (cur >> 16) != 0;
+        if (cur >= 0) {
+            const int cell = cur & 65535;
+            const bool young = (cur >> 16) != 0;
 #pragma unroll
-        for (int j = 0; j < kLamPerThread; ++j) {
-            if (!ok[j]) continue;
-            const int lam = lam0 + j * kDustThreads;
-            const float inc = p.inc[(size_t)cell * p.n_lam + lam];
-            float& rbc = (j & 1) ? bc[j / 2].y : bc[j / 2].x;
-            float& rtot = (j & 1) ? tot[j / 2].y : tot[j / 2].x;
-            float& rnoh = (j & 1) ? noh[j / 2].y : noh[j / 2].x;
-            const float v1 = (j & 1) ? d1[j / 2].y : d1[j / 2].x;
-            const float v2 = (j & 1) ? d2[j / 2].y : d2[j / 2].x;
-            const float v3 = (j & 1) ? d3[j / 2].y : d3[j / 2].x;
-            rnoh = fmaf(v1, inc, rnoh);
-            if (young) {
-                const float tn = p.tn[(size_t)cell * p.n_lam + lam];
-                rbc += fesc * ms * inc + ofe * v3 * tn;
-                rtot += fesc * v1 * inc + ofe * v2 * tn;
-            } else {
-                rbc = fmaf(ms, inc, rbc);
-                rtot = fmaf(v1, inc, rtot);
+            for (int j = 0; j < kLamPerThread; ++j) {
+                if (!ok[j]) continue;
+                const int lam = lam0 + j * kDustThreads;
+                const float inc = p.inc[(size_t)cell * p.n_lam + lam];
+                float& rbc = (j & 1) ? bc[j / 2].y : bc[j / 2].x;
+                float& rtot = (j & 1) ? tot[j / 2].y : tot[j / 2].x;
+                float& rnoh = (j & 1) ? noh[j / 2].y : noh[j / 2].x;
+                const float v1 = (j & 1) ? d1[j / 2].y : d1[j / 2].x;
+                const float v2 = (j & 1) ? d2[j / 2].y : d2[j / 2].x;
+                const float v3 = (j & 1) ? d3[j / 2].y : d3[j / 2].x;
+                rnoh = fmaf(v1, inc, rnoh);
+                if (young) {
+                    const float tn = p.tn[(size_t)cell * p.n_lam + lam];
+                    rbc += fesc * ms * inc + ofe * v3 * tn;
+                    rtot += fesc * v1 * inc + ofe * v2 * tn;
+                } else {
+                    rbc = fmaf(ms, inc, rbc);
+                    rtot = fmaf(v1, inc, rtot);
+                }
             }
+        }
+        ms = 0.f;
+#pragma unroll
+        for (int h = 0; h < kLamPerThread / 2; ++h) { d1[h] = d2[h] = d3[h] = z2; }
+    };
+    auto old_one = [&](const float4 r, const bool poly) {
+        const float2 m2 = make_float2(r.x, r.x), ti2 = make_float2(r.y, r.y);
+        ms += r.x;
+#pragma unroll
+        for (int h = 0; h < kLamPerThread / 2; ++h) {
+            const float2 a = __fmul2_rn(ti2, kI[h]);
+            d1[h] = __ffma2_rn(m2, poly ? ex2_poly2(a) : ex2_mufu2(a), d1[h]);
+        }
+    };
+    auto young_one = [&](const float4 r, const bool poly) {
+        const float2 m2 = make_float2(r.x, r.x), ti2 = make_float2(r.y, r.y), tb2 = make_float2(r.z, r.z);
+        ms += r.x;
+#pragma unroll
+        for (int h = 0; h < kLamPerThread / 2; ++h) {
+            const float2 a = __fmul2_rn(ti2, kI[h]), b = __fmul2_rn(tb2, kB[h]);
+            const float2 TI = poly ? ex2_poly2(a) : ex2_mufu2(a);
+            d1[h] = __ffma2_rn(m2, TI, d1[h]);
+            const float2 mTB = __fmul2_rn(m2, poly ? ex2_poly2(b) : ex2_mufu2(b));
+            d3[h] = __fadd2_rn(d3[h], mTB);
+            d2[h] = __ffma2_rn(mTB, TI, d2[h]);
         }
     };
 
     for (int64_t base = p0; base < p1; base += kStage) {
         const int cnt = (int)min((int64_t)kStage, p1 - base);
         __syncthreads();
-        if (threadIdx.x < cnt) {
-            const int64_t s = base + threadIdx.x;
-            const int i = p.order[s];
-            s_m[threadIdx.x] = (float)p.masses[i];
-            s_ti[threadIdx.x] = p.tau_ism ? (float)p.tau_ism[i] : 0.f;
-            s_tb[threadIdx.x] = p.tau_bc ? (float)p.tau_bc[i] : 0.f;
-            s_key[threadIdx.x] = p.key[s];
+        for (int t = threadIdx.x; t < kStage; t += kDustThreads) {
+            const int64_t s = base + t;
+            int key = -2, next = -3;
+            if (t < cnt) {
+                const int i = p.order[s];
+                key = p.key[s];
+                next = (t + 1 < cnt) ? p.key[s + 1] : -3;
+                s_rec[t] = make_float4((float)p.masses[i], p.tau_ism ? (float)p.tau_ism[i] : 0.f,
+                                       p.tau_bc ? (float)p.tau_bc[i] : 0.f, __int_as_float(key));
+            }
+            const unsigned ends = __ballot_sync(0xffffffffu, t < cnt && key != next);   // last particle of a run
+            if ((t & 31) == 0) s_end[t >> 5] = ends;
         }
         __syncthreads();
-        for (int q = 0; q < cnt; ++q) {
-            const int key = s_key[q];
-            if (key != cur) {           // uniform across the CTA
-                flush();
-                cur = key; ms = 0.f;
-#pragma unroll
-                for (int h = 0; h < kLamPerThread / 2; ++h) { d1[h] = d2[h] = d3[h] = z2; }
-            }
-            const float m = s_m[q];
-            const float2 m2 = make_float2(m, m), ti2 = make_float2(s_ti[q], s_ti[q]);
-            ms += m;
-            if (key >> 16) {
-                const float2 tb2 = make_float2(s_tb[q], s_tb[q]);
-#pragma unroll
-                for (int h = 0; h < kLamPerThread / 2; ++h) {
-                    const float2 aI = __fmul2_rn(ti2, kI[h]);
-                    const float2 TI = make_float2(ex2a(aI.x), ex2a(aI.y));
-                    d1[h] = __ffma2_rn(m2, TI, d1[h]);
-                    const float2 aB = __fmul2_rn(tb2, kB[h]);
-                    const float2 mTB = __fmul2_rn(m2, make_float2(ex2a(aB.x), ex2a(aB.y)));
-                    d3[h] = __fadd2_rn(d3[h], mTB);
-                    d2[h] = __ffma2_rn(mTB, TI, d2[h]);
-                }
+        int q = 0;
+        while (q < cnt) {                                  // one iteration per run (uniform across the CTA)
+            const int key = __float_as_int(s_rec[q].w);
+            if (key != cur) { flush(); cur = key; }
+            int w = q >> 5;
+            unsigned bits = s_end[w] >> (q & 31);
+            int e = q;
+            if (bits) {
+                e = q + __ffs(bits);
             } else {
-#pragma unroll
-                for (int h = 0; h < kLamPerThread / 2; ++h) {
-                    const float2 aI = __fmul2_rn(ti2, kI[h]);
-                    d1[h] = __ffma2_rn(m2, make_float2(ex2a(aI.x), ex2a(aI.y)), d1[h]);
+                do { ++w; bits = s_end[w]; } while (!bits);
+                e = (w << 5) + __ffs(bits);
+            }
+            if (cur >> 16) {
+                for (; q + 4 <= e; q += 4) {
+                    const float4 r0 = s_rec[q], r1 = s_rec[q + 1], r2 = s_rec[q + 2], r3 = s_rec[q + 3];
+                    young_one(r0, false); young_one(r1, false); young_one(r2, false); young_one(r3, HYBRID);
                 }
+#pragma unroll 1
+                for (; q < e; ++q) young_one(s_rec[q], false);
+            } else {
+                for (; q + 4 <= e; q += 4) {
+                    const float4 r0 = s_rec[q], r1 = s_rec[q + 1], r2 = s_rec[q + 2], r3 = s_rec[q + 3];
+                    old_one(r0, false); old_one(r1, false); old_one(r2, false); old_one(r3, HYBRID);
+                }
+#pragma unroll 1
+                for (; q < e; ++q) old_one(s_rec[q], false);
             }
         }
     }
@@ -175,6 +235,13 @@ __global__ void dust_reduce_kernel(const float* __restrict__ partial, int pblock
     if (o_bc) o_bc[o] = (float)a;
     if (o_tot) o_tot[o] = (float)b;
     if (o_noh) o_noh[o] = (float)c;
+}
+
+// SO_DUST_HYBRID=0 selects the MUFU-only variant (profiling aid); default is the hybrid kernel
+static bool so_dust_hybrid() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SO_DUST_HYBRID"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 
 static int dust_pblocks(int64_t n, int64_t n_seg, int n_lam) {
@@ -218,7 +285,8 @@ extern "C" int so_sed_dust_spectra(const double* masses, const double* tau_ism, 
     p.inc = grid_inc; p.tn = grid_tn; p.ncell = ncell; p.n_lam = n_lam; p.k_ism = k_ism_lam; p.k_bc = k_bc_lam;
     p.fesc = (float)fesc; p.partial = partial; p.pblocks = pb; p.seg = seg_offsets;
     dim3 grid((n_lam + kDustThreads * kLamPerThread - 1) / (kDustThreads * kLamPerThread), (unsigned)(n_seg * pb));
-    dust_spectra_kernel<<<grid, kDustThreads, 0, st>>>(p);
+    if (so_dust_hybrid()) dust_spectra_kernel<true><<<grid, kDustThreads, 0, st>>>(p);
+    else dust_spectra_kernel<false><<<grid, kDustThreads, 0, st>>>(p);
     SO_LAUNCH_CHECK();
     dim3 rgrid((n_lam + 255) / 256, (unsigned)n_seg);
     dust_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, pb, n_lam, out_bc, out_total, out_nohii);
