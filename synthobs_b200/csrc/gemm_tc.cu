@@ -12,14 +12,18 @@
 // < 4e-7): each chunk accumulates into one of two TMEM buffers, the epilogue warps drain the finished
 // chunk into round-to-nearest FP32 running sums in registers while the next chunk is being computed.
 //
-// Structure (one CTA per 128x128 output tile, 384 threads):
+// Structure (persistent: one CTA per SM walks 128x128 output tiles in a grouped raster order, so the
+// CTAs running at the same time share 16 A row-tiles and ~9 B column-tiles in L2; the barrier rings
+// run on across tiles, so the producer prefetches the next tile while the last chunk drains; 384 threads):
 //   warp 0   TMA producer: per K-block of 32 floats (=128 B, one SWIZZLE_128B atom row) four
 //            cp.async.bulk.tensor loads (Ahi, Alo, Bhi, Blo tiles, 16 KB each) into a 3-stage ring
 //   warp 1   MMA issuer: one elected thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128,N=128,
 //            K=8) per stage, commits the stage back to the producer and finally the accumulator
 //   warp 2   TMEM allocator (2 x 128 columns)
 //   warps 4-11 epilogue/drain: warp w owns TMEM lanes 32*(w%4).. and column half (w-4)/4;
-//            tcgen05.ld 32 lanes x 32 columns -> registers (+= running sums) -> global stores
+//            tcgen05.ld 32 lanes x 32 columns -> registers (+= running sums); at the end of a tile the
+//            sums go through a swizzled 16 KB staging buffer per column half and out with TMA stores
+//            (cp.async.bulk.tensor, asynchronous: the warps return to draining the next tile at once)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -34,7 +38,10 @@ constexpr int kGemmThreads = 384;
 constexpr int kTmemCols = 256;                 // two 128-column accumulators
 constexpr int kChunk = 2;                      // K-blocks per TMEM accumulation chunk
 constexpr int kDrainWarps = 8;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int kGroupM = 16;                    // row-tiles per raster group
+constexpr int kSlabCols = 32;                  // columns per epilogue slab (one 128-byte swizzle row)
+constexpr int kSlabBytes = BM * kSlabCols * 4; // 16 KB staging buffer per column half
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kSlabBytes + 1024 /*alignment*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,11 +89,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                   float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K) {
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
+                   float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int tiles_m, int tiles_n, int tma_store) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    unsigned char* slab = smem + kStages * kStageBytes;          // [2][kSlabBytes] epilogue staging (TMA store source)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab + 2 * kSlabBytes);
     uint64_t* full = bars;                 // [kStages]
     uint64_t* empty = bars + kStages;      // [kStages]
     uint64_t* tmem_full = bars + 2 * kStages;          // [2]
@@ -94,9 +102,19 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int nkb = (int)((K + BK - 1) / BK);
     const int nchunk = (nkb + kChunk - 1) / kChunk;
+    const int64_t n_tiles = (int64_t)tiles_m * tiles_n;
+    // grouped raster: tile t -> (m tile, n tile); groups of kGroupM row-tiles are swept along n
+    auto tile_origin = [&](int64_t t, int& m0, int& n0) {
+        const int64_t per_group = (int64_t)kGroupM * tiles_n;
+        const int group = (int)(t / per_group);
+        const int first_m = group * kGroupM;
+        const int gsz = min(kGroupM, tiles_m - first_m);
+        const int r = (int)(t - (int64_t)group * per_group);
+        m0 = (first_m + r % gsz) * BM;
+        n0 = (r / gsz) * BN;
+    };
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -114,97 +132,131 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                unsigned char* st = smem + s * kStageBytes;
-                mbar_expect_tx(&full[s], kStageBytes);
-                tma_load_2d(st + 0 * kTileBytes, &tmAh, &full[s], kb * BK, m0);
-                tma_load_2d(st + 1 * kTileBytes, &tmAl, &full[s], kb * BK, m0);
-                tma_load_2d(st + 2 * kTileBytes, &tmBh, &full[s], kb * BK, n0);
-                tma_load_2d(st + 3 * kTileBytes, &tmBl, &full[s], kb * BK, n0);
+            uint32_t it = 0;                      // K-block counter over all of this CTA's tiles (ring position)
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int m0, n0;
+                tile_origin(t, m0, n0);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char* st = smem + s * kStageBytes;
+                    mbar_expect_tx(&full[s], kStageBytes);
+                    tma_load_2d(st + 0 * kTileBytes, &tmAh, &full[s], kb * BK, m0);
+                    tma_load_2d(st + 1 * kTileBytes, &tmAl, &full[s], kb * BK, m0);
+                    tma_load_2d(st + 2 * kTileBytes, &tmBh, &full[s], kb * BK, n0);
+                    tma_load_2d(st + 3 * kTileBytes, &tmBl, &full[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int c = 0; c < nchunk; ++c) {
-                const int buf = c & 1;
-                mbar_wait(&tmem_empty[buf], ((c >> 1) & 1) ^ 1);      // drained by the epilogue warps
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                uint32_t acc = 0;
-                const int kb_end = min(nkb, (c + 1) * kChunk);
-                for (int kb = c * kChunk; kb < kb_end; ++kb) {
-                    const int s = kb % kStages;
-                    const uint32_t ph = (kb / kStages) & 1;
-                    mbar_wait(&full[s], ph);
+            uint32_t it = 0, cc = 0;              // ring position, chunk counter over all tiles
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                for (int c = 0; c < nchunk; ++c, ++cc) {
+                    const int buf = cc & 1;
+                    mbar_wait(&tmem_empty[buf], ((cc >> 1) & 1) ^ 1);      // drained by the epilogue warps
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    unsigned char* st = smem + s * kStageBytes;
-                    const uint64_t dAh = umma_desc(st + 0 * kTileBytes), dAl = umma_desc(st + 1 * kTileBytes);
-                    const uint64_t dBh = umma_desc(st + 2 * kTileBytes), dBl = umma_desc(st + 3 * kTileBytes);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                    uint32_t acc = 0;
+                    const int kb_end = min(nkb, (c + 1) * kChunk);
+                    for (int kb = c * kChunk; kb < kb_end; ++kb, ++it) {
+                        const int s = it % kStages;
+                        const uint32_t ph = (it / kStages) & 1;
+                        mbar_wait(&full[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        unsigned char* st = smem + s * kStageBytes;
+                        const uint64_t dAh = umma_desc(st + 0 * kTileBytes), dAl = umma_desc(st + 1 * kTileBytes);
+                        const uint64_t dBh = umma_desc(st + 2 * kTileBytes), dBl = umma_desc(st + 3 * kTileBytes);
 #pragma unroll
-                    for (int k4 = 0; k4 < BK / 8; ++k4) {
-                        const uint64_t adv = (uint64_t)(k4 * 2);     // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle atom
-                        umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, acc);   // small terms first
-                        acc = 1;
-                        umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, acc);
-                        umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, acc);
+                        for (int k4 = 0; k4 < BK / 8; ++k4) {
+                            const uint64_t adv = (uint64_t)(k4 * 2);     // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle atom
+                            umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, acc);   // small terms first
+                            acc = 1;
+                            umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, acc);
+                            umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, acc);
+                        }
+                        umma_commit(&empty[s]);       // frees the stage once these MMAs have read it
                     }
-                    umma_commit(&empty[s]);       // frees the stage once these MMAs have read it
+                    umma_commit(&tmem_full[buf]);     // chunk accumulator complete
                 }
-                umma_commit(&tmem_full[buf]);     // chunk accumulator complete
             }
         }
     } else if (warp >= 4) {
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int half = (warp - 4) >> 2;         // which 64 of the 128 columns
-        const int64_t row = (int64_t)m0 + q * 32 + lane;
-        float sum[64];
+        uint32_t cc = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            int m0, n0;
+            tile_origin(t, m0, n0);
+            const int64_t row = (int64_t)m0 + q * 32 + lane;
+            float sum[64];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) sum[j] = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
-            const int buf = c & 1;
-            mbar_wait(&tmem_full[buf], (c >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+            for (int c = 0; c < nchunk; ++c, ++cc) {
+                const int buf = cc & 1;
+                mbar_wait(&tmem_full[buf], (cc >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 64 + h * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 64 + h * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[h * 32 + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) sum[h * 32 + j] += __uint_as_float(v[j]);
+                }
+                // hand the buffer back to the MMA warp
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
             }
-            // hand the buffer back to the MMA warp
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
-        }
-        if (row < M) {
-            const int64_t col0 = (int64_t)n0 + half * 64;
-            float* out = C + row * ldc + col0;
-            if (col0 + 64 <= N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+            if (tma_store) {
+                // tile -> global through shared memory and TMA: each column half (4 warps) owns one 16 KB
+                // staging buffer laid out as the 128-byte-swizzled box [128 rows][32 columns]
+                unsigned char* buf = slab + half * kSlabBytes;
+                const int r = q * 32 + lane;
+                const bool leader = (q == 0 && lane == 0);
 #pragma unroll
-                for (int j = 0; j < 64; j += 4)
-                    *reinterpret_cast<float4*>(out + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
-            } else {
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int col = n0 + (half * 2 + sl) * kSlabCols;
+                    if (col >= N) break;                                   // uniform
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // buffer no longer being read
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int j = sl * 32 + c * 4;
+                        *reinterpret_cast<float4*>(buf + r * 128 + ((c ^ (r & 7)) << 4)) =
+                            make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                    if (leader) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmC), "r"(smem_u32(buf)), "r"(col), "r"(m0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else if (row < M) {
+                const int64_t col0 = (int64_t)n0 + half * 64;
+                float* out = C + row * ldc + col0;
 #pragma unroll
                 for (int j = 0; j < 64; ++j)
                     if (col0 + j < N) out[j] = sum[j];
             }
         }
+        if (tma_store && q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -230,12 +282,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D K-major operand [rows, K] with row stride ld (floats): box = 32 floats x 128 rows, 128 B swizzle
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_k = BK) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return SO_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)BM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -259,9 +311,17 @@ extern "C" int so_gemm_3xtf32(const float* A_hi, const float* A_lo, int64_t lda,
     if ((rc = make_map(&mAl, A_lo, M, K, lda)) != SO_OK) return rc;
     if ((rc = make_map(&mBh, B_hi, N, K, ldb)) != SO_OK) return rc;
     if ((rc = make_map(&mBl, B_lo, N, K, ldb)) != SO_OK) return rc;
+    // the epilogue stores C with TMA when its rows are 16-byte aligned; plain stores otherwise
+    CUtensorMap mC = mAh;
+    const int tma_store = ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+    if (tma_store && (rc = make_map(&mC, C, M, N, ldc, kSlabCols)) != SO_OK) return rc;
     SO_CUDA(cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-    gemm_3xtf32_kernel<<<grid, kGemmThreads, kSmemBytes, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, C, ldc, M, N, K);
+    const int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    if (tiles_m > (1 << 24) || tiles_n > (1 << 24)) return SO_ERR_TOO_LARGE;
+    int64_t grid = tiles_m * tiles_n;
+    if (grid > so_num_sms()) grid = so_num_sms();
+    gemm_3xtf32_kernel<<<(unsigned)grid, kGemmThreads, kSmemBytes, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, mC, C, ldc, M, N, K,
+                                                                                        (int)tiles_m, (int)tiles_n, tma_store);
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
