@@ -214,6 +214,17 @@ int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int3
 int so_complex_mul_bcast(const float* a, const float* b, float* out, int64_t n_complex, int32_t n_img,
                          int32_t b_per_image, void* stream);
 
+/* Analytic source — observed.Sersic (synthobs/morph/images.py:219-238): the Sersic2D
+ * profile (amplitude 1; r_eff, n, ellip, theta; centre x0, y0 in the units of G) on the
+ * pixel grid G x G (row = y), normalised to unit sum over the image and scaled per
+ * channel: out[c] = L[c] * profile / sum(profile), float32 [n_chan, ndim, ndim].
+ * bn = gammaincinv(2n, 0.5) is supplied by the host; L is a DEVICE float64 [n_chan].
+ * float64 evaluation and fixed-order sum. */
+int64_t so_img_sersic_workspace_bytes(int32_t ndim);
+int so_img_sersic(const double* G, int32_t ndim, double r_eff, double n, double x0, double y0,
+                  double ellip, double theta, double bn, const double* L, int32_t n_chan,
+                  float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

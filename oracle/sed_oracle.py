@@ -178,3 +178,44 @@ def cell_histogram(log10age_grid, log10Z_grid, Masses, Ages, Metallicities, log1
     H = np.zeros((2, na, nZ))
     np.add.at(H, (young, ia, iZ), np.asarray(Masses, dtype=np.float64))
     return H
+
+
+def line_luminosity(lgrid, line, Masses, Ages, Metallicities, tauVs_ISM=None, tauVs_BC=None,
+                    k_ISM=None, k_BC=None, fesc=0.0, log10t_BC=7.):
+    """synthobs/sed/models.py:382-448 -- EmissionLines.get_line_luminosity for one (possibly
+    blended 'a,b') line.  `lgrid` is the lines.p dict AFTER the constructor's derivation of
+    the incident/transmitted continua (:363-367); k_ISM / k_BC = dust-curve value at the mean
+    line wavelength (:401,418,426) or None when that dust model is off (T = 1.0)."""
+    names = line.split(',')
+    Masses = np.asarray(Masses, dtype=np.float64)
+    n = Masses.shape[0]
+    tauVs_ISM = np.zeros(n) if tauVs_ISM is None else tauVs_ISM                                 # :386-392
+    tauVs_BC = np.zeros(n) if tauVs_BC is None else tauVs_BC
+    lam = np.mean([lgrid[l]['lam'] for l in names])                                             # :401
+    ia, iZ, log10age = ngp_indices(lgrid['log10age'], lgrid['log10Z'], Ages, Metallicities)     # :411-416
+    T_ISM = np.exp(-(tauVs_ISM * k_ISM)) if k_ISM is not None else np.ones(n)                   # :418-422
+    T_BC = np.exp(-(tauVs_BC * k_BC)) if k_BC is not None else np.ones(n)                       # :426-430
+    with np.errstate(invalid='ignore'):
+        young = log10age < log10t_BC                                                            # :424
+    lum = 0.0
+    cont = 0.0
+    for l in names:
+        g = lgrid[l]
+        inc = g['stellar_incident_continuum'][ia, iZ]
+        tn = g['stellar_transmitted_continuum'][ia, iZ] + g['nebular_continuum'][ia, iZ]
+        lum += np.sum(np.where(young, Masses * T_BC * T_ISM * (1. - fesc) * 10 ** g['luminosity'][ia, iZ], 0.0))   # :433
+        cont += np.sum(np.where(young, Masses * (T_ISM * fesc * inc + (T_ISM * T_BC) * (1 - fesc) * tn),          # :434
+                                Masses * T_ISM * inc))                                                            # :438
+    o = {'luminosity': lum, 'continuum': cont}
+    total_continuum = (cont / float(len(names))) * (3E8) / ((lam / float(len(names))) ** 2 * 1E-10)              # :442
+    o['EW'] = lum / total_continuum                                                                               # :444
+    return o
+
+
+def ensure_line_continua(lgrid):
+    """synthobs/sed/models.py:363-367."""
+    if 'stellar_transmitted_continuum' not in lgrid[lgrid['lines'][0]]:
+        for l in lgrid['lines']:
+            lgrid[l]['stellar_transmitted_continuum'] = lgrid[l]['stellar_continuum']
+            lgrid[l]['stellar_incident_continuum'] = lgrid[l]['stellar_continuum']
+    return lgrid

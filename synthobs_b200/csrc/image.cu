@@ -453,6 +453,53 @@ __global__ void rebin_kernel(const float* __restrict__ in, float* __restrict__ o
     out[((size_t)img * n_out + oy) * n_out + ox] = tot;
 }
 
+// Sersic2D profile on the pixel grid (astropy.modeling.models.Sersic2D.evaluate, amplitude 1):
+//   exp(-b_n ((z)^(1/n) - 1)),  z = sqrt((x_maj/a)^2 + (x_min/b)^2),  a = r_eff, b = (1 - ellip) r_eff
+// float64 throughout; per-block partial sums (fixed order) for the normalisation of images.py:233
+__global__ void __launch_bounds__(256) sersic_kernel(const double* __restrict__ G, int ndim, double r_eff, double n,
+                                                     double x0, double y0, double ellip, double theta, double bn,
+                                                     double* __restrict__ out, double* __restrict__ block_sums) {
+    __shared__ double s[256];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (i < (int64_t)ndim * ndim) {
+        const int row = (int)(i / ndim), col = (int)(i % ndim);      // row = y, column = x (np.meshgrid(g, g))
+        const double x = G[col], y = G[row];
+        const double a = r_eff, b = (1.0 - ellip) * r_eff;
+        const double ct = cos(theta), st = sin(theta);
+        const double x_maj = (x - x0) * ct + (y - y0) * st;
+        const double x_min = -(x - x0) * st + (y - y0) * ct;
+        const double qa = x_maj / a, qb = x_min / b;
+        const double z = sqrt(qa * qa + qb * qb);
+        v = exp(-bn * (pow(z, 1.0 / n) - 1.0));
+        out[i] = v;
+    }
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s[0];
+}
+
+// out[c] = (float)(L[c] * profile / sum(block_sums))    (images.py:233,238)
+__global__ void __launch_bounds__(256) sersic_scale_kernel(const double* __restrict__ prof, const double* __restrict__ block_sums,
+                                                           int n_blocks, const double* __restrict__ L, int n_chan, int64_t npix,
+                                                           float* __restrict__ out) {
+    __shared__ double s_tot;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int b = 0; b < n_blocks; ++b) t += block_sums[b];     // fixed order
+        s_tot = t;
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const double v = prof[i] / s_tot;
+    for (int c = 0; c < n_chan; ++c) out[(size_t)c * npix + i] = (float)(L[c] * v);
+}
+
 __global__ void complex_mul_kernel(const float2* __restrict__ a, const float2* __restrict__ b,
                                    float2* __restrict__ out, int64_t nc, int b_per_image) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,6 +694,29 @@ extern "C" int so_complex_mul_bcast(const float* a, const float* b, float* out, 
     dim3 grid((unsigned)((n_complex + 255) / 256), (unsigned)n_img);
     complex_mul_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)a, (const float2*)b, (float2*)out, n_complex,
                                                                b_per_image);
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
+
+extern "C" int64_t so_img_sersic_workspace_bytes(int32_t ndim) {
+    const int64_t npix = (int64_t)ndim * ndim;
+    return so_align_up(npix * 8, 256) + so_align_up(((npix + 255) / 256) * 8, 256) + 256;
+}
+
+extern "C" int so_img_sersic(const double* G, int32_t ndim, double r_eff, double n, double x0, double y0,
+                             double ellip, double theta, double bn, const double* L, int32_t n_chan,
+                             float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!G || ndim < 1 || n_chan < 1 || !L || !out || !(r_eff > 0.0) || !(n > 0.0)) return SO_ERR_BAD_ARG;
+    const int64_t npix = (int64_t)ndim * ndim;
+    const int64_t nblk = (npix + 255) / 256;
+    SoArena a(workspace, workspace_bytes);
+    double* prof = a.take<double>(npix);
+    double* sums = a.take<double>(nblk);
+    if (!workspace || !a.ok()) return SO_ERR_WORKSPACE;
+    sersic_kernel<<<(unsigned)nblk, 256, 0, st>>>(G, ndim, r_eff, n, x0, y0, ellip, theta, bn, prof, sums);
+    SO_LAUNCH_CHECK();
+    sersic_scale_kernel<<<(unsigned)nblk, 256, 0, st>>>(prof, sums, (int)nblk, L, n_chan, npix, out);
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

@@ -107,32 +107,10 @@ def trapz_weights(x):
 # model
 # --------------------------------------------------------------------------
 
-class define_model():
-    """SSP grid container (reference: synthobs/sed/models.py:17-67)."""
+class _NGPGrid():
+    """(log10age, log10Z) node axes of a grid dict + the device-side threshold caches
+    shared by define_model and EmissionLines (both do the NGP look-up of models.py:108-114)."""
 
-    def __init__(self, grid, path_to_SPS_grid=FLARE_dir + '/data/SPS/nebular/3.0/'):
-
-        if isinstance(grid, dict):   # convenience for synthetic grids: pass the dict itself
-            self.grid = grid
-        else:
-            self.grid = pickle.load(open(path_to_SPS_grid + grid + '/nebular.p', 'rb'), encoding='latin1')
-
-        self.lam = self.grid['lam']
-
-        self.dust_ISM = False
-        self.dust_BC = False
-
-        print(list(self.grid.keys()))
-
-        if 'stellar_incident' not in self.grid:
-            # canonical derivation (models.py:30-35)
-            self.grid['stellar_incident'] = copy.copy(self.grid['stellar'])
-            self.grid['stellar_transmitted'] = copy.copy(self.grid['stellar'])
-            self.grid['stellar_transmitted'][:, :, self.lam < 912] = 0.0
-
-        self._dev = {}
-
-    # ---- device-side caches -------------------------------------------------
     @property
     def na(self):
         return int(self.grid['log10age'].size)
@@ -159,6 +137,33 @@ class define_model():
             c[key] = young_threshold(key)
         return c[key]
 
+
+class define_model(_NGPGrid):
+    """SSP grid container (reference: synthobs/sed/models.py:17-67)."""
+
+    def __init__(self, grid, path_to_SPS_grid=FLARE_dir + '/data/SPS/nebular/3.0/'):
+
+        if isinstance(grid, dict):   # convenience for synthetic grids: pass the dict itself
+            self.grid = grid
+        else:
+            self.grid = pickle.load(open(path_to_SPS_grid + grid + '/nebular.p', 'rb'), encoding='latin1')
+
+        self.lam = self.grid['lam']
+
+        self.dust_ISM = False
+        self.dust_BC = False
+
+        print(list(self.grid.keys()))
+
+        if 'stellar_incident' not in self.grid:
+            # canonical derivation (models.py:30-35)
+            self.grid['stellar_incident'] = copy.copy(self.grid['stellar'])
+            self.grid['stellar_transmitted'] = copy.copy(self.grid['stellar'])
+            self.grid['stellar_transmitted'][:, :, self.lam < 912] = 0.0
+
+        self._dev = {}
+
+    # ---- device-side caches -------------------------------------------------
     def _grid_rows(self):
         """[3*ncell, n_lam] float32 on the device (incident, transmitted, nebular
         rows), wavelength contiguous: the K-major left operand of the grid x
@@ -291,6 +296,24 @@ def _dust_k(model, which, wavelength):
     return getattr(dust_curves, dust_model)(params=dust_model_params).tau(wavelength)   # models.py:97
 
 
+def _pow2_scale(*arrays):
+    """Per-row power of two >= max|value| (1 for all-zero rows): dividing by it is exact in
+    binary floating point, and keeps M * table inside FP32 range whatever the units (line
+    luminosities per Msol reach 1e34 erg/s, beyond FP32 once multiplied by a particle mass)."""
+    m = np.max(np.stack([np.abs(a).max(axis=1) for a in arrays]), axis=0)
+    with np.errstate(divide='ignore'):
+        e = np.where(m > 0, np.ceil(np.log2(np.where(m > 0, m, 1.0))), 0.0)
+    return np.ldexp(1.0, e.astype(np.int64))
+
+
+def _scaled_tables(inc, tn):
+    """float64 [F, ncell] tables -> (device float32 inc/scale, tn/scale, device float64 scale [F])"""
+    scale = _pow2_scale(inc, tn)
+    return (dv.to_dev((inc / scale[:, None]).astype(np.float32), torch.float32),
+            dv.to_dev((tn / scale[:, None]).astype(np.float32), torch.float32),
+            dv.to_dev(scale, torch.float64))
+
+
 def _tables(model, kind, filters):
     """Device tables [F, ncell] float32 built from whatever model.Lnu / model.Fnu
     currently hold (the reference reads them at call time, models.py:131-133)."""
@@ -302,7 +325,7 @@ def _tables(model, kind, filters):
         tn = np.stack([(np.asarray(src[f].stellar_transmitted, dtype=np.float64)
                         + np.asarray(src[f].nebular, dtype=np.float64)).reshape(-1) for f in filters])
         cache.clear()
-        cache[key] = (dv.to_dev(inc.astype(np.float32), torch.float32), dv.to_dev(tn.astype(np.float32), torch.float32))
+        cache[key] = _scaled_tables(inc, tn)
     return cache[key]
 
 
@@ -315,15 +338,7 @@ def _opt(x, like):
 def _broadband(model, kind, F, filters, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC,
                offsets=None, want_pf=False, want_sums=True, want_cell=False):
     _cabi.require_device()
-    M = dv.to_dev(Masses)
-    A = dv.to_dev(Ages)
-    Z = dv.to_dev(Metallicities)
-    tI = _opt(tauVs_ISM, M)
-    tB = _opt(tauVs_BC, M)
-    n = M.numel()
-    nf = len(filters)
-    thr = model._thresholds()
-    tab_inc, tab_tn = _tables(model, kind, filters)
+    tabs = _tables(model, kind, filters)
     zshift = (1. + model.Fnu['z']) if kind == 'Fnu' else 1.0                    # models.py:163,167
     ckey = (kind, id(F), tuple(filters), repr(model.dust_ISM), repr(model.dust_BC), zshift)
     kcache = model._dev.setdefault('dustk', {})
@@ -333,6 +348,25 @@ def _broadband(model, kind, F, filters, Masses, Ages, Metallicities, tauVs_ISM, 
         kcache[ckey] = (None if not model.dust_ISM else [float(_dust_k(model, 'ISM', p)) for p in piv],
                         None if not model.dust_BC else [float(_dust_k(model, 'BC', p)) for p in piv])
     kI, kB = kcache[ckey]
+    return _broadband_launch(model, tabs, kI, kB, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC,
+                             offsets=offsets, want_pf=want_pf, want_sums=want_sums, want_cell=want_cell)
+
+
+def _broadband_launch(ngp, tabs, kI, kB, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC,
+                      offsets=None, want_pf=False, want_sums=True, want_cell=False):
+    """One so_sed_broadband pass.  `ngp` supplies the grid axes (_NGPGrid), `tabs` =
+    (inc/scale, tn/scale, scale) device tables [F, ncell], kI / kB = per-table dust-curve
+    values (lists) or None.  Returns (per-particle [F, n] float32 | None, sums [n_seg, F]
+    float64 | None, cell ids | None), already multiplied back by `scale`."""
+    tab_inc, tab_tn, scale = tabs
+    M = dv.to_dev(Masses)
+    A = dv.to_dev(Ages)
+    Z = dv.to_dev(Metallicities)
+    tI = _opt(tauVs_ISM, M)
+    tB = _opt(tauVs_BC, M)
+    n = M.numel()
+    nf = tab_inc.shape[0]
+    thr = ngp._thresholds()
     if offsets is not None:
         off = dv.to_dev(offsets, torch.int64)
         nseg = off.numel() - 1
@@ -347,12 +381,16 @@ def _broadband(model, kind, F, filters, Masses, Ages, Metallicities, tauVs_ISM, 
     rc = _cabi.lib.so_sed_broadband(
         _cabi.ptr(M), _cabi.ptr(A), _cabi.ptr(Z), _cabi.ptr(tI), _cabi.ptr(tB), n,
         _cabi.ptr(off), nseg,
-        thr['age'], model.na, thr['z'], model.nz, model._young_thr(log10t_BC),
+        thr['age'], ngp.na, thr['z'], ngp.nz, ngp._young_thr(log10t_BC),
         _cabi.ptr(tab_inc), _cabi.ptr(tab_tn), nf,
         _cabi.host_doubles(kI), _cabi.host_doubles(kB), float(fesc),
         _cabi.ptr(out_pf), _cabi.ptr(out_sums), _cabi.ptr(out_cell),
         _cabi.ptr(ws), wsb, _cabi.stream())
     _cabi.check(rc, 'so_sed_broadband')
+    if out_sums is not None:
+        out_sums *= scale[None, :]
+    if out_pf is not None:
+        out_pf *= scale.to(torch.float32)[:, None]
     return out_pf, out_sums, out_cell
 
 
@@ -608,3 +646,141 @@ def generate_SED_batch(model, Masses, Ages, Metallicities, offsets, tauVs_ISM=Fa
     if _host_like(Masses):
         return {k: dv.to_host(v) for k, v in out.items()}
     return out
+
+
+# --------------------------------------------------------------------------
+# emission lines
+# --------------------------------------------------------------------------
+
+class EmissionLines(_NGPGrid):
+    """reference: synthobs/sed/models.py:326-448.  Same NGP look-up, LOS dust and sum over
+    particles as generate_Lnu, over the `lines.p` grids: per (possibly blended, 'a,b') line the
+    kernel carries two tables -- luminosity (transmitted part only: 10**luminosity, young
+    particles) and continuum (incident / transmitted+nebular) -- with the dust curves
+    evaluated at the mean line wavelength.  All requested lines share ONE so_sed_broadband
+    pass (get_line_luminosities), where the reference loops over lines and particles."""
+
+    def __init__(self, SPSIMF, dust_ISM=False, dust_BC=False, verbose=True,
+                 path_to_SPS_grid=FLARE_dir + '/data/SPS/nebular/3.0/'):
+
+        self.SPSIMF = SPSIMF
+
+        if isinstance(SPSIMF, dict):   # convenience for synthetic grids: pass the dict itself
+            self.grid = SPSIMF
+        else:
+            self.grid = pickle.load(open(f'{path_to_SPS_grid}/{SPSIMF}/lines.p', 'rb'), encoding='latin1')
+
+        self.lines = self.grid['lines']
+
+        self.lam = {l: self.grid[l]['lam'] for l in self.lines}
+        self.lams = np.array([self.lam[l] for l in self.lines])
+
+        if verbose:
+            print('Available lines:')
+            for lam, line in sorted(zip(self.lams, self.lines)):
+                print(f'{line}')
+
+        self.dust_BC = dust_BC
+        self.dust_ISM = dust_ISM
+
+        if self.dust_ISM:
+            dust_model, dust_model_params = self.dust_ISM
+            self.dust_curve_ISM = getattr(dust_curves, dust_model)(params=dust_model_params)
+
+        if self.dust_BC:
+            dust_model, dust_model_params = self.dust_BC
+            self.dust_curve_BC = getattr(dust_curves, dust_model)(params=dust_model_params)
+
+        self.units = {'luminosity': 'erg/s', 'nebular_continuum': 'erg/s/Hz', 'stellar_incident_continuum': 'erg/s/Hz',
+                      'stellar_transmitted_continuum': 'erg/s/Hz', 'continuum': 'erg/s/Hz', 'EW': 'AA'}
+
+        if 'stellar_transmitted_continuum' not in self.grid[self.lines[0]]:
+            # canonical derivation (models.py:363-367)
+            for l in self.lines:
+                self.grid[l]['stellar_transmitted_continuum'] = self.grid[l]['stellar_continuum']
+                self.grid[l]['stellar_incident_continuum'] = self.grid[l]['stellar_continuum']
+
+        self._dev = {}
+
+    def _line_tables(self, lines):
+        """Two kernel tables per requested line: [luminosity, continuum] (see class docstring)."""
+        key = tuple(lines)
+        cache = self._dev.setdefault('tabs', {})
+        if key not in cache:
+            ncell = self.na * self.nz
+            inc = np.zeros((2 * len(lines), ncell))
+            tn = np.zeros((2 * len(lines), ncell))
+            for i, line in enumerate(lines):
+                for l in line.split(','):
+                    g = self.grid[l]
+                    tn[2 * i] += (10 ** np.asarray(g['luminosity'], dtype=np.float64)).reshape(-1)       # models.py:433
+                    inc[2 * i + 1] += np.asarray(g['stellar_incident_continuum'], dtype=np.float64).reshape(-1)
+                    tn[2 * i + 1] += (np.asarray(g['stellar_transmitted_continuum'], dtype=np.float64)
+                                      + np.asarray(g['nebular_continuum'], dtype=np.float64)).reshape(-1)  # :434
+            cache.clear()
+            cache[key] = _scaled_tables(inc, tn)
+        return cache[key]
+
+    def _line_sums(self, lines, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC, offsets=None):
+        _cabi.require_device()
+        lam = [np.mean([self.grid[l]['lam'] for l in line.split(',')]) for line in lines]              # models.py:401
+        kI = [float(self.dust_curve_ISM.tau(w)) for w in lam for _ in (0, 1)] if self.dust_ISM else None
+        kB = [float(self.dust_curve_BC.tau(w)) for w in lam for _ in (0, 1)] if self.dust_BC else None
+        sums = []
+        for c0 in range(0, len(lines), 16):       # so_sed_broadband takes up to 32 tables per call
+            sub = lines[c0:c0 + 16]
+            _, s_, _ = _broadband_launch(self, self._line_tables(sub), None if kI is None else kI[2 * c0:2 * c0 + 2 * len(sub)],
+                                         None if kB is None else kB[2 * c0:2 * c0 + 2 * len(sub)],
+                                         Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC,
+                                         offsets=offsets)
+            sums.append(s_)
+        return torch.cat(sums, dim=1), lam
+
+    def _finish(self, line, lam, luminosity, continuum):
+        nl = float(len(line.split(',')))
+        o = {'luminosity': luminosity, 'continuum': continuum}
+        with np.errstate(divide='ignore', invalid='ignore'):
+            total_continuum = (o['continuum'] / nl) * (3E8) / ((lam / nl) ** 2 * 1E-10)                # models.py:442
+            o['EW'] = o['luminosity'] / total_continuum
+        return o
+
+    def get_line_luminosities(self, lines, Masses, Ages, Metallicities, tauVs_ISM=False, tauVs_BC=False, fesc=0.0,
+                              log10t_BC=7., verbose=False):
+        """reference: models.py:371-379 -- {line: {'luminosity', 'continuum', 'EW'}}; one kernel pass."""
+        print('--- calculate quantities for multiple emission lines')
+        print(lines)
+        lines = list(lines)
+        sums, lam = self._line_sums(lines, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC)
+        s = sums[0].cpu().numpy()
+        o = {}
+        for i, line in enumerate(lines):
+            o[line] = self._finish(line, lam[i], s[2 * i], s[2 * i + 1])
+            if verbose:
+                self._report(line, lam[i], o[line])
+        return o
+
+    def get_line_luminosity(self, line, Masses, Ages, Metallicities, tauVs_ISM=False, tauVs_BC=False, fesc=0.0,
+                            log10t_BC=7., verbose=False):
+        """reference: models.py:382-448."""
+        sums, lam = self._line_sums([line], Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC)
+        s = sums[0].cpu().numpy()
+        o = self._finish(line, lam[0], s[0], s[1])
+        if verbose:
+            self._report(line, lam[0], o)
+        return o
+
+    def get_line_luminosities_batch(self, lines, Masses, Ages, Metallicities, offsets, tauVs_ISM=False, tauVs_BC=False,
+                                    fesc=0.0, log10t_BC=7.):
+        """Many galaxies in one call (CSR `offsets`, no upstream equivalent): {line: {quantity: [G]}}."""
+        lines = list(lines)
+        sums, lam = self._line_sums(lines, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, fesc, log10t_BC,
+                                    offsets=offsets)
+        s = sums.cpu().numpy()
+        return {line: self._finish(line, lam[i], s[:, 2 * i], s[:, 2 * i + 1]) for i, line in enumerate(lines)}
+
+    def _report(self, line, lam, o):
+        print(f'----- {line.split(",")}')
+        print(f'line wavelength/\\AA: {lam}')
+        with np.errstate(divide='ignore'):
+            for k, v in o.items():
+                print(f'log10({k}/{self.units[k]}): {np.log10(v):.2f}')

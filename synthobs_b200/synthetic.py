@@ -55,6 +55,42 @@ def write_grid_pickle(grid, root, name='synthetic_grid'):
     return name
 
 
+LINE_LIST = {'HI3750': 3750.15, 'HI4861': 4861.32, 'HI6563': 6562.80, 'OIII4959': 4958.91, 'OIII5007': 5006.84,
+             'OII3726': 3726.03, 'OII3729': 3728.81, 'NII6583': 6583.45, 'CIII1907': 1906.68, 'CIII1909': 1908.73}
+
+
+def lines_grid(n_age=51, seed=0, with_incident=False):
+    """`lines.p`-shape emission-line grid dict with the keys EmissionLines reads
+    (reference: synthobs/sed/models.py:334-367,401,433-438): 'lines', 'log10age', 'log10Z'
+    and per line 'lam', 'luminosity' (log10 erg/s per Msol), 'nebular_continuum',
+    'stellar_continuum' (erg/s/Hz per Msol)."""
+    rng = np.random.default_rng(seed + 77)
+    log10age = 6.0 + 0.1 * np.arange(n_age)
+    log10Z = np.log10(BPASS_Z)
+    nZ = log10Z.size
+    grid = {'lines': list(LINE_LIST), 'log10age': log10age, 'log10Z': log10Z}
+    for name, lam in LINE_LIST.items():
+        lum = 34.0 - 2.5 * (log10age[:, None] - 6.0) + 0.4 * rng.standard_normal((n_age, nZ))
+        cont = 10.0 ** (20.0 - 2.0 * (log10age[:, None] - 6.0) + 0.3 * rng.standard_normal((n_age, nZ)))
+        g = {'lam': lam, 'luminosity': lum, 'nebular_continuum': 0.2 * cont * rng.random((n_age, nZ)),
+             'stellar_continuum': cont}
+        if with_incident:
+            g['stellar_incident_continuum'] = cont.copy()
+            g['stellar_transmitted_continuum'] = cont * (0.5 + 0.5 * rng.random((n_age, nZ)))
+        grid[name] = g
+    return grid
+
+
+def write_lines_pickle(grid, root, name='synthetic_grid'):
+    """Write <root>/<name>/lines.p so EmissionLines(name, path_to_SPS_grid=root) loads it
+    (reference: synthobs/sed/models.py:334)."""
+    d = os.path.join(root, name)
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, 'lines.p'), 'wb') as fh:
+        pickle.dump(grid, fh, protocol=2)
+    return name
+
+
 class Filter:
     """Stand-in for a flare.filters filter object: .lam, .T, .pivwv()
     (protocol used at synthobs/sed/models.py:43,47,97)."""

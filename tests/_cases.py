@@ -11,6 +11,7 @@ from synthobs_b200 import providers, synthetic
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 GRID_KW = dict(n_lam=300, n_age=51, seed=0)
 SED_CASES = ['lnu_dust', 'fnu_mixed', 'lnu_nodust', 'lnu_ismonly_notau']
+LINES_CASES = ['dust', 'nodust_incident', 'ismonly_notau']
 IMG_CASES = ['ngp', 'convgauss', 'convgauss_odd', 'adaptive16', 'adaptive8f', 'adaptive_odd', 'adaptive_kbig',
              'adaptive_underflow']
 
@@ -62,3 +63,18 @@ def smoothing_of(g):
         return False
     s = float(s)
     return (str(m), s)
+
+
+def lines_inputs(tag):
+    """-> (g, lines grid dict, dust_ISM, dust_BC, kwargs) of a lines_* fixture"""
+    g = load('lines_' + tag)
+    lgrid = synthetic.lines_grid(n_age=GRID_KW['n_age'], seed=0, with_incident=bool(g['with_incident']))
+    chk = np.array([lgrid['HI6563']['luminosity'].sum(), lgrid['OII3729']['stellar_continuum'].sum()])
+    np.testing.assert_allclose(chk, g['grid_checksum'], rtol=0, atol=0,
+                               err_msg='synthetic.lines_grid no longer reproduces the grid of the golden fixtures')
+    dust_ISM = ast.literal_eval(str(g['dust_ISM']))
+    dust_BC = ast.literal_eval(str(g['dust_BC']))
+    kw = dict(fesc=float(g['fesc']), log10t_BC=float(g['log10t_BC']))
+    if bool(g['pass_tau']):
+        kw.update(tauVs_ISM=g['tauVs_ISM'], tauVs_BC=g['tauVs_BC'])
+    return g, lgrid, dust_ISM, dust_BC, kw

@@ -89,6 +89,37 @@ def sed_case(ref, tag, n, seed, dust_ISM, dust_BC, fesc, log10t_BC, observed, wi
     print('sed_%s' % tag, 'sums', out['sums'])
 
 
+def lines_case(ref, tag, n, seed, dust_ISM, dust_BC, fesc, log10t_BC, with_incident=False, pass_tau=True):
+    """EmissionLines.get_line_luminosity / get_line_luminosities of the unmodified reference
+    (models.py:326-448) on a synthetic lines.p grid, single and blended lines."""
+    import contextlib
+    import io
+    models = ref.sed.models
+    lgrid = synthetic.lines_grid(n_age=GRID_KW['n_age'], seed=0, with_incident=with_incident)
+    tmp = tempfile.mkdtemp()
+    name = synthetic.write_lines_pickle(lgrid, tmp)
+    with contextlib.redirect_stdout(io.StringIO()):
+        el = models.EmissionLines(name, dust_ISM=dust_ISM, dust_BC=dust_BC, verbose=False, path_to_SPS_grid=tmp)
+    p = synthetic.particles(n, seed=seed, lognormal_mass=True)
+    kw = dict(fesc=fesc, log10t_BC=log10t_BC)
+    if pass_tau:
+        kw.update(tauVs_ISM=p['tauVs_ISM'], tauVs_BC=p['tauVs_BC'])
+    lines = ['HI6563', 'OIII4959,OIII5007', 'HI4861', 'OII3726,OII3729', 'CIII1907,CIII1909']
+    with contextlib.redirect_stdout(io.StringIO()):
+        o = el.get_line_luminosities(lines, p['Masses'], p['Ages'], p['Metallicities'], **kw)
+        single = el.get_line_luminosity('NII6583', p['Masses'], p['Ages'], p['Metallicities'], **kw)
+    out = {'n': n, 'seed': seed, 'fesc': fesc, 'log10t_BC': log10t_BC, 'with_incident': with_incident,
+           'pass_tau': pass_tau, 'dust_ISM': repr(dust_ISM), 'dust_BC': repr(dust_BC), 'lines': np.array(lines),
+           'grid_checksum': np.array([lgrid['HI6563']['luminosity'].sum(), lgrid['OII3729']['stellar_continuum'].sum()])}
+    for k in ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC'):
+        out[k] = p[k]
+    for q in ('luminosity', 'continuum', 'EW'):
+        out[q] = np.array([o[l][q] for l in lines])
+        out['single_' + q] = single[q]
+    np.savez_compressed(os.path.join(HERE, 'lines_%s.npz' % tag), **out)
+    print('lines_%s' % tag, 'luminosity', out['luminosity'], 'EW', out['EW'])
+
+
 def sed_index_case(ref):
     """NGP indices as the reference sees them, including adversarial samples at
     cell midpoints +- ulps: the per-filter table is replaced by a cell-id code
@@ -210,6 +241,9 @@ def main():
     sed_case(ref, 'lnu_ismonly_notau', 800, 24, simple, False, 0.1, 7.3, observed=False, pass_tau=False,
              lognormal_mass=False)
     sed_index_case(ref)
+    lines_case(ref, 'dust', 1500, 41, simple, ('Calzetti_like', {}), 0.2, 7.0)
+    lines_case(ref, 'nodust_incident', 1000, 42, False, False, 0.0, 6.9, with_incident=True)
+    lines_case(ref, 'ismonly_notau', 800, 43, simple, False, 0.5, 7.0, pass_tau=False)
 
     image_case(ref, 'ngp', 3000, 31, 0.1, 50, False)
     image_case(ref, 'convgauss', 3000, 32, 0.1, 50, ('convolved_gaussian', 0.2))

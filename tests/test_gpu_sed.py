@@ -251,3 +251,49 @@ def test_generate_SED_batch_equals_loop():
                                      fesc=0.25, log10t_BC=6.9)
         for k in ('stellar', 'intrinsic', 'BC', 'total', 'no_HII_no_BC'):
             np.testing.assert_allclose(out[k][gi], ref[k], rtol=RTOL_PARTICLE, atol=1e-6 * np.abs(ref[k]).max(), err_msg=k)
+
+
+@pytest.mark.parametrize('tag', _cases.LINES_CASES)
+def test_emission_lines_match_reference(tag):
+    """EmissionLines.get_line_luminosities / get_line_luminosity (one so_sed_broadband pass over all
+    lines) vs the golden vectors of the unmodified reference (models.py:371-448)."""
+    from synthobs_b200.sed import models
+    g, lgrid, dI, dB, kw = _cases.lines_inputs(tag)
+    with contextlib.redirect_stdout(io.StringIO()):
+        el = models.EmissionLines(lgrid, dust_ISM=dI, dust_BC=dB, verbose=False)
+        lines = [str(l) for l in g['lines']]
+        o = el.get_line_luminosities(lines, g['Masses'], g['Ages'], g['Metallicities'], **kw)
+        single = el.get_line_luminosity('NII6583', g['Masses'], g['Ages'], g['Metallicities'], **kw)
+    for i, line in enumerate(lines):
+        for q in ('luminosity', 'continuum', 'EW'):
+            np.testing.assert_allclose(o[line][q], g[q][i], rtol=RTOL_SUM, err_msg='%s %s' % (line, q))
+    for q in ('luminosity', 'continuum', 'EW'):
+        np.testing.assert_allclose(single[q], g['single_' + q], rtol=RTOL_SUM)
+
+
+def test_emission_lines_batch_and_pickle(tmp_path):
+    """lines.p loaded from disk like the reference (models.py:334); the batched entry point equals a
+    loop over galaxies; more lines than one kernel launch carries (> 16)."""
+    from synthobs_b200.sed import models
+    lgrid = synthetic.lines_grid(seed=0)
+    name = synthetic.write_lines_pickle(lgrid, str(tmp_path))
+    simple = ('simple', {'slope': -1.0})
+    with contextlib.redirect_stdout(io.StringIO()):
+        el = models.EmissionLines(name, dust_ISM=simple, dust_BC=simple, verbose=True, path_to_SPS_grid=str(tmp_path))
+    b = synthetic.galaxy_batch(5, n_min=50, n_max=3000, seed=9)
+    lines = list(synthetic.LINE_LIST) + ['OIII4959,OIII5007', 'OII3726,OII3729'] + list(synthetic.LINE_LIST)[:6]
+    assert len(lines) > 16
+    args = (b['Masses'], b['Ages'], b['Metallicities'])
+    kw = dict(tauVs_ISM=b['tauVs_ISM'], tauVs_BC=b['tauVs_BC'], fesc=0.1)
+    ob = el.get_line_luminosities_batch(lines, *args, b['offsets'], **kw)
+    olg = sed_oracle.ensure_line_continua(synthetic.lines_grid(seed=0))
+    for gi in range(5):
+        s, e = b['offsets'][gi], b['offsets'][gi + 1]
+        for line in (lines[0], lines[10], lines[17]):
+            lam = np.mean([olg[l]['lam'] for l in line.split(',')])
+            k = providers.simple({'slope': -1.0}).tau(lam)
+            r = sed_oracle.line_luminosity(olg, line, b['Masses'][s:e], b['Ages'][s:e], b['Metallicities'][s:e],
+                                           tauVs_ISM=b['tauVs_ISM'][s:e], tauVs_BC=b['tauVs_BC'][s:e], k_ISM=k, k_BC=k,
+                                           fesc=0.1)
+            for q in ('luminosity', 'continuum', 'EW'):
+                np.testing.assert_allclose(ob[line][q][gi], r[q], rtol=RTOL_SUM)

@@ -47,6 +47,26 @@ def test_sed_oracle_matches_reference(tag):
         np.testing.assert_allclose(o[k], g['sed_' + k], rtol=1e-8, atol=1e-12, equal_nan=True)
 
 
+@pytest.mark.parametrize('tag', _cases.LINES_CASES)
+def test_line_oracle_matches_reference(tag):
+    """oracle line_luminosity vs EmissionLines.get_line_luminosity[ies] of the unmodified reference"""
+    g, lgrid, dust_ISM, dust_BC, kw = _cases.lines_inputs(tag)
+    sed_oracle.ensure_line_continua(lgrid)
+    pkw = dict(fesc=kw['fesc'], log10t_BC=kw['log10t_BC'], tauVs_ISM=kw.get('tauVs_ISM'), tauVs_BC=kw.get('tauVs_BC'))
+
+    def one(line):
+        lam = np.mean([lgrid[l]['lam'] for l in line.split(',')])
+        return sed_oracle.line_luminosity(lgrid, line, g['Masses'], g['Ages'], g['Metallicities'],
+                                          k_ISM=_cases.dust_k(dust_ISM, lam), k_BC=_cases.dust_k(dust_BC, lam), **pkw)
+    for i, line in enumerate(g['lines']):
+        o = one(str(line))
+        for q in ('luminosity', 'continuum', 'EW'):
+            np.testing.assert_allclose(o[q], g[q][i], rtol=1e-11)
+    o = one('NII6583')
+    for q in ('luminosity', 'continuum', 'EW'):
+        np.testing.assert_allclose(o[q], g['single_' + q], rtol=1e-11)
+
+
 def test_sed_indices_match_reference():
     g = _cases.load('sed_indices')
     grid = synthetic.ssp_grid(**_cases.GRID_KW)
