@@ -201,6 +201,59 @@ def observed_particle(g, X, Y, L, psf_f, smoothing=False):
             'no_PSF': rebin(no_PSF, (nd, nd)), 'data': rebin(data, (nd, nd))}
 
 
+def observed_sersic(g, L, p, psf_f, sersic2d):
+    """images.py:219-257 -- observed.Sersic: unit-sum Sersic2D profile on the super-sampled
+    grid times L, PSF convolution, rebin.  `sersic2d` is the Sersic2D class (third party:
+    astropy; restated in synthobs_b200/providers.py, parity unpinned at that boundary)."""
+    gg = np.linspace(-g['width'] / 2., g['width'] / 2., g['ndim_super'])                         # :224
+    xx, yy = np.meshgrid(gg, gg)
+    mod = sersic2d(amplitude=1, r_eff=p['r_eff'], n=p['n'], x_0=g['xoffset'], y_0=g['yoffset'],
+                   ellip=p['ellip'], theta=p['theta'])                                           # :228
+    sersic = mod(xx, yy)
+    sersic /= np.sum(sersic)                                                                     # :233
+    no_PSF = L * sersic                                                                          # :238
+    half = g['width_arcsec'] / g['pixel_scale'] / 2.
+    xa = np.linspace(-half, half, g['ndim_super'])                                               # :242 (pixel_scale, not native)
+    psf = psf_f(xa, xa)
+    data = convolve_fft_same(no_PSF, psf)                                                        # :246
+    nd = g['ndim']
+    return {'super_no_PSF': no_PSF, 'super_data': data, 'no_PSF': rebin(no_PSF, (nd, nd)),
+            'data': rebin(data, (nd, nd))}
+
+
+def point_source(flux, native_pixel_scale, target_width_arcsec, PSF, resampling_factor=False, pixel_scale=False,
+                 super_sampling=5, xoffset_pix=0.0, yoffset_pix=0.0):
+    """images.py:320-414 -- point()."""
+    if resampling_factor:                                                                        # :325-333
+        pixel_scale = native_pixel_scale / resampling_factor
+    elif pixel_scale:
+        resampling_factor = native_pixel_scale / pixel_scale
+    else:
+        pixel_scale = native_pixel_scale
+    ndim = int(target_width_arcsec / pixel_scale)                                                # :337
+    ndim_super = ndim * super_sampling
+    width_arcsec = ndim * pixel_scale
+    xo, yo = xoffset_pix * pixel_scale, yoffset_pix * pixel_scale
+    hist = np.zeros((ndim_super, ndim_super))
+    simple = np.zeros((ndim_super, ndim_super))
+    gg = np.linspace(-width_arcsec / 2., width_arcsec / 2., ndim_super)                          # :370
+    i, j = (np.abs(gg - xo)).argmin(), (np.abs(gg - yo)).argmin()
+    hist[j, i] += 1
+    simple[j, i] += flux
+    xx = np.linspace(-(width_arcsec / native_pixel_scale) / 2, width_arcsec / native_pixel_scale / 2, ndim_super)
+    psf = PSF.f(xx, xx)                                                                          # :379
+    psf = psf / np.sum(psf)
+    d = int(PSF.ndim * width_arcsec / PSF.width / 2)                                             # :387
+    c = PSF.ndim // 2
+    psf_data = np.sum(PSF.data[c - d:c + d + 1, c - d:c + d + 1]) / np.sum(PSF.data)
+    sdata = convolve_fft_same(simple, psf) * psf_data                                            # :396
+    no_PSF = rebin(simple, (ndim, ndim))
+    data = rebin(sdata, (ndim, ndim))
+    data = data / np.sum(data) * flux                                                            # :410-411
+    return {'super_hist': hist, 'super_simple': simple, 'super_data': sdata, 'no_PSF': no_PSF, 'data': data,
+            'ndim': ndim, 'pixel_scale': pixel_scale}
+
+
 def support_halfwidth(dk, pitch, R):
     """Product-side rule restated for the tile-assignment parity test: a
     particle's truncated support is +-W pixels around its NGP pixel,

@@ -81,7 +81,7 @@ def _install_stubs():
     astropy.convolution = _mod('astropy.convolution', convolve=None, convolve_fft=convolve_fft,
                                Gaussian2DKernel=None)
     astropy.modeling = _mod('astropy.modeling')
-    astropy.modeling.models = _mod('astropy.modeling.models', Sersic2D=None, Gaussian2D=None)
+    astropy.modeling.models = _mod('astropy.modeling.models', Sersic2D=providers.Sersic2D, Gaussian2D=None)
     astropy.io = _mod('astropy.io', fits=None)
 
     interrogator = _mod('interrogator')

@@ -32,6 +32,21 @@ try:
 except Exception:
     filter_info = {}     # offline: callers register {'<filter>': {'pixel_scale': arcsec}}
 
+
+class _PixelScaleView:
+    """flare.filters.pixel_scale[filter] (used by Sersic / point, images.py:300,323) read
+    through filter_info so offline callers register a filter once."""
+
+    def __getitem__(self, f):
+        return filter_info[f]['pixel_scale']
+
+
+try:
+    import flare.filters as _flt   # type: ignore
+    pixel_scale_of = _flt.pixel_scale
+except Exception:
+    pixel_scale_of = _PixelScaleView()
+
 SUPPORT_SIGMAS = 7.0
 
 
@@ -393,6 +408,57 @@ class observed():
         return imgs
 
 
+def _sersic_device(G, p, x0, y0, Ld):
+    """L[c] * Sersic2D / sum(Sersic2D) on the grid G x G -> [C, n, n] float32 CUDA (so_img_sersic)."""
+    from ..providers import Sersic2D
+    _cabi.require_device()
+    ndim = int(G.size)
+    Gd = dv.to_dev(G)
+    C = Ld.numel()
+    out = torch.empty((C, ndim, ndim), dtype=torch.float32, device=Gd.device)
+    wsb = _cabi.lib.so_img_sersic_workspace_bytes(ndim)
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_img_sersic(_cabi.ptr(Gd), ndim, float(p['r_eff']), float(p['n']), float(x0), float(y0),
+                                        float(p['ellip']), float(p['theta']), Sersic2D.bn(float(p['n'])),
+                                        _cabi.ptr(Ld), C, _cabi.ptr(out), _cabi.ptr(ws), wsb, _cabi.stream()),
+                'so_img_sersic')
+    return out
+
+
+def _observed_Sersic(self, L, p):
+    """reference: images.py:219-257 -- analytic Sersic source through the same back half as
+    .particle (PSF convolution on the super-sampled grid, rebin).  L: scalar (or [C] array /
+    CUDA tensor for C channels sharing the profile: then every product has a leading C axis)."""
+    scalar = np.ndim(L) == 0 and not isinstance(L, torch.Tensor)
+    host = not dv.is_device_tensor(L)
+    Ld = dv.to_dev(np.atleast_1d(np.asarray(L, dtype=np.float64))) if host else L.reshape(-1).to(torch.float64)
+    g = np.linspace(-self.width / 2., self.width / 2., self.ndim_super)                         # images.py:224
+    no_psf = _sersic_device(g, p, self.xoffset, self.yoffset, Ld)                               # images.py:228-238
+    # NB the reference builds this PSF grid in units of pixel_scale, not native_pixel_scale (images.py:242)
+    if getattr(self, '_psf_spec_sersic', None) is None:
+        half = self.width_arcsec / self.pixel_scale / 2.
+        xx = yy = np.linspace(-half, half, self.ndim_super)
+        self._psf_spec_sersic = KernelSpectrum(self.PSF.f(xx, yy), self.ndim_super, self.ndim_super)
+    conv = convolve_fft_device(no_psf, self._psf_spec_sersic)                                   # images.py:246
+    pick = (lambda t: t[0]) if scalar else (lambda t: t)
+    fin = (lambda t: dv.to_host(pick(t))) if host else pick
+    imgs = empty()
+    imgs.super = empty()
+    imgs.super.pixel_scale = self.pixel_scale / self.super_sampling
+    imgs.super.pixel_scale_kpc = self.pixel_scale_kpc / self.super_sampling
+    imgs.super.no_PSF = fin(no_psf)
+    imgs.super.data = fin(conv)
+    imgs.img = empty()
+    imgs.img.pixel_scale = self.pixel_scale
+    imgs.img.pixel_scale_kpc = self.pixel_scale_kpc
+    imgs.img.no_PSF = fin(rebin_device(no_psf, self.ndim))                                      # images.py:255-256
+    imgs.img.data = fin(rebin_device(conv, self.ndim))
+    return imgs
+
+
+observed.Sersic = _observed_Sersic
+
+
 def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=False, pixel_scale=False,
              smoothing=False, PSFs=False, super_sampling=10, verbose=False, offsets=False):
     """reference: images.py:263-286 — one observed image per filter."""
@@ -412,5 +478,124 @@ def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=
                         pixel_scale=pixel_scale, smoothing=smoothing, PSF=PSFs[filter],
                         super_sampling=super_sampling, verbose=verbose, xoffset_pix=xoffset_pix,
                         yoffset_pix=xoffset_pix).particle(X, Y, L[filter])
+        IMGs[filter] = imgs.img
+    return IMGs
+
+
+def Sersic(L, p, filters, cosmo, z, target_width_arcsec, resampling_factor=False, pixel_scale=False, smoothing=False,
+           PSFs=False, super_sampling=10, verbose=False, offsets=False):
+    """reference: images.py:290-313 -- one observed Sersic image per filter."""
+    if offsets:
+        xoffset_pix_base = np.random.random() - 0.5
+        yoffset_pix_base = np.random.random() - 0.5
+    else:
+        xoffset_pix_base = yoffset_pix_base = 0.0
+
+    max_pixel_scale = np.max([pixel_scale_of[filter] for filter in filters])
+
+    IMGs = {}
+    for filter in filters:
+        xoffset_pix = xoffset_pix_base * (max_pixel_scale / pixel_scale_of[filter])
+        yoffset_pix = yoffset_pix_base * (max_pixel_scale / pixel_scale_of[filter])  # noqa: F841 (unused upstream too)
+        imgs = observed(filter, cosmo, z, target_width_arcsec, resampling_factor=resampling_factor,
+                        pixel_scale=pixel_scale, smoothing=smoothing, PSF=PSFs[filter],
+                        super_sampling=super_sampling, verbose=verbose, xoffset_pix=xoffset_pix,
+                        yoffset_pix=xoffset_pix).Sersic(L[filter], p)
+        IMGs[filter] = imgs.img
+    return IMGs
+
+
+def point(flux, filter, target_width_arcsec, resampling_factor=False, pixel_scale=False, PSF=False, verbose=False,
+          super_sampling=5, xoffset_pix=0.0, yoffset_pix=0.0):
+    """reference: images.py:320-414 -- a point source: one NGP deposit on the super-sampled
+    grid, PSF convolution (PSF normalised on the image, times the PSF fraction enclosed by the
+    image footprint), rebin, renormalisation of the final image to `flux`."""
+    native_pixel_scale = pixel_scale_of[filter]
+
+    if resampling_factor:
+        pixel_scale = native_pixel_scale / resampling_factor
+    elif pixel_scale:
+        resampling_factor = native_pixel_scale / pixel_scale
+    else:
+        pixel_scale = native_pixel_scale
+        resampling_factor = 1.0
+
+    ndim = int(target_width_arcsec / pixel_scale)
+    ndim_super = ndim * super_sampling
+    width_arcsec = ndim * pixel_scale
+    xoffset_arcsec = xoffset_pix * pixel_scale
+    yoffset_arcsec = yoffset_pix * pixel_scale
+
+    if verbose:
+        print('*' * 5, 'POINT')
+        print('-' * 10)
+        print('target width/": {0:.2f}'.format(target_width_arcsec))
+        print('width/": {0:.2f}'.format(width_arcsec))
+        print('-' * 10)
+        print('native pixel scale/": {0:.2f}'.format(native_pixel_scale))
+        print('pixel scale/": {0:.2f}'.format(pixel_scale))
+        print('super sampling: {0:.2f}'.format(super_sampling))
+        print('ndim: {0:.2f}'.format(ndim))
+        print('-' * 10)
+
+    host = not dv.is_device_tensor(flux)
+    fd = dv.to_dev(np.atleast_1d(np.asarray(flux, dtype=np.float64))) if host else flux.reshape(-1).to(torch.float64)
+    # the single source lands on its nearest super-pixel (images.py:370-373): one index pair, computed
+    # with the reference's own expression; the images live on the device from here on
+    g = np.linspace(-width_arcsec / 2., width_arcsec / 2., ndim_super)
+    i, j = (np.abs(g - xoffset_arcsec)).argmin(), (np.abs(g - yoffset_arcsec)).argmin()
+    hist = torch.zeros((ndim_super, ndim_super), dtype=torch.float32, device=fd.device)
+    simple = torch.zeros((fd.numel(), ndim_super, ndim_super), dtype=torch.float32, device=fd.device)
+    hist[j, i] += 1
+    simple[:, j, i] += fd.to(torch.float32)
+
+    xx = yy = np.linspace(-(width_arcsec / native_pixel_scale) / 2, width_arcsec / native_pixel_scale / 2, ndim_super)
+    psf = PSF.f(xx, yy)                                                                         # images.py:379
+    psf = psf / np.sum(psf)                                                                     # images.py:381
+
+    d = int(PSF.ndim * width_arcsec / PSF.width / 2)                                            # images.py:387-389
+    c = PSF.ndim // 2
+    psf_data = np.sum(PSF.data[c - d:c + d + 1, c - d:c + d + 1]) / np.sum(PSF.data)
+
+    if verbose:
+        print('sum(PSF width): {0:.2f}'.format(PSF.width))
+        print('sum(psf_data): {0:.2f}'.format(psf_data))
+        print('sum(PSF): {0:.2f}'.format(np.sum(psf)))
+
+    data_super = convolve_fft_device(simple, psf) * float(psf_data)                             # images.py:396
+    no_psf = rebin_device(simple, ndim)                                                         # images.py:407
+    data = rebin_device(data_super, ndim)                                                       # images.py:408
+    tot = data.to(torch.float64).sum(dim=(-2, -1), keepdim=True)
+    data = (data.to(torch.float64) / tot * fd.reshape(-1, 1, 1)).to(torch.float32)              # images.py:410-411
+
+    scalar = np.ndim(flux) == 0 and not isinstance(flux, torch.Tensor)
+    pick = (lambda t: t[0]) if scalar else (lambda t: t)
+    fin = (lambda t: dv.to_host(pick(t))) if host else pick
+    imgs = empty()
+    imgs.super = empty()
+    imgs.super.ndim = ndim_super
+    imgs.super.pixel_scale = pixel_scale / super_sampling
+    imgs.super.hist = dv.to_host(hist) if host else hist
+    imgs.super.simple = fin(simple)
+    imgs.super.data = fin(data_super)
+    imgs.img = empty()
+    imgs.img.ndim = ndim
+    imgs.img.pixel_scale = pixel_scale
+    imgs.img.no_PSF = fin(no_psf)
+    imgs.img.data = fin(data)
+    return imgs
+
+
+def points(fluxes, filters, width_arcsec, resampling_factor=False, pixel_scale=False, PSFs=False, verbose=False):
+    """reference: images.py:419-432 -- one point-source image per filter at a common random
+    sub-pixel offset (global np.random, as upstream)."""
+    xoffset_pix = np.random.random() - 0.5
+    yoffset_pix = np.random.random() - 0.5
+
+    IMGs = {}
+    for filter in filters:
+        imgs = point(fluxes[filter], filter, width_arcsec, resampling_factor=resampling_factor,
+                     pixel_scale=pixel_scale, PSF=PSFs[filter], verbose=verbose, xoffset_pix=xoffset_pix,
+                     yoffset_pix=yoffset_pix)
         IMGs[filter] = imgs.img
     return IMGs

@@ -93,6 +93,31 @@ class sed:
         return self.Fnu
 
 
+class Sersic2D:
+    """astropy.modeling.models.Sersic2D restated [recall of the published evaluate(); used at
+    synthobs/morph/images.py:229-231 as Sersic2D(amplitude, r_eff, n, x_0, y_0, ellip, theta)(xx, yy)]:
+    amplitude * exp(-b_n ((z)^(1/n) - 1)), z = sqrt((x_maj/a)^2 + (x_min/b)^2), a = r_eff,
+    b = (1 - ellip) r_eff, b_n = gammaincinv(2n, 0.5)."""
+
+    def __init__(self, amplitude=1, r_eff=1, n=4, x_0=0, y_0=0, ellip=0, theta=0):
+        self.amplitude, self.r_eff, self.n = amplitude, r_eff, n
+        self.x_0, self.y_0, self.ellip, self.theta = x_0, y_0, ellip, theta
+
+    @staticmethod
+    def bn(n):
+        from scipy.special import gammaincinv
+        return float(gammaincinv(2.0 * n, 0.5))
+
+    def __call__(self, x, y):
+        bn = self.bn(self.n)
+        a, b = self.r_eff, (1 - self.ellip) * self.r_eff
+        cos_theta, sin_theta = np.cos(self.theta), np.sin(self.theta)
+        x_maj = (x - self.x_0) * cos_theta + (y - self.y_0) * sin_theta
+        x_min = -(x - self.x_0) * sin_theta + (y - self.y_0) * cos_theta
+        z = np.sqrt((x_maj / a) ** 2 + (x_min / b) ** 2)
+        return self.amplitude * np.exp(-bn * (z ** (1 / self.n) - 1))
+
+
 dust_curves = types.SimpleNamespace(simple=simple, Calzetti_like=Calzetti_like)
 IGM = types.SimpleNamespace(madau=madau)
 core = types.SimpleNamespace(sed=sed)

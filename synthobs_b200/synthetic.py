@@ -160,6 +160,39 @@ class GaussianPSF:
         return np.exp(-4 * np.log(2) * (xx ** 2 + yy ** 2) / self.FWHM ** 2)
 
 
+class TabulatedPSF:
+    """Tabulated PSF provider with the attributes the reference's FITS-backed PSFs carry
+    (synthobs/morph/PSF.py:69-105 HubblePSF: .data, .ndim, .width ["], .f = bilinear
+    interpolation over native pixels with 0 outside) -- the protocol `point()` needs
+    (synthobs/morph/images.py:384-392).  `sub` = samples per native pixel."""
+
+    def __init__(self, data, sub, pixel_scale):
+        from scipy.interpolate import RegularGridInterpolator
+        self.data = np.asarray(data, dtype=np.float64)
+        self.ndim = self.data.shape[0]
+        self.width = self.ndim * pixel_scale / sub
+        x = np.linspace(-(self.ndim / 2.) / sub, (self.ndim / 2.) / sub, self.ndim)
+        self._interp = RegularGridInterpolator((x, x), self.data, method='linear', bounds_error=False, fill_value=0.0)
+
+    def f(self, x, y):
+        yy, xx = np.meshgrid(y, x, indexing='ij')
+        return self._interp(np.stack([yy.ravel(), xx.ravel()], axis=1)).reshape(len(y), len(x))
+
+
+def airy_like_psf(ndim=101, sub=5, fwhm_pix=2.0, pixel_scale=0.031, seed=0):
+    """A non-separable, slightly asymmetric tabulated PSF (core + ring + diffraction-spike-like
+    cross) so the tabulated-PSF path is not exercised by a pure Gaussian only."""
+    rng = np.random.default_rng(seed)
+    x = np.linspace(-(ndim / 2.) / sub, (ndim / 2.) / sub, ndim)
+    xx, yy = np.meshgrid(x, x)
+    r = np.hypot(xx, yy)
+    core = np.exp(-4 * np.log(2) * r ** 2 / fwhm_pix ** 2)
+    ring = 0.05 * np.exp(-0.5 * ((r - 1.6 * fwhm_pix) / (0.3 * fwhm_pix)) ** 2)
+    spikes = 0.02 * (np.exp(-np.abs(xx) / 0.2) + np.exp(-np.abs(yy + 0.1 * xx) / 0.2)) * np.exp(-r / (3 * fwhm_pix))
+    data = (core + ring + spikes) * (1.0 + 0.01 * rng.standard_normal((ndim, ndim)))
+    return TabulatedPSF(np.abs(data), sub, pixel_scale)
+
+
 def particles(n, seed=1, lognormal_mass=False, clumps=3, scale_kpc=1.5):
     """Star-particle catalogue: clustered positions (wide kNN range), ages in
     Myr, metallicities, masses, LOS metal surface densities and the two optical

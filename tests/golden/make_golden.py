@@ -232,6 +232,39 @@ def observed_case(ref):
     print('img_observed', out['obs_data'].shape, [out['multi_%d_data' % i].shape for i in range(2)])
 
 
+def analytic_case(ref):
+    """observed.Sersic, Sersic(), point() of the unmodified reference (images.py:219-257, 290-313,
+    320-414).  Sersic2D is the restated astropy model (providers.Sersic2D, via the stub)."""
+    images = ref.morph.images
+    cosmo = synthetic.FixedCosmology()
+    z = 8.0
+    out = {}
+    p = {'r_eff': 0.9, 'n': 1.7, 'ellip': 0.35, 'theta': 0.6}
+    out['sersic_p'] = np.array([p['r_eff'], p['n'], p['ellip'], p['theta']])
+    o = images.observed('JWST.NIRCAM.F150W', cosmo, z, 0.8, resampling_factor=2, PSF=synthetic.GaussianPSF(2.1),
+                        super_sampling=3, xoffset_pix=0.3, yoffset_pix=-0.2).Sersic(3.5e28, p)
+    out.update(ser_super_no_PSF=o.super.no_PSF, ser_super_data=o.super.data, ser_no_PSF=o.img.no_PSF,
+               ser_data=o.img.data, ser_pixel_scale=o.img.pixel_scale, ser_pixel_scale_kpc=o.img.pixel_scale_kpc)
+    filters = ['JWST.NIRCAM.F150W', 'JWST.NIRCAM.F356W']
+    PSFs = {'JWST.NIRCAM.F150W': synthetic.GaussianPSF(2.1), 'JWST.NIRCAM.F356W': synthetic.GaussianPSF(1.8)}
+    L = {'JWST.NIRCAM.F150W': 1.0e28, 'JWST.NIRCAM.F356W': 2.5e28}
+    IMGs = images.Sersic(L, {'r_eff': 0.5, 'n': 4.0, 'ellip': 0.0, 'theta': 0.0}, filters, cosmo, z, 1.2, PSFs=PSFs,
+                         super_sampling=2)
+    for fi, f in enumerate(filters):
+        out['sermulti_%d_data' % fi] = IMGs[f].data
+        out['sermulti_%d_no_PSF' % fi] = IMGs[f].no_PSF
+    # point source through a tabulated PSF (the protocol of the FITS-backed PSFs: .f, .data, .ndim, .width)
+    psf = synthetic.airy_like_psf(ndim=101, sub=5, fwhm_pix=2.0, pixel_scale=0.031)
+    o = images.point(7.0e3, 'JWST.NIRCAM.F150W', 0.55, PSF=psf, super_sampling=5, xoffset_pix=0.21, yoffset_pix=-0.37)
+    out.update(pt_super_hist=o.super.hist, pt_super_simple=o.super.simple, pt_super_data=o.super.data,
+               pt_no_PSF=o.img.no_PSF, pt_data=o.img.data, pt_ndim=o.img.ndim, pt_pixel_scale=o.img.pixel_scale)
+    o = images.point(2.0, 'JWST.NIRCAM.F356W', 1.5, resampling_factor=2, super_sampling=3,
+                     PSF=synthetic.airy_like_psf(ndim=75, sub=5, fwhm_pix=1.4, pixel_scale=0.063, seed=4))
+    out.update(pt2_super_data=o.super.data, pt2_no_PSF=o.img.no_PSF, pt2_data=o.img.data)
+    np.savez_compressed(os.path.join(HERE, 'img_analytic.npz'), **out)
+    print('img_analytic', out['ser_data'].shape, out['ser_data'].sum(), out['pt_data'].shape, out['pt_data'].sum())
+
+
 def main():
     ref = ref_loader.load()
     simple = ('simple', {'slope': -1.0})
@@ -264,6 +297,7 @@ def main():
 
     pixel_index_case(ref)
     observed_case(ref)
+    analytic_case(ref)
 
 
 if __name__ == '__main__':

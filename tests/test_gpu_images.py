@@ -210,3 +210,50 @@ def test_image_huge_single_rank_equals_core():
     img = sdist.image_huge(p['X'], p['Y'], p['Masses'], 0.02, 400, 8).cpu().numpy().astype(np.float64)
     o = image_oracle.core(p['X'], p['Y'], p['Masses'], resolution=0.02, ndim=400, smoothing=('adaptive', 8))
     assert_image_close(img, o['data'])
+
+
+def test_analytic_sources_match_reference():
+    """observed.Sersic / Sersic() / point() vs the golden vectors of the
+    unmodified reference: Sersic profile kernel (float64 evaluation), cuFFT PSF step, rebin."""
+    from synthobs_b200.morph import images
+    images.filter_info.update({'JWST.NIRCAM.F150W': {'pixel_scale': 0.031}, 'JWST.NIRCAM.F356W': {'pixel_scale': 0.063}})
+    g = _cases.load('img_analytic')
+    cosmo = synthetic.FixedCosmology()
+    p = dict(zip(('r_eff', 'n', 'ellip', 'theta'), [float(v) for v in g['sersic_p']]))
+    o = images.observed('JWST.NIRCAM.F150W', cosmo, 8.0, 0.8, resampling_factor=2, PSF=synthetic.GaussianPSF(2.1),
+                        super_sampling=3, xoffset_pix=0.3, yoffset_pix=-0.2).Sersic(3.5e28, p)
+    assert_image_close(o.super.no_PSF, g['ser_super_no_PSF'])
+    assert_image_close(o.super.data, g['ser_super_data'])
+    assert_image_close(o.img.no_PSF, g['ser_no_PSF'])
+    assert_image_close(o.img.data, g['ser_data'])
+    np.testing.assert_allclose(o.super.no_PSF, g['ser_super_no_PSF'], rtol=2e-7)      # float64 profile, one rounding
+    assert o.img.pixel_scale == float(g['ser_pixel_scale']) and o.img.pixel_scale_kpc == float(g['ser_pixel_scale_kpc'])
+    filters = ['JWST.NIRCAM.F150W', 'JWST.NIRCAM.F356W']
+    PSFs = {'JWST.NIRCAM.F150W': synthetic.GaussianPSF(2.1), 'JWST.NIRCAM.F356W': synthetic.GaussianPSF(1.8)}
+    L = {'JWST.NIRCAM.F150W': 1.0e28, 'JWST.NIRCAM.F356W': 2.5e28}
+    IMGs = images.Sersic(L, {'r_eff': 0.5, 'n': 4.0, 'ellip': 0.0, 'theta': 0.0}, filters, cosmo, 8.0, 1.2, PSFs=PSFs,
+                         super_sampling=2)
+    for fi, f in enumerate(filters):
+        assert_image_close(IMGs[f].data, g['sermulti_%d_data' % fi])
+        assert_image_close(IMGs[f].no_PSF, g['sermulti_%d_no_PSF' % fi])
+    psf = synthetic.airy_like_psf(ndim=101, sub=5, fwhm_pix=2.0, pixel_scale=0.031)
+    o = images.point(7.0e3, 'JWST.NIRCAM.F150W', 0.55, PSF=psf, super_sampling=5, xoffset_pix=0.21, yoffset_pix=-0.37)
+    assert np.array_equal(o.super.hist, g['pt_super_hist'])                            # the source's pixel: bit-exact
+    assert np.array_equal(o.super.simple != 0, g['pt_super_simple'] != 0)
+    assert_image_close(o.super.data, g['pt_super_data'])
+    assert_image_close(o.img.no_PSF, g['pt_no_PSF'])
+    assert_image_close(o.img.data, g['pt_data'])
+    assert o.img.data.sum() == pytest.approx(7.0e3, rel=1e-6)
+    assert o.img.ndim == int(g['pt_ndim']) and o.img.pixel_scale == float(g['pt_pixel_scale'])
+    psf2 = synthetic.airy_like_psf(ndim=75, sub=5, fwhm_pix=1.4, pixel_scale=0.063, seed=4)
+    o = images.point(2.0, 'JWST.NIRCAM.F356W', 1.5, resampling_factor=2, super_sampling=3, PSF=psf2)
+    assert_image_close(o.super.data, g['pt2_super_data'])
+    assert_image_close(o.img.data, g['pt2_data'])
+    # points(): common random offset from the global np.random, as upstream (images.py:421-422)
+    np.random.seed(3)
+    xo, yo = np.random.random() - 0.5, np.random.random() - 0.5
+    np.random.seed(3)
+    P = images.points({'JWST.NIRCAM.F150W': 5.0, 'JWST.NIRCAM.F356W': 9.0}, filters, 0.9,
+                      PSFs={'JWST.NIRCAM.F150W': psf, 'JWST.NIRCAM.F356W': psf2})
+    r = image_oracle.point_source(9.0, 0.063, 0.9, psf2, xoffset_pix=xo, yoffset_pix=yo)
+    assert_image_close(P['JWST.NIRCAM.F356W'].data, r['data'])

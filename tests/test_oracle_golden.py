@@ -133,3 +133,32 @@ def test_flux_conservation_property():
     np.testing.assert_allclose(o['data'].sum(), g['L'][o['aux']['sel']].sum(), rtol=1e-12)
     assert o['hist'].sum() == o['aux']['sel'].sum()
     assert image_oracle.rebin(o['data'], (25, 25)).sum() == pytest.approx(o['data'].sum(), rel=1e-13)
+
+
+def test_analytic_sources_match_reference():
+    """oracle observed_sersic / point_source vs observed.Sersic, Sersic(), point() of the unmodified reference"""
+    g = _cases.load('img_analytic')
+    cosmo = synthetic.FixedCosmology()
+    p = dict(zip(('r_eff', 'n', 'ellip', 'theta'), g['sersic_p']))
+    geo = image_oracle.observed_geometry(0.031, cosmo.arcsec_per_kpc, 0.8, resampling_factor=2, super_sampling=3,
+                                         xoffset_pix=0.3, yoffset_pix=-0.2)
+    o = image_oracle.observed_sersic(geo, 3.5e28, p, synthetic.GaussianPSF(2.1).f, providers.Sersic2D)
+    for k in ('super_no_PSF', 'super_data', 'no_PSF', 'data'):
+        np.testing.assert_allclose(o[k], g['ser_' + k], rtol=1e-9, atol=1e-12 * np.abs(g['ser_' + k]).max())
+    assert geo['pixel_scale'] == g['ser_pixel_scale'] and geo['pixel_scale_kpc'] == g['ser_pixel_scale_kpc']
+    for fi, (ps, fw, L) in enumerate(((0.031, 2.1, 1.0e28), (0.063, 1.8, 2.5e28))):
+        geo = image_oracle.observed_geometry(ps, cosmo.arcsec_per_kpc, 1.2, super_sampling=2)
+        o = image_oracle.observed_sersic(geo, L, {'r_eff': 0.5, 'n': 4.0, 'ellip': 0.0, 'theta': 0.0},
+                                         synthetic.GaussianPSF(fw).f, providers.Sersic2D)
+        np.testing.assert_allclose(o['data'], g['sermulti_%d_data' % fi], rtol=1e-9, atol=1e-12 * o['data'].max())
+        np.testing.assert_allclose(o['no_PSF'], g['sermulti_%d_no_PSF' % fi], rtol=1e-9)
+    psf = synthetic.airy_like_psf(ndim=101, sub=5, fwhm_pix=2.0, pixel_scale=0.031)
+    o = image_oracle.point_source(7.0e3, 0.031, 0.55, psf, super_sampling=5, xoffset_pix=0.21, yoffset_pix=-0.37)
+    assert np.array_equal(o['super_hist'], g['pt_super_hist']) and np.array_equal(o['super_simple'], g['pt_super_simple'])
+    for k in ('super_data', 'no_PSF', 'data'):
+        np.testing.assert_allclose(o[k], g['pt_' + k], rtol=1e-9, atol=1e-12 * np.abs(g['pt_' + k]).max())
+    assert o['ndim'] == int(g['pt_ndim']) and o['pixel_scale'] == float(g['pt_pixel_scale'])
+    psf2 = synthetic.airy_like_psf(ndim=75, sub=5, fwhm_pix=1.4, pixel_scale=0.063, seed=4)
+    o = image_oracle.point_source(2.0, 0.063, 1.5, psf2, resampling_factor=2, super_sampling=3)
+    for k in ('super_data', 'no_PSF', 'data'):
+        np.testing.assert_allclose(o[k], g['pt2_' + k], rtol=1e-9, atol=1e-12 * np.abs(g['pt2_' + k]).max())
