@@ -286,22 +286,12 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
     keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
     d = {k: torch.from_numpy(batch[k]).to(dev) for k in keys}
     off = torch.from_numpy(batch['offsets']).to(dev)
-    # filter weights for the spectra -> flux contraction (trapz weights * T / norm, folded on the host)
-    Wt = np.stack([models.trapz_weights(F[f].lam) * F[f].T / np.trapezoid(F[f].T, x=F[f].lam) for f in F['filters']])
-    Wt = Wt / np.abs(Wt).max(axis=1, keepdims=True)
-    nlp = (Wt.shape[1] + 3) // 4 * 4
-    Wp = np.zeros((Wt.shape[0], nlp), dtype=np.float32)
-    Wp[:, :Wt.shape[1]] = Wt
-    Wd = torch.from_numpy(Wp).to(dev)
-    W_split = models.split_tf32(Wd)
+    cosmo = synthetic.FixedCosmology()
 
     def step():
         o = models.sed_spectra_device(model, d['Masses'], d['Ages'], d['Metallicities'], d['tauVs_ISM'], d['tauVs_BC'],
                                       0.0, 7.0, offsets=off)
-        tot = o['total']
-        if tot.shape[1] != nlp:
-            tot = torch.nn.functional.pad(tot, (0, nlp - tot.shape[1]))
-        return models.gemm(tot, Wd, B_split=W_split)            # [G, F] band fluxes from the spectra
+        return models.spectra_Fnu(model, F, o['total'], Z, cosmo)      # [G, F] band fluxes from the spectra
 
     for _ in range(2):
         step()

@@ -21,7 +21,7 @@ constexpr int kItem = kThreads * kPerThread;  // particles per work item
 constexpr int kMaxThr = 127;                  // max thresholds per axis (kernel-parameter resident)
 constexpr int kLut = 6144;                    // index table entries per axis (256 per octave, 24 octaves)
 constexpr int kLutShift = 12;                 // bin = (high 32 bits of the double >> 12): exponent + 8 mantissa bits
-constexpr int kYWarp = 32 * (kPerThread + 1); // per-warp ring of compacted young particles
+constexpr int kYWarp = 32 * (kPerThread + 1); // per-warp buffer of compacted young particles (< 32 left over + one item)
 
 // One NGP axis: ascending float64 thresholds + an index table over bins of the double's own bit
 // pattern (sign/exponent/top 8 mantissa bits: 256 bins per octave, exact edges, integer ALU only).
@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     float4* my_y = s_y + warp * kYWarp;
-    int ytail = 0, yhead = 0;      // this warp's ring positions (warp-uniform)
+    int ytail = 0;                 // young particles waiting in this warp's buffer (warp-uniform, < 32 between items)
+    const unsigned lane_lt = (1u << lane) - 1u;
 
     // stage the per-filter tables as [cell][filter] (transposed from [filter][cell])
     for (int idx = tid; idx < ncell * FP; idx += kThreads) {
@@ -158,15 +159,45 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
 
         double age[kPerThread], zz[kPerThread];
         float mm[kPerThread], ti[kPerThread], tb[kPerThread];
+        if (count == kItem) {
+            // full item (all but the last of a galaxy): plain strided loads off one base offset
+            const int64_t i0 = begin + tid;
+            const double* pa = p.ages + i0;
+            const double* pz = p.metals + i0;
+            const double* pm = p.masses + i0;
 #pragma unroll
-        for (int j = 0; j < kPerThread; ++j) {
-            const int64_t i = begin + j * kThreads + tid;
-            const bool on = (j * kThreads + tid) < count;
-            age[j] = on ? ldg_stream(p.ages + i) : 1.0;
-            zz[j] = on ? ldg_stream(p.metals + i) : 1.0;
-            mm[j] = on ? (float)ldg_stream(p.masses + i) : 0.f;
-            ti[j] = (on && p.tau_ism) ? (float)ldg_stream(p.tau_ism + i) : 0.f;
-            tb[j] = (on && p.tau_bc) ? (float)ldg_stream(p.tau_bc + i) : 0.f;
+            for (int j = 0; j < kPerThread; ++j) {
+                age[j] = ldg_stream(pa + j * kThreads);
+                zz[j] = ldg_stream(pz + j * kThreads);
+                mm[j] = (float)ldg_stream(pm + j * kThreads);
+            }
+            if (p.tau_ism) {
+                const double* pt = p.tau_ism + i0;
+#pragma unroll
+                for (int j = 0; j < kPerThread; ++j) ti[j] = (float)ldg_stream(pt + j * kThreads);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kPerThread; ++j) ti[j] = 0.f;
+            }
+            if (p.tau_bc) {
+                const double* pt = p.tau_bc + i0;
+#pragma unroll
+                for (int j = 0; j < kPerThread; ++j) tb[j] = (float)ldg_stream(pt + j * kThreads);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kPerThread; ++j) tb[j] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                const int64_t i = begin + j * kThreads + tid;
+                const bool on = (j * kThreads + tid) < count;
+                age[j] = on ? ldg_stream(p.ages + i) : 1.0;
+                zz[j] = on ? ldg_stream(p.metals + i) : 1.0;
+                mm[j] = on ? (float)ldg_stream(p.masses + i) : 0.f;
+                ti[j] = (on && p.tau_ism) ? (float)ldg_stream(p.tau_ism + i) : 0.f;
+                tb[j] = (on && p.tau_bc) ? (float)ldg_stream(p.tau_bc + i) : 0.f;
+            }
         }
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
@@ -182,11 +213,7 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
                 // warp-level compaction of the young particles (fixed order: slot, lane)
                 const bool isy = young && on;
                 const unsigned bal = __ballot_sync(0xffffffffu, isy);
-                if (isy) {
-                    int pos = ytail + __popc(bal & ((1u << lane) - 1u));
-                    pos = pos >= kYWarp ? pos - kYWarp : pos;
-                    my_y[pos] = make_float4(mm[j] * ofe, ti[j], tb[j], __int_as_float(cell));
-                }
+                if (isy) my_y[ytail + __popc(bal & lane_lt)] = make_float4(mm[j] * ofe, ti[j], tb[j], __int_as_float(cell));
                 ytail += __popc(bal);
             }
 
@@ -247,12 +274,11 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
         if constexpr (!WRITE_PF) {
             // dense evaluation of the birth-cloud term  m (1-fesc) 2^(tI kI + tB kB) (tra+neb)
             __syncwarp();
+            int yhead = 0;
             while (ytail - yhead >= 32 || (run_end && ytail > yhead)) {
                 const int cnt = min(32, ytail - yhead);
                 if (lane < cnt) {
-                    int pos = yhead + lane;
-                    pos = pos >= kYWarp ? pos - kYWarp : pos;
-                    const float4 rec = my_y[pos];
+                    const float4 rec = my_y[yhead + lane];
                     const float2 mo2 = make_float2(rec.x, rec.x), tI2 = make_float2(rec.y, rec.y);
                     const float2 tB2 = make_float2(rec.z, rec.z);
                     const float4* rtn = reinterpret_cast<const float4*>(s_tn + __float_as_int(rec.w) * kStride);
@@ -273,7 +299,15 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
                 }
                 yhead += cnt;
             }
-            if (yhead >= kYWarp) { ytail -= kYWarp; yhead -= kYWarp; }
+            // fewer than 32 records are left: move them to the front of the buffer
+            if (yhead > 0) {
+                const int left = ytail - yhead;
+                float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < left) keep = my_y[yhead + lane];
+                __syncwarp();
+                if (lane < left) my_y[lane] = keep;
+                ytail = left;
+            }
             __syncwarp();
         }
 

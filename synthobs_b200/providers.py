@@ -92,6 +92,14 @@ class sed:
                     for f in F['filters']}
         return self.Fnu
 
+    def return_log10Q(self):
+        """log10 of the ionising photon rate [1/s]: integral of L_nu / (h nu) d nu blueward of
+        912 A = integral of lnu / (h lam) d lam  [recall of interrogator core.sed.return_log10Q;
+        call site examples/SED_Lion.py:38]."""
+        h = 6.626E-27  # erg s
+        sel = self.lam < 912.
+        return np.log10(np.trapezoid(self.lnu[sel] / (h * self.lam[sel]), x=self.lam[sel]))
+
 
 class Sersic2D:
     """astropy.modeling.models.Sersic2D restated [recall of the published evaluate(); used at

@@ -297,21 +297,23 @@ def _dust_k(model, which, wavelength):
 
 
 def _pow2_scale(*arrays):
-    """Per-row power of two >= max|value| (1 for all-zero rows): dividing by it is exact in
-    binary floating point, and keeps M * table inside FP32 range whatever the units (line
-    luminosities per Msol reach 1e34 erg/s, beyond FP32 once multiplied by a particle mass)."""
+    """Per-row power of two >= max|value| when that maximum would leave the FP32 range once
+    multiplied by a particle mass (line luminosities per Msol reach 1e34 erg/s); 1 otherwise.
+    Dividing by a power of two is exact in binary floating point."""
     m = np.max(np.stack([np.abs(a).max(axis=1) for a in arrays]), axis=0)
+    need = (m > 1e24) | ((m < 1e-24) & (m > 0))
     with np.errstate(divide='ignore'):
-        e = np.where(m > 0, np.ceil(np.log2(np.where(m > 0, m, 1.0))), 0.0)
+        e = np.where(need, np.ceil(np.log2(np.where(m > 0, m, 1.0))), 0.0)
     return np.ldexp(1.0, e.astype(np.int64))
 
 
 def _scaled_tables(inc, tn):
-    """float64 [F, ncell] tables -> (device float32 inc/scale, tn/scale, device float64 scale [F])"""
+    """float64 [F, ncell] tables -> (device float32 inc/scale, tn/scale, device float64 scale [F] or
+    None when no row needs scaling)"""
     scale = _pow2_scale(inc, tn)
     return (dv.to_dev((inc / scale[:, None]).astype(np.float32), torch.float32),
             dv.to_dev((tn / scale[:, None]).astype(np.float32), torch.float32),
-            dv.to_dev(scale, torch.float64))
+            dv.to_dev(scale, torch.float64) if np.any(scale != 1.0) else None)
 
 
 def _tables(model, kind, filters):
@@ -387,10 +389,11 @@ def _broadband_launch(ngp, tabs, kI, kB, Masses, Ages, Metallicities, tauVs_ISM,
         _cabi.ptr(out_pf), _cabi.ptr(out_sums), _cabi.ptr(out_cell),
         _cabi.ptr(ws), wsb, _cabi.stream())
     _cabi.check(rc, 'so_sed_broadband')
-    if out_sums is not None:
-        out_sums *= scale[None, :]
-    if out_pf is not None:
-        out_pf *= scale.to(torch.float32)[:, None]
+    if scale is not None:
+        if out_sums is not None:
+            out_sums *= scale[None, :]
+        if out_pf is not None:
+            out_pf *= scale.to(torch.float32)[:, None]
     return out_pf, out_sums, out_cell
 
 
@@ -646,6 +649,66 @@ def generate_SED_batch(model, Masses, Ages, Metallicities, offsets, tauVs_ISM=Fa
     if _host_like(Masses):
         return {k: dv.to_host(v) for k, v in out.items()}
     return out
+
+
+# --------------------------------------------------------------------------
+# spectra -> broadband (the second contraction)
+# --------------------------------------------------------------------------
+
+def _filter_weight_operand(model, F, kind, z=None, cosmo=None, include_IGM=True):
+    """W[F, n_lam] (float32, rows scaled to unit maximum, TF32-split) + float64 row scale, for
+    core.sed.get_Lnu (kind 'Lnu': trapz(lnu T)/trapz(T) on the rest-frame grid) or
+    get_fnu + get_Fnu (kind 'Fnu': nJy, IGM and flux scaling folded in; F on lam(1+z))."""
+    key = (kind, id(F), tuple(F['filters']), z, include_IGM, id(cosmo))
+    cache = model._dev.setdefault('specW', {})
+    if key not in cache:
+        filters = F['filters']
+        Wt = np.stack([trapz_weights(F[f].lam) * F[f].T / np.trapezoid(F[f].T, x=F[f].lam) for f in filters])
+        if kind == 'Fnu':
+            dl = cosmo.luminosity_distance(z).to('cm').value
+            Wt = Wt * (1E23 * 1E9 * (1. + z) / (4. * np.pi * dl ** 2))
+            if include_IGM:
+                Wt = Wt * np.stack([IGM.madau(F[f].lam, z) for f in filters])
+        scale = np.abs(Wt).max(axis=1)
+        scale[scale == 0] = 1.0
+        nl = Wt.shape[1]
+        nlp = (nl + 3) // 4 * 4
+        Wp = np.zeros((len(filters), nlp), dtype=np.float32)
+        Wp[:, :nl] = Wt / scale[:, None]
+        Wd = dv.to_dev(Wp, torch.float32)
+        cache.clear()
+        cache[key] = (Wd, split_tf32(Wd), dv.to_dev(scale, torch.float64))
+    return cache[key]
+
+
+def _spectra_contract(model, spectra, op):
+    Wd, W_split, scale = op
+    host = not dv.is_device_tensor(spectra)
+    S = dv.to_dev(spectra, torch.float32)
+    one = S.dim() == 1
+    S = S.reshape(1, -1) if one else S
+    nlp = Wd.shape[1]
+    if S.shape[1] != nlp:
+        S = torch.nn.functional.pad(S, (0, nlp - S.shape[1]))
+    # spectra span many decades between galaxies: scale each row to unit maximum (a power of two: exact)
+    rmax = S.abs().amax(dim=1).clamp_min(1e-30)
+    rs = torch.exp2(torch.ceil(torch.log2(rmax)))
+    out = gemm(S / rs[:, None], Wd, B_split=W_split).to(torch.float64) * rs.to(torch.float64)[:, None] * scale[None, :]
+    out = out[0] if one else out
+    return dv.to_host(out) if host else out
+
+
+def spectra_Lnu(model, F, spectra):
+    """core.sed.get_Lnu(F) (examples/SED_spectra.py:103) for one spectrum [n_lam] or a batch
+    [G, n_lam] (e.g. generate_SED_batch(...)['total']): [F] / [G, F] rest-frame band
+    luminosities, one tensor-core contraction spectra x filter weights."""
+    return _spectra_contract(model, spectra, _filter_weight_operand(model, F, 'Lnu'))
+
+
+def spectra_Fnu(model, F, spectra, z, cosmo, include_IGM=True):
+    """core.sed.get_fnu(cosmo, z) followed by get_Fnu(F) (examples/SED_spectra.py:112): observed
+    band fluxes in nJy, F defined on model.lam * (1 + z)."""
+    return _spectra_contract(model, spectra, _filter_weight_operand(model, F, 'Fnu', z, cosmo, include_IGM))
 
 
 # --------------------------------------------------------------------------

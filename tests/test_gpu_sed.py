@@ -297,3 +297,38 @@ def test_emission_lines_batch_and_pickle(tmp_path):
                                            fesc=0.1)
             for q in ('luminosity', 'continuum', 'EW'):
                 np.testing.assert_allclose(ob[line][q][gi], r[q], rtol=RTOL_SUM)
+
+
+def test_spectra_to_broadband_contraction():
+    """spectra_Lnu / spectra_Fnu (the [G, n_lam] x [n_lam, F] tensor-core contraction) == core.sed.get_Lnu /
+    get_fnu + get_Fnu applied per galaxy to the oracle's float64 spectra; 1e-4 (filter fluxes)."""
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=1203, seed=0)
+    dI = ('simple', {'slope': -1.0})
+    model = make_model(grid, dI, dI)
+    b = synthetic.galaxy_batch(6, n_min=200, n_max=4000, seed=12)
+    kw = dict(tauVs_ISM=b['tauVs_ISM'], tauVs_BC=b['tauVs_BC'], fesc=0.05)
+    out = models.generate_SED_batch(model, b['Masses'], b['Ages'], b['Metallicities'], b['offsets'], **kw)
+    z = 7.0
+    cosmo = synthetic.FixedCosmology()
+    F = synthetic.filter_set(grid['lam'], n_filters=5, kind='tophat', lo=1500., hi=8000.)
+    Fz = synthetic.filter_set(grid['lam'] * (1. + z), n_filters=5, kind='gauss', lo=12000., hi=50000., prefix='JWST.FAKE.')
+    L = models.spectra_Lnu(model, F, out['total'])
+    Fn = models.spectra_Fnu(model, Fz, out['total'], z, cosmo)
+    assert L.shape == (6, 5) and Fn.shape == (6, 5)
+    kl = providers.simple({'slope': -1.0}).tau(grid['lam'])
+    og = sed_oracle.ensure_incident(synthetic.ssp_grid(n_lam=1203, seed=0))
+    for gi in range(6):
+        s, e = b['offsets'][gi], b['offsets'][gi + 1]
+        r = sed_oracle.sed_spectra(og, b['Masses'][s:e], b['Ages'][s:e], b['Metallicities'][s:e],
+                                   tauVs_ISM=b['tauVs_ISM'][s:e], tauVs_BC=b['tauVs_BC'][s:e], k_ISM_lam=kl, k_BC_lam=kl,
+                                   fesc=0.05)
+        sed = providers.sed(grid['lam'])
+        sed.lnu = r['total']
+        ref_L = sed.get_Lnu(F)
+        sed.get_fnu(cosmo, z)
+        ref_F = sed.get_Fnu(Fz)
+        np.testing.assert_allclose(L[gi], [ref_L[f] for f in F['filters']], rtol=RTOL_SUM)
+        np.testing.assert_allclose(Fn[gi], [ref_F[f] for f in Fz['filters']], rtol=RTOL_SUM)
+    one = models.spectra_Lnu(model, F, out['total'][2])
+    np.testing.assert_allclose(one, L[2], rtol=1e-6)
