@@ -374,8 +374,8 @@ def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
     stats = {}
 
     def step_device(Xd, Yd, Ld):
-        X = Xd - torch.median(Xd)            # recentring (images.py:183-184) on device copies
-        Y = Yd - torch.median(Yd)
+        X = Xd - images.median_device(Xd)    # recentring (images.py:183-184, np.median semantics) on device copies
+        Y = Yd - images.median_device(Yd)
         r = images.particle_device_multi(obs, X, Y, Ld)
         stats.update(r['stats'])
         return r['data']

@@ -225,6 +225,15 @@ int so_img_sersic(const double* G, int32_t ndim, double r_eff, double n, double 
                   double ellip, double theta, double bn, const double* L, int32_t n_chan,
                   float* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* np.median of n_arrays float64 arrays of length n (array a starts at x + a*stride), the
+ * recentring step of observed.particle (synthobs/morph/images.py:183-184): element n//2 for
+ * odd n, mean of the two middle elements for even n, bit-identical to NumPy for finite data.
+ * 8-bit radix selection on the order-preserving integer image of the doubles: eight
+ * prefix-filtered histogram passes, no sort.  out: DEVICE double[n_arrays]. */
+int64_t so_median_workspace_bytes(int32_t n_arrays);
+int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

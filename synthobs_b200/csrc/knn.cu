@@ -4,11 +4,12 @@
 // from every selected particle to its k-th neighbour, the particle itself being the first
 // (distance 0).
 //
-// Particles are sorted by the Morton code of their cell on a 2^L x 2^L grid over the image.  In that
-// order every quadtree node (any level) is one contiguous range, found in O(1) from a single
-// upper-bound table over the finest cells (E[c] = #particles with code <= c).  A query walks the tree
-// depth-first, nearest child first, pruning nodes whose square is farther than the current k-th best,
-// and scans leaves (<= kLeaf points or finest level).  Exact for any clustering: dense cores,
+// Particles are sorted by the 30-bit Morton code of their cell on a 32768 x 32768 grid over the image.
+// In that order every quadtree node (any of 15 levels) is one contiguous range: found in O(1) from an
+// upper-bound table over the cells of level Lt (E[c] = #particles in table cells <= c, Lt ~ log4 n),
+// and by bisection of the sorted keys inside one table cell for the deeper levels.  A query walks the
+// tree depth-first, nearest child first, pruning nodes whose square is farther than the current k-th
+// best, and scans leaves (<= kLeaf points or finest level).  Exact for any clustering: dense cores,
 // sparse outskirts and isolated particles all cost O(log) node visits plus a few leaf scans.
 // The squared distance is formed with separately rounded products and sum (no FMA contraction) and
 // an IEEE sqrt, i.e. the same float64 arithmetic as a straightforward C loop.
@@ -18,42 +19,45 @@
 
 namespace {
 
-constexpr int kLeaf = 32;
-constexpr int kMaxLevel = 12;
-constexpr int kStack = 3 * kMaxLevel + 4;
+constexpr int kLeaf = 32;           // nodes with at most this many points are scanned
+constexpr int kBits = 15;           // Morton bits per axis: the implicit quadtree has levels 0..15
+constexpr int kTableLevelMax = 11;  // node ranges down to this level come from the table E, deeper ones by bisection
+constexpr int kStack = 3 * kBits + 8;
+constexpr uint32_t kUnselected = 1u << (2 * kBits);   // key of particles outside the image: sorts last
 
 struct KnnLayout {
-    int32_t *keys0, *vals0, *keys1, *vals1;
+    uint32_t *keys0, *keys1;
+    int32_t *vals0, *vals1;
     double *xs, *ys;
-    int32_t* E;                    // [4^L] upper bounds
+    int32_t* E;                    // [4^Lt] upper bounds per table cell
     unsigned long long* counter;   // [0] selected count
     void* cub_tmp;
     int64_t cub_tmp_bytes;
-    int L;
+    int Lt;
     int64_t total;
 };
 
-static int knn_level(int64_t n) {
+static int knn_table_level(int64_t n) {
     int L = 4;
-    while (L < kMaxLevel && ((int64_t)1 << (2 * (L - 1))) < n) ++L;   // ~ceil(log2(sqrt(n))) + 1
+    while (L < kTableLevelMax && ((int64_t)1 << (2 * (L - 1))) < n) ++L;   // ~ one particle per 4 table cells
     return L;
 }
 
 static KnnLayout carve_knn(void* ws, int64_t bytes, int64_t n, bool* ok) {
     KnnLayout l;
-    l.L = knn_level(n);
-    const int64_t ncell = (int64_t)1 << (2 * l.L);
+    l.Lt = knn_table_level(n);
+    const int64_t ncell = (int64_t)1 << (2 * l.Lt);
     SoArena a(ws, bytes);
-    l.keys0 = a.take<int32_t>(n);
+    l.keys0 = a.take<uint32_t>(n);
     l.vals0 = a.take<int32_t>(n);
-    l.keys1 = a.take<int32_t>(n);
+    l.keys1 = a.take<uint32_t>(n);
     l.vals1 = a.take<int32_t>(n);
     l.xs = a.take<double>(n);
     l.ys = a.take<double>(n);
     l.E = a.take<int32_t>(ncell);
     l.counter = a.take<unsigned long long>(2);
     size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs((void*)nullptr, b1, (const int32_t*)nullptr, (int32_t*)nullptr,
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, b1, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (const int32_t*)nullptr, (int32_t*)nullptr, (int)(n > 0 ? n : 1), 0, 32);
     cub::DeviceScan::InclusiveScan((void*)nullptr, b2, (int32_t*)nullptr, (int32_t*)nullptr, cub::Max(), (int)ncell);
     l.cub_tmp_bytes = (int64_t)(b1 > b2 ? b1 : b2);
@@ -63,8 +67,8 @@ static KnnLayout carve_knn(void* ws, int64_t bytes, int64_t n, bool* ok) {
     return l;
 }
 
-__host__ __device__ __forceinline__ uint32_t spread_bits(uint32_t v) {   // 12 bits -> even bit positions
-    v &= 0xfff;
+__host__ __device__ __forceinline__ uint32_t spread_bits(uint32_t v) {   // 16 bits -> even bit positions
+    v &= 0xffff;
     v = (v | (v << 8)) & 0x00ff00ff;
     v = (v | (v << 4)) & 0x0f0f0f0f;
     v = (v | (v << 2)) & 0x33333333;
@@ -72,21 +76,28 @@ __host__ __device__ __forceinline__ uint32_t spread_bits(uint32_t v) {   // 12 b
     return v;
 }
 __device__ __forceinline__ uint32_t morton(uint32_t cx, uint32_t cy) { return spread_bits(cx) | (spread_bits(cy) << 1); }
+__device__ __forceinline__ uint32_t compact_bits(uint32_t c) {   // even bit positions -> 16 bits
+    c &= 0x55555555u;
+    c = (c | (c >> 1)) & 0x33333333u; c = (c | (c >> 2)) & 0x0f0f0f0fu;
+    c = (c | (c >> 4)) & 0x00ff00ffu; c = (c | (c >> 8)) & 0xffffu;
+    return c;
+}
 
 __global__ void knn_key_kernel(const double* __restrict__ X, const double* __restrict__ Y,
-                               const int32_t* __restrict__ ix, int64_t n, double hw, double inv_h, int nc,
-                               int32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                               const int32_t* __restrict__ ix, int64_t n, double hw, double inv_h,
+                               uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
                                unsigned long long* __restrict__ counter) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool sel = false;
     if (i < n) {
         sel = ix[i] >= 0;
-        int key = nc * nc;   // sentinel: not selected, sorts to the end
+        uint32_t key = kUnselected;
         if (sel) {
+            const int nc = 1 << kBits;
             int cx = (int)((X[i] + hw) * inv_h), cy = (int)((Y[i] + hw) * inv_h);
             cx = max(0, min(nc - 1, cx));
             cy = max(0, min(nc - 1, cy));
-            key = (int)morton((uint32_t)cx, (uint32_t)cy);
+            key = morton((uint32_t)cx, (uint32_t)cy);
         }
         keys[i] = key;
         vals[i] = (int32_t)i;
@@ -105,99 +116,170 @@ __global__ void knn_gather_kernel(const double* __restrict__ X, const double* __
     ys[i] = Y[p];
 }
 
-// E[c] = i + 1 at the last sorted element of code c (others stay 0); a max-scan then makes
-// E[c] = #selected particles with code <= c
-__global__ void knn_mark_kernel(const int32_t* __restrict__ keys, int64_t n, int ncell, int32_t* __restrict__ E) {
+// E[c] = i + 1 at the last sorted element of table cell c (others stay 0); a max-scan then makes
+// E[c] = #selected particles whose table cell is <= c
+__global__ void knn_mark_kernel(const uint32_t* __restrict__ keys, int64_t n, int tshift, int32_t* __restrict__ E) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int k = keys[i];
-    if (k >= ncell) return;
-    if (i + 1 == n || keys[i + 1] != k) E[k] = (int32_t)(i + 1);
+    const uint32_t k = keys[i];
+    if (k >= kUnselected) return;
+    if (i + 1 == n || (keys[i + 1] >> tshift) != (k >> tshift)) E[k >> tshift] = (int32_t)(i + 1);
 }
 
+// scan sorted positions [a, b) minus the window [wa, wb) that is already in the list
 __device__ __forceinline__ void knn_scan_range(const double* __restrict__ xs, const double* __restrict__ ys,
-                                               int a, int b, double x, double y, double* best, int k, int stride) {
+                                               int a, int b, int wa, int wb, double x, double y, double* best, int k,
+                                               int stride) {
+    double kth = best[(k - 1) * stride];
+    if (a >= wa && a < wb) a = wb;                        // range starts inside the pre-scanned window
     for (int q = a; q < b; ++q) {
+        if (q == wa) { q = wb; if (q >= b) break; }       // skip the pre-scanned window
         const double dx = xs[q] - x, dy = ys[q] - y;
         const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (d2 < best[(k - 1) * stride]) {
+        if (d2 < kth) {
             int j = k - 1;
             while (j > 0 && best[(j - 1) * stride] > d2) {
                 best[j * stride] = best[(j - 1) * stride];
                 --j;
             }
             best[j * stride] = d2;
+            kth = best[(k - 1) * stride];
         }
     }
 }
 
-// squared distance (in cell units) from (u, v) to the square of node (level, code); 0 inside
-__device__ __forceinline__ double node_dmin2(int level, uint32_t code, int L, double u, double v) {
-    // de-interleave the node coordinates
-    uint32_t cx = code & 0x55555555u, cy = (code >> 1) & 0x55555555u;
-    cx = (cx | (cx >> 1)) & 0x33333333u; cx = (cx | (cx >> 2)) & 0x0f0f0f0fu; cx = (cx | (cx >> 4)) & 0x00ff00ffu; cx = (cx | (cx >> 8)) & 0xffffu;
-    cy = (cy | (cy >> 1)) & 0x33333333u; cy = (cy | (cy >> 2)) & 0x0f0f0f0fu; cy = (cy | (cy >> 4)) & 0x00ff00ffu; cy = (cy | (cy >> 8)) & 0xffffu;
-    const double s = (double)(1u << (L - level));
-    const double x0 = cx * s, y0 = cy * s;
-    const double dx = fmax(fmax(x0 - u, u - (x0 + s)), 0.0);
-    const double dy = fmax(fmax(y0 - v, v - (y0 + s)), 0.0);
-    return dx * dx + dy * dy;
+// conservative lower bound (fine-cell units, FP32) of the distance from (u, v) to the square of the
+// node with cell coordinates (cx, cy) and edge 2^shift: the true distance minus more than the FP32
+// rounding of the inputs; 0 inside
+__device__ __forceinline__ float node_dmin(int shift, uint32_t cx, uint32_t cy, float u, float v) {
+    const float s = (float)(1u << shift);
+    const float x0 = (float)cx * s, y0 = (float)cy * s;
+    const float dx = fmaxf(fmaxf(x0 - u, u - (x0 + s)), 0.f);
+    const float dy = fmaxf(fmaxf(y0 - v, v - (y0 + s)), 0.f);
+    return fmaxf(sqrtf(dx * dx + dy * dy) * (1.f - 1e-5f) - 1.6e-2f, 0.f);
 }
 
-__global__ void knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
-                                 const int32_t* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
-                                 const int32_t* __restrict__ E, int L, double hw, double inv_h, int k,
+// first position in [a, b) whose key is >= key (keys ascending)
+__device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys, int a, int b, uint32_t key) {
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (keys[mid] < key) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+
+struct KnnTree {
+    const uint32_t* keys;
+    const int32_t* E;
+    int Lt;       // table level
+    int nsel;
+};
+
+// sorted range of node (level, code): table look-up down to level Lt, bisection inside the table cell below
+__device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t code, int& a, int& b) {
+    if (level <= t.Lt) {
+        const int sh = 2 * (t.Lt - level);
+        a = (code == 0) ? 0 : t.E[(code << sh) - 1];
+        b = t.E[((code + 1) << sh) - 1];
+    } else {
+        const uint32_t tc = code >> (2 * (level - t.Lt));
+        const int ta = (tc == 0) ? 0 : t.E[tc - 1], tb = t.E[tc];
+        const int sh = 2 * (kBits - level);
+        a = lower_bound_key(t.keys, ta, tb, code << sh);
+        b = lower_bound_key(t.keys, a, tb, (code + 1) << sh);
+    }
+}
+
+// One thread per query, in Morton order (neighbouring lanes walk neighbouring parts of the tree).
+//  1. the 2k+1 sorted neighbours of the query (itself included) give a first k-best list: an upper
+//     bound r on the k-th distance that is already tight in the bulk of a smooth distribution;
+//  2. the walk starts at the (at most four) tree nodes of the level whose cells are >= 2r wide and
+//     that cover the box [u-r, u+r] x [v-r, v+r], instead of at the root;
+//  3. depth-first, nearest child first, pruning on the current k-th best; leaves (<= kLeaf points
+//     or finest level) are scanned, skipping the window of step 1.
+// The tree is 15 levels deep whatever the particle number, so the dense cores of a clustered
+// catalogue (hundreds of particles per table cell) are resolved instead of being scanned linearly.
+__global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
+                                 const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
+                                 const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
                                  const unsigned long long* __restrict__ counter, double* __restrict__ dk) {
     extern __shared__ double s_best[];
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int pid = vals[s];
-    const int key = keys[s];
-    const int ncell = 1 << (2 * L);
-    if (key >= ncell) { dk[pid] = 0.0; return; }
+    if (keys[s] >= kUnselected) { dk[pid] = 0.0; return; }
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    if ((unsigned long long)k > *counter) { dk[pid] = INF; return; }
+    KnnTree t{keys, E, Lt, (int)*counter};
+    if (k > t.nsel) { dk[pid] = INF; return; }
     const int stride = blockDim.x;
     double* best = s_best + threadIdx.x;
     for (int j = 0; j < k; ++j) best[j * stride] = INF;
     const double x = xs[s], y = ys[s];
-    const double u = (x + hw) * inv_h, v = (y + hw) * inv_h;     // cell units, as used for the keys
-    const double h2 = 1.0 / (inv_h * inv_h) * (1.0 - 1e-9);      // cell units^2 -> length^2, conservative
+    const double ud = (x + hw) * inv_h, vd = (y + hw) * inv_h;   // fine-cell units, as used for the keys
+    const float u = (float)ud, v = (float)vd;
+    const double h = 1.0 / inv_h;                                 // fine-cell units -> length
 
-    uint32_t stack[kStack];       // (level << 26) | code
+    // 1. window of sorted neighbours
+    int wb = min(t.nsel, (int)s + k + 1);
+    const int wa = max(0, wb - (2 * k + 1));
+    wb = min(t.nsel, wa + 2 * k + 1);
+    knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
+
+    // 2. start nodes
+    uint32_t stack[kStack];       // node = (1 << 2 level) | code: the leading one marks the level
     int sp = 0;
-    stack[sp++] = 0u;             // root: level 0, code 0
+    {
+        const double rc = sqrt(best[(k - 1) * stride]) * inv_h * (1.0 + 1e-9) + 1e-9;   // fine-cell units
+        int e = 0;
+        if (rc >= 0.5) e = ilogb(2.0 * rc) + 1;                 // 2^e >= 2 rc
+        if (!(rc < (double)(1 << kBits)) || e >= kBits) {
+            stack[sp++] = 1u;                                   // root
+        } else {
+            const int level = kBits - e;
+            const double sc = (double)(1 << e);
+            const int top = (1 << level) - 1;
+            const int cx0 = max(0, min(top, (int)floor((ud - rc) / sc))), cx1 = max(0, min(top, (int)floor((ud + rc) / sc)));
+            const int cy0 = max(0, min(top, (int)floor((vd - rc) / sc))), cy1 = max(0, min(top, (int)floor((vd + rc) / sc)));
+            for (int cy = cy0; cy <= cy1; ++cy)
+                for (int cx = cx0; cx <= cx1; ++cx) {
+                    stack[sp++] = (1u << (2 * level)) | morton((uint32_t)cx, (uint32_t)cy);
+                }
+        }
+    }
+
+    // 3. pruned depth-first walk
     while (sp > 0) {
         const uint32_t node = stack[--sp];
-        const int level = (int)(node >> 26);
-        const uint32_t code = node & 0x3ffffffu;
-        const int sh = 2 * (L - level);
-        const int a = (code == 0) ? 0 : E[(code << sh) - 1];
-        const int b = E[((code + 1) << sh) - 1];
+        const int level = (31 - __clz(node)) >> 1;
+        const uint32_t code = node ^ (1u << (2 * level));
+        const uint32_t ncx = compact_bits(code), ncy = compact_bits(code >> 1);
+        const double dm = (double)node_dmin(kBits - level, ncx, ncy, u, v) * h;
+        if (dm * dm >= best[(k - 1) * stride]) continue;
+        int a, b;
+        node_range(t, level, code, a, b);
         if (a == b) continue;
-        if (node_dmin2(level, code, L, u, v) * h2 >= best[(k - 1) * stride]) continue;
-        if (b - a <= kLeaf || level == L) {
-            knn_scan_range(xs, ys, a, b, x, y, best, k, stride);
+        if (b - a <= kLeaf || level == kBits) {
+            knn_scan_range(xs, ys, a, b, wa, wb, x, y, best, k, stride);
             continue;
         }
         // children, pushed farthest first so the nearest is expanded next
         uint32_t cc[4];
-        double dd[4];
+        float dd[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             cc[c] = (code << 2) | c;
-            dd[c] = node_dmin2(level + 1, cc[c], L, u, v);
+            dd[c] = node_dmin(kBits - level - 1, (ncx << 1) + (c & 1), (ncy << 1) + (c >> 1), u, v);
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3 - i; ++j)
                 if (dd[j] < dd[j + 1]) {
-                    const double td = dd[j]; dd[j] = dd[j + 1]; dd[j + 1] = td;
+                    const float td = dd[j]; dd[j] = dd[j + 1]; dd[j + 1] = td;
                     const uint32_t tc = cc[j]; cc[j] = cc[j + 1]; cc[j + 1] = tc;
                 }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) stack[sp++] = ((uint32_t)(level + 1) << 26) | cc[c];
+        for (int c = 0; c < 4; ++c) stack[sp++] = (1u << (2 * level + 2)) | cc[c];
     }
     dk[pid] = sqrt(best[(k - 1) * stride]);
 }
@@ -224,26 +306,25 @@ extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32
     size_t smem = (size_t)k * threads * sizeof(double);
     if (smem > 200 * 1024) { threads = 32; smem = (size_t)k * threads * sizeof(double); }
     if (smem > 200 * 1024) return SO_ERR_UNSUPPORTED;
-    const int L = l.L;
-    const int nc = 1 << L;
-    const int ncell = nc * nc;
-    const double inv_h = nc / (2.0 * half_width);
+    const int Lt = l.Lt;
+    const int ncell = 1 << (2 * Lt);
+    const double inv_h = (double)(1 << kBits) / (2.0 * half_width);
     SO_CUDA(cudaMemsetAsync(l.counter, 0, 2 * sizeof(unsigned long long), st));
     SO_CUDA(cudaMemsetAsync(l.E, 0, sizeof(int32_t) * (size_t)ncell, st));
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    knn_key_kernel<<<blocks, 256, 0, st>>>(X, Y, ix, n, half_width, inv_h, nc, l.keys0, l.vals0, l.counter);
+    knn_key_kernel<<<blocks, 256, 0, st>>>(X, Y, ix, n, half_width, inv_h, l.keys0, l.vals0, l.counter);
     SO_LAUNCH_CHECK();
     size_t tmp = (size_t)l.cub_tmp_bytes;
-    SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, l.keys0, l.keys1, l.vals0, l.vals1, (int)n, 0, 2 * L + 1, st));
+    SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, l.keys0, l.keys1, l.vals0, l.vals1, (int)n, 0, 2 * kBits + 1, st));
     knn_gather_kernel<<<blocks, 256, 0, st>>>(X, Y, l.vals1, n, l.xs, l.ys);
     SO_LAUNCH_CHECK();
-    knn_mark_kernel<<<blocks, 256, 0, st>>>(l.keys1, n, ncell, l.E);
+    knn_mark_kernel<<<blocks, 256, 0, st>>>(l.keys1, n, 2 * (kBits - Lt), l.E);
     SO_LAUNCH_CHECK();
     tmp = (size_t)l.cub_tmp_bytes;
     SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), ncell, st));
     SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-        l.xs, l.ys, l.keys1, l.vals1, n, l.E, L, half_width, inv_h, k, l.counter, dk);
+        l.xs, l.ys, l.keys1, l.vals1, n, l.E, Lt, half_width, inv_h, k, l.counter, dk);
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

@@ -42,7 +42,129 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
         }
 }
 
+// ---- np.median of float64 arrays by 8-bit radix selection (no sort) --------------------------------
+// order-preserving map double -> uint64 (negative values: all bits flipped, others: sign bit set)
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+struct SelectState {
+    unsigned long long prefix;      // high bytes of the selected key found so far
+    unsigned long long rank;        // rank of the wanted element among the keys that match the prefix
+    unsigned long long below_max;   // largest key below the selected one (0 if none)
+    unsigned int hist[256];
+};
+
+// pass p: histogram of byte (7 - p) over the keys whose p high bytes equal the prefix
+__global__ void __launch_bounds__(512) select_hist_kernel(const double* __restrict__ x, int64_t n, int64_t stride,
+                                                          SelectState* __restrict__ st, int pass) {
+    __shared__ unsigned int s_h[256];
+    const double* xa = x + (size_t)blockIdx.y * stride;
+    SelectState* sa = st + blockIdx.y;
+    if (threadIdx.x < 256) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long prefix = sa->prefix;
+    const int hs = 64 - 8 * pass;                   // bits above the byte of this pass
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = f64_key(xa[i]);
+        if (pass == 0 || (k >> hs) == (prefix >> hs)) atomicAdd(&s_h[(k >> (hs - 8)) & 255], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256 && s_h[threadIdx.x]) atomicAdd(&sa->hist[threadIdx.x], s_h[threadIdx.x]);
+}
+
+// one block per array: pick the byte value whose bin holds the wanted rank, descend into it
+__global__ void __launch_bounds__(256) select_pick_kernel(SelectState* __restrict__ st, int pass) {
+    __shared__ unsigned int s_h[256];
+    SelectState* sa = st + blockIdx.x;
+    s_h[threadIdx.x] = sa->hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long r = sa->rank, acc = 0;
+        int b = 0;
+        for (; b < 255; ++b) {
+            if (acc + s_h[b] > r) break;
+            acc += s_h[b];
+        }
+        sa->rank = r - acc;
+        sa->prefix |= (unsigned long long)b << (56 - 8 * pass);
+    }
+    __syncthreads();
+    sa->hist[threadIdx.x] = 0;
+}
+
+// largest key strictly below the selected one (the lower middle element when n is even and distinct)
+__global__ void __launch_bounds__(512) select_below_kernel(const double* __restrict__ x, int64_t n, int64_t stride,
+                                                           SelectState* __restrict__ st) {
+    const double* xa = x + (size_t)blockIdx.y * stride;
+    SelectState* sa = st + blockIdx.y;
+    const unsigned long long sel = sa->prefix;
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = f64_key(xa[i]);
+        if (k < sel && k > m) m = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&sa->below_max, m);
+}
+
+// np.median: element n//2 for odd n, mean of elements n//2 - 1 and n//2 for even n.  After the
+// eight passes sa->rank is the rank of the selected value among its duplicates: when it is > 0
+// (or n is odd) the lower middle element equals the upper one
+__global__ void select_finish_kernel(const SelectState* __restrict__ st, int64_t n, double* __restrict__ out) {
+    const SelectState* sa = st + threadIdx.x;
+    const double hi = key_f64(sa->prefix);
+    double lo = hi;
+    if ((n & 1) == 0 && sa->rank == 0) lo = key_f64(sa->below_max);
+    out[threadIdx.x] = (n & 1) ? hi : __dmul_rn(__dadd_rn(lo, hi), 0.5);
+}
+
+__global__ void select_init_kernel(SelectState* __restrict__ st, int64_t n) {
+    SelectState* sa = st + blockIdx.x;
+    if (threadIdx.x == 0) { sa->prefix = 0; sa->rank = (unsigned long long)(n / 2); sa->below_max = 0; }
+    sa->hist[threadIdx.x] = 0;
+}
+
 }  // namespace
+
+extern "C" int64_t so_median_workspace_bytes(int32_t n_arrays) {
+    return so_align_up((int64_t)n_arrays * (int64_t)sizeof(SelectState), 256) + 256;
+}
+
+extern "C" int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !out || n < 1 || n_arrays < 1 || n_arrays > 1024 || stride < n) return SO_ERR_BAD_ARG;
+    SoArena a(workspace, workspace_bytes);
+    SelectState* state = a.take<SelectState>(n_arrays);
+    if (!workspace || !a.ok()) return SO_ERR_WORKSPACE;
+    int64_t blocks = (n + 512 * 8 - 1) / (512 * 8);
+    if (blocks > 2 * so_num_sms()) blocks = 2 * so_num_sms();
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, (unsigned)n_arrays);
+    select_init_kernel<<<n_arrays, 256, 0, st>>>(state, n);
+    SO_LAUNCH_CHECK();
+    for (int pass = 0; pass < 8; ++pass) {
+        select_hist_kernel<<<grid, 512, 0, st>>>(x, n, stride, state, pass);
+        SO_LAUNCH_CHECK();
+        select_pick_kernel<<<n_arrays, 256, 0, st>>>(state, pass);
+        SO_LAUNCH_CHECK();
+    }
+    select_below_kernel<<<grid, 512, 0, st>>>(x, n, stride, state);
+    SO_LAUNCH_CHECK();
+    select_finish_kernel<<<1, n_arrays, 0, st>>>(state, n, out);
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
 
 extern "C" const char* so_version(void) { return "synthobs_b200 0.1 (sm_100a, " __DATE__ ")"; }
 

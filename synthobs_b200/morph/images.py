@@ -263,10 +263,18 @@ def core(X, Y, L, resolution=0.1, ndim=100, smoothing=False, verbose=False):
 
 
 def median_device(x):
-    """np.median semantics (mean of the two middle values for even n) on a CUDA tensor."""
-    srt = torch.sort(x.reshape(-1)).values
-    m = srt.numel()
-    return srt[m // 2] if m % 2 else 0.5 * (srt[m // 2 - 1] + srt[m // 2])
+    """np.median of a CUDA float64 tensor (mean of the two middle values for even n) as a 0-d
+    CUDA tensor; [m, n] input -> [m] medians of the rows.  Radix selection (so_median_f64), no sort."""
+    _cabi.require_device()
+    x2 = x.reshape(1, -1) if x.dim() == 1 else x
+    x2 = x2.to(torch.float64).contiguous()
+    m, n = x2.shape
+    out = torch.empty(m, dtype=torch.float64, device=x2.device)
+    wsb = _cabi.lib.so_median_workspace_bytes(m)
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_median_f64(_cabi.ptr(x2), n, m, x2.stride(0), _cabi.ptr(out), _cabi.ptr(ws), wsb,
+                                        _cabi.stream()), 'so_median_f64')
+    return out[0] if x.dim() == 1 else out
 
 
 def particle_device_multi(obs_list, Xd, Yd, Ld):

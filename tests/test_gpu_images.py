@@ -257,3 +257,22 @@ def test_analytic_sources_match_reference():
                       PSFs={'JWST.NIRCAM.F150W': psf, 'JWST.NIRCAM.F356W': psf2})
     r = image_oracle.point_source(9.0, 0.063, 0.9, psf2, xoffset_pix=xo, yoffset_pix=yo)
     assert_image_close(P['JWST.NIRCAM.F356W'].data, r['data'])
+
+
+def test_median_matches_numpy_bitwise():
+    """so_median_f64 (radix selection) == np.median bit for bit: odd / even n, duplicates around the
+    middle, negative values, batched rows"""
+    import torch
+    from synthobs_b200.morph import images
+    rng = np.random.default_rng(17)
+    cases = [rng.normal(0, 3, 1001), rng.normal(0, 3, 1000), np.array([2.5]), np.array([1.0, -3.0]),
+             np.concatenate([np.full(50, 0.25), rng.normal(0.25, 1e-3, 49)]),
+             np.concatenate([np.full(40, -1.5), np.full(40, 2.0)]),
+             np.round(rng.normal(0, 2, 5000), 1), -np.abs(rng.normal(5, 1, 4096)) * 1e-300,
+             rng.normal(0, 1, 300001) * 1e200]
+    for a in cases:
+        got = float(images.median_device(torch.from_numpy(a).cuda()).cpu())
+        assert got == np.median(a), (a.size, got, np.median(a))
+    rows = rng.normal(1.0, 5.0, (7, 2048))
+    got = images.median_device(torch.from_numpy(rows).cuda()).cpu().numpy()
+    assert np.array_equal(got, np.median(rows, axis=1))
