@@ -186,45 +186,71 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ i
     }
 }
 
-// one warp per particle, only for supports wider than kWideW (marked wnorm < 0)
+// supports wider than kWideW (marked wnorm < 0): each warp looks at 32 consecutive particles and sums the
+// factors of the marked ones cooperatively, one particle at a time
 __global__ void __launch_bounds__(256) plan_wide_kernel(int64_t n, int ndim, PlanView pv) {
     const int lane = threadIdx.x & 31;
-    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (p >= n) return;
-    if (!(pv.wnorm[p] < 0.f)) return;
-    const int ip = pv.ix[p], jp = pv.iy[p], W = pv.W[p];
-    const float cpx = pv.cpx[p], ux = pv.ux[p], uy = pv.uy[p];
-    const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
-    const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
-    float sx = 0.f, sy = 0.f;
-    for (int k = kx0 + lane; k <= kx1; k += 32) sx += gauss_factor(cpx, k, ux);
-    for (int k = ky0 + lane; k <= ky1; k += 32) sy += gauss_factor(cpx, k, uy);
-    sx = warp_sum(sx);
-    sy = warp_sum(sy);
-    __syncwarp();
-    if (lane == 0) pv.wnorm[p] = 1.0f / (sx * sy);
+    const int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
+    if (base >= n) return;
+    const int64_t mine = base + lane;
+    unsigned todo = __ballot_sync(0xffffffffu, mine < n && pv.wnorm[mine] < 0.f);
+    while (todo) {
+        const int64_t p = base + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const int ip = pv.ix[p], jp = pv.iy[p], W = pv.W[p];
+        const float cpx = pv.cpx[p], ux = pv.ux[p], uy = pv.uy[p];
+        const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
+        const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
+        float sx = 0.f, sy = 0.f;
+        for (int k = kx0 + lane; k <= kx1; k += 32) sx += gauss_factor(cpx, k, ux);
+        for (int k = ky0 + lane; k <= ky1; k += 32) sy += gauss_factor(cpx, k, uy);
+        sx = warp_sum(sx);
+        sy = warp_sum(sy);
+        __syncwarp();
+        if (lane == 0) pv.wnorm[p] = 1.0f / (sx * sy);
+    }
 }
 
-// one warp per particle: write its (tile, pid) pairs at offs[p].. (row-major over the tile box)
+// (tile, pid) pairs at offs[p].. (row-major over the particle's tile box).  One thread per particle writes
+// short lists itself; the particles of a warp with more than kExpandSerial pairs are then expanded by
+// the whole warp, one particle at a time
+constexpr int kExpandSerial = 8;
 __global__ void __launch_bounds__(256) expand_kernel(PlanView pv, int64_t n, int ndim, int ntx,
                                                      int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int lane = threadIdx.x & 31;
-    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (p >= n) return;
-    const int ip = pv.ix[p];
-    if (ip < 0) return;
-    const int jp = pv.iy[p], W = pv.W[p];
-    const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
-    const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
-    const int tx0 = (ip + kx0) / kT, tx1 = (ip + kx1) / kT;
-    const int ty0 = (jp + ky0) / kT, ty1 = (jp + ky1) / kT;
-    const int nx = tx1 - tx0 + 1;
-    const int cnt = nx * (ty1 - ty0 + 1);
-    const int64_t o = pv.offs[p];
-    for (int q = lane; q < cnt; q += 32) {
-        const int ty = ty0 + q / nx, tx = tx0 + q % nx;
-        keys[o + q] = ty * ntx + tx;
-        vals[o + q] = (int32_t)p;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int tx0 = 0, ty0 = 0, nx = 0, cnt = 0;
+    int64_t o = 0;
+    if (p < n) {
+        const int ip = pv.ix[p];
+        if (ip >= 0) {
+            const int jp = pv.iy[p], W = pv.W[p];
+            const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
+            const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
+            tx0 = (ip + kx0) / kT;
+            ty0 = (jp + ky0) / kT;
+            nx = (ip + kx1) / kT - tx0 + 1;
+            cnt = nx * ((jp + ky1) / kT - ty0 + 1);
+            o = pv.offs[p];
+            if (cnt <= kExpandSerial)
+                for (int q = 0; q < cnt; ++q) {
+                    keys[o + q] = (ty0 + q / nx) * ntx + tx0 + q % nx;
+                    vals[o + q] = (int32_t)p;
+                }
+        }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, cnt > kExpandSerial);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int c = __shfl_sync(0xffffffffu, cnt, src), w = __shfl_sync(0xffffffffu, nx, src);
+        const int x0 = __shfl_sync(0xffffffffu, tx0, src), y0 = __shfl_sync(0xffffffffu, ty0, src);
+        const int64_t oo = __shfl_sync(0xffffffffu, o, src);
+        const int32_t pid = (int32_t)(p - lane + src);
+        for (int q = lane; q < c; q += 32) {
+            keys[oo + q] = (y0 + q / w) * ntx + x0 + q % w;
+            vals[oo + q] = pid;
+        }
     }
 }
 
@@ -596,7 +622,7 @@ extern "C" int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X
     plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix, iy, X, Y, dk, n, G, ndim, support_sigmas, pv);
     SO_LAUNCH_CHECK();
     if (dk) {
-        plan_wide_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(n, ndim, pv);
+        plan_wide_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ndim, pv);
         SO_LAUNCH_CHECK();
     }
     size_t tmp = (size_t)pv.cub_tmp_bytes;
@@ -637,8 +663,7 @@ extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64
         if (hist) SO_CUDA(cudaMemsetAsync(hist, 0, img_bytes, st));
         return SO_OK;
     }
-    const int64_t pthreads = n * 32;
-    expand_kernel<<<(unsigned)((pthreads + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, d.keys0, d.vals0);
+    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, d.keys0, d.vals0);
     SO_LAUNCH_CHECK();
     int bits = 1;
     while ((1 << bits) < d.ntiles) ++bits;

@@ -87,26 +87,57 @@ def rebin(arr, new_shape):
     return dv.to_host(rebin_device(dv.to_dev(arr, torch.float32), new_shape[0]))
 
 
+KERNEL_CROP_EPS = 1e-14     # kernel elements below this fraction of the peak are outside the cropped support
+
+
+def _fft_len(n):
+    """smallest 2^a 3^b 5^c 7^d >= n (the radices cuFFT runs at full speed)"""
+    best = 1 << (int(n) - 1).bit_length()
+    p7 = 1
+    while p7 < best:
+        p5 = p7
+        while p5 < best:
+            p3 = p5
+            while p3 < best:
+                m = p3
+                while m < n:
+                    m *= 2
+                best = min(best, m)
+                p3 *= 3
+            p5 *= 5
+        p7 *= 7
+    return best
+
+
 class KernelSpectrum:
-    """A convolution kernel prepared for an image size: normalised (float64), zero-padded,
-    transformed once.  Re-usable across calls (the PSF image of an observed() set-up only
-    depends on its geometry)."""
+    """A convolution kernel prepared for an image size: normalised (float64), cropped to the box
+    that holds every element above KERNEL_CROP_EPS of its peak (a PSF sampled on the full
+    super-sampled grid, images.py:198-200, is mostly exact or negligible zeros: the dropped mass
+    is < 1e-8 of the flux and the transforms shrink from 2n to ~n), zero-padded, transformed
+    once.  Re-usable across calls (the PSF image of an observed() set-up only depends on its
+    geometry)."""
 
     def __init__(self, kernel, n_y, n_x):
-        import scipy.fft as sfft
         dev = dv.device()
         if isinstance(kernel, torch.Tensor):
             k = kernel.to(dev, torch.float64)
-            k = (k / k.sum(dim=(-2, -1), keepdim=True)).to(torch.float32)
         else:
-            kh = np.asarray(kernel, dtype=np.float64)
-            k = dv.to_dev((kh / kh.sum(axis=(-2, -1), keepdims=True)).astype(np.float32), torch.float32)
+            k = dv.to_dev(np.asarray(kernel, dtype=np.float64))
+        k = k / k.sum(dim=(-2, -1), keepdim=True)
         self.per_image = k.dim() == 3
         self.n_kernels = k.shape[0] if self.per_image else 1
+        cy, cx = k.shape[-2] // 2, k.shape[-1] // 2            # astropy centres the kernel on element n//2
+        a = k.abs().reshape(-1, k.shape[-2], k.shape[-1])
+        big = (a > KERNEL_CROP_EPS * a.amax(dim=(-2, -1), keepdim=True)).any(dim=0)
+        rows = torch.nonzero(big.any(dim=1)).reshape(-1)
+        cols = torch.nonzero(big.any(dim=0)).reshape(-1)
+        r0, r1 = min(int(rows[0]), cy), max(int(rows[-1]), cy) + 1   # the box always contains the centre element
+        c0, c1 = min(int(cols[0]), cx), max(int(cols[-1]), cx) + 1
+        k = k[..., r0:r1, c0:c1].to(torch.float32).contiguous()
         self.n_y, self.n_x = n_y, n_x
-        self.py = sfft.next_fast_len(n_y + k.shape[-2] - 1, real=True)
-        self.px = sfft.next_fast_len(n_x + k.shape[-1] - 1, real=True)
-        self.oy, self.ox = k.shape[-2] // 2, k.shape[-1] // 2     # astropy centres the kernel on element n//2
+        self.py = _fft_len(n_y + k.shape[-2] - 1)
+        self.px = _fft_len(n_x + k.shape[-1] - 1)
+        self.oy, self.ox = cy - r0, cx - c0
         self.K = torch.fft.rfft2(k, s=(self.py, self.px)).contiguous()   # 2-D rfft2 returns a strided view
 
 
