@@ -148,6 +148,7 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')    # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     _cabi.require_device()
     dev = torch.device('cuda', local)

@@ -9,6 +9,7 @@
 //   synthobs/sed/models.py:88-135, :153-200  per-particle loop of generate_{L,F}nu_array
 //   synthobs/sed/models.py:74-85, :139-150   np.sum of generate_{L,F}nu
 //   synthobs/sed/models.py:108-114           NGP argmin (via float64 thresholds, see header)
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -21,6 +22,7 @@ constexpr int kItem = kThreads * kPerThread;  // particles per work item
 constexpr int kMaxThr = 127;                  // max thresholds per axis (kernel-parameter resident)
 constexpr int kLut = 6144;                    // index table entries per axis (256 per octave, 24 octaves)
 constexpr int kLutShift = 12;                 // bin = (high 32 bits of the double >> 12): exponent + 8 mantissa bits
+constexpr int kPrefetchItems = 1;               // L2 prefetch distance in work items, sums-only variant (measured: 1 best, 0.260 -> 0.241 ms)
 constexpr int kYWarp = 32 * (kPerThread + 1); // per-warp buffer of compacted young particles (< 32 left over + one item)
 
 // One NGP axis: ascending float64 thresholds + an index table over bins of the double's own bit
@@ -59,6 +61,7 @@ struct BroadbandParams {
     float* out_pf;                // [F_total, n]
     double* partial;              // [n_items, F_total]
     int32_t* out_cell;
+    int32_t prefetch;             // L2 prefetch distance in work items (0 = off)
     Axis age, z;
 };
 
@@ -159,6 +162,17 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
 
         double age[kPerThread], zz[kPerThread];
         float mm[kPerThread], ti[kPerThread], tb[kPerThread];
+        if (p.prefetch > 0 && item + p.prefetch < item_hi) {
+            // pull a later item's 128-byte lines towards L2 while this one is being processed
+            // (contiguous in memory unless a galaxy boundary intervenes: then the hint is merely wasted)
+            constexpr int kLines = kItem * 8 / 128;          // lines per array per item
+            if (tid < 5 * kLines) {
+                const int arr = tid / kLines, line = tid - arr * kLines;
+                const double* base = arr == 0 ? p.ages : arr == 1 ? p.metals : arr == 2 ? p.masses : arr == 3 ? p.tau_ism : p.tau_bc;
+                const int64_t idx = begin + (int64_t)p.prefetch * kItem + line * 16;
+                if (base && idx < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + idx));
+            }
+        }
         if (count == kItem) {
             // full item (all but the last of a galaxy): plain strided loads off one base offset
             const int64_t i0 = begin + tid;
@@ -573,6 +587,8 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
     fill_axis(p.age, age_thr, na - 1);
     fill_axis(p.z, z_thr, nz - 1);
     p.tab_inc = tab_inc; p.tab_tn = tab_tn; p.n_filters_total = n_filters;
+    // the per-particle-output variant is store-bound and loses with the prefetch (measured): off there
+    { const char* e = getenv("SO_SED_PREFETCH"); p.prefetch = e ? atoi(e) : (out_pf ? 0 : kPrefetchItems); }
     p.fesc = (float)fesc; p.out_pf = out_pf; p.partial = out_sums ? partial : nullptr; p.out_cell = out_cell;
 
     if (segmented) {
