@@ -1,8 +1,11 @@
 """Drop-in alias: `import synthobs` resolves to the B200 implementation
 (synthobs_b200).  Only the hot-path modules exist: synthobs.sed.models,
-synthobs.morph.images, synthobs.morph.PSF."""
+synthobs.morph.images, synthobs.morph.PSF, synthobs.core (particle-schema loaders)."""
 
 from synthobs_b200 import empty, __version__  # noqa: F401
 from . import sed, morph  # noqa: F401
+from synthobs_b200 import core  # noqa: F401
+import sys as _sys
+_sys.modules[__name__ + '.core'] = core
 
 __all__ = ['morph', 'sed']

@@ -70,3 +70,33 @@ def test_observed_geometry_matches_oracle():
         for k in ('pixel_scale', 'pixel_scale_kpc', 'ndim', 'width_arcsec', 'width', 'resolution', 'ndim_super',
                   'xoffset', 'yoffset', 'resampling_factor'):
             assert getattr(o, k) == g[k], k
+
+
+def test_core_loaders_roundtrip(tmp_path):
+    """synthobs.core schema (reference core.py:13-89): write synthetic objects, load them back through the
+    reference-named loaders, batch them into CSR."""
+    from synthobs_b200 import core, synthetic
+    root = str(tmp_path) + '/'
+    sizes = {}
+    for i, n in enumerate((300, 120, 900)):
+        p = synthetic.particles(n, seed=50 + i)
+        core.write_object(root + 'snapA/%03d/0' % i, p['X'], p['Y'], p['MetSurfaceDensities'], p['Ages'], p['Metallicities'])
+        sizes['snapA/%03d/0' % i] = n
+    allobj = core.all_test_data('snapA', path_to_example_data=root)
+    assert allobj.N == 3 and list(allobj.M) == sorted(allobj.M)
+    first = allobj.next()
+    assert first.id == 'snapA/001/0' and len(first.Ages) == 120
+    assert np.all(first.Masses == core.PARTICLE_MASS)
+    one = core.get_object_data('snapA', '002', '0', data_path=root[:-1])
+    ref = synthetic.particles(900, seed=52)
+    assert np.array_equal(one.X, ref['X']) and np.array_equal(one.Ages, ref['Ages'])
+    td = core.test_data(root + 'snapA/000/0')
+    assert len(td.X) == 300
+    b = core.csr_batch(allobj.get(i) for i in range(allobj.N))
+    assert list(b['offsets']) == [0, 120, 420, 1320]
+    np.testing.assert_allclose(b['tauVs_ISM'][120:420], ref_t(300, 50)['tauVs_ISM'], rtol=1e-15)
+
+
+def ref_t(n, seed):
+    from synthobs_b200 import synthetic
+    return synthetic.particles(n, seed=seed)
