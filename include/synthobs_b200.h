@@ -160,6 +160,16 @@ int64_t so_knn_workspace_bytes(int64_t n, int32_t k);
 int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
                         int32_t k, double half_width, double* dk,
                         void* workspace, int64_t workspace_bytes, void* stream);
+/* The same search over ALL positions, answered only for part `part` of `n_parts` equal shares of
+ * the selected particles taken in Morton order (a spatially compact share: the partition used when
+ * one huge image is split over GPUs, BASELINE config 5).  dk is written for this share only.
+ * order_out (optional): [n] int32, the Morton-sorted permutation (selected particles first);
+ * range_out (optional): DEVICE int64[3] = {begin, end} of this share in that order, and the
+ * number of selected particles. */
+int so_knn_kth_distance_part(const double* X, const double* Y, const int32_t* ix, int64_t n,
+                             int32_t k, double half_width, int32_t part, int32_t n_parts,
+                             double* dk, int32_t* order_out, int64_t* range_out,
+                             void* workspace, int64_t workspace_bytes, void* stream);
 
 /* K8b..K9 — kernel-smoothed deposition.  Replaces the adaptive loop of
  * images.core (synthobs/morph/images.py:87-97): per particle a Gaussian of

@@ -202,7 +202,8 @@ __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t
 __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
                                  const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
                                  const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
-                                 const unsigned long long* __restrict__ counter, double* __restrict__ dk) {
+                                 const unsigned long long* __restrict__ counter, int part, int n_parts,
+                                 double* __restrict__ dk) {
     extern __shared__ double s_best[];
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -210,6 +211,8 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict
     if (keys[s] >= kUnselected) { dk[pid] = 0.0; return; }
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     KnnTree t{keys, E, Lt, (int)*counter};
+    // this call's share of the queries: a contiguous range of the Morton order (spatially compact)
+    if (s < (int64_t)t.nsel * part / n_parts || s >= (int64_t)t.nsel * (part + 1) / n_parts) return;
     if (k > t.nsel) { dk[pid] = INF; return; }
     const int stride = blockDim.x;
     double* best = s_best + threadIdx.x;
@@ -284,6 +287,14 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict
     dk[pid] = sqrt(best[(k - 1) * stride]);
 }
 
+__global__ void knn_range_kernel(const unsigned long long* __restrict__ counter, int part, int n_parts,
+                                 int64_t* __restrict__ range_out) {
+    const int64_t nsel = (int64_t)*counter;
+    range_out[0] = nsel * part / n_parts;
+    range_out[1] = nsel * (part + 1) / n_parts;
+    range_out[2] = nsel;
+}
+
 }  // namespace
 
 extern "C" int64_t so_knn_workspace_bytes(int64_t n, int32_t k) {
@@ -292,12 +303,12 @@ extern "C" int64_t so_knn_workspace_bytes(int64_t n, int32_t k) {
     return l.total + 256;
 }
 
-extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
-                                   int32_t k, double half_width, double* dk,
-                                   void* workspace, int64_t workspace_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int knn_run(const double* X, const double* Y, const int32_t* ix, int64_t n, int32_t k, double half_width,
+                   int32_t part, int32_t n_parts, double* dk, int32_t* order_out, int64_t* range_out,
+                   void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     if (n == 0) return SO_OK;
     if (n < 0 || k < 1 || !(half_width > 0.0) || !X || !Y || !ix || !dk) return SO_ERR_BAD_ARG;
+    if (n_parts < 1 || part < 0 || part >= n_parts) return SO_ERR_BAD_ARG;
     if (n >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
     bool ok = false;
     KnnLayout l = carve_knn(workspace, workspace_bytes, n, &ok);
@@ -324,7 +335,26 @@ extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32
     SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), ncell, st));
     SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-        l.xs, l.ys, l.keys1, l.vals1, n, l.E, Lt, half_width, inv_h, k, l.counter, dk);
+        l.xs, l.ys, l.keys1, l.vals1, n, l.E, Lt, half_width, inv_h, k, l.counter, part, n_parts, dk);
     SO_LAUNCH_CHECK();
+    if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+    if (range_out) {
+        knn_range_kernel<<<1, 1, 0, st>>>(l.counter, part, n_parts, range_out);
+        SO_LAUNCH_CHECK();
+    }
     return SO_OK;
+}
+
+extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
+                                   int32_t k, double half_width, double* dk,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
+    return knn_run(X, Y, ix, n, k, half_width, 0, 1, dk, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int so_knn_kth_distance_part(const double* X, const double* Y, const int32_t* ix, int64_t n,
+                                        int32_t k, double half_width, int32_t part, int32_t n_parts,
+                                        double* dk, int32_t* order_out, int64_t* range_out,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
+    return knn_run(X, Y, ix, n, k, half_width, part, n_parts, dk, order_out, range_out, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
 }

@@ -141,20 +141,22 @@ def generate_Fnu_sharded(model, F, batch, kind='Fnu', **kw):
 
 
 def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None):
-    """One huge adaptive-smoothed image, particle-block sharded (BASELINE config 5).
-    Every rank holds all positions (the k-NN needs neighbours across blocks), computes the
-    k-th neighbour distance and the deposit only for its own block of particles onto a private
-    full image, then the partial images are summed with one all-reduce.  Returns the full
-    [ndim, ndim] float32 CUDA image on every rank."""
+    """One huge adaptive-smoothed image split over the ranks (BASELINE config 5).  Every rank holds all
+    positions (neighbours cross any partition) and builds the same search tree, but answers the k-NN
+    queries and deposits only for ITS share of the particles: a contiguous range of the Morton order,
+    i.e. a spatially compact block, so the work per rank is 1/N and each partial image touches a
+    fraction of the tiles.  The partial images are summed with one all-reduce (NCCL over NVLink).
+    Returns the full [C, ndim, ndim] (or [ndim, ndim] for 1-D L) float32 CUDA image on every rank."""
     from . import device as dv
     from .morph import images
     rank, ws = world()
     Xd, Yd, Ld = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L)
+    one = Ld.dim() == 1
+    Ld = Ld.reshape(1, -1) if one else Ld
     width, G = images.pixel_grid(resolution, ndim)
     ix, iy = images.ngp_index_device(Xd, Yd, dv.to_dev(G), ndim, width / 2.)
-    dk = images.knn_device(Xd, Yd, ix, int(k), width / 2.)       # all points; queries are cheap to replicate
-    b, e = particle_block(Xd.numel(), rank, ws)
-    r = images.deposit_device(Xd[b:e], Yd[b:e], Ld[..., b:e], resolution, ndim, adaptive_k=int(k), want_ngp=False,
-                              support_sigmas=support_sigmas, dk=dk[b:e])
-    img = r['data'][0]
-    return reduce_image(img)
+    dk, pids = images.knn_device_part(Xd, Yd, ix, int(k), width / 2., rank, ws)
+    r = images.deposit_device(Xd[pids], Yd[pids], Ld[:, pids], resolution, ndim, adaptive_k=int(k), want_ngp=False,
+                              support_sigmas=support_sigmas, dk=dk[pids])
+    img = reduce_image(r['data'])
+    return img[0] if one else img

@@ -48,6 +48,7 @@ except Exception:
     pixel_scale_of = _PixelScaleView()
 
 SUPPORT_SIGMAS = 7.0
+MAX_PAIRS = 1 << 30        # (particle, sub-tile) pairs per binning pass; larger jobs are split by particle halves
 
 
 class empty():
@@ -193,6 +194,24 @@ def knn_device(Xd, Yd, ix, k, half_width):
     return dk
 
 
+def knn_device_part(Xd, Yd, ix, k, half_width, part, n_parts):
+    """k-th neighbour distances for share `part` of `n_parts` of the selected particles in Morton
+    order (searching all positions).  Returns (dk [n] valid for the share only, pids [m] int64:
+    the particles of the share)."""
+    n = Xd.numel()
+    dk = torch.zeros(n, dtype=torch.float64, device=Xd.device)
+    order = torch.empty(n, dtype=torch.int32, device=Xd.device)
+    rng = torch.zeros(3, dtype=torch.int64, device=Xd.device)
+    wsb = _cabi.lib.so_knn_workspace_bytes(n, int(k))
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_knn_kth_distance_part(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), n, int(k),
+                                                   float(half_width), int(part), int(n_parts), _cabi.ptr(dk),
+                                                   _cabi.ptr(order), _cabi.ptr(rng), _cabi.ptr(ws), wsb, _cabi.stream()),
+                'so_knn_kth_distance_part')
+    b, e, _ = (int(v) for v in rng.cpu())
+    return dk, order[b:e].to(torch.int64)
+
+
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
                    support_sigmas=None, dk=None, return_pairs=False):
     """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
@@ -219,6 +238,21 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
                                       _cabi.ptr(dk) if adaptive else None, n, _cabi.ptr(Gd), ndim, float(R),
                                       _cabi.ptr(pws), pws_b, n_pairs, stats, _cabi.stream()), 'so_img_plan')
     npairs = n_pairs.value
+    if npairs > MAX_PAIRS and n > 1:
+        # more (particle, sub-tile) pairs than one binning pass indexes (int32) or should hold in memory:
+        # deposit the two halves of the particle list separately and add the images (the sum is associative)
+        h = n // 2
+        sub = lambda t, a, b: None if t is None else t[..., a:b]   # noqa: E731
+        r1 = deposit_device(Xd[:h], Yd[:h], Ld[:, :h], resolution, ndim, adaptive_k, want_data, want_ngp,
+                            support_sigmas, sub(dk, 0, h), False)
+        r2 = deposit_device(Xd[h:], Yd[h:], Ld[:, h:], resolution, ndim, adaptive_k, want_data, want_ngp,
+                            support_sigmas, sub(dk, h, n), False)
+        for key in ('data', 'simple', 'hist'):
+            if r1[key] is not None:
+                r1[key] += r2[key]
+        r1['stats'] = {q: r1['stats'][q] + r2['stats'][q] for q in r1['stats']}
+        r1['ix'], r1['iy'], r1['dk'], r1['tiles'], r1['pids'] = ix, iy, dk, None, None
+        return r1
     dev = Xd.device
     data = torch.empty((C, ndim, ndim), dtype=torch.float32, device=dev) if (adaptive and want_data) else None
     simple = torch.empty((C, ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
