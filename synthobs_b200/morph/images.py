@@ -213,7 +213,7 @@ def knn_device_part(Xd, Yd, ix, k, half_width, part, n_parts):
 
 
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
-                   support_sigmas=None, dk=None, return_pairs=False):
+                   support_sigmas=None, dk=None, return_pairs=False, L_event=None):
     """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
     CUDA (C images sharing positions).  Returns dict of float32 CUDA tensors:
     data [C, ndim, ndim] (adaptive only), simple [C, ndim, ndim], hist [ndim, ndim],
@@ -261,6 +261,8 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
     pids = torch.empty(npairs, dtype=torch.int32, device=dev) if return_pairs else None
     wsb = _cabi.lib.so_img_deposit_workspace_bytes(n, npairs, ndim, C)
     ws = dv.workspace(wsb)
+    if L_event is not None:        # the weights may still be arriving on a copy stream (k-NN and binning need positions only)
+        torch.cuda.current_stream().wait_event(L_event)
     _cabi.check(_cabi.lib.so_img_deposit(_cabi.ptr(pws), _cabi.ptr(Ld), n, C, ndim, npairs,
                                          _cabi.ptr(data), _cabi.ptr(simple), _cabi.ptr(hist),
                                          _cabi.ptr(tiles), _cabi.ptr(pids), _cabi.ptr(ws), wsb, _cabi.stream()),
@@ -342,7 +344,7 @@ def median_device(x):
     return out[0] if x.dim() == 1 else out
 
 
-def particle_device_multi(obs_list, Xd, Yd, Ld):
+def particle_device_multi(obs_list, Xd, Yd, Ld, L_event=None):
     """Several observed() set-ups that share one geometry (same pixel scale, width,
     super-sampling, offsets, smoothing) imaged in one pass: one k-NN, one tile
     binning, a C-channel deposit, one batched FFT with a PSF per channel, one
@@ -358,9 +360,12 @@ def particle_device_multi(obs_list, Xd, Yd, Ld):
     X = Xd + o0.xoffset if o0.xoffset else Xd
     Y = Yd + o0.yoffset if o0.yoffset else Yd
     if method == 'adaptive':
-        r = deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=int(scale), want_ngp=False)
+        r = deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=int(scale), want_ngp=False,
+                           L_event=L_event)
         no_psf = r['data']
     else:
+        if L_event is not None:
+            torch.cuda.current_stream().wait_event(L_event)
         no_psf, _, _, r = core_device(X, Y, Ld, o0.resolution, o0.ndim_super, o0.smoothing)
     key = tuple(id(o) for o in obs_list)
     if getattr(o0, '_multi_spec', (None, None))[0] != key:
@@ -369,6 +374,32 @@ def particle_device_multi(obs_list, Xd, Yd, Ld):
     conv = convolve_fft_device(no_psf, o0._multi_spec[1])
     return {'super_no_PSF': no_psf, 'super_data': conv, 'no_PSF': rebin_device(no_psf, o0.ndim),
             'data': rebin_device(conv, o0.ndim), 'stats': r['stats']}
+
+
+_copy_stream = {}
+
+
+def particle_host_multi(obs_list, Xh, Yh, Lh):
+    """particle_device_multi for HOST inputs (NumPy arrays or CPU tensors, ideally pinned): the
+    positions go up first, the [C, n] weights follow on a copy stream while the k-NN and the tile
+    binning run, the deposit waits for them; recentring by the medians as observed.particle does
+    (images.py:183-184) on the device copies (the caller's arrays are left alone).  Returns the
+    final images [C, ndim, ndim] as a float32 CPU tensor plus the run statistics."""
+    dev = dv.device()
+    main = torch.cuda.current_stream()
+    side = _copy_stream.setdefault(dev.index, torch.cuda.Stream(device=dev))
+    as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))   # noqa: E731
+    Xd = as_t(Xh).to(dev, non_blocking=True)
+    Yd = as_t(Yh).to(dev, non_blocking=True)
+    with torch.cuda.stream(side):
+        Ld = as_t(Lh).to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    Ld.record_stream(main)
+    Xd = Xd - median_device(Xd)
+    Yd = Yd - median_device(Yd)
+    r = particle_device_multi(obs_list, Xd, Yd, Ld if Ld.dim() == 2 else Ld.reshape(1, -1), L_event=ev)
+    return r['data'].cpu(), r['stats']
 
 
 def _median_inplace_shift(A, offset):
