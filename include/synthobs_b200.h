@@ -171,6 +171,14 @@ int so_knn_kth_distance_part(const double* X, const double* Y, const int32_t* ix
                              double* dk, int32_t* order_out, int64_t* range_out,
                              void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Batch of images (galaxies) in one call, BASELINE config 4: `img` [n] int32 gives each particle's
+ * image; neighbours are searched inside the particle's own image only (the image id is the high part
+ * of the sort key, the node tables of the images are concatenated).  Same arithmetic as above. */
+int64_t so_knn_batch_workspace_bytes(int64_t n, int64_t n_img, int32_t k);
+int so_knn_kth_distance_batch(const double* X, const double* Y, const int32_t* ix, const int32_t* img,
+                              int64_t n, int64_t n_img, int32_t k, double half_width, double* dk,
+                              void* workspace, int64_t workspace_bytes, void* stream);
+
 /* K8b..K9 — kernel-smoothed deposition.  Replaces the adaptive loop of
  * images.core (synthobs/morph/images.py:87-97): per particle a Gaussian of
  * FWHM = max(dk, 0.01), normalised by its SUM OVER THE IMAGE PIXELS, times L.
@@ -213,6 +221,17 @@ int so_img_deposit(const void* plan_workspace, const double* L, int64_t n, int32
                    int32_t* tile_ids, int32_t* pair_pids,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same for a batch of n_img images sharing geometry (all ndim x ndim on the same pixel grid):
+ * `img` [n] int32 = image of each particle (NULL when n_img == 1); outputs gain a leading image axis:
+ * data / simple [n_img, n_chan, ndim, ndim], hist [n_img, ndim, ndim].  so_img_plan is per particle
+ * and is shared. */
+int64_t so_img_deposit_batch_workspace_bytes(int64_t n, int64_t n_pairs, int32_t ndim, int32_t n_chan, int32_t n_img);
+int so_img_deposit_batch(const void* plan_workspace, const double* L, const int32_t* img, int64_t n,
+                         int32_t n_chan, int32_t n_img, int32_t ndim, int64_t n_pairs,
+                         float* data, float* simple, float* hist,
+                         int32_t* tile_ids, int32_t* pair_pids,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 /* K11 — rebin by block SUM (synthobs/morph/images.py:19-22): in [n_img, n*s, n*s]
  * -> out [n_img, n, n]. */
 int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int32_t s, void* stream);
@@ -243,6 +262,13 @@ int so_img_sersic(const double* G, int32_t ndim, double r_eff, double n, double 
 int64_t so_median_workspace_bytes(int32_t n_arrays);
 int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out,
                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* np.median per CSR segment (one object of a batch per segment; out: DEVICE double[n_seg], NaN for
+ * an empty segment) and the in-place recentring x[i] += shift - med[segment(i)] of
+ * observed.particle (synthobs/morph/images.py:183-187) for every object of the batch. */
+int so_median_segmented(const double* x, const int64_t* seg_offsets, int64_t n_seg, double* out, void* stream);
+int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, const double* med, double shift,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,14 +43,20 @@ SIGNATURES = {
     'so_knn_workspace_bytes': (I64, [I64, I32]),
     'so_knn_kth_distance': (c_int, [P, P, P, I64, I32, D, P, P, I64, P]),
     'so_knn_kth_distance_part': (c_int, [P, P, P, I64, I32, D, I32, I32, P, P, P, P, I64, P]),
+    'so_knn_batch_workspace_bytes': (I64, [I64, I64, I32]),
+    'so_knn_kth_distance_batch': (c_int, [P, P, P, P, I64, I64, I32, D, P, P, I64, P]),
     'so_img_plan_workspace_bytes': (I64, [I64]),
     'so_img_plan': (c_int, [P, P, P, P, P, I64, P, I32, D, P, I64, POINTER(c_int64), POINTER(c_double), P]),
     'so_img_deposit_workspace_bytes': (I64, [I64, I64, I32, I32]),
     'so_img_deposit': (c_int, [P, P, I64, I32, I32, I64, P, P, P, P, P, P, I64, P]),
+    'so_img_deposit_batch_workspace_bytes': (I64, [I64, I64, I32, I32, I32]),
+    'so_img_deposit_batch': (c_int, [P, P, P, I64, I32, I32, I32, I64, P, P, P, P, P, P, I64, P]),
     'so_img_rebin': (c_int, [P, P, I32, I32, I32, P]),
     'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, I32, P]),
     'so_median_workspace_bytes': (I64, [I32]),
     'so_median_f64': (c_int, [P, I64, I32, I64, P, P, I64, P]),
+    'so_median_segmented': (c_int, [P, P, I64, P, P]),
+    'so_recentre_segmented': (c_int, [P, P, I64, P, D, P]),
     'so_img_sersic_workspace_bytes': (I64, [I32]),
     'so_img_sersic': (c_int, [P, I32, D, D, D, D, D, D, D, P, I32, P, P, I64, P]),
 }

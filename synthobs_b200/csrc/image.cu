@@ -216,14 +216,16 @@ __global__ void __launch_bounds__(256) plan_wide_kernel(int64_t n, int ndim, Pla
 // the whole warp, one particle at a time
 constexpr int kExpandSerial = 8;
 __global__ void __launch_bounds__(256) expand_kernel(PlanView pv, int64_t n, int ndim, int ntx,
+                                                     const int32_t* __restrict__ img, int ntiles_img,
                                                      int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int lane = threadIdx.x & 31;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int tx0 = 0, ty0 = 0, nx = 0, cnt = 0;
+    int tx0 = 0, ty0 = 0, nx = 0, cnt = 0, kb = 0;     // kb: first tile key of the particle's image
     int64_t o = 0;
     if (p < n) {
         const int ip = pv.ix[p];
         if (ip >= 0) {
+            kb = img ? img[p] * ntiles_img : 0;
             const int jp = pv.iy[p], W = pv.W[p];
             const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
             const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(256) expand_kernel(PlanView pv, int64_t n, int
             o = pv.offs[p];
             if (cnt <= kExpandSerial)
                 for (int q = 0; q < cnt; ++q) {
-                    keys[o + q] = (ty0 + q / nx) * ntx + tx0 + q % nx;
+                    keys[o + q] = kb + (ty0 + q / nx) * ntx + tx0 + q % nx;
                     vals[o + q] = (int32_t)p;
                 }
         }
@@ -245,10 +247,11 @@ __global__ void __launch_bounds__(256) expand_kernel(PlanView pv, int64_t n, int
         todo &= todo - 1;
         const int c = __shfl_sync(0xffffffffu, cnt, src), w = __shfl_sync(0xffffffffu, nx, src);
         const int x0 = __shfl_sync(0xffffffffu, tx0, src), y0 = __shfl_sync(0xffffffffu, ty0, src);
+        const int k0 = __shfl_sync(0xffffffffu, kb, src);
         const int64_t oo = __shfl_sync(0xffffffffu, o, src);
         const int32_t pid = (int32_t)(p - lane + src);
         for (int q = lane; q < c; q += 32) {
-            keys[oo + q] = (y0 + q / w) * ntx + x0 + q % w;
+            keys[oo + q] = k0 + (y0 + q / w) * ntx + x0 + q % w;
             vals[oo + q] = pid;
         }
     }
@@ -332,6 +335,7 @@ struct DepositParams {
     float* partial;           // [max_items, C_total, kT*kT]
     int n_chan;               // C_total
     int chan0;                // first channel of this launch
+    int ntiles_img;           // sub-tiles per image; tile key = image * ntiles_img + tile (batch of images)
 };
 
 // One warp = one work item (sub-tile, slice of its particle list), C channels in registers.
@@ -345,7 +349,8 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     const int64_t start = t0 + (item - p.item_start[tile]) * p.chunk;
     const int64_t end = min(t1, start + p.chunk);
     const bool single = (p.item_start[tile + 1] - p.item_start[tile]) == 1;
-    const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
+    const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
+    const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
 
     __shared__ float s_u[kDepWarps][2][kP], s_c[kDepWarps][kP], s_w[kDepWarps][C][kP];
     __shared__ int s_i[kDepWarps][2][kP], s_W[kDepWarps][kP];
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     for (int c = 0; c < C; ++c) {
         if (single) {
             if (r < p.ndim) {
-                float* out = p.data + ((size_t)(p.chan0 + c) * p.ndim + r) * p.ndim + px0 + col0;
+                float* out = p.data + (((size_t)image * p.n_chan + p.chan0 + c) * p.ndim + r) * p.ndim + px0 + col0;
                 if (px0 + col0 + 8 <= p.ndim && (p.ndim & 3) == 0) {
                     *reinterpret_cast<float4*>(out) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
                     *reinterpret_cast<float4*>(out + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
@@ -423,12 +428,13 @@ __global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParam
     const int tile = blockIdx.x, chan = blockIdx.y;
     const int64_t i0 = p.item_start[tile], i1 = p.item_start[tile + 1];
     if (i1 - i0 == 1) return;
-    const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
+    const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
+    const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
     const int e = threadIdx.x;
     float s = 0.f;
     for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
     const int row = py0 + e / kT, col = px0 + e % kT;
-    if (row < p.ndim && col < p.ndim) p.data[((size_t)chan * p.ndim + row) * p.ndim + col] = s;
+    if (row < p.ndim && col < p.ndim) p.data[(((size_t)image * n_chan + chan) * p.ndim + row) * p.ndim + col] = s;
 }
 
 // NGP products: one CTA per sub-tile; shared-memory accumulation (float64 sums, integer counts)
@@ -437,7 +443,8 @@ __global__ void __launch_bounds__(64) ngp_tile_kernel(const DepositParams p, int
     __shared__ double s_sum[kT * kT];
     __shared__ unsigned int s_cnt[kT * kT];
     const int tile = blockIdx.x;
-    const int py0 = (tile / p.ntx) * kT, px0 = (tile % p.ntx) * kT;
+    const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
+    const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
     const int64_t t0 = p.tile_start[tile], t1 = p.tile_start[tile + 1];
     for (int chan = 0; chan < (simple ? n_chan : 1); ++chan) {
         for (int e = threadIdx.x; e < kT * kT; e += 64) { s_sum[e] = 0.0; s_cnt[e] = 0; }
@@ -455,8 +462,8 @@ __global__ void __launch_bounds__(64) ngp_tile_kernel(const DepositParams p, int
         for (int e = threadIdx.x; e < kT * kT; e += 64) {
             const int row = py0 + e / kT, col = px0 + e % kT;
             if (row < p.ndim && col < p.ndim) {
-                if (simple) simple[((size_t)chan * p.ndim + row) * p.ndim + col] = (float)s_sum[e];
-                if (hist && chan == 0) hist[(size_t)row * p.ndim + col] = (float)s_cnt[e];
+                if (simple) simple[(((size_t)image * n_chan + chan) * p.ndim + row) * p.ndim + col] = (float)s_sum[e];
+                if (hist && chan == 0) hist[((size_t)image * p.ndim + row) * p.ndim + col] = (float)s_cnt[e];
             }
         }
         __syncthreads();
@@ -552,10 +559,10 @@ static int64_t sort_tmp_bytes(int64_t n_pairs) {
     return (int64_t)b;
 }
 
-static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n_pairs, int ndim, int n_chan, bool* ok) {
+static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n_pairs, int ndim, int n_chan, int n_img, bool* ok) {
     DepositLayout d;
     d.ntx = (ndim + kT - 1) / kT;
-    d.ntiles = d.ntx * d.ntx;
+    d.ntiles = d.ntx * d.ntx * n_img;       // over the whole batch of images
     // one warp per work item: aim for ~32 items (warps) per SM, never below two staging phases
     const int64_t target = 32 * 148;
     int64_t chunk = (n_pairs + target - 1) / target;
@@ -637,36 +644,45 @@ extern "C" int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X
     return SO_OK;
 }
 
-extern "C" int64_t so_img_deposit_workspace_bytes(int64_t n, int64_t n_pairs, int32_t ndim, int32_t n_chan) {
+extern "C" int64_t so_img_deposit_batch_workspace_bytes(int64_t n, int64_t n_pairs, int32_t ndim, int32_t n_chan,
+                                                        int32_t n_img) {
     (void)n;
-    DepositLayout d = carve_deposit(nullptr, 0, n_pairs, ndim, n_chan, nullptr);
+    DepositLayout d = carve_deposit(nullptr, 0, n_pairs, ndim, n_chan, n_img < 1 ? 1 : n_img, nullptr);
     return d.cub_tmp_bytes + 256;
 }
 
-extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64_t n, int32_t n_chan,
-                              int32_t ndim, int64_t n_pairs,
-                              float* data, float* simple, float* hist,
-                              int32_t* tile_ids, int32_t* pair_pids,
-                              void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int64_t so_img_deposit_workspace_bytes(int64_t n, int64_t n_pairs, int32_t ndim, int32_t n_chan) {
+    return so_img_deposit_batch_workspace_bytes(n, n_pairs, ndim, n_chan, 1);
+}
+
+extern "C" int so_img_deposit_batch(const void* plan_workspace, const double* L, const int32_t* img, int64_t n,
+                                    int32_t n_chan, int32_t n_img, int32_t ndim, int64_t n_pairs,
+                                    float* data, float* simple, float* hist,
+                                    int32_t* tile_ids, int32_t* pair_pids,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (n < 0 || ndim < 1 || n_chan < 1 || n_pairs < 0 || !plan_workspace) return SO_ERR_BAD_ARG;
+    if (n < 0 || ndim < 1 || n_chan < 1 || n_pairs < 0 || !plan_workspace || n_img < 1) return SO_ERR_BAD_ARG;
+    if (n_img > 1 && !img && n > 0) return SO_ERR_BAD_ARG;
     if (n_pairs >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
     if (n > 0 && (data || simple) && !L) return SO_ERR_BAD_ARG;
+    const int64_t ntx0 = (ndim + kT - 1) / kT;
+    if (ntx0 * ntx0 * (int64_t)n_img >= ((int64_t)1 << 31) - 1) return SO_ERR_TOO_LARGE;
     bool ok = false;
     PlanView pv = carve_plan(const_cast<void*>(plan_workspace), (int64_t)1 << 60, n, &ok);
-    DepositLayout d = carve_deposit(workspace, workspace_bytes, n_pairs, ndim, n_chan, &ok);
+    DepositLayout d = carve_deposit(workspace, workspace_bytes, n_pairs, ndim, n_chan, n_img, &ok);
     if (!ok || !workspace) return SO_ERR_WORKSPACE;
-    const size_t img_bytes = (size_t)ndim * ndim * sizeof(float);
+    const size_t img_bytes = (size_t)ndim * ndim * sizeof(float) * n_img;
     if (n_pairs == 0) {
         if (data) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
         if (simple) SO_CUDA(cudaMemsetAsync(simple, 0, img_bytes * n_chan, st));
         if (hist) SO_CUDA(cudaMemsetAsync(hist, 0, img_bytes, st));
         return SO_OK;
     }
-    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, d.keys0, d.vals0);
+    const int ntiles_img = d.ntx * d.ntx;
+    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, img, ntiles_img, d.keys0, d.vals0);
     SO_LAUNCH_CHECK();
     int bits = 1;
-    while ((1 << bits) < d.ntiles) ++bits;
+    while (((int64_t)1 << bits) < d.ntiles) ++bits;
     size_t tmp = (size_t)d.cub_tmp_bytes;
     SO_CUDA(cub::DeviceRadixSort::SortPairs(d.cub_tmp, tmp, d.keys0, d.keys1, d.vals0, d.vals1, (int)n_pairs, 0, bits, st));
     tile_start_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.keys1, n_pairs, d.ntiles, d.tile_start);
@@ -675,7 +691,7 @@ extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64
     if (pair_pids) SO_CUDA(cudaMemcpyAsync(pair_pids, d.vals1, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToDevice, st));
 
     DepositParams p{};
-    p.pv = pv; p.L = L; p.n = n; p.ndim = ndim; p.ntx = d.ntx; p.ntiles = d.ntiles;
+    p.pv = pv; p.L = L; p.n = n; p.ndim = ndim; p.ntx = d.ntx; p.ntiles = d.ntiles; p.ntiles_img = ntiles_img;
     p.pids = d.vals1; p.tile_start = d.tile_start; p.item_start = d.item_start; p.item_tile = d.item_tile;
     p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0;
     if (data) {
@@ -703,6 +719,15 @@ extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64
         SO_LAUNCH_CHECK();
     }
     return SO_OK;
+}
+
+extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64_t n, int32_t n_chan,
+                              int32_t ndim, int64_t n_pairs,
+                              float* data, float* simple, float* hist,
+                              int32_t* tile_ids, int32_t* pair_pids,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+    return so_img_deposit_batch(plan_workspace, L, nullptr, n, n_chan, 1, ndim, n_pairs, data, simple, hist, tile_ids,
+                                pair_pids, workspace, workspace_bytes, stream);
 }
 
 extern "C" int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int32_t s, void* stream) {

@@ -23,10 +23,13 @@ constexpr int kLeaf = 32;           // nodes with at most this many points are s
 constexpr int kBits = 15;           // Morton bits per axis: the implicit quadtree has levels 0..15
 constexpr int kTableLevelMax = 11;  // node ranges down to this level come from the table E, deeper ones by bisection
 constexpr int kStack = 3 * kBits + 8;
-constexpr uint32_t kUnselected = 1u << (2 * kBits);   // key of particles outside the image: sorts last
+constexpr int kMaxTableBits = 26;   // at most 2^26 table cells over all images of a batch
 
+// Sort key = (image id << 30) | 30-bit Morton code; particles outside their image get image id n_img and
+// sort last.  A batch of images (galaxies) is searched in one pass: the node tables of the images are
+// simply concatenated, because (key >> shift) enumerates (image, cell) pairs in sorted order.
 struct KnnLayout {
-    uint32_t *keys0, *keys1;
+    unsigned long long *keys0, *keys1;
     int32_t *vals0, *vals1;
     double *xs, *ys;
     int32_t* E;                    // [4^Lt] upper bounds per table cell
@@ -37,28 +40,30 @@ struct KnnLayout {
     int64_t total;
 };
 
-static int knn_table_level(int64_t n) {
-    int L = 4;
-    while (L < kTableLevelMax && ((int64_t)1 << (2 * (L - 1))) < n) ++L;   // ~ one particle per 4 table cells
+static int knn_table_level(int64_t n, int64_t n_img) {
+    const int64_t per = (n + n_img - 1) / n_img;
+    int L = 2;
+    while (L < kTableLevelMax && ((int64_t)1 << (2 * (L - 1))) < per) ++L;   // ~ one particle per 4 table cells
+    while (L > 0 && (n_img << (2 * L)) > ((int64_t)1 << kMaxTableBits)) --L;
     return L;
 }
 
-static KnnLayout carve_knn(void* ws, int64_t bytes, int64_t n, bool* ok) {
+static KnnLayout carve_knn(void* ws, int64_t bytes, int64_t n, int64_t n_img, bool* ok) {
     KnnLayout l;
-    l.Lt = knn_table_level(n);
-    const int64_t ncell = (int64_t)1 << (2 * l.Lt);
+    l.Lt = knn_table_level(n, n_img);
+    const int64_t ncell = n_img << (2 * l.Lt);
     SoArena a(ws, bytes);
-    l.keys0 = a.take<uint32_t>(n);
+    l.keys0 = a.take<unsigned long long>(n);
     l.vals0 = a.take<int32_t>(n);
-    l.keys1 = a.take<uint32_t>(n);
+    l.keys1 = a.take<unsigned long long>(n);
     l.vals1 = a.take<int32_t>(n);
     l.xs = a.take<double>(n);
     l.ys = a.take<double>(n);
     l.E = a.take<int32_t>(ncell);
     l.counter = a.take<unsigned long long>(2);
     size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs((void*)nullptr, b1, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)(n > 0 ? n : 1), 0, 32);
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, b1, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)(n > 0 ? n : 1), 0, 64);
     cub::DeviceScan::InclusiveScan((void*)nullptr, b2, (int32_t*)nullptr, (int32_t*)nullptr, cub::Max(), (int)ncell);
     l.cub_tmp_bytes = (int64_t)(b1 > b2 ? b1 : b2);
     l.cub_tmp = a.take<char>(l.cub_tmp_bytes);
@@ -84,20 +89,21 @@ __device__ __forceinline__ uint32_t compact_bits(uint32_t c) {   // even bit pos
 }
 
 __global__ void knn_key_kernel(const double* __restrict__ X, const double* __restrict__ Y,
-                               const int32_t* __restrict__ ix, int64_t n, double hw, double inv_h,
-                               uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                               const int32_t* __restrict__ ix, const int32_t* __restrict__ img, int64_t n, int64_t n_img,
+                               double hw, double inv_h,
+                               unsigned long long* __restrict__ keys, int32_t* __restrict__ vals,
                                unsigned long long* __restrict__ counter) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool sel = false;
     if (i < n) {
         sel = ix[i] >= 0;
-        uint32_t key = kUnselected;
+        unsigned long long key = (unsigned long long)n_img << (2 * kBits);
         if (sel) {
             const int nc = 1 << kBits;
             int cx = (int)((X[i] + hw) * inv_h), cy = (int)((Y[i] + hw) * inv_h);
             cx = max(0, min(nc - 1, cx));
             cy = max(0, min(nc - 1, cy));
-            key = morton((uint32_t)cx, (uint32_t)cy);
+            key = ((unsigned long long)(img ? img[i] : 0) << (2 * kBits)) | morton((uint32_t)cx, (uint32_t)cy);
         }
         keys[i] = key;
         vals[i] = (int32_t)i;
@@ -118,11 +124,12 @@ __global__ void knn_gather_kernel(const double* __restrict__ X, const double* __
 
 // E[c] = i + 1 at the last sorted element of table cell c (others stay 0); a max-scan then makes
 // E[c] = #selected particles whose table cell is <= c
-__global__ void knn_mark_kernel(const uint32_t* __restrict__ keys, int64_t n, int tshift, int32_t* __restrict__ E) {
+__global__ void knn_mark_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t n_img, int tshift,
+                                int32_t* __restrict__ E) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t k = keys[i];
-    if (k >= kUnselected) return;
+    const unsigned long long k = keys[i];
+    if ((k >> (2 * kBits)) >= (unsigned long long)n_img) return;
     if (i + 1 == n || (keys[i + 1] >> tshift) != (k >> tshift)) E[k >> tshift] = (int32_t)(i + 1);
 }
 
@@ -160,7 +167,8 @@ __device__ __forceinline__ float node_dmin(int shift, uint32_t cx, uint32_t cy, 
 }
 
 // first position in [a, b) whose key is >= key (keys ascending)
-__device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys, int a, int b, uint32_t key) {
+__device__ __forceinline__ int lower_bound_key(const unsigned long long* __restrict__ keys, int a, int b,
+                                               unsigned long long key) {
     while (a < b) {
         const int mid = (a + b) >> 1;
         if (keys[mid] < key) a = mid + 1; else b = mid;
@@ -169,24 +177,27 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys
 }
 
 struct KnnTree {
-    const uint32_t* keys;
+    const unsigned long long* keys;
     const int32_t* E;
-    int Lt;       // table level
-    int nsel;
+    int Lt;                    // table level
+    unsigned long long img;    // image (galaxy) of the query
 };
 
-// sorted range of node (level, code): table look-up down to level Lt, bisection inside the table cell below
+// sorted range of node (level, code) of image t.img: table look-up down to level Lt, bisection inside the
+// table cell below.  (image << 2 level) | code enumerates the nodes of a level over the whole batch.
 __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t code, int& a, int& b) {
+    const unsigned long long xc = (t.img << (2 * level)) | code;
     if (level <= t.Lt) {
         const int sh = 2 * (t.Lt - level);
-        a = (code == 0) ? 0 : t.E[(code << sh) - 1];
-        b = t.E[((code + 1) << sh) - 1];
+        const unsigned long long lo = xc << sh;
+        a = (lo == 0) ? 0 : t.E[lo - 1];
+        b = t.E[((xc + 1) << sh) - 1];
     } else {
-        const uint32_t tc = code >> (2 * (level - t.Lt));
+        const unsigned long long tc = xc >> (2 * (level - t.Lt));
         const int ta = (tc == 0) ? 0 : t.E[tc - 1], tb = t.E[tc];
         const int sh = 2 * (kBits - level);
-        a = lower_bound_key(t.keys, ta, tb, code << sh);
-        b = lower_bound_key(t.keys, a, tb, (code + 1) << sh);
+        a = lower_bound_key(t.keys, ta, tb, xc << sh);
+        b = lower_bound_key(t.keys, a, tb, (xc + 1) << sh);
     }
 }
 
@@ -200,20 +211,24 @@ __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t
 // The tree is 15 levels deep whatever the particle number, so the dense cores of a clustered
 // catalogue (hundreds of particles per table cell) are resolved instead of being scanned linearly.
 __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
-                                 const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
-                                 const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
-                                 const unsigned long long* __restrict__ counter, int part, int n_parts,
-                                 double* __restrict__ dk) {
+                                 const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
+                                 int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
+                                 int part, int n_parts, double* __restrict__ dk) {
     extern __shared__ double s_best[];
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int pid = vals[s];
-    if (keys[s] >= kUnselected) { dk[pid] = 0.0; return; }
+    const unsigned long long key = keys[s];
+    if ((key >> (2 * kBits)) >= (unsigned long long)n_img) { dk[pid] = 0.0; return; }
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    KnnTree t{keys, E, Lt, (int)*counter};
+    KnnTree t{keys, E, Lt, key >> (2 * kBits)};
+    // sorted range of the query's own image: its neighbours are searched there only
+    int g_lo, g_hi;
+    node_range(t, 0, 0u, g_lo, g_hi);
+    const int nsel = g_hi - g_lo;
     // this call's share of the queries: a contiguous range of the Morton order (spatially compact)
-    if (s < (int64_t)t.nsel * part / n_parts || s >= (int64_t)t.nsel * (part + 1) / n_parts) return;
-    if (k > t.nsel) { dk[pid] = INF; return; }
+    if (s - g_lo < (int64_t)nsel * part / n_parts || s - g_lo >= (int64_t)nsel * (part + 1) / n_parts) return;
+    if (k > nsel) { dk[pid] = INF; return; }
     const int stride = blockDim.x;
     double* best = s_best + threadIdx.x;
     for (int j = 0; j < k; ++j) best[j * stride] = INF;
@@ -223,9 +238,9 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict
     const double h = 1.0 / inv_h;                                 // fine-cell units -> length
 
     // 1. window of sorted neighbours
-    int wb = min(t.nsel, (int)s + k + 1);
-    const int wa = max(0, wb - (2 * k + 1));
-    wb = min(t.nsel, wa + 2 * k + 1);
+    int wb = min(g_hi, (int)s + k + 1);
+    const int wa = max(g_lo, wb - (2 * k + 1));
+    wb = min(g_hi, wa + 2 * k + 1);
     knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
 
     // 2. start nodes
@@ -299,43 +314,46 @@ __global__ void knn_range_kernel(const unsigned long long* __restrict__ counter,
 
 extern "C" int64_t so_knn_workspace_bytes(int64_t n, int32_t k) {
     (void)k;
-    KnnLayout l = carve_knn(nullptr, 0, n, nullptr);
+    KnnLayout l = carve_knn(nullptr, 0, n, 1, nullptr);
     return l.total + 256;
 }
 
-static int knn_run(const double* X, const double* Y, const int32_t* ix, int64_t n, int32_t k, double half_width,
-                   int32_t part, int32_t n_parts, double* dk, int32_t* order_out, int64_t* range_out,
-                   void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+static int knn_run(const double* X, const double* Y, const int32_t* ix, const int32_t* img, int64_t n, int64_t n_img,
+                   int32_t k, double half_width, int32_t part, int32_t n_parts, double* dk, int32_t* order_out,
+                   int64_t* range_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     if (n == 0) return SO_OK;
-    if (n < 0 || k < 1 || !(half_width > 0.0) || !X || !Y || !ix || !dk) return SO_ERR_BAD_ARG;
-    if (n_parts < 1 || part < 0 || part >= n_parts) return SO_ERR_BAD_ARG;
-    if (n >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
+    if (n < 0 || k < 1 || !(half_width > 0.0) || !X || !Y || !ix || !dk || n_img < 1) return SO_ERR_BAD_ARG;
+    if (n_parts < 1 || part < 0 || part >= n_parts || (n_img > 1 && (n_parts != 1 || !img))) return SO_ERR_BAD_ARG;
+    if (n >= (int64_t)1 << 31 || n_img >= (int64_t)1 << 30) return SO_ERR_TOO_LARGE;
     bool ok = false;
-    KnnLayout l = carve_knn(workspace, workspace_bytes, n, &ok);
+    KnnLayout l = carve_knn(workspace, workspace_bytes, n, n_img, &ok);
     if (!ok || !workspace) return SO_ERR_WORKSPACE;
     int threads = 128;
     size_t smem = (size_t)k * threads * sizeof(double);
     if (smem > 200 * 1024) { threads = 32; smem = (size_t)k * threads * sizeof(double); }
     if (smem > 200 * 1024) return SO_ERR_UNSUPPORTED;
     const int Lt = l.Lt;
-    const int ncell = 1 << (2 * Lt);
+    const int64_t ncell = n_img << (2 * Lt);
     const double inv_h = (double)(1 << kBits) / (2.0 * half_width);
+    int img_bits = 1;
+    while (((int64_t)1 << img_bits) <= n_img) ++img_bits;
     SO_CUDA(cudaMemsetAsync(l.counter, 0, 2 * sizeof(unsigned long long), st));
     SO_CUDA(cudaMemsetAsync(l.E, 0, sizeof(int32_t) * (size_t)ncell, st));
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    knn_key_kernel<<<blocks, 256, 0, st>>>(X, Y, ix, n, half_width, inv_h, l.keys0, l.vals0, l.counter);
+    knn_key_kernel<<<blocks, 256, 0, st>>>(X, Y, ix, img, n, n_img, half_width, inv_h, l.keys0, l.vals0, l.counter);
     SO_LAUNCH_CHECK();
     size_t tmp = (size_t)l.cub_tmp_bytes;
-    SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, l.keys0, l.keys1, l.vals0, l.vals1, (int)n, 0, 2 * kBits + 1, st));
+    SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, l.keys0, l.keys1, l.vals0, l.vals1, (int)n, 0,
+                                            2 * kBits + img_bits, st));
     knn_gather_kernel<<<blocks, 256, 0, st>>>(X, Y, l.vals1, n, l.xs, l.ys);
     SO_LAUNCH_CHECK();
-    knn_mark_kernel<<<blocks, 256, 0, st>>>(l.keys1, n, 2 * (kBits - Lt), l.E);
+    knn_mark_kernel<<<blocks, 256, 0, st>>>(l.keys1, n, n_img, 2 * (kBits - Lt), l.E);
     SO_LAUNCH_CHECK();
     tmp = (size_t)l.cub_tmp_bytes;
-    SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), ncell, st));
+    SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), (int)ncell, st));
     SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-        l.xs, l.ys, l.keys1, l.vals1, n, l.E, Lt, half_width, inv_h, k, l.counter, part, n_parts, dk);
+        l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, dk);
     SO_LAUNCH_CHECK();
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
     if (range_out) {
@@ -348,13 +366,27 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, int64_t 
 extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
                                    int32_t k, double half_width, double* dk,
                                    void* workspace, int64_t workspace_bytes, void* stream) {
-    return knn_run(X, Y, ix, n, k, half_width, 0, 1, dk, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+    return knn_run(X, Y, ix, nullptr, n, 1, k, half_width, 0, 1, dk, nullptr, nullptr, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int so_knn_kth_distance_part(const double* X, const double* Y, const int32_t* ix, int64_t n,
                                         int32_t k, double half_width, int32_t part, int32_t n_parts,
                                         double* dk, int32_t* order_out, int64_t* range_out,
                                         void* workspace, int64_t workspace_bytes, void* stream) {
-    return knn_run(X, Y, ix, n, k, half_width, part, n_parts, dk, order_out, range_out, workspace, workspace_bytes,
+    return knn_run(X, Y, ix, nullptr, n, 1, k, half_width, part, n_parts, dk, order_out, range_out, workspace,
+                   workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int64_t so_knn_batch_workspace_bytes(int64_t n, int64_t n_img, int32_t k) {
+    (void)k;
+    KnnLayout l = carve_knn(nullptr, 0, n, n_img < 1 ? 1 : n_img, nullptr);
+    return l.total + 256;
+}
+
+extern "C" int so_knn_kth_distance_batch(const double* X, const double* Y, const int32_t* ix, const int32_t* img,
+                                         int64_t n, int64_t n_img, int32_t k, double half_width, double* dk,
+                                         void* workspace, int64_t workspace_bytes, void* stream) {
+    return knn_run(X, Y, ix, img, n, n_img, k, half_width, 0, 1, dk, nullptr, nullptr, workspace, workspace_bytes,
                    (cudaStream_t)stream);
 }

@@ -134,7 +134,85 @@ __global__ void select_init_kernel(SelectState* __restrict__ st, int64_t n) {
     sa->hist[threadIdx.x] = 0;
 }
 
+// np.median per CSR segment: one CTA walks its segment nine times (eight digit passes + the lower middle)
+__global__ void __launch_bounds__(256) median_segmented_kernel(const double* __restrict__ x,
+                                                               const int64_t* __restrict__ seg, double* __restrict__ out) {
+    __shared__ unsigned int s_h[256];
+    __shared__ unsigned long long s_prefix, s_rank, s_below;
+    const int64_t a = seg[blockIdx.x], b = seg[blockIdx.x + 1];
+    const int64_t n = b - a;
+    if (n <= 0) {
+        if (threadIdx.x == 0) out[blockIdx.x] = __longlong_as_double(0x7ff8000000000000LL);   // NaN, like np.median([])
+        return;
+    }
+    if (threadIdx.x == 0) { s_prefix = 0; s_rank = (unsigned long long)(n / 2); s_below = 0; }
+    for (int pass = 0; pass < 8; ++pass) {
+        s_h[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const int hs = 64 - 8 * pass;
+        for (int64_t i = a + threadIdx.x; i < b; i += 256) {
+            const unsigned long long k = f64_key(x[i]);
+            if (pass == 0 || (k >> hs) == (prefix >> hs)) atomicAdd(&s_h[(k >> (hs - 8)) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long r = s_rank, acc = 0;
+            int bin = 0;
+            for (; bin < 255; ++bin) {
+                if (acc + s_h[bin] > r) break;
+                acc += s_h[bin];
+            }
+            s_rank = r - acc;
+            s_prefix = prefix | ((unsigned long long)bin << (56 - 8 * pass));
+        }
+        __syncthreads();
+    }
+    const unsigned long long sel = s_prefix;
+    unsigned long long m = 0;
+    for (int64_t i = a + threadIdx.x; i < b; i += 256) {
+        const unsigned long long k = f64_key(x[i]);
+        if (k < sel && k > m) m = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_below, m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double hi = key_f64(sel);
+        double lo = hi;
+        if ((n & 1) == 0 && s_rank == 0) lo = key_f64(s_below);
+        out[blockIdx.x] = (n & 1) ? hi : __dmul_rn(__dadd_rn(lo, hi), 0.5);
+    }
+}
+
+// x[i] += shift - med[segment of i]   (recentring of every object of a batch, images.py:183-187)
+__global__ void __launch_bounds__(256) recentre_segmented_kernel(double* __restrict__ x, const int64_t* __restrict__ seg,
+                                                                 const double* __restrict__ med, double shift) {
+    const int64_t a = seg[blockIdx.x], b = seg[blockIdx.x + 1];
+    const double m = med[blockIdx.x];
+    for (int64_t i = a + threadIdx.x; i < b; i += 256) x[i] = __dadd_rn(__dsub_rn(x[i], m), shift);
+}
+
 }  // namespace
+
+extern "C" int so_median_segmented(const double* x, const int64_t* seg_offsets, int64_t n_seg, double* out, void* stream) {
+    if (!x || !seg_offsets || !out || n_seg < 1 || n_seg >= ((int64_t)1 << 31)) return SO_ERR_BAD_ARG;
+    median_segmented_kernel<<<(unsigned)n_seg, 256, 0, (cudaStream_t)stream>>>(x, seg_offsets, out);
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
+
+extern "C" int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, const double* med, double shift,
+                                     void* stream) {
+    if (!x || !seg_offsets || !med || n_seg < 1 || n_seg >= ((int64_t)1 << 31)) return SO_ERR_BAD_ARG;
+    recentre_segmented_kernel<<<(unsigned)n_seg, 256, 0, (cudaStream_t)stream>>>(x, seg_offsets, med, shift);
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
 
 extern "C" int64_t so_median_workspace_bytes(int32_t n_arrays) {
     return so_align_up((int64_t)n_arrays * (int64_t)sizeof(SelectState), 256) + 256;

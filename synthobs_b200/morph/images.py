@@ -182,15 +182,24 @@ def ngp_index_device(Xd, Yd, Gd, ndim, half_width):
     return ix, iy
 
 
-def knn_device(Xd, Yd, ix, k, half_width):
-    """distance to the k-th neighbour (self = first) among the selected particles (K7)."""
+def knn_device(Xd, Yd, ix, k, half_width, img=None, n_img=1):
+    """distance to the k-th neighbour (self = first) among the selected particles (K7); with
+    `img` [n] int32 / n_img, among the selected particles of the particle's own image."""
     n = Xd.numel()
     dk = torch.empty(n, dtype=torch.float64, device=Xd.device)
-    wsb = _cabi.lib.so_knn_workspace_bytes(n, int(k))
-    ws = dv.workspace(wsb)
-    _cabi.check(_cabi.lib.so_knn_kth_distance(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), n, int(k),
-                                              float(half_width), _cabi.ptr(dk), _cabi.ptr(ws), wsb, _cabi.stream()),
-                'so_knn_kth_distance')
+    if img is None:
+        wsb = _cabi.lib.so_knn_workspace_bytes(n, int(k))
+        ws = dv.workspace(wsb)
+        _cabi.check(_cabi.lib.so_knn_kth_distance(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), n, int(k),
+                                                  float(half_width), _cabi.ptr(dk), _cabi.ptr(ws), wsb, _cabi.stream()),
+                    'so_knn_kth_distance')
+    else:
+        wsb = _cabi.lib.so_knn_batch_workspace_bytes(n, int(n_img), int(k))
+        ws = dv.workspace(wsb)
+        _cabi.check(_cabi.lib.so_knn_kth_distance_batch(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), _cabi.ptr(img), n,
+                                                        int(n_img), int(k), float(half_width), _cabi.ptr(dk),
+                                                        _cabi.ptr(ws), wsb, _cabi.stream()),
+                    'so_knn_kth_distance_batch')
     return dk
 
 
@@ -213,7 +222,7 @@ def knn_device_part(Xd, Yd, ix, k, half_width, part, n_parts):
 
 
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
-                   support_sigmas=None, dk=None, return_pairs=False, L_event=None):
+                   support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1):
     """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
     CUDA (C images sharing positions).  Returns dict of float32 CUDA tensors:
     data [C, ndim, ndim] (adaptive only), simple [C, ndim, ndim], hist [ndim, ndim],
@@ -228,7 +237,7 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
     ix, iy = ngp_index_device(Xd, Yd, Gd, ndim, width / 2.)
     adaptive = adaptive_k is not None
     if adaptive and dk is None:
-        dk = knn_device(Xd, Yd, ix, adaptive_k, width / 2.)
+        dk = knn_device(Xd, Yd, ix, adaptive_k, width / 2., img=img, n_img=n_img)
     R = SUPPORT_SIGMAS if support_sigmas is None else support_sigmas
     pws_b = _cabi.lib.so_img_plan_workspace_bytes(n)
     pws = dv.workspace(pws_b)
@@ -244,9 +253,9 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
         h = n // 2
         sub = lambda t, a, b: None if t is None else t[..., a:b]   # noqa: E731
         r1 = deposit_device(Xd[:h], Yd[:h], Ld[:, :h], resolution, ndim, adaptive_k, want_data, want_ngp,
-                            support_sigmas, sub(dk, 0, h), False)
+                            support_sigmas, sub(dk, 0, h), False, img=sub(img, 0, h), n_img=n_img)
         r2 = deposit_device(Xd[h:], Yd[h:], Ld[:, h:], resolution, ndim, adaptive_k, want_data, want_ngp,
-                            support_sigmas, sub(dk, h, n), False)
+                            support_sigmas, sub(dk, h, n), False, img=sub(img, h, n), n_img=n_img)
         for key in ('data', 'simple', 'hist'):
             if r1[key] is not None:
                 r1[key] += r2[key]
@@ -254,19 +263,20 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
         r1['ix'], r1['iy'], r1['dk'], r1['tiles'], r1['pids'] = ix, iy, dk, None, None
         return r1
     dev = Xd.device
-    data = torch.empty((C, ndim, ndim), dtype=torch.float32, device=dev) if (adaptive and want_data) else None
-    simple = torch.empty((C, ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
-    hist = torch.empty((ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
+    lead = () if img is None else (int(n_img),)     # a batch of images adds a leading axis
+    data = torch.empty(lead + (C, ndim, ndim), dtype=torch.float32, device=dev) if (adaptive and want_data) else None
+    simple = torch.empty(lead + (C, ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
+    hist = torch.empty(lead + (ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
     tiles = torch.empty(npairs, dtype=torch.int32, device=dev) if return_pairs else None
     pids = torch.empty(npairs, dtype=torch.int32, device=dev) if return_pairs else None
-    wsb = _cabi.lib.so_img_deposit_workspace_bytes(n, npairs, ndim, C)
+    wsb = _cabi.lib.so_img_deposit_batch_workspace_bytes(n, npairs, ndim, C, int(n_img))
     ws = dv.workspace(wsb)
     if L_event is not None:        # the weights may still be arriving on a copy stream (k-NN and binning need positions only)
         torch.cuda.current_stream().wait_event(L_event)
-    _cabi.check(_cabi.lib.so_img_deposit(_cabi.ptr(pws), _cabi.ptr(Ld), n, C, ndim, npairs,
-                                         _cabi.ptr(data), _cabi.ptr(simple), _cabi.ptr(hist),
-                                         _cabi.ptr(tiles), _cabi.ptr(pids), _cabi.ptr(ws), wsb, _cabi.stream()),
-                'so_img_deposit')
+    _cabi.check(_cabi.lib.so_img_deposit_batch(_cabi.ptr(pws), _cabi.ptr(Ld), _cabi.ptr(img), n, C, int(n_img), ndim,
+                                               npairs, _cabi.ptr(data), _cabi.ptr(simple), _cabi.ptr(hist),
+                                               _cabi.ptr(tiles), _cabi.ptr(pids), _cabi.ptr(ws), wsb, _cabi.stream()),
+                'so_img_deposit_batch')
     return {'data': data, 'simple': simple, 'hist': hist, 'ix': ix, 'iy': iy, 'dk': dk, 'G': G,
             'stats': {'pairs': stats[0], 'deposits': stats[1], 'selected': stats[2], 'dropped': stats[3]},
             'tiles': tiles, 'pids': pids}
@@ -278,13 +288,14 @@ def _parse_smoothing(smoothing):
     return False, None
 
 
-def core_device(Xd, Yd, Ld, resolution=0.1, ndim=100, smoothing=False, want_ngp=True):
-    """images.core for [C, n] weights on the device; returns (data, simple, hist, info)."""
+def core_device(Xd, Yd, Ld, resolution=0.1, ndim=100, smoothing=False, want_ngp=True, img=None, n_img=1):
+    """images.core for [C, n] weights on the device; returns (data, simple, hist, info).  With `img`
+    [n] int32 / n_img the particles belong to n_img separate images (leading axis on every product)."""
     method, scale = _parse_smoothing(smoothing)
     if method == 'adaptive':
-        r = deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=int(scale), want_ngp=want_ngp)
+        r = deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=int(scale), want_ngp=want_ngp, img=img, n_img=n_img)
         return r['data'], r['simple'], r['hist'], r
-    r = deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_ngp=True)
+    r = deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_ngp=True, img=img, n_img=n_img)
     if method == 'convolved_gaussian':
         width, G = pixel_grid(resolution, ndim)
         Gx, Gy = np.meshgrid(G, G)
@@ -327,6 +338,50 @@ def core(X, Y, L, resolution=0.1, ndim=100, smoothing=False, verbose=False):
         img.data = img.simple if same else data[0]
     img.info = info['stats']
     return img
+
+
+def _image_ids(offsets, dev):
+    off = dv.to_dev(offsets, torch.int64)
+    G = off.numel() - 1
+    ids = torch.repeat_interleave(torch.arange(G, device=dev, dtype=torch.int32), (off[1:] - off[:-1]))
+    return off, ids, G
+
+
+def core_batch(X, Y, L, offsets, resolution=0.1, ndim=100, smoothing=False):
+    """images.core for a batch of objects in ONE pass (BASELINE config 4; no upstream equivalent, the
+    reference loops over objects, examples/core_manytestobjects.py:17-22).  X, Y, L: concatenated
+    particles, `offsets` = CSR [G+1]; L may be [C, n] for C images per object sharing positions.
+    Returns an object with .hist [G, ndim, ndim], .simple and .data [G, (C,) ndim, ndim], equal to a loop
+    of core() over the objects (the k-NN of an object only sees its own particles)."""
+    host = not any(dv.is_device_tensor(a) for a in (X, Y, L))
+    Xd, Yd, Ld = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L)
+    one = Ld.dim() == 1
+    off, ids, G = _image_ids(offsets, Xd.device)
+    data, simple, hist, info = core_device(Xd, Yd, Ld, resolution, ndim, smoothing, img=ids, n_img=G)
+    pick = (lambda t: t[:, 0]) if one else (lambda t: t)
+    fin = (lambda t: dv.to_host(pick(t))) if host else pick
+    img = empty()
+    img.hist = dv.to_host(hist) if host else hist
+    img.simple = fin(simple)
+    img.data = img.simple if data is simple else fin(data)
+    img.info = info['stats']
+    return img
+
+
+def median_segmented_device(x, off):
+    """np.median of every CSR segment of a CUDA float64 tensor -> [G] CUDA tensor"""
+    G = off.numel() - 1
+    out = torch.empty(G, dtype=torch.float64, device=x.device)
+    _cabi.check(_cabi.lib.so_median_segmented(_cabi.ptr(x), _cabi.ptr(off), G, _cabi.ptr(out), _cabi.stream()),
+                'so_median_segmented')
+    return out
+
+
+def _recentre_segmented(x, off, shift):
+    med = median_segmented_device(x, off)
+    _cabi.check(_cabi.lib.so_recentre_segmented(_cabi.ptr(x), _cabi.ptr(off), off.numel() - 1, _cabi.ptr(med),
+                                                float(shift), _cabi.stream()), 'so_recentre_segmented')
+    return med
 
 
 def median_device(x):
@@ -561,6 +616,30 @@ def _observed_Sersic(self, L, p):
 
 
 observed.Sersic = _observed_Sersic
+
+
+def _observed_particle_batch(self, X, Y, L, offsets):
+    """observed.particle for a batch of objects in one pass (CSR `offsets` [G+1]): every object is
+    recentred on its own medians (images.py:183-187; on device copies, the caller's arrays are left
+    alone), imaged on its own super-sampled grid, convolved with the PSF and rebinned.  L: [n] or
+    [C, n].  Returns dict of arrays [G, (C,) ndim, ndim]: 'no_PSF', 'data' (+ the super-sampled pair),
+    NumPy float64 for host inputs, CUDA float32 otherwise."""
+    host = not any(dv.is_device_tensor(a) for a in (X, Y, L))
+    Xd, Yd, Ld = dv.to_dev(X).clone(), dv.to_dev(Y).clone(), dv.to_dev(L)
+    one = Ld.dim() == 1
+    off, ids, G = _image_ids(offsets, Xd.device)
+    _recentre_segmented(Xd, off, self.xoffset)
+    _recentre_segmented(Yd, off, self.yoffset)
+    no_psf, _, _, r = core_device(Xd, Yd, Ld, self.resolution, self.ndim_super, self.smoothing, want_ngp=False,
+                                  img=ids, n_img=G)
+    conv = convolve_fft_device(no_psf, self.psf_spectrum())
+    pick = (lambda t: t[:, 0]) if one else (lambda t: t)
+    fin = (lambda t: dv.to_host(pick(t))) if host else pick
+    return {'super_no_PSF': fin(no_psf), 'super_data': fin(conv), 'no_PSF': fin(rebin_device(no_psf, self.ndim)),
+            'data': fin(rebin_device(conv, self.ndim)), 'stats': r['stats']}
+
+
+observed.particle_batch = _observed_particle_batch
 
 
 def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=False, pixel_scale=False,

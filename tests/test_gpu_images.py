@@ -276,3 +276,66 @@ def test_median_matches_numpy_bitwise():
     rows = rng.normal(1.0, 5.0, (7, 2048))
     got = images.median_device(torch.from_numpy(rows).cuda()).cpu().numpy()
     assert np.array_equal(got, np.median(rows, axis=1))
+
+
+def _batch_catalogue():
+    sizes = [700, 5, 0, 2300, 64, 1500]            # incl. fewer particles than k, and an empty object
+    parts = [synthetic.particles(max(n, 1), seed=70 + i, scale_kpc=0.6 + 0.3 * i) for i, n in enumerate(sizes)]
+    cat = {k: np.concatenate([p[k][:n] for p, n in zip(parts, sizes)]) for k in ('X', 'Y', 'Masses')}
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    rng = np.random.default_rng(4)
+    cat['L'] = cat['Masses'] * (0.5 + rng.random(cat['Masses'].size))
+    return cat, off, sizes
+
+
+@pytest.mark.parametrize('smoothing', [False, ('convolved_gaussian', 0.25), ('adaptive', 8)])
+def test_core_batch_equals_loop(smoothing):
+    """core_batch (one pass over all objects: image id in the k-NN sort key and in the tile key) == a loop
+    of core() over the objects == the oracle; NGP counts bit-exact"""
+    from synthobs_b200.morph import images
+    cat, off, sizes = _batch_catalogue()
+    b = images.core_batch(cat['X'], cat['Y'], cat['L'], off, resolution=0.08, ndim=60, smoothing=smoothing)
+    assert b.hist.shape == (len(sizes), 60, 60) and b.data.shape == (len(sizes), 60, 60)
+    for g, n in enumerate(sizes):
+        s, e = off[g], off[g + 1]
+        if n == 0:
+            assert not b.hist[g].any() and not b.data[g].any()
+            continue
+        one = images.core(cat['X'][s:e], cat['Y'][s:e], cat['L'][s:e], resolution=0.08, ndim=60, smoothing=smoothing)
+        assert np.array_equal(b.hist[g], one.hist)
+        np.testing.assert_allclose(b.simple[g], one.simple, rtol=1e-6)
+        assert_image_close(b.data[g], one.data, tol=2e-6)
+        ref = image_oracle.core(cat['X'][s:e], cat['Y'][s:e], cat['L'][s:e], resolution=0.08, ndim=60, smoothing=smoothing)
+        assert np.array_equal(b.hist[g], ref['hist'])
+        assert_image_close(b.data[g], ref['data'])
+
+
+def test_observed_particle_batch_equals_loop():
+    """observed.particle_batch (segmented medians, batched deposit, PSF FFT, rebin) == loop of observed.particle;
+    multi-channel weights"""
+    from synthobs_b200.morph import images
+    images.filter_info.update({'JWST.NIRCAM.F150W': {'pixel_scale': 0.031}})
+    cat, off, sizes = _batch_catalogue()
+    cosmo = synthetic.FixedCosmology()
+    L2 = np.stack([cat['L'], 0.3 * cat['L'][::-1].copy()])
+    obs = images.observed('JWST.NIRCAM.F150W', cosmo, 8.0, 1.0, smoothing=('adaptive', 8.), PSF=synthetic.GaussianPSF(2.1),
+                          super_sampling=2, xoffset_pix=0.2, yoffset_pix=-0.1)
+    X0, Y0 = cat['X'].copy(), cat['Y'].copy()
+    out = obs.particle_batch(cat['X'], cat['Y'], L2, off)
+    assert np.array_equal(cat['X'], X0) and np.array_equal(cat['Y'], Y0)        # batch entry leaves the inputs alone
+    assert out['data'].shape == (len(sizes), 2, obs.ndim, obs.ndim)
+    for g, n in enumerate(sizes):
+        if n == 0:
+            assert not out['data'][g].any()
+            continue
+        s, e = off[g], off[g + 1]
+        for c in range(2):
+            one = obs.particle(cat['X'][s:e].copy(), cat['Y'][s:e].copy(), L2[c, s:e].copy())
+            assert_image_close(out['no_PSF'][g, c], one.img.no_PSF, tol=2e-6)
+            assert_image_close(out['data'][g, c], one.img.data, tol=2e-6)
+    med = images.median_segmented_device(images.dv.to_dev(cat['X']), images.dv.to_dev(off, __import__('torch').int64)).cpu().numpy()
+    for g, n in enumerate(sizes):
+        if n:
+            assert med[g] == np.median(cat['X'][off[g]:off[g + 1]])
+        else:
+            assert np.isnan(med[g])
