@@ -13,6 +13,8 @@
 // sparse outskirts and isolated particles all cost O(log) node visits plus a few leaf scans.
 // The squared distance is formed with separately rounded products and sum (no FMA contraction) and
 // an IEEE sqrt, i.e. the same float64 arithmetic as a straightforward C loop.
+#include <stdlib.h>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -213,7 +215,7 @@ __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t
 __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
                                  const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
                                  int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
-                                 int part, int n_parts, double* __restrict__ dk) {
+                                 int part, int n_parts, int leaf, double* __restrict__ dk) {
     extern __shared__ double s_best[];
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict
         int a, b;
         node_range(t, level, code, a, b);
         if (a == b) continue;
-        if (b - a <= kLeaf || level == kBits) {
+        if (b - a <= leaf || level == kBits) {
             knn_scan_range(xs, ys, a, b, wa, wb, x, y, best, k, stride);
             continue;
         }
@@ -300,6 +302,145 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict
         for (int c = 0; c < 4; ++c) stack[sp++] = (1u << (2 * level + 2)) | cc[c];
     }
     dk[pid] = sqrt(best[(k - 1) * stride]);
+}
+
+// Warp-cooperative variant (default): one warp answers 32 consecutive queries of the Morton order, which
+// are neighbours in space.  The tree walk is shared (uniform control flow): a node is opened when ANY
+// lane still needs it (its own lower bound vs its own k-th best, __any_sync), a leaf is loaded once,
+// coalesced, into shared memory and every lane tests every candidate against its own list.  Per query
+// this scans more candidates than the private walk above but with all 32 lanes busy (the private walk
+// runs at ~9 of 32 active lanes), and the node tests, table look-ups and point loads are paid once per warp.
+constexpr int kWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
+        const double* __restrict__ xs, const double* __restrict__ ys, const unsigned long long* __restrict__ keys,
+        const int32_t* __restrict__ vals, int64_t n, int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw,
+        double inv_h, int k, int part, int n_parts, int leaf, double* __restrict__ dk) {
+    extern __shared__ double s_dyn[];
+    __shared__ double s_px[kWarpsPerCta][32], s_py[kWarpsPerCta][32];
+    __shared__ uint32_t s_stack[kWarpsPerCta][kStack];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = blockDim.x;
+    double* best = s_dyn + threadIdx.x;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const unsigned FULL = 0xffffffffu;
+
+    // per-lane query
+    bool valid = s < n;
+    unsigned long long key = valid ? keys[s] : ~0ull;
+    const int pid = valid ? vals[s] : 0;
+    unsigned long long image = key >> (2 * kBits);
+    if (valid && image >= (unsigned long long)n_img) { dk[pid] = 0.0; valid = false; }
+    double x = 0.0, y = 0.0;
+    if (valid) { x = xs[s]; y = ys[s]; }
+    const double ud = (x + hw) * inv_h, vd = (y + hw) * inv_h;   // fine-cell units, as used for the keys
+    const float u = (float)ud, v = (float)vd;
+    const double h = 1.0 / inv_h;
+
+    unsigned todo = __ballot_sync(FULL, valid);
+    while (todo) {                                   // one pass per image present in the warp (almost always one)
+        const int leader = __ffs(todo) - 1;
+        const unsigned long long g = __shfl_sync(FULL, image, leader);
+        bool mine = valid && image == g;
+        todo &= ~__ballot_sync(FULL, mine);
+        KnnTree t{keys, E, Lt, g};
+        int g_lo, g_hi;
+        node_range(t, 0, 0u, g_lo, g_hi);
+        const int nsel = g_hi - g_lo;
+        if (mine && (s - g_lo < (int64_t)nsel * part / n_parts || s - g_lo >= (int64_t)nsel * (part + 1) / n_parts)) mine = false;
+        if (mine && k > nsel) { dk[pid] = INF; mine = false; }
+        if (!__any_sync(FULL, mine)) continue;
+
+        // 1. private window of sorted neighbours -> first k-best list
+        for (int j = 0; j < k; ++j) best[j * stride] = INF;
+        int wa = 0, wb = 0;
+        if (mine) {
+            wb = min(g_hi, (int)s + k + 1);
+            wa = max(g_lo, wb - (2 * k + 1));
+            wb = min(g_hi, wa + 2 * k + 1);
+            knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
+        }
+        double kth = best[(k - 1) * stride];
+
+        // 2. start nodes: the level whose cells are at least as wide as the box around all the lanes' balls
+        const float rc = mine ? (float)(sqrt(kth) * inv_h) * (1.f + 1e-5f) + 1.6e-2f : 0.f;
+        float x0 = mine ? u - rc : 3.0e38f, x1 = mine ? u + rc : -3.0e38f;
+        float y0 = mine ? v - rc : 3.0e38f, y1 = mine ? v + rc : -3.0e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
+            y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
+        }
+        int sp = 0;
+        {
+            const float ext = fmaxf(x1 - x0, y1 - y0);
+            int e = 0;
+            if (ext >= 1.f) e = ilogbf(ext) + 1;                // 2^e > ext: the box spans at most 2 cells per axis
+            if (!(ext < (float)(1 << kBits)) || e >= kBits) {
+                if (lane == 0) s_stack[warp][0] = 1u;           // root
+                sp = 1;
+            } else {
+                const int level = kBits - e;
+                const float sc = (float)(1 << e);
+                const int top = (1 << level) - 1;
+                const int cx0 = max(0, min(top, (int)floorf(x0 / sc))), cx1 = max(0, min(top, (int)floorf(x1 / sc)));
+                const int cy0 = max(0, min(top, (int)floorf(y0 / sc))), cy1 = max(0, min(top, (int)floorf(y1 / sc)));
+                for (int cy = cy0; cy <= cy1; ++cy)
+                    for (int cx = cx0; cx <= cx1; ++cx) {
+                        if (lane == 0) s_stack[warp][sp] = (1u << (2 * level)) | morton((uint32_t)cx, (uint32_t)cy);
+                        ++sp;
+                    }
+            }
+        }
+        __syncwarp();
+
+        // 3. shared depth-first walk
+        while (sp > 0) {
+            const uint32_t node = s_stack[warp][--sp];
+            __syncwarp();
+            const int level = (31 - __clz(node)) >> 1;
+            const uint32_t code = node ^ (1u << (2 * level));
+            const uint32_t ncx = compact_bits(code), ncy = compact_bits(code >> 1);
+            const double dm = (double)node_dmin(kBits - level, ncx, ncy, u, v) * h;
+            const bool need = mine && dm * dm < kth;
+            if (!__any_sync(FULL, need)) continue;
+            int a, b;
+            node_range(t, level, code, a, b);
+            if (a == b) continue;
+            if (b - a <= leaf || level == kBits) {
+                for (int base = a; base < b; base += 32) {
+                    const int m = min(32, b - base);
+                    if (lane < m) { s_px[warp][lane] = xs[base + lane]; s_py[warp][lane] = ys[base + lane]; }
+                    __syncwarp();
+                    if (need) {
+                        for (int c = 0; c < m; ++c) {
+                            const int q = base + c;
+                            if (q >= wa && q < wb) continue;            // already in the list (window)
+                            const double dx = s_px[warp][c] - x, dy = s_py[warp][c] - y;
+                            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                            if (d2 < kth) {
+                                int j = k - 1;
+                                while (j > 0 && best[(j - 1) * stride] > d2) {
+                                    best[j * stride] = best[(j - 1) * stride];
+                                    --j;
+                                }
+                                best[j * stride] = d2;
+                                kth = best[(k - 1) * stride];
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
+            if (lane < 4) s_stack[warp][sp + lane] = (1u << (2 * level + 2)) | (code << 2) | (uint32_t)lane;
+            sp += 4;
+            __syncwarp();
+        }
+        if (mine) dk[pid] = sqrt(kth);
+        __syncwarp();
+    }
 }
 
 __global__ void knn_range_kernel(const unsigned long long* __restrict__ counter, int part, int n_parts,
@@ -351,9 +492,26 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, const in
     SO_LAUNCH_CHECK();
     tmp = (size_t)l.cub_tmp_bytes;
     SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), (int)ncell, st));
-    SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-        l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, dk);
+    // measured on B200 (1e6 clustered particles): the private walk wins for k <= 8 (0.71 vs 0.76 ms), the shared
+    // walk for larger k (k = 16: 1.17 vs 1.27 ms).  SO_KNN_PRIVATE=0/1 and SO_KNN_LEAF override (A/B aids).
+    static int force_private = -2, leaf = 0;
+    if (force_private == -2) {
+        const char* e = getenv("SO_KNN_PRIVATE");
+        force_private = e ? (e[0] == '1' ? 1 : 0) : -1;
+        const char* lf = getenv("SO_KNN_LEAF");
+        leaf = lf ? atoi(lf) : kLeaf;
+        if (leaf < 1) leaf = kLeaf;
+    }
+    const bool private_walk = force_private >= 0 ? force_private == 1 : k <= 8;
+    if (private_walk || threads != kWarpsPerCta * 32) {
+        SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
+            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, dk);
+    } else {
+        SO_CUDA(cudaFuncSetAttribute(knn_query_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_query_warp_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
+            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, dk);
+    }
     SO_LAUNCH_CHECK();
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
     if (range_out) {
