@@ -163,11 +163,12 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
         double age[kPerThread], zz[kPerThread];
         float mm[kPerThread], ti[kPerThread], tb[kPerThread];
         if (p.prefetch > 0 && item + p.prefetch < item_hi) {
-            // pull a later item's 128-byte lines towards L2 while this one is being processed
-            // (contiguous in memory unless a galaxy boundary intervenes: then the hint is merely wasted)
+            // pull a later item's 128-byte lines towards L2 while this one is being processed (contiguous in
+            // memory unless a galaxy boundary intervenes: then the hint is merely wasted).  One line per thread,
+            // spread over 320 threads: issuing the five lines of a column from 64 threads only was slower.
             constexpr int kLines = kItem * 8 / 128;          // lines per array per item
-            if (tid < 5 * kLines) {
-                const int arr = tid / kLines, line = tid - arr * kLines;
+            for (int t = tid; t < 5 * kLines; t += kThreads) {
+                const int arr = t / kLines, line = t - arr * kLines;
                 const double* base = arr == 0 ? p.ages : arr == 1 ? p.metals : arr == 2 ? p.masses : arr == 3 ? p.tau_ism : p.tau_bc;
                 const int64_t idx = begin + (int64_t)p.prefetch * kItem + line * 16;
                 if (base && idx < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + idx));
@@ -213,6 +214,46 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
                 tb[j] = (on && p.tau_bc) ? (float)ldg_stream(p.tau_bc + i) : 0.f;
             }
         }
+        if constexpr (!WRITE_PF) {
+            // sums only.  Phase A: NGP cells of the thread's particles, young ones appended to the warp's buffer
+            int cellj[kPerThread];
+            float wj[kPerThread];
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                const int64_t i = begin + j * kThreads + tid;
+                const bool on = (j * kThreads + tid) < count;
+                const int ia = locate(s_age_thr, s_age_lut, p.age.n, p.age.base, age[j]);
+                const int iz = locate(s_z_thr, s_z_lut, p.z.n, p.z.base, zz[j]);
+                const bool young = (age[j] < p.young_thr) && (age[j] >= 0.0);
+                const int cell = ia * p.nz + iz;
+                if (p.out_cell && on) p.out_cell[i] = cell + (young ? 65536 : 0);
+                const bool isy = young && on;
+                const unsigned bal = __ballot_sync(0xffffffffu, isy);      // fixed order: slot, lane
+                if (isy) my_y[ytail + __popc(bal & lane_lt)] = make_float4(mm[j] * ofe, ti[j], tb[j], __int_as_float(cell));
+                ytail += __popc(bal);
+                cellj[j] = cell;
+                wj[j] = young ? mm[j] * fesc : mm[j];          // m == 0 for lanes past the end
+            }
+            // Phase B: acc += w 2^(tI kI) inc for all filters, the particles interleaved (independent chains);
+            // the birth-cloud term of the young ones follows in the dense pass below
+#pragma unroll
+            for (int q = 0; q < FP / 4; ++q) {
+#pragma unroll
+                for (int j = 0; j < kPerThread; ++j) {
+                    const float4 vi = reinterpret_cast<const float4*>(s_inc + cellj[j] * kStride)[q];
+                    const float2 inc2[2] = {make_float2(vi.x, vi.y), make_float2(vi.z, vi.w)};
+                    const float2 w2 = make_float2(wj[j], wj[j]), tI2 = make_float2(ti[j], ti[j]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int pr = q * 2 + h;                       // filter pair (2 pr, 2 pr + 1)
+                        if (q < FP / 4 - 1 || h == 0 || 2 * pr < nf) {  // uniform; only the last quad can be partial
+                            const float2 argI = __fmul2_rn(tI2, make_float2(p.k_ism[2 * pr], p.k_ism[2 * pr + 1]));
+                            acc[pr] = __ffma2_rn(__fmul2_rn(w2, ex2_approx2(argI)), inc2[h], acc[pr]);
+                        }
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
             const int64_t i = begin + j * kThreads + tid;
@@ -274,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
             }
         }
 
+        }
         // advance to the next work item; a run ends with the galaxy (or with this CTA's range)
         int64_t next_begin = begin + kItem;
         bool run_end = (item + 1 == item_hi);
