@@ -57,13 +57,17 @@ struct SelectState {
     unsigned long long prefix;      // high bytes of the selected key found so far
     unsigned long long rank;        // rank of the wanted element among the keys that match the prefix
     unsigned long long below_max;   // largest key below the selected one (0 if none)
+    unsigned int ticket;            // blocks of the current pass that have added their histogram
     unsigned int hist[256];
 };
 
-// pass p: histogram of byte (7 - p) over the keys whose p high bytes equal the prefix
+// pass p: histogram of byte (7 - p) over the keys whose p high bytes equal the prefix; the block that adds
+// its histogram last (ticket counter) picks the byte value whose bin holds the wanted rank, descends into
+// it and clears the histogram for the next pass
 __global__ void __launch_bounds__(512) select_hist_kernel(const double* __restrict__ x, int64_t n, int64_t stride,
                                                           SelectState* __restrict__ st, int pass) {
     __shared__ unsigned int s_h[256];
+    __shared__ bool s_last;
     const double* xa = x + (size_t)blockIdx.y * stride;
     SelectState* sa = st + blockIdx.y;
     if (threadIdx.x < 256) s_h[threadIdx.x] = 0;
@@ -76,13 +80,13 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const double* __restri
     }
     __syncthreads();
     if (threadIdx.x < 256 && s_h[threadIdx.x]) atomicAdd(&sa->hist[threadIdx.x], s_h[threadIdx.x]);
-}
-
-// one block per array: pick the byte value whose bin holds the wanted rank, descend into it
-__global__ void __launch_bounds__(256) select_pick_kernel(SelectState* __restrict__ st, int pass) {
-    __shared__ unsigned int s_h[256];
-    SelectState* sa = st + blockIdx.x;
-    s_h[threadIdx.x] = sa->hist[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&sa->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 256) s_h[threadIdx.x] = *(volatile unsigned int*)&sa->hist[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long r = sa->rank, acc = 0;
@@ -92,10 +96,10 @@ __global__ void __launch_bounds__(256) select_pick_kernel(SelectState* __restric
             acc += s_h[b];
         }
         sa->rank = r - acc;
-        sa->prefix |= (unsigned long long)b << (56 - 8 * pass);
+        sa->prefix = prefix | ((unsigned long long)b << (56 - 8 * pass));
+        sa->ticket = 0;
     }
-    __syncthreads();
-    sa->hist[threadIdx.x] = 0;
+    if (threadIdx.x < 256) sa->hist[threadIdx.x] = 0;
 }
 
 // largest key strictly below the selected one (the lower middle element when n is even and distinct)
@@ -130,7 +134,7 @@ __global__ void select_finish_kernel(const SelectState* __restrict__ st, int64_t
 
 __global__ void select_init_kernel(SelectState* __restrict__ st, int64_t n) {
     SelectState* sa = st + blockIdx.x;
-    if (threadIdx.x == 0) { sa->prefix = 0; sa->rank = (unsigned long long)(n / 2); sa->below_max = 0; }
+    if (threadIdx.x == 0) { sa->prefix = 0; sa->rank = (unsigned long long)(n / 2); sa->below_max = 0; sa->ticket = 0; }
     sa->hist[threadIdx.x] = 0;
 }
 
@@ -233,8 +237,6 @@ extern "C" int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64
     SO_LAUNCH_CHECK();
     for (int pass = 0; pass < 8; ++pass) {
         select_hist_kernel<<<grid, 512, 0, st>>>(x, n, stride, state, pass);
-        SO_LAUNCH_CHECK();
-        select_pick_kernel<<<n_arrays, 256, 0, st>>>(state, pass);
         SO_LAUNCH_CHECK();
     }
     select_below_kernel<<<grid, 512, 0, st>>>(x, n, stride, state);
