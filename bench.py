@@ -390,8 +390,9 @@ def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
     stats = {}
 
     def step_device(Xd, Yd, Ld):
-        X = Xd - images.median_device(Xd)    # recentring (images.py:183-184, np.median semantics) on device copies
-        Y = Yd - images.median_device(Yd)
+        mx, my = images.median_device_pair(Xd, Yd)    # recentring (images.py:183-184, np.median semantics)
+        X = Xd - mx                                   # on device copies
+        Y = Yd - my
         r = images.particle_device_multi(obs, X, Y, Ld)
         stats.update(r['stats'])
         return r['data']

@@ -276,6 +276,10 @@ def test_median_matches_numpy_bitwise():
     rows = rng.normal(1.0, 5.0, (7, 2048))
     got = images.median_device(torch.from_numpy(rows).cuda()).cpu().numpy()
     assert np.array_equal(got, np.median(rows, axis=1))
+    a, b = torch.from_numpy(cases[0]).cuda(), torch.from_numpy(rng.normal(2, 1, 1001)).cuda()
+    for u, v in ((a, b), (b, a)):
+        mu, mv = images.median_device_pair(u, v)
+        assert float(mu.cpu()) == np.median(u.cpu().numpy()) and float(mv.cpu()) == np.median(v.cpu().numpy())
 
 
 def _batch_catalogue():
