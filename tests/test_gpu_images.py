@@ -292,7 +292,7 @@ def _batch_catalogue():
     return cat, off, sizes
 
 
-@pytest.mark.parametrize('smoothing', [False, ('convolved_gaussian', 0.25), ('adaptive', 8)])
+@pytest.mark.parametrize('smoothing', [False, ('convolved_gaussian', 0.25), ('adaptive', 8), ('adaptive', 12)])
 def test_core_batch_equals_loop(smoothing):
     """core_batch (one pass over all objects: image id in the k-NN sort key and in the tile key) == a loop
     of core() over the objects == the oracle; NGP counts bit-exact"""
