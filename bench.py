@@ -348,6 +348,22 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
     except Exception:
         bf16_peak, src = 1590.0, 'fallback bf16 / 2'
     tf32_peak = bf16_peak / 2
+    # context for the denominator: cuBLAS TF32 (one pass, no error compensation) on 8192^3, measured live
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a32 = torch.rand((8192, 8192), device=dev)
+    b32 = torch.rand((8192, 8192), device=dev)
+    for _ in range(3):
+        c32 = a32 @ b32
+    barrier()
+    e0.record()
+    for _ in range(10):
+        c32 = a32 @ b32
+    e1.record()
+    barrier()
+    cublas_tf32 = 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) / 10) / 1e9
+    torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    del a32, b32, c32
     return {
         'metric': 'galaxy SEDs/sec (5 spectra x %d wavelengths, ISM+BC dust) + %d band fluxes' % (n_lam, len(F['filters'])),
         'value': world * G / (ms * 1e-3), 'unit': 'galaxy_SEDs/s', 'ms_per_step': ms,
@@ -362,6 +378,7 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
                                           'traffic_note': 'ncu dram read 1.2 GB + write 0.70 GB per launch vs 1.03 GB of '
                                                           'operands (hi+lo) and result (profiles/r01_ncu_kernels.md)',
                                           'peak_source': src,
+                                          'cublas_tf32_8192_tflops': cublas_tf32,
                                           'note': 'achieved counts the three TF32 MMAs actually executed per '
                                                   'algorithmic product (3xTF32); algorithmic fraction is a third'}},
     }
