@@ -692,7 +692,7 @@ def _spectra_contract(model, spectra, op):
         S = torch.nn.functional.pad(S, (0, nlp - S.shape[1]))
     # spectra span many decades between galaxies: scale each row to unit maximum (a power of two: exact)
     rmax = S.abs().amax(dim=1).clamp_min(1e-30)
-    rs = torch.exp2(torch.ceil(torch.log2(rmax)))
+    rs = torch.pow(2.0, torch.ceil(torch.log2(rmax)))      # (torch.exp2 is a jiterator kernel: needs NVRTC at run time)
     out = gemm(S / rs[:, None], Wd, B_split=W_split).to(torch.float64) * rs.to(torch.float64)[:, None] * scale[None, :]
     out = out[0] if one else out
     return dv.to_host(out) if host else out
