@@ -370,6 +370,7 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
         'galaxy_SEDs_x_filters_per_s': world * G * len(F['filters']) / (ms * 1e-3),
         'particle_wavelengths_per_s': world * n_part * n_lam / (ms * 1e-3),
         'config': {'workload': '%d galaxies x 1e5 particles per GPU, generate_SED_batch + spectra x filters' % G},
+        'ex2_roofline': _ex2_roofline(batch, n_part, n_lam, ms),
         'gemm_hist_x_grid': {'M': M, 'N': n_lam, 'K': K, 'ms': gms, 'algorithmic_tflops': flops / gms / 1e9,
                              'executed_tf32_tflops': 3 * flops / gms / 1e9,
                              'roofline': {'bound': 'tensor', 'achieved': 3 * flops / gms / 1e9, 'peak': tf32_peak,
@@ -382,6 +383,19 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
                                           'note': 'achieved counts the three TF32 MMAs actually executed per '
                                                   'algorithmic product (3xTF32); algorithmic fraction is a third'}},
     }
+
+
+def _ex2_roofline(batch, n_part, n_lam, ms):
+    """The dust-spectra kernel is bound by exponentials: one per (old particle, wavelength), two per young one
+    (models.py:285-304).  Peak = 16 MUFU.EX2 per clock and SM at the maximum SM clock; the step time (which also
+    holds the histogram, sort and GEMM launches) is used, so the fraction is a lower bound for the kernel.  The
+    kernel evaluates a quarter of them on the FMA pipe instead, which is how it can pass the MUFU-only roof."""
+    young = float((batch['Ages'] < 10.0).mean())
+    exps = n_part * n_lam * (1.0 + young)
+    peak = 148 * 16 * 1.965e9
+    return {'bound': 'mufu_ex2', 'achieved': exps / (ms * 1e-3), 'peak': peak, 'unit': 'ex2/s',
+            'frac': exps / (ms * 1e-3) / peak, 'young_fraction': young,
+            'peak_source': '148 SMs x 16 MUFU.EX2/clk x 1.965 GHz (nominal XU rate; no measured entry)'}
 
 
 def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
