@@ -46,7 +46,6 @@ struct BroadbandParams {
     const int64_t* seg_offsets;   // device, null = single segment
     int64_t n_seg;
     const int64_t* item_start;    // [n_seg+1] device (null when single segment)
-    const int32_t* item_gal;      // [n_items] device (null when single segment)
     int64_t n_items;              // exact when single segment, else read from item_start[n_seg]
     int32_t na, nz;
     double young_thr;
@@ -133,6 +132,9 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
         reinterpret_cast<unsigned*>(s_z_lut)[i] = reinterpret_cast<const unsigned*>(p.z.lut)[i];
     }
     __syncthreads();
+    // programmatic dependent launch: everything above (table staging) overlaps the item-scan kernel; its
+    // output (item_start) is read from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // contiguous range of work items per CTA so consecutive items share a galaxy
     const bool segmented = p.item_start != nullptr;
@@ -145,7 +147,12 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
     // running (galaxy, segment end, chunk start): advanced incrementally, no per-item lookups
     int64_t gal = 0, s1 = p.n, begin = item_lo * kItem;
     if (segmented) {
-        gal = p.item_gal[item_lo];
+        int64_t lo = 0, hi = p.n_seg;             // last galaxy whose first item is <= item_lo
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (p.item_start[mid] <= item_lo) lo = mid; else hi = mid;
+        }
+        gal = lo;
         const int64_t s0 = p.seg_offsets[gal];
         s1 = p.seg_offsets[gal + 1];
         begin = s0 + (item_lo - p.item_start[gal]) * kItem;
@@ -397,6 +404,7 @@ __global__ void __launch_bounds__(1024) item_scan_kernel(const int64_t* __restri
                                                          int64_t* __restrict__ item_start) {
     __shared__ int64_t s_warp[32];
     __shared__ int64_t s_carry;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the broadband kernel may stage its tables now
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -432,26 +440,13 @@ __global__ void __launch_bounds__(1024) item_scan_kernel(const int64_t* __restri
     if (tid == 0) item_start[n_seg] = s_carry;
 }
 
-// item -> galaxy map (binary search per item; item_start is L2 resident)
-__global__ void item_fill_kernel(const int64_t* __restrict__ item_start, int64_t n_seg,
-                                 int32_t* __restrict__ item_gal, int64_t max_items) {
-    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= max_items) return;
-    if (it >= item_start[n_seg]) return;
-    int64_t lo = 0, hi = n_seg;  // last g with item_start[g] <= it
-    while (hi - lo > 1) {
-        int64_t mid = (lo + hi) >> 1;
-        if (item_start[mid] <= it) lo = mid; else hi = mid;
-    }
-    item_gal[it] = (int32_t)lo;
-}
-
 // per-galaxy sum of the per-item partials, fixed order -> deterministic
 __global__ void __launch_bounds__(256) seg_reduce_kernel(const double* __restrict__ partial,
                                                          const int64_t* __restrict__ item_start,
                                                          int64_t n_items_single, int32_t F,
                                                          double* __restrict__ out) {
     __shared__ double s[256];
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // launched ahead of the broadband kernel's end
     const int64_t g = blockIdx.x;
     const int64_t i0 = item_start ? item_start[g] : 0;
     const int64_t i1 = item_start ? item_start[g + 1] : n_items_single;
@@ -483,8 +478,19 @@ int launch_broadband_impl(const BroadbandParams& p, cudaStream_t st) {
     int64_t grid = (int64_t)so_num_sms() * per_sm;
     if (grid > p.n_items) grid = p.n_items;
     if (grid < 1) grid = 1;
-    sed_broadband_kernel<FP, WRITE_PF><<<(unsigned)grid, kThreads, smem, st>>>(p);
-    SO_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // only behind our own item-scan kernel (segmented path): the table staging must not overtake a foreign
+    // predecessor that might still be writing the tables
+    cfg.numAttrs = p.item_start ? 1 : 0;
+    SO_CUDA(cudaLaunchKernelEx(&cfg, sed_broadband_kernel<FP, WRITE_PF>, p));
     return SO_OK;
 }
 
@@ -620,7 +626,8 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
     int64_t* item_start = a.take<int64_t>(n_seg + 1);
     int32_t* item_gal = a.take<int32_t>(max_items);
     double* partial = a.take<double>(max_items * n_filters);
-    if (!a.ok() || (out_sums && !partial) || (segmented && (!item_start || !item_gal))) return SO_ERR_WORKSPACE;
+    (void)item_gal;      // (slot kept so the workspace layout of earlier builds still fits)
+    if (!a.ok() || (out_sums && !partial) || (segmented && !item_start)) return SO_ERR_WORKSPACE;
 
     BroadbandParams p{};
     p.masses = masses; p.ages = ages; p.metals = metals; p.tau_ism = tau_ism; p.tau_bc = tau_bc; p.n = n;
@@ -636,12 +643,10 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
     if (segmented) {
         item_scan_kernel<<<1, 1024, 0, st>>>(seg_offsets, n_seg, item_start);
         SO_LAUNCH_CHECK();
-        item_fill_kernel<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(item_start, n_seg, item_gal, max_items);
-        SO_LAUNCH_CHECK();
-        p.item_start = item_start; p.item_gal = item_gal;
+        p.item_start = item_start;
         p.n_items = max_items;  // upper bound for the grid; the exact count is read on the device
     } else {
-        p.item_start = nullptr; p.item_gal = nullptr;
+        p.item_start = nullptr;
         p.n_items = (n + kItem - 1) / kItem;
     }
 
@@ -680,9 +685,18 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
         if (rc != SO_OK) return rc;
     }
     if (out_sums) {
-        seg_reduce_kernel<<<(unsigned)n_seg, 256, 0, st>>>(partial, segmented ? item_start : nullptr, p.n_items,
-                                                          n_filters, out_sums);
-        SO_LAUNCH_CHECK();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_seg);
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SO_CUDA(cudaLaunchKernelEx(&cfg, seg_reduce_kernel, (const double*)partial,
+                                   (const int64_t*)(segmented ? item_start : nullptr), (int64_t)p.n_items,
+                                   (int32_t)n_filters, out_sums));
     }
     return SO_OK;
 }
