@@ -25,23 +25,34 @@
 //            sums go through a swizzled 16 KB staging buffer per column half and out with TMA stores
 //            (cp.async.bulk.tensor, asynchronous: the warps return to draining the next tile at once)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int kStages = 3;
-constexpr int kTileBytes = BM * BK * 4;            // 16 KB
-constexpr int kStageBytes = 4 * kTileBytes;        // Ahi, Alo, Bhi, Blo
+constexpr int kTileBytes = BM * BK * 4;            // 16 KB: one 128-row operand tile
+// kCtas = 1: one CTA per 128x128 tile, stage = {Ahi, Alo, Bhi, Blo} x 16 KB, 3 stages.
+// kCtas = 2: a CTA pair (cta_group::2) per 256x128 tile: each CTA holds its own 128 A rows and HALF of the B
+//            tile (64 rows), the pair's tensor cores read both halves; stage = 48 KB per CTA, 4 stages.
+template <int kCtas> struct Cfg {
+    static constexpr int kBTileBytes = kTileBytes / kCtas;
+    static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBTileBytes;
+    static constexpr int kStages = kCtas == 1 ? 3 : 4;
+};
 constexpr int kGemmThreads = 384;
-constexpr int kTmemCols = 256;                 // two 128-column accumulators
+constexpr int kAccBufs = 2;                    // TMEM accumulator buffers (four were measured: no gain)
+constexpr int kTmemCols = kAccBufs * 128;      // 128-column accumulators
 constexpr int kChunk = 2;                      // K-blocks per TMEM accumulation chunk
 constexpr int kDrainWarps = 8;
 constexpr int kGroupM = 16;                    // row-tiles per raster group
 constexpr int kSlabCols = 32;                  // columns per epilogue slab (one 128-byte swizzle row)
 constexpr int kSlabBytes = BM * kSlabCols * 4; // 16 KB staging buffer per column half
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kSlabBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+template <int kCtas> constexpr int smem_bytes() {
+    return Cfg<kCtas>::kStages * Cfg<kCtas>::kStageBytes + 2 * kSlabBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: rank 0 of the pair
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,77 +98,128 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---- cta_group::2 variants (the CTA pair of one 256x128 tile) ----
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    // executed by both CTAs; the transaction bytes are counted on the barrier of rank 0
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {     // arrives on the barrier of BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
                    float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int tiles_m, int tiles_n, int tma_store) {
+    constexpr int kStages = Cfg<kCtas>::kStages, kStageBytes = Cfg<kCtas>::kStageBytes, kBTileBytes = Cfg<kCtas>::kBTileBytes;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* slab = smem + kStages * kStageBytes;          // [2][kSlabBytes] epilogue staging (TMA store source)
+    uint32_t rank = 0;                                           // CTA rank in the pair
+    if constexpr (kCtas == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     uint64_t* bars = reinterpret_cast<uint64_t*>(slab + 2 * kSlabBytes);
     uint64_t* full = bars;                 // [kStages]
     uint64_t* empty = bars + kStages;      // [kStages]
-    uint64_t* tmem_full = bars + 2 * kStages;          // [2]
-    uint64_t* tmem_empty = bars + 2 * kStages + 2;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* tmem_full = bars + 2 * kStages;                   // [kAccBufs]
+    uint64_t* tmem_empty = bars + 2 * kStages + kAccBufs;       // [kAccBufs]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccBufs);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (int)((K + BK - 1) / BK);
     const int nchunk = (nkb + kChunk - 1) / kChunk;
+    // tiles_m counts (kCtas * 128)-row tiles.  Grouped raster: tile t -> (m tile, n tile); groups of kGroupM / kCtas
+    // row-tiles are swept along n.  m0 = this CTA's first row.
     const int64_t n_tiles = (int64_t)tiles_m * tiles_n;
-    // grouped raster: tile t -> (m tile, n tile); groups of kGroupM row-tiles are swept along n
+    const int64_t t_first = blockIdx.x / kCtas, t_step = gridDim.x / kCtas;
     auto tile_origin = [&](int64_t t, int& m0, int& n0) {
-        const int64_t per_group = (int64_t)kGroupM * tiles_n;
+        constexpr int kG = kGroupM / kCtas;
+        const int64_t per_group = (int64_t)kG * tiles_n;
         const int group = (int)(t / per_group);
-        const int first_m = group * kGroupM;
-        const int gsz = min(kGroupM, tiles_m - first_m);
+        const int first_m = group * kG;
+        const int gsz = min(kG, tiles_m - first_m);
         const int r = (int)(t - (int64_t)group * per_group);
-        m0 = (first_m + r % gsz) * BM;
+        m0 = (first_m + r % gsz) * BM * kCtas + (int)rank * BM;
         n0 = (r / gsz) * BN;
     };
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kDrainWarps); }
+        // tmem_empty of rank 0 collects the drain warps of the whole pair
+        for (int b = 0; b < kAccBufs; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kDrainWarps * kCtas); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (kCtas == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kCtas == 2) cluster_sync();       // the peer's barriers and TMEM are ready too
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;                      // K-block counter over all of this CTA's tiles (ring position)
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int64_t t = t_first; t < n_tiles; t += t_step) {
                 int m0, n0;
                 tile_origin(t, m0, n0);
+                const int nb = n0 + (int)rank * (BN / kCtas);       // this CTA's part of the B tile
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     unsigned char* st = smem + s * kStageBytes;
-                    mbar_expect_tx(&full[s], kStageBytes);
-                    tma_load_2d(st + 0 * kTileBytes, &tmAh, &full[s], kb * BK, m0);
-                    tma_load_2d(st + 1 * kTileBytes, &tmAl, &full[s], kb * BK, m0);
-                    tma_load_2d(st + 2 * kTileBytes, &tmBh, &full[s], kb * BK, n0);
-                    tma_load_2d(st + 3 * kTileBytes, &tmBl, &full[s], kb * BK, n0);
+                    if constexpr (kCtas == 2) {
+                        // both CTAs' bytes are counted on rank 0's barrier, which its MMA thread waits on
+                        if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);
+                        tma_load_2d_pair(st, &tmAh, &full[s], kb * BK, m0);
+                        tma_load_2d_pair(st + kTileBytes, &tmAl, &full[s], kb * BK, m0);
+                        tma_load_2d_pair(st + 2 * kTileBytes, &tmBh, &full[s], kb * BK, nb);
+                        tma_load_2d_pair(st + 2 * kTileBytes + kBTileBytes, &tmBl, &full[s], kb * BK, nb);
+                    } else {
+                        mbar_expect_tx(&full[s], kStageBytes);
+                        tma_load_2d(st, &tmAh, &full[s], kb * BK, m0);
+                        tma_load_2d(st + kTileBytes, &tmAl, &full[s], kb * BK, m0);
+                        tma_load_2d(st + 2 * kTileBytes, &tmBh, &full[s], kb * BK, nb);
+                        tma_load_2d(st + 2 * kTileBytes + kBTileBytes, &tmBl, &full[s], kb * BK, nb);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {             // one thread of the pair's rank 0 issues the MMAs of both CTAs
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major, N>>3, M>>4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)((BM * kCtas) >> 4) << 24);
             uint32_t it = 0, cc = 0;              // ring position, chunk counter over all tiles
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int64_t t = t_first; t < n_tiles; t += t_step) {
                 for (int c = 0; c < nchunk; ++c, ++cc) {
-                    const int buf = cc & 1;
-                    mbar_wait(&tmem_empty[buf], ((cc >> 1) & 1) ^ 1);      // drained by the epilogue warps
+                    const int buf = cc % kAccBufs;
+                    mbar_wait(&tmem_empty[buf], ((cc / kAccBufs) & 1) ^ 1);      // drained by the epilogue warps
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
                     uint32_t acc = 0;
@@ -168,19 +230,28 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                         mbar_wait(&full[s], ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         unsigned char* st = smem + s * kStageBytes;
-                        const uint64_t dAh = umma_desc(st + 0 * kTileBytes), dAl = umma_desc(st + 1 * kTileBytes);
-                        const uint64_t dBh = umma_desc(st + 2 * kTileBytes), dBl = umma_desc(st + 3 * kTileBytes);
+                        const uint64_t dAh = umma_desc(st), dAl = umma_desc(st + kTileBytes);
+                        const uint64_t dBh = umma_desc(st + 2 * kTileBytes), dBl = umma_desc(st + 2 * kTileBytes + kBTileBytes);
 #pragma unroll
                         for (int k4 = 0; k4 < BK / 8; ++k4) {
                             const uint64_t adv = (uint64_t)(k4 * 2);     // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle atom
-                            umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, acc);   // small terms first
-                            acc = 1;
-                            umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, acc);
-                            umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, acc);
+                            if constexpr (kCtas == 2) {
+                                umma_tf32_pair(tmem_d, dAl + adv, dBh + adv, idesc, acc);   // small terms first
+                                acc = 1;
+                                umma_tf32_pair(tmem_d, dAh + adv, dBl + adv, idesc, acc);
+                                umma_tf32_pair(tmem_d, dAh + adv, dBh + adv, idesc, acc);
+                            } else {
+                                umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, acc);
+                                acc = 1;
+                                umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, acc);
+                                umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, acc);
+                            }
                         }
-                        umma_commit(&empty[s]);       // frees the stage once these MMAs have read it
+                        // frees the stage (in both CTAs) once these MMAs have read it
+                        if constexpr (kCtas == 2) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);
                     }
-                    umma_commit(&tmem_full[buf]);     // chunk accumulator complete
+                    // chunk accumulator complete (in both CTAs' tensor memory)
+                    if constexpr (kCtas == 2) umma_commit_pair(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
                 }
             }
         }
@@ -188,7 +259,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int half = (warp - 4) >> 2;         // which 64 of the 128 columns
         uint32_t cc = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int64_t t = t_first; t < n_tiles; t += t_step) {
             int m0, n0;
             tile_origin(t, m0, n0);
             const int64_t row = (int64_t)m0 + q * 32 + lane;
@@ -196,31 +267,39 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 64; ++j) sum[j] = 0.f;
             for (int c = 0; c < nchunk; ++c, ++cc) {
-                const int buf = cc & 1;
-                mbar_wait(&tmem_full[buf], (cc >> 1) & 1);
+                const int buf = cc % kAccBufs;
+                mbar_wait(&tmem_full[buf], (cc / kAccBufs) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // both 32-column loads go out before the single wait, and the buffer is handed back to the MMA
+                // warp as soon as the values are in registers (the additions overlap the next chunk's MMAs)
+                uint32_t v[64];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 64 + h * 32);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "=r"(v[h * 32 + 0]), "=r"(v[h * 32 + 1]), "=r"(v[h * 32 + 2]), "=r"(v[h * 32 + 3]),
+                          "=r"(v[h * 32 + 4]), "=r"(v[h * 32 + 5]), "=r"(v[h * 32 + 6]), "=r"(v[h * 32 + 7]),
+                          "=r"(v[h * 32 + 8]), "=r"(v[h * 32 + 9]), "=r"(v[h * 32 + 10]), "=r"(v[h * 32 + 11]),
+                          "=r"(v[h * 32 + 12]), "=r"(v[h * 32 + 13]), "=r"(v[h * 32 + 14]), "=r"(v[h * 32 + 15]),
+                          "=r"(v[h * 32 + 16]), "=r"(v[h * 32 + 17]), "=r"(v[h * 32 + 18]), "=r"(v[h * 32 + 19]),
+                          "=r"(v[h * 32 + 20]), "=r"(v[h * 32 + 21]), "=r"(v[h * 32 + 22]), "=r"(v[h * 32 + 23]),
+                          "=r"(v[h * 32 + 24]), "=r"(v[h * 32 + 25]), "=r"(v[h * 32 + 26]), "=r"(v[h * 32 + 27]),
+                          "=r"(v[h * 32 + 28]), "=r"(v[h * 32 + 29]), "=r"(v[h * 32 + 30]), "=r"(v[h * 32 + 31])
                         : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[h * 32 + j] += __uint_as_float(v[j]);
                 }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 // hand the buffer back to the MMA warp
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                if (lane == 0) {
+                    if constexpr (kCtas == 2) mbar_arrive_rank0(&tmem_empty[buf]);
+                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 64; ++j) sum[j] += __uint_as_float(v[j]);
             }
             if (tma_store) {
                 // tile -> global through shared memory and TMA: each column half (4 warps) owns one 16 KB
@@ -260,8 +339,12 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kCtas == 2) cluster_sync();      // neither CTA leaves while the other may still read its memory
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if constexpr (kCtas == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -282,12 +365,13 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D K-major operand [rows, K] with row stride ld (floats): box = 32 floats x 128 rows, 128 B swizzle
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_k = BK) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_k = BK,
+                    int box_rows = BM) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return SO_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -305,23 +389,48 @@ extern "C" int so_gemm_3xtf32(const float* A_hi, const float* A_lo, int64_t lda,
     if ((reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) | reinterpret_cast<uintptr_t>(B_hi) |
          reinterpret_cast<uintptr_t>(B_lo)) & 15)
         return SO_ERR_BAD_ARG;
+    // SO_GEMM_PAIR=1: a CTA pair (cta_group::2) per 256x128 tile when there are at least two 128-row tiles.
+    // Correct and as fast as single CTAs (2.17 vs 2.16 ms), not faster: the kernel is bound by the per-chunk
+    // drain of the accumulator (tcgen05.ld blocks the tensor pipe for ~500 cycles per chunk), not by shared memory.
+    static int allow_pair = -1;
+    if (allow_pair < 0) { const char* e = getenv("SO_GEMM_PAIR"); allow_pair = (e && e[0] == '1') ? 1 : 0; }
+    const bool pair = allow_pair && M > BM;
+    const int kc = pair ? 2 : 1;
     CUtensorMap mAh, mAl, mBh, mBl;
     int rc;
     if ((rc = make_map(&mAh, A_hi, M, K, lda)) != SO_OK) return rc;
     if ((rc = make_map(&mAl, A_lo, M, K, lda)) != SO_OK) return rc;
-    if ((rc = make_map(&mBh, B_hi, N, K, ldb)) != SO_OK) return rc;
-    if ((rc = make_map(&mBl, B_lo, N, K, ldb)) != SO_OK) return rc;
+    if ((rc = make_map(&mBh, B_hi, N, K, ldb, BK, BN / kc)) != SO_OK) return rc;
+    if ((rc = make_map(&mBl, B_lo, N, K, ldb, BK, BN / kc)) != SO_OK) return rc;
     // the epilogue stores C with TMA when its rows are 16-byte aligned; plain stores otherwise
     CUtensorMap mC = mAh;
     const int tma_store = ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
     if (tma_store && (rc = make_map(&mC, C, M, N, ldc, kSlabCols)) != SO_OK) return rc;
-    SO_CUDA(cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    const int64_t tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const int64_t tiles_m = (M + BM * kc - 1) / (BM * kc), tiles_n = (N + BN - 1) / BN;
     if (tiles_m > (1 << 24) || tiles_n > (1 << 24)) return SO_ERR_TOO_LARGE;
-    int64_t grid = tiles_m * tiles_n;
-    if (grid > so_num_sms()) grid = so_num_sms();
-    gemm_3xtf32_kernel<<<(unsigned)grid, kGemmThreads, kSmemBytes, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, mC, C, ldc, M, N, K,
-                                                                                        (int)tiles_m, (int)tiles_n, tma_store);
-    SO_LAUNCH_CHECK();
+    int64_t groups = tiles_m * tiles_n;                       // CTAs (kc = 1) or CTA pairs (kc = 2)
+    if (groups > so_num_sms() / kc) groups = so_num_sms() / kc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * kc));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kc;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (pair) {
+        cfg.dynamicSmemBytes = smem_bytes<2>();
+        SO_CUDA(cudaFuncSetAttribute(gemm_3xtf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<2>()));
+        SO_CUDA(cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel<2>, mAh, mAl, mBh, mBl, mC, C, ldc, M, N, K, (int)tiles_m,
+                                   (int)tiles_n, tma_store));
+    } else {
+        cfg.dynamicSmemBytes = smem_bytes<1>();
+        SO_CUDA(cudaFuncSetAttribute(gemm_3xtf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<1>()));
+        SO_CUDA(cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel<1>, mAh, mAl, mBh, mBl, mC, C, ldc, M, N, K, (int)tiles_m,
+                                   (int)tiles_n, tma_store));
+    }
     return SO_OK;
 }

@@ -332,3 +332,27 @@ def test_spectra_to_broadband_contraction():
         np.testing.assert_allclose(Fn[gi], [ref_F[f] for f in Fz['filters']], rtol=RTOL_SUM)
     one = models.spectra_Lnu(model, F, out['total'][2])
     np.testing.assert_allclose(one, L[2], rtol=1e-6)
+
+
+def test_gemm_cta_pair_variant_in_subprocess():
+    """SO_GEMM_PAIR=1 selects the cta_group::2 kernel (CTA pair per 256x128 tile); same accuracy bound.  The switch
+    is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch\n"
+        "from synthobs_b200.sed import models\n"
+        "rng = np.random.default_rng(0)\n"
+        "for (M, N, K) in ((300, 520, 1326), (1989, 12, 700), (2048, 9000, 96)):\n"
+        "    A = torch.from_numpy(rng.uniform(0.5, 1.5, (M, K)).astype(np.float32)).cuda()\n"
+        "    B = torch.from_numpy(rng.uniform(0.5, 1.5, (N, K)).astype(np.float32)).cuda()\n"
+        "    C = models.gemm(A, B).double().cpu().numpy()\n"
+        "    ref = A.double().cpu().numpy() @ B.double().cpu().numpy().T\n"
+        "    err = np.abs(C / ref - 1).max()\n"
+        "    assert err < 1e-5, (M, N, K, err)\n"
+        "print('pair ok')\n")
+    env = dict(os.environ, SO_GEMM_PAIR='1')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-c', code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'pair ok' in r.stdout, r.stdout + r.stderr
