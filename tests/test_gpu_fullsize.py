@@ -137,3 +137,47 @@ def test_large_image_flux_and_odd_sizes():
     sel = (np.abs(p['X']) < width / 2) & (np.abs(p['Y']) < width / 2)
     assert r['stats']['selected'] == sel.sum()
     assert float(r['data'].double().sum()) == pytest.approx(p['Masses'][sel].sum(), rel=5e-6)
+
+
+def test_config4_batch_properties(model_full):
+    """config[3] (one GPU's share, scaled to 300 galaxies of 1e3..1e5 particles): batched SEDs, emission lines and
+    images.  Batch rows == the single-call result on the concatenation; flux and counts conserved per object; the
+    batch image of a sampled object == core() on that object alone."""
+    from synthobs_b200.sed import models
+    from synthobs_b200.morph import images
+    model, F = model_full
+    b = synthetic.galaxy_batch(300, n_min=1000, n_max=100000, seed=77)
+    off = b['offsets']
+    n = b['Masses'].size
+    assert n > 4e6
+    args = (b['Masses'], b['Ages'], b['Metallicities'])
+    kw = dict(tauVs_ISM=b['tauVs_ISM'], tauVs_BC=b['tauVs_BC'])
+    rows = models.generate_Fnu_batch(model, F, *args, off, **kw)
+    tot = models.generate_Fnu(model, F, *args, **kw)
+    np.testing.assert_allclose(rows.sum(axis=0), [tot[k] for k in F['filters']], rtol=2e-6)
+    g = 123
+    s, e = off[g], off[g + 1]
+    one = models.generate_Fnu(model, F, b['Masses'][s:e], b['Ages'][s:e], b['Metallicities'][s:e],
+                              tauVs_ISM=b['tauVs_ISM'][s:e], tauVs_BC=b['tauVs_BC'][s:e])
+    np.testing.assert_allclose(rows[g], [one[k] for k in F['filters']], rtol=2e-6)
+    # emission lines, batched: rows add up to the whole catalogue
+    with contextlib.redirect_stdout(io.StringIO()):
+        el = models.EmissionLines(synthetic.lines_grid(seed=0), dust_ISM=('simple', {'slope': -1.0}),
+                                  dust_BC=('simple', {'slope': -1.0}), verbose=False)
+        lb = el.get_line_luminosities_batch(['HI6563', 'OIII4959,OIII5007'], *args, off, **kw)
+        lt = el.get_line_luminosities(['HI6563', 'OIII4959,OIII5007'], *args, **kw)
+    for line in lb:
+        for q in ('luminosity', 'continuum'):
+            np.testing.assert_allclose(lb[line][q].sum(), lt[line][q], rtol=2e-6)
+    # images: 300 objects, 100 x 100, adaptive smoothing, one pass
+    L = b['Masses'] * (0.5 + np.random.default_rng(3).random(n))
+    img = images.core_batch(b['X'], b['Y'], L, off, resolution=0.1, ndim=100, smoothing=('adaptive', 16))
+    assert img.data.shape == (300, 100, 100)
+    sel = (np.abs(b['X']) < 5.0) & (np.abs(b['Y']) < 5.0)
+    flux = np.add.reduceat(np.where(sel, L, 0.0), off[:-1])
+    cnt = np.add.reduceat(sel.astype(np.float64), off[:-1])
+    np.testing.assert_allclose(img.data.reshape(300, -1).sum(axis=1), flux, rtol=1e-5)
+    assert np.array_equal(img.hist.reshape(300, -1).sum(axis=1), cnt)
+    one = images.core(b['X'][s:e], b['Y'][s:e], L[s:e], resolution=0.1, ndim=100, smoothing=('adaptive', 16))
+    assert np.array_equal(img.hist[g], one.hist)
+    assert np.abs(img.data[g] - one.data).max() <= 2e-6 * one.data.max()
