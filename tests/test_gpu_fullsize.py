@@ -181,3 +181,42 @@ def test_config4_batch_properties(model_full):
     one = images.core(b['X'][s:e], b['Y'][s:e], L[s:e], resolution=0.1, ndim=100, smoothing=('adaptive', 16))
     assert np.array_equal(img.hist[g], one.hist)
     assert np.abs(img.data[g] - one.data).max() <= 2e-6 * one.data.max()
+
+
+def test_config5_huge_image_properties():
+    """config[4]: 1e8 particles onto 8192 x 8192, adaptive smoothing (single rank of the particle-share path):
+    flux and selected-particle count conserved, non-negative, and the two halves of the Morton-ordered particle
+    shares (what two ranks would deposit) add up to the whole image."""
+    import torch
+    from synthobs_b200 import device as dv
+    from synthobs_b200.morph import images
+    dev = dv.device()
+    N, ndim, S = 100000000, 8192, 10.0
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    X = S * torch.randn(N, dtype=torch.float64, device=dev, generator=g)
+    Y = S * torch.randn(N, dtype=torch.float64, device=dev, generator=g)
+    m = N // 20
+    X[:m] = 3.0 + 0.5 * torch.randn(m, dtype=torch.float64, device=dev, generator=g)      # a dense clump
+    Y[:m] = -7.0 + 0.5 * torch.randn(m, dtype=torch.float64, device=dev, generator=g)
+    L = 8.47e5 * (0.5 + torch.rand(N, dtype=torch.float64, device=dev, generator=g))
+    res = 8.0 * S / ndim
+    width, G = images.pixel_grid(res, ndim)
+    ix, iy = images.ngp_index_device(X, Y, dv.to_dev(G), ndim, width / 2.)
+    sel = ix >= 0
+    flux = float(L[sel].sum())
+    parts = []
+    for part in range(2):
+        dk, pids = images.knn_device_part(X, Y, ix, 8, width / 2., part, 2)
+        r = images.deposit_device(X[pids], Y[pids], L[pids].reshape(1, -1), res, ndim, adaptive_k=8, want_ngp=False,
+                                  dk=dk[pids])
+        parts.append((r['data'][0], int(pids.numel()), r['stats']))
+        del dk, pids, r
+    assert parts[0][1] + parts[1][1] == int(sel.sum())
+    img = parts[0][0] + parts[1][0]
+    assert float(img.min()) >= 0.0
+    assert abs(float(img.to(torch.float64).sum()) / flux - 1.0) < 2e-6
+    assert parts[0][2]['dropped'] == 0 and parts[1][2]['dropped'] == 0
+    # the shares are spatially compact: each touches clearly fewer pixels than the whole image
+    nz0, nz1, nz = (int((parts[0][0] > 0).sum()), int((parts[1][0] > 0).sum()), int((img > 0).sum()))
+    assert nz0 < 0.8 * nz and nz1 < 0.8 * nz
