@@ -212,7 +212,7 @@ __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t
 //     or finest level) are scanned, skipping the window of step 1.
 // The tree is 15 levels deep whatever the particle number, so the dense cores of a clustered
 // catalogue (hundreds of particles per table cell) are resolved instead of being scanned linearly.
-__global__ void __launch_bounds__(128) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
+__global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
                                  const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
                                  int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
                                  int part, int n_parts, int leaf, double* __restrict__ dk) {
