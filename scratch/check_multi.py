@@ -25,4 +25,14 @@ one = images.core(p['X'], p['Y'], p['Masses'], resolution=0.01, ndim=2048, smoot
 e2 = np.abs(img.cpu().numpy() - one).max() / one.max()
 print('rank %d/%d: sharded SED max rel diff %.2e ; huge image vs single-rank max diff/peak %.2e ; image_huge %.1f ms' % (rank, ws, e1, e2, dt * 1e3))
 assert e1 < 1e-6 and e2 < 2e-6   # per-rank sub-batches group the FP32 partial sums differently
+pp = synthetic.particles(200000, seed=13)
+kw = dict(tauVs_ISM=pp['tauVs_ISM'], tauVs_BC=pp['tauVs_BC'], fesc=0.1)
+sh = sdist.generate_SED_huge(model, pp['Masses'], pp['Ages'], pp['Metallicities'], **kw)
+rf = models.sed_spectra_device(model, pp['Masses'], pp['Ages'], pp['Metallicities'], pp['tauVs_ISM'], pp['tauVs_BC'], 0.1, 7.0)
+e3 = max(float(((sh[k] - rf[k]).abs().max() / rf[k].abs().max()).cpu()) for k in rf)
+fh = sdist.generate_Fnu_huge(model, F, pp['Masses'], pp['Ages'], pp['Metallicities'], kind='Lnu', **kw)
+fr = models.generate_Lnu(model, F, pp['Masses'], pp['Ages'], pp['Metallicities'], **kw)
+e4 = max(abs(fh[f] / fr[f] - 1) for f in F['filters'])
+print('rank %d: huge-galaxy spectra vs single rank %.2e ; fluxes %.2e' % (rank, e3, e4))
+assert e3 < 2e-6 and e4 < 1e-6
 dist.destroy_process_group()

@@ -160,3 +160,40 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None):
                               support_sigmas=support_sigmas, dk=dk[pids])
     img = reduce_image(r['data'])
     return img[0] if one else img
+
+
+def generate_SED_huge(model, Masses, Ages, Metallicities, tauVs_ISM=False, tauVs_BC=False, fesc=0.0, log10t_BC=7.):
+    """generate_SED of ONE giant galaxy, particle-block sharded: every rank computes the five
+    spectra of its contiguous block of particles, the partial spectra add (all-reduce of 5 x n_lam floats over
+    NVLink).  Inputs are the full host arrays on every rank (each uploads only its block).  Returns dict of
+    [n_lam] float32 CUDA tensors, identical on all ranks."""
+    from .sed import models
+    rank, ws = world()
+    n = len(Masses)
+    b, e = particle_block(n, rank, ws)
+    opt = lambda t: t[b:e] if isinstance(t, (np.ndarray, torch.Tensor)) else t   # noqa: E731
+    out = models.sed_spectra_device(model, Masses[b:e], Ages[b:e], Metallicities[b:e], opt(tauVs_ISM), opt(tauVs_BC),
+                                    fesc, log10t_BC)
+    keys = ('stellar', 'intrinsic', 'BC', 'total', 'no_HII_no_BC')
+    stack = torch.stack([out[k] for k in keys])
+    if ws > 1:
+        dist.all_reduce(stack, op=dist.ReduceOp.SUM)
+    return {k: stack[i] for i, k in enumerate(keys)}
+
+
+def generate_Fnu_huge(model, F, Masses, Ages, Metallicities, tauVs_ISM=False, tauVs_BC=False, fesc=0.0, log10t_BC=7.,
+                      kind='Fnu'):
+    """Broadband fluxes of one giant galaxy, particle-block sharded: per-rank sums over its block (float64),
+    all-reduce of [F] doubles.  Returns {filter: value} like generate_Fnu."""
+    from .sed import models
+    rank, ws = world()
+    n = len(Masses)
+    b, e = particle_block(n, rank, ws)
+    opt = lambda t: t[b:e] if isinstance(t, (np.ndarray, torch.Tensor)) else t   # noqa: E731
+    _, sums, _ = models._broadband(model, kind, F, F['filters'], Masses[b:e], Ages[b:e], Metallicities[b:e],
+                                   opt(tauVs_ISM), opt(tauVs_BC), fesc, log10t_BC)
+    s = sums[0].clone()
+    if ws > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    s = s.cpu().numpy()
+    return {f: s[i] for i, f in enumerate(F['filters'])}

@@ -356,3 +356,23 @@ def test_gemm_cta_pair_variant_in_subprocess():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, '-c', code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'pair ok' in r.stdout, r.stdout + r.stderr
+
+
+def test_huge_galaxy_block_sharded_single_rank():
+    """dist.generate_SED_huge / generate_Fnu_huge (particle-block shares + all-reduce) on one rank == the plain calls"""
+    from synthobs_b200 import dist as sdist
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=400, seed=0)
+    model = make_model(grid, ('simple', {'slope': -1.0}), ('simple', {'slope': -1.0}))
+    F = synthetic.filter_set(grid['lam'], n_filters=4)
+    model.create_Lnu_grid(F)
+    p = synthetic.particles(30000, seed=8)
+    kw = dict(tauVs_ISM=p['tauVs_ISM'], tauVs_BC=p['tauVs_BC'], fesc=0.1)
+    a = sdist.generate_Fnu_huge(model, F, p['Masses'], p['Ages'], p['Metallicities'], kind='Lnu', **kw)
+    b = models.generate_Lnu(model, F, p['Masses'], p['Ages'], p['Metallicities'], **kw)
+    for f in F['filters']:
+        assert a[f] == b[f]
+    sp = sdist.generate_SED_huge(model, p['Masses'], p['Ages'], p['Metallicities'], **kw)
+    ref = models.sed_spectra_device(model, p['Masses'], p['Ages'], p['Metallicities'], p['tauVs_ISM'], p['tauVs_BC'], 0.1, 7.0)
+    for k in ref:
+        assert bool((sp[k] == ref[k]).all())
