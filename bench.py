@@ -403,6 +403,44 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
     }
 
 
+def imaging_stage_times(obs, Xd, Yd, Ld):
+    """Device time of the stages of one imaging step (CUDA events between the stage calls; the stages are
+    the same C-ABI calls particle_device_multi makes)."""
+    import torch
+    from synthobs_b200.morph import images
+    o0 = obs[0]
+    spec = images.KernelSpectrum(np.stack([o.psf_kernel() for o in obs]), o0.ndim_super, o0.ndim_super)
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+    names = ['recentre (two medians)', 'nearest-pixel index', 'k-NN', 'plan + binning + deposit', 'PSF FFT', 'rebin']
+    acc = np.zeros(len(names))
+    reps = 5
+    for it in range(reps + 1):
+        t = [ev()]
+        mx, my = images.median_device_pair(Xd, Yd)
+        X, Y = Xd - mx, Yd - my
+        t.append(ev())
+        width, G = images.pixel_grid(o0.resolution, o0.ndim_super)
+        ix, iy = images.ngp_index_device(X, Y, images.dv.to_dev(G), o0.ndim_super, width / 2.)
+        t.append(ev())
+        dk = images.knn_device(X, Y, ix, IMG_K, width / 2.)
+        t.append(ev())
+        r = images.deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=IMG_K, want_ngp=False, dk=dk)
+        t.append(ev())
+        conv = images.convolve_fft_device(r['data'], spec)
+        t.append(ev())
+        images.rebin_device(r['data'], o0.ndim)
+        images.rebin_device(conv, o0.ndim)
+        t.append(ev())
+        torch.cuda.synchronize()
+        if it:
+            acc += [t[i].elapsed_time(t[i + 1]) for i in range(len(names))]
+    return {n: float(v / reps) for n, v in zip(names, acc)}
+
+
 def _ex2_roofline(batch, n_part, n_lam, ms):
     """The dust-spectra kernel is bound by exponentials: one per (old particle, wavelength), two per young one
     (models.py:285-304).  Peak = 16 MUFU.EX2 per clock and SM at the maximum SM clock; the step time (which also
@@ -466,6 +504,7 @@ def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
         step_e2e()
     barrier()
     e2e_ms = max_over_ranks((time.time() - t0) * 1e3 / steps)
+    stages = imaging_stage_times(obs, Xd, Yd, Ld)
     deposits = stats.get('deposits', 0.0) * IMG_FILTERS
     nsel = stats.get('selected', 0.0)
     ref_equiv = nsel * (IMG_NDIM * IMG_SS) ** 2 * IMG_FILTERS
@@ -480,6 +519,7 @@ def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
                              'launches), not one kernel: at ~18 pixels per particle the step is a chain of '
                              'latency-bound stages (tree walk, radix sorts, FFT) and sits far below the HBM roof; '
                              'per-kernel figures are in profiles/'},
+        'stages_ms': stages,
         'metric': 'particles/sec imaged', 'unit': 'particles/s (all %d filter images)' % IMG_FILTERS,
         'value': world * IMG_PARTICLES / (ms * 1e-3), 'ms_per_step': ms,
         'particle_filter_images_per_s': world * IMG_PARTICLES * IMG_FILTERS / (ms * 1e-3),
