@@ -35,4 +35,13 @@ fr = models.generate_Lnu(model, F, pp['Masses'], pp['Ages'], pp['Metallicities']
 e4 = max(abs(fh[f] / fr[f] - 1) for f in F['filters'])
 print('rank %d: huge-galaxy spectra vs single rank %.2e ; fluxes %.2e' % (rank, e3, e4))
 assert e3 < 2e-6 and e4 < 1e-6
+b2 = synthetic.galaxy_batch(40, n_min=500, n_max=20000, seed=9)
+img = sdist.core_batch_sharded(b2['X'], b2['Y'], b2['Masses'], b2['offsets'], resolution=0.1, ndim=64, smoothing=('adaptive', 8))
+one = images.core_batch(b2['X'], b2['Y'], b2['Masses'], b2['offsets'], resolution=0.1, ndim=64, smoothing=('adaptive', 8)).data
+e5 = np.abs(img.cpu().numpy() - one).max() / one.max()
+sp = sdist.generate_SED_sharded(model, b2, fesc=0.1)
+rf2 = models.generate_SED_batch(model, b2['Masses'], b2['Ages'], b2['Metallicities'], b2['offsets'], tauVs_ISM=b2['tauVs_ISM'], tauVs_BC=b2['tauVs_BC'], fesc=0.1)
+e6 = max(np.abs(sp[k].cpu().numpy() - rf2[k]).max() / np.abs(rf2[k]).max() for k in rf2)
+print('rank %d: sharded batch images vs one rank %.2e ; sharded spectra %.2e' % (rank, e5, e6))
+assert e5 < 3e-6 and e6 < 2e-6
 dist.destroy_process_group()

@@ -140,6 +140,41 @@ def generate_Fnu_sharded(model, F, batch, kind='Fnu', **kw):
     return sharded_galaxy_map(compute, batch['offsets'])
 
 
+def generate_SED_sharded(model, batch, **kw):
+    """The five spectra of generate_SED for a batch of galaxies, sharded by galaxy (config 4): returns a dict of
+    [G, n_lam] float32 CUDA tensors, complete on every rank (one gather per spectrum)."""
+    from .sed import models
+    keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
+    names = ('stellar', 'intrinsic', 'BC', 'total', 'no_HII_no_BC')
+
+    def compute(indices):
+        sub, off = subset_csr({k: batch[k] for k in keys if k in batch}, batch['offsets'], indices)
+        out = models.sed_spectra_device(model, sub['Masses'], sub['Ages'], sub['Metallicities'],
+                                        sub.get('tauVs_ISM', False), sub.get('tauVs_BC', False),
+                                        kw.get('fesc', 0.0), kw.get('log10t_BC', 7.), offsets=off)
+        return torch.stack([out[k] for k in names], dim=1)          # [g, 5, n_lam]
+
+    full = sharded_galaxy_map(compute, batch['offsets'])
+    return {k: full[:, i] for i, k in enumerate(names)}
+
+
+def core_batch_sharded(X, Y, L, offsets, resolution=0.1, ndim=100, smoothing=False):
+    """images.core for a batch of objects, sharded by object over the ranks (config 4): every rank images its
+    share in one pass (images.core_batch) and the [G, ndim, ndim] stack is gathered on every rank."""
+    from . import device as dv
+    from .morph import images
+
+    def compute(indices):
+        sub, off = subset_csr({'X': np.asarray(X), 'Y': np.asarray(Y), 'L': np.asarray(L)}, offsets, indices)
+        if len(indices) == 0:
+            return torch.zeros((0, ndim, ndim), dtype=torch.float32, device=dv.device())
+        data, _, _, _ = images.core_device(dv.to_dev(sub['X']), dv.to_dev(sub['Y']), dv.to_dev(sub['L']), resolution, ndim,
+                                           smoothing, img=images._image_ids(off, dv.device())[1], n_img=len(indices))
+        return data[:, 0]
+
+    return sharded_galaxy_map(compute, offsets)
+
+
 def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None):
     """One huge adaptive-smoothed image split over the ranks (BASELINE config 5).  Every rank holds all
     positions (neighbours cross any partition) and builds the same search tree, but answers the k-NN

@@ -376,3 +376,22 @@ def test_huge_galaxy_block_sharded_single_rank():
     ref = models.sed_spectra_device(model, p['Masses'], p['Ages'], p['Metallicities'], p['tauVs_ISM'], p['tauVs_BC'], 0.1, 7.0)
     for k in ref:
         assert bool((sp[k] == ref[k]).all())
+
+
+def test_sharded_spectra_and_images_single_rank():
+    """dist.generate_SED_sharded / core_batch_sharded on one rank == the batched calls (host logic of the shards is
+    covered with two gloo ranks in tests/test_dist_gloo.py)"""
+    from synthobs_b200 import dist as sdist
+    from synthobs_b200.morph import images
+    from synthobs_b200.sed import models
+    grid = synthetic.ssp_grid(n_lam=300, seed=0)
+    model = make_model(grid, ('simple', {'slope': -1.0}), ('simple', {'slope': -1.0}))
+    b = synthetic.galaxy_batch(7, n_min=100, n_max=3000, seed=21)
+    sp = sdist.generate_SED_sharded(model, b, fesc=0.2)
+    ref = models.generate_SED_batch(model, b['Masses'], b['Ages'], b['Metallicities'], b['offsets'],
+                                    tauVs_ISM=b['tauVs_ISM'], tauVs_BC=b['tauVs_BC'], fesc=0.2)
+    for k in ref:
+        np.testing.assert_allclose(sp[k].cpu().numpy(), ref[k], rtol=1e-6, atol=1e-6 * np.abs(ref[k]).max())
+    img = sdist.core_batch_sharded(b['X'], b['Y'], b['Masses'], b['offsets'], resolution=0.1, ndim=40, smoothing=('adaptive', 8))
+    one = images.core_batch(b['X'], b['Y'], b['Masses'], b['offsets'], resolution=0.1, ndim=40, smoothing=('adaptive', 8))
+    np.testing.assert_allclose(img.cpu().numpy(), one.data, rtol=0, atol=2e-6 * one.data.max())
