@@ -73,6 +73,18 @@ def _worker(rank, ws, port, q):
         img.index_add_(0, torch.from_numpy(pix[b:e]), torch.from_numpy(w[b:e]))
         sdist.reduce_image(img)
         ok2 = np.allclose(img.numpy(), np.bincount(pix, weights=w, minlength=16), rtol=1e-13)
+
+        # rows with more than one trailing axis (spectra [g, 5, n_lam], images [g, ndim, ndim]), float32
+        def compute3(indices):
+            return torch.tensor([[[g, sizes[g]], [2 * g, 1], [0, -g]] for g in indices], dtype=torch.float32).reshape(-1, 3, 2)
+
+        full3 = sdist.sharded_galaxy_map(compute3, offsets)
+        ref3 = np.array([[[g, sizes[g]], [2 * g, 1], [0, -g]] for g in range(37)], dtype=np.float32)
+        ok1 = ok1 and full3.shape == (37, 3, 2) and np.array_equal(full3.numpy(), ref3)
+        # one giant galaxy in particle blocks: per-rank partial sums + all-reduce == the whole
+        blk = torch.tensor([vals[slice(*sdist.particle_block(vals.size))].sum()], dtype=torch.float64)
+        dist.all_reduce(blk)
+        ok2 = ok2 and np.isclose(float(blk), vals.sum(), rtol=1e-13)
         q.put((rank, ok1, ok2))
     finally:
         dist.destroy_process_group()
