@@ -426,7 +426,7 @@ def imaging_stage_times(obs, Xd, Yd, Ld):
         width, G = images.pixel_grid(o0.resolution, o0.ndim_super)
         ix, iy = images.ngp_index_device(X, Y, images.dv.to_dev(G), o0.ndim_super, width / 2.)
         t.append(ev())
-        dk = images.knn_device(X, Y, ix, IMG_K, width / 2.)
+        dk = images.knn_device(X, Y, ix, IMG_K, width / 2., floor=images.FWHM_FLOOR)
         t.append(ev())
         r = images.deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=IMG_K, want_ngp=False, dk=dk)
         t.append(ev())

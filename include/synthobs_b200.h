@@ -179,6 +179,16 @@ int so_knn_kth_distance_batch(const double* X, const double* Y, const int32_t* i
                               int64_t n, int64_t n_img, int32_t k, double half_width, double* dk,
                               void* workspace, int64_t workspace_bytes, void* stream);
 
+/* General form of the three calls above (img NULL / n_img 1: one image; part 0 of 1: all queries) with a
+ * `floor`: the reference uses FWHM = max(dk, 0.01) (synthobs/morph/images.py:89), so a particle that already
+ * has k neighbours within `floor` needs no exact answer: for it dk is only guaranteed to be an upper bound
+ * <= floor (max(dk, floor) is unchanged), and its tree walk is skipped.  floor = 0: exact everywhere.
+ * Workspace: so_knn_batch_workspace_bytes(n, n_img, k). */
+int so_knn_kth_distance_ex(const double* X, const double* Y, const int32_t* ix, const int32_t* img,
+                           int64_t n, int64_t n_img, int32_t k, double half_width, int32_t part, int32_t n_parts,
+                           double floor, double* dk, int32_t* order_out, int64_t* range_out,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* K8b..K9 — kernel-smoothed deposition.  Replaces the adaptive loop of
  * images.core (synthobs/morph/images.py:87-97): per particle a Gaussian of
  * FWHM = max(dk, 0.01), normalised by its SUM OVER THE IMAGE PIXELS, times L.

@@ -215,7 +215,7 @@ __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t
 __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
                                  const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
                                  int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
-                                 int part, int n_parts, int leaf, double* __restrict__ dk) {
+                                 int part, int n_parts, int leaf, double floor2, double* __restrict__ dk) {
     extern __shared__ double s_best[];
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -244,6 +244,8 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
     const int wa = max(g_lo, wb - (2 * k + 1));
     wb = min(g_hi, wa + 2 * k + 1);
     knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
+    // the caller only needs max(dk, floor): k neighbours inside the floor radius settle the answer
+    if (best[(k - 1) * stride] <= floor2) { dk[pid] = sqrt(best[(k - 1) * stride]); return; }
 
     // 2. start nodes
     uint32_t stack[kStack];       // node = (1 << 2 level) | code: the leading one marks the level
@@ -315,7 +317,7 @@ constexpr int kWarpsPerCta = 4;
 __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
         const double* __restrict__ xs, const double* __restrict__ ys, const unsigned long long* __restrict__ keys,
         const int32_t* __restrict__ vals, int64_t n, int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw,
-        double inv_h, int k, int part, int n_parts, int leaf, double* __restrict__ dk) {
+        double inv_h, int k, int part, int n_parts, int leaf, double floor2, double* __restrict__ dk) {
     extern __shared__ double s_dyn[];
     __shared__ double s_px[kWarpsPerCta][32], s_py[kWarpsPerCta][32];
     __shared__ uint32_t s_stack[kWarpsPerCta][kStack];
@@ -362,6 +364,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
             knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
         }
         double kth = best[(k - 1) * stride];
+        if (mine && kth <= floor2) { dk[pid] = sqrt(kth); mine = false; }   // settled below the caller's floor
+        if (!__any_sync(FULL, mine)) continue;
 
         // 2. start nodes: the level whose cells are at least as wide as the box around all the lanes' balls
         const float rc = mine ? (float)(sqrt(kth) * inv_h) * (1.f + 1e-5f) + 1.6e-2f : 0.f;
@@ -460,7 +464,7 @@ extern "C" int64_t so_knn_workspace_bytes(int64_t n, int32_t k) {
 }
 
 static int knn_run(const double* X, const double* Y, const int32_t* ix, const int32_t* img, int64_t n, int64_t n_img,
-                   int32_t k, double half_width, int32_t part, int32_t n_parts, double* dk, int32_t* order_out,
+                   int32_t k, double half_width, int32_t part, int32_t n_parts, double floor, double* dk, int32_t* order_out,
                    int64_t* range_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     if (n == 0) return SO_OK;
     if (n < 0 || k < 1 || !(half_width > 0.0) || !X || !Y || !ix || !dk || n_img < 1) return SO_ERR_BAD_ARG;
@@ -503,14 +507,15 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, const in
         if (leaf < 1) leaf = kLeaf;
     }
     const bool private_walk = force_private >= 0 ? force_private == 1 : k <= 8;
+    const double floor2 = floor > 0.0 ? floor * floor : -1.0;
     if (private_walk || threads != kWarpsPerCta * 32) {
         SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, dk);
+            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, floor2, dk);
     } else {
         SO_CUDA(cudaFuncSetAttribute(knn_query_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_query_warp_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, dk);
+            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, floor2, dk);
     }
     SO_LAUNCH_CHECK();
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
@@ -524,7 +529,7 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, const in
 extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
                                    int32_t k, double half_width, double* dk,
                                    void* workspace, int64_t workspace_bytes, void* stream) {
-    return knn_run(X, Y, ix, nullptr, n, 1, k, half_width, 0, 1, dk, nullptr, nullptr, workspace, workspace_bytes,
+    return knn_run(X, Y, ix, nullptr, n, 1, k, half_width, 0, 1, 0.0, dk, nullptr, nullptr, workspace, workspace_bytes,
                    (cudaStream_t)stream);
 }
 
@@ -532,7 +537,7 @@ extern "C" int so_knn_kth_distance_part(const double* X, const double* Y, const 
                                         int32_t k, double half_width, int32_t part, int32_t n_parts,
                                         double* dk, int32_t* order_out, int64_t* range_out,
                                         void* workspace, int64_t workspace_bytes, void* stream) {
-    return knn_run(X, Y, ix, nullptr, n, 1, k, half_width, part, n_parts, dk, order_out, range_out, workspace,
+    return knn_run(X, Y, ix, nullptr, n, 1, k, half_width, part, n_parts, 0.0, dk, order_out, range_out, workspace,
                    workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -545,6 +550,14 @@ extern "C" int64_t so_knn_batch_workspace_bytes(int64_t n, int64_t n_img, int32_
 extern "C" int so_knn_kth_distance_batch(const double* X, const double* Y, const int32_t* ix, const int32_t* img,
                                          int64_t n, int64_t n_img, int32_t k, double half_width, double* dk,
                                          void* workspace, int64_t workspace_bytes, void* stream) {
-    return knn_run(X, Y, ix, img, n, n_img, k, half_width, 0, 1, dk, nullptr, nullptr, workspace, workspace_bytes,
+    return knn_run(X, Y, ix, img, n, n_img, k, half_width, 0, 1, 0.0, dk, nullptr, nullptr, workspace, workspace_bytes,
                    (cudaStream_t)stream);
+}
+
+extern "C" int so_knn_kth_distance_ex(const double* X, const double* Y, const int32_t* ix, const int32_t* img,
+                                      int64_t n, int64_t n_img, int32_t k, double half_width, int32_t part, int32_t n_parts,
+                                      double floor, double* dk, int32_t* order_out, int64_t* range_out,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
+    return knn_run(X, Y, ix, img, n, n_img < 1 ? 1 : n_img, k, half_width, part, n_parts, floor, dk, order_out, range_out,
+                   workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -182,47 +182,40 @@ def ngp_index_device(Xd, Yd, Gd, ndim, half_width):
     return ix, iy
 
 
-def knn_device(Xd, Yd, ix, k, half_width, img=None, n_img=1):
-    """distance to the k-th neighbour (self = first) among the selected particles (K7); with
-    `img` [n] int32 / n_img, among the selected particles of the particle's own image."""
+FWHM_FLOOR = 0.01           # images.py:89: FWHM = max(d_k, 0.01)
+
+
+def knn_device(Xd, Yd, ix, k, half_width, img=None, n_img=1, floor=0.0, part=0, n_parts=1, want_order=False):
+    """distance to the k-th neighbour (self = first) among the selected particles (K7); with `img` [n] int32 /
+    n_img, among the selected particles of the particle's own image.  floor > 0: particles that already have k
+    neighbours within `floor` get an upper bound <= floor instead of the exact distance (enough for
+    max(dk, floor), and their tree walk is skipped).  part / n_parts: answer only that share of the selected
+    particles in Morton order (then the result is (dk, pids of the share))."""
     n = Xd.numel()
-    dk = torch.empty(n, dtype=torch.float64, device=Xd.device)
-    if img is None:
-        wsb = _cabi.lib.so_knn_workspace_bytes(n, int(k))
-        ws = dv.workspace(wsb)
-        _cabi.check(_cabi.lib.so_knn_kth_distance(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), n, int(k),
-                                                  float(half_width), _cabi.ptr(dk), _cabi.ptr(ws), wsb, _cabi.stream()),
-                    'so_knn_kth_distance')
-    else:
-        wsb = _cabi.lib.so_knn_batch_workspace_bytes(n, int(n_img), int(k))
-        ws = dv.workspace(wsb)
-        _cabi.check(_cabi.lib.so_knn_kth_distance_batch(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), _cabi.ptr(img), n,
-                                                        int(n_img), int(k), float(half_width), _cabi.ptr(dk),
-                                                        _cabi.ptr(ws), wsb, _cabi.stream()),
-                    'so_knn_kth_distance_batch')
+    dk = (torch.zeros if n_parts > 1 else torch.empty)(n, dtype=torch.float64, device=Xd.device)
+    order = torch.empty(n, dtype=torch.int32, device=Xd.device) if want_order else None
+    rng = torch.zeros(3, dtype=torch.int64, device=Xd.device) if want_order else None
+    wsb = _cabi.lib.so_knn_batch_workspace_bytes(n, int(n_img), int(k))
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_knn_kth_distance_ex(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), _cabi.ptr(img), n,
+                                                 int(n_img), int(k), float(half_width), int(part), int(n_parts),
+                                                 float(floor), _cabi.ptr(dk), _cabi.ptr(order), _cabi.ptr(rng),
+                                                 _cabi.ptr(ws), wsb, _cabi.stream()), 'so_knn_kth_distance_ex')
+    if want_order:
+        b, e, _ = (int(v) for v in rng.cpu())
+        return dk, order[b:e].to(torch.int64)
     return dk
 
 
-def knn_device_part(Xd, Yd, ix, k, half_width, part, n_parts):
+def knn_device_part(Xd, Yd, ix, k, half_width, part, n_parts, floor=0.0):
     """k-th neighbour distances for share `part` of `n_parts` of the selected particles in Morton
     order (searching all positions).  Returns (dk [n] valid for the share only, pids [m] int64:
     the particles of the share)."""
-    n = Xd.numel()
-    dk = torch.zeros(n, dtype=torch.float64, device=Xd.device)
-    order = torch.empty(n, dtype=torch.int32, device=Xd.device)
-    rng = torch.zeros(3, dtype=torch.int64, device=Xd.device)
-    wsb = _cabi.lib.so_knn_workspace_bytes(n, int(k))
-    ws = dv.workspace(wsb)
-    _cabi.check(_cabi.lib.so_knn_kth_distance_part(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), n, int(k),
-                                                   float(half_width), int(part), int(n_parts), _cabi.ptr(dk),
-                                                   _cabi.ptr(order), _cabi.ptr(rng), _cabi.ptr(ws), wsb, _cabi.stream()),
-                'so_knn_kth_distance_part')
-    b, e, _ = (int(v) for v in rng.cpu())
-    return dk, order[b:e].to(torch.int64)
+    return knn_device(Xd, Yd, ix, k, half_width, floor=floor, part=part, n_parts=n_parts, want_order=True)
 
 
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
-                   support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1):
+                   support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1, exact_dk=False):
     """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
     CUDA (C images sharing positions).  Returns dict of float32 CUDA tensors:
     data [C, ndim, ndim] (adaptive only), simple [C, ndim, ndim], hist [ndim, ndim],
@@ -237,7 +230,8 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
     ix, iy = ngp_index_device(Xd, Yd, Gd, ndim, width / 2.)
     adaptive = adaptive_k is not None
     if adaptive and dk is None:
-        dk = knn_device(Xd, Yd, ix, adaptive_k, width / 2., img=img, n_img=n_img)
+        # only max(dk, FWHM_FLOOR) enters the image: particles settled below the floor skip the exact search
+        dk = knn_device(Xd, Yd, ix, adaptive_k, width / 2., img=img, n_img=n_img, floor=0.0 if exact_dk else FWHM_FLOOR)
     R = SUPPORT_SIGMAS if support_sigmas is None else support_sigmas
     pws_b = _cabi.lib.so_img_plan_workspace_bytes(n)
     pws = dv.workspace(pws_b)

@@ -107,7 +107,8 @@ def test_tile_assignment_bit_exact():
     g = _cases.load('img_adaptive8f')
     ndim, res = 200, 0.02
     X, Y, L = g['X'], g['Y'], g['L']
-    r = images.deposit_device(dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L), res, ndim, adaptive_k=8, return_pairs=True)
+    r = images.deposit_device(dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L), res, ndim, adaptive_k=8, return_pairs=True,
+                              exact_dk=True)
     o = image_oracle.core(X, Y, L, resolution=res, ndim=ndim, smoothing=('adaptive', 8), return_aux=True)
     sel = o['aux']['sel']
     ix = r['ix'].cpu().numpy()
@@ -343,3 +344,27 @@ def test_observed_particle_batch_equals_loop():
             assert med[g] == np.median(cat['X'][off[g]:off[g + 1]])
         else:
             assert np.isnan(med[g])
+
+
+@pytest.mark.parametrize('k', [8, 12])
+def test_knn_floor_shortcut_leaves_the_image_unchanged(k):
+    """FWHM = max(dk, 0.01) (images.py:89): with floor = 0.01 the k-NN may return any upper bound <= 0.01 for
+    particles that have k neighbours inside the floor radius.  Above the floor the distances are the exact ones,
+    below they stay below, and the image is bit-identical to the one from exact distances."""
+    import torch
+    from synthobs_b200 import device as dv
+    from synthobs_b200.morph import images
+    p = synthetic.particles(60000, seed=5, scale_kpc=0.4)            # dense: many particles below the floor
+    Xd, Yd, Ld = dv.to_dev(p['X']), dv.to_dev(p['Y']), dv.to_dev(p['Masses']).reshape(1, -1)
+    res, ndim = 0.02, 128
+    width, G = images.pixel_grid(res, ndim)
+    ix, _ = images.ngp_index_device(Xd, Yd, dv.to_dev(G), ndim, width / 2.)
+    exact = images.knn_device(Xd, Yd, ix, k, width / 2.)
+    fl = images.knn_device(Xd, Yd, ix, k, width / 2., floor=images.FWHM_FLOOR)
+    above = exact > images.FWHM_FLOOR
+    assert 0.05 < float((~above).double().mean()) < 0.95             # the case exercises both branches
+    assert bool((fl[above] == exact[above]).all())
+    assert bool((fl[~above] <= images.FWHM_FLOOR).all()) and bool((fl[~above] >= exact[~above]).all())
+    a = images.deposit_device(Xd, Yd, Ld, res, ndim, adaptive_k=k, want_ngp=False, exact_dk=True)['data']
+    b = images.deposit_device(Xd, Yd, Ld, res, ndim, adaptive_k=k, want_ngp=False)['data']
+    assert bool((a == b).all())
