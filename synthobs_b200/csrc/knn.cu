@@ -215,7 +215,7 @@ __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t
 __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
                                  const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
                                  int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
-                                 int part, int n_parts, int leaf, double floor2, double* __restrict__ dk) {
+                                 int part, int n_parts, int leaf, int win, double floor2, double* __restrict__ dk) {
     extern __shared__ double s_best[];
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -240,9 +240,9 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
     const double h = 1.0 / inv_h;                                 // fine-cell units -> length
 
     // 1. window of sorted neighbours
-    int wb = min(g_hi, (int)s + k + 1);
-    const int wa = max(g_lo, wb - (2 * k + 1));
-    wb = min(g_hi, wa + 2 * k + 1);
+    int wb = min(g_hi, (int)s + win + 1);
+    const int wa = max(g_lo, wb - (2 * win + 1));
+    wb = min(g_hi, wa + 2 * win + 1);
     knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
     // the caller only needs max(dk, floor): k neighbours inside the floor radius settle the answer
     if (best[(k - 1) * stride] <= floor2) { dk[pid] = sqrt(best[(k - 1) * stride]); return; }
@@ -317,7 +317,7 @@ constexpr int kWarpsPerCta = 4;
 __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
         const double* __restrict__ xs, const double* __restrict__ ys, const unsigned long long* __restrict__ keys,
         const int32_t* __restrict__ vals, int64_t n, int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw,
-        double inv_h, int k, int part, int n_parts, int leaf, double floor2, double* __restrict__ dk) {
+        double inv_h, int k, int part, int n_parts, int leaf, int win, double floor2, double* __restrict__ dk) {
     extern __shared__ double s_dyn[];
     __shared__ double s_px[kWarpsPerCta][32], s_py[kWarpsPerCta][32];
     __shared__ uint32_t s_stack[kWarpsPerCta][kStack];
@@ -358,9 +358,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
         for (int j = 0; j < k; ++j) best[j * stride] = INF;
         int wa = 0, wb = 0;
         if (mine) {
-            wb = min(g_hi, (int)s + k + 1);
-            wa = max(g_lo, wb - (2 * k + 1));
-            wb = min(g_hi, wa + 2 * k + 1);
+            wb = min(g_hi, (int)s + win + 1);
+            wa = max(g_lo, wb - (2 * win + 1));
+            wb = min(g_hi, wa + 2 * win + 1);
             knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
         }
         double kth = best[(k - 1) * stride];
@@ -508,14 +508,18 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, const in
     }
     const bool private_walk = force_private >= 0 ? force_private == 1 : k <= 8;
     const double floor2 = floor > 0.0 ? floor * floor : -1.0;
+    // half-width of the window of sorted neighbours scanned first (SO_KNN_WIN = multiple of k, default 1)
+    static int win_mul = 0;
+    if (win_mul == 0) { const char* e = getenv("SO_KNN_WIN"); win_mul = e ? atoi(e) : 1; if (win_mul < 1) win_mul = 1; }
+    const int win = k * win_mul;
     if (private_walk || threads != kWarpsPerCta * 32) {
         SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, floor2, dk);
+            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
     } else {
         SO_CUDA(cudaFuncSetAttribute(knn_query_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_query_warp_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, floor2, dk);
+            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
     }
     SO_LAUNCH_CHECK();
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
