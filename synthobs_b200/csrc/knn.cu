@@ -31,7 +31,7 @@ constexpr int kMaxTableBits = 26;   // at most 2^26 table cells over all images 
 // sort last.  A batch of images (galaxies) is searched in one pass: the node tables of the images are
 // simply concatenated, because (key >> shift) enumerates (image, cell) pairs in sorted order.
 struct KnnLayout {
-    unsigned long long *keys0, *keys1;
+    void *keys0, *keys1;            // uint32 keys for one image (31 bits), uint64 for a batch of images
     int32_t *vals0, *vals1;
     double *xs, *ys;
     int32_t* E;                    // [4^Lt] upper bounds per table cell
@@ -55,7 +55,7 @@ static KnnLayout carve_knn(void* ws, int64_t bytes, int64_t n, int64_t n_img, bo
     l.Lt = knn_table_level(n, n_img);
     const int64_t ncell = n_img << (2 * l.Lt);
     SoArena a(ws, bytes);
-    l.keys0 = a.take<unsigned long long>(n);
+    l.keys0 = a.take<unsigned long long>(n);     // sized for the wider key type
     l.vals0 = a.take<int32_t>(n);
     l.keys1 = a.take<unsigned long long>(n);
     l.vals1 = a.take<int32_t>(n);
@@ -90,10 +90,11 @@ __device__ __forceinline__ uint32_t compact_bits(uint32_t c) {   // even bit pos
     return c;
 }
 
+template <typename KeyT>
 __global__ void knn_key_kernel(const double* __restrict__ X, const double* __restrict__ Y,
                                const int32_t* __restrict__ ix, const int32_t* __restrict__ img, int64_t n, int64_t n_img,
                                double hw, double inv_h,
-                               unsigned long long* __restrict__ keys, int32_t* __restrict__ vals,
+                               KeyT* __restrict__ keys, int32_t* __restrict__ vals,
                                unsigned long long* __restrict__ counter) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool sel = false;
@@ -107,7 +108,7 @@ __global__ void knn_key_kernel(const double* __restrict__ X, const double* __res
             cy = max(0, min(nc - 1, cy));
             key = ((unsigned long long)(img ? img[i] : 0) << (2 * kBits)) | morton((uint32_t)cx, (uint32_t)cy);
         }
-        keys[i] = key;
+        keys[i] = (KeyT)key;
         vals[i] = (int32_t)i;
     }
     const unsigned m = __ballot_sync(0xffffffffu, sel);
@@ -126,13 +127,14 @@ __global__ void knn_gather_kernel(const double* __restrict__ X, const double* __
 
 // E[c] = i + 1 at the last sorted element of table cell c (others stay 0); a max-scan then makes
 // E[c] = #selected particles whose table cell is <= c
-__global__ void knn_mark_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t n_img, int tshift,
+template <typename KeyT>
+__global__ void knn_mark_kernel(const KeyT* __restrict__ keys, int64_t n, int64_t n_img, int tshift,
                                 int32_t* __restrict__ E) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k = keys[i];
     if ((k >> (2 * kBits)) >= (unsigned long long)n_img) return;
-    if (i + 1 == n || (keys[i + 1] >> tshift) != (k >> tshift)) E[k >> tshift] = (int32_t)(i + 1);
+    if (i + 1 == n || ((unsigned long long)keys[i + 1] >> tshift) != (k >> tshift)) E[k >> tshift] = (int32_t)(i + 1);
 }
 
 // scan sorted positions [a, b) minus the window [wa, wb) that is already in the list
@@ -169,8 +171,8 @@ __device__ __forceinline__ float node_dmin(int shift, uint32_t cx, uint32_t cy, 
 }
 
 // first position in [a, b) whose key is >= key (keys ascending)
-__device__ __forceinline__ int lower_bound_key(const unsigned long long* __restrict__ keys, int a, int b,
-                                               unsigned long long key) {
+template <typename KeyT>
+__device__ __forceinline__ int lower_bound_key(const KeyT* __restrict__ keys, int a, int b, unsigned long long key) {
     while (a < b) {
         const int mid = (a + b) >> 1;
         if (keys[mid] < key) a = mid + 1; else b = mid;
@@ -178,8 +180,9 @@ __device__ __forceinline__ int lower_bound_key(const unsigned long long* __restr
     return a;
 }
 
+template <typename KeyT>
 struct KnnTree {
-    const unsigned long long* keys;
+    const KeyT* keys;
     const int32_t* E;
     int Lt;                    // table level
     unsigned long long img;    // image (galaxy) of the query
@@ -187,7 +190,8 @@ struct KnnTree {
 
 // sorted range of node (level, code) of image t.img: table look-up down to level Lt, bisection inside the
 // table cell below.  (image << 2 level) | code enumerates the nodes of a level over the whole batch.
-__device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t code, int& a, int& b) {
+template <typename KeyT>
+__device__ __forceinline__ void node_range(const KnnTree<KeyT>& t, int level, uint32_t code, int& a, int& b) {
     const unsigned long long xc = (t.img << (2 * level)) | code;
     if (level <= t.Lt) {
         const int sh = 2 * (t.Lt - level);
@@ -212,8 +216,9 @@ __device__ __forceinline__ void node_range(const KnnTree& t, int level, uint32_t
 //     or finest level) are scanned, skipping the window of step 1.
 // The tree is 15 levels deep whatever the particle number, so the dense cores of a clustered
 // catalogue (hundreds of particles per table cell) are resolved instead of being scanned linearly.
+template <typename KeyT>
 __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
-                                 const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
+                                 const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
                                  int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
                                  int part, int n_parts, int leaf, int win, double floor2, double* __restrict__ dk) {
     extern __shared__ double s_best[];
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
     const unsigned long long key = keys[s];
     if ((key >> (2 * kBits)) >= (unsigned long long)n_img) { dk[pid] = 0.0; return; }
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    KnnTree t{keys, E, Lt, key >> (2 * kBits)};
+    KnnTree<KeyT> t{keys, E, Lt, key >> (2 * kBits)};
     // sorted range of the query's own image: its neighbours are searched there only
     int g_lo, g_hi;
     node_range(t, 0, 0u, g_lo, g_hi);
@@ -314,8 +319,9 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
 // runs at ~9 of 32 active lanes), and the node tests, table look-ups and point loads are paid once per warp.
 constexpr int kWarpsPerCta = 4;
 
+template <typename KeyT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
-        const double* __restrict__ xs, const double* __restrict__ ys, const unsigned long long* __restrict__ keys,
+        const double* __restrict__ xs, const double* __restrict__ ys, const KeyT* __restrict__ keys,
         const int32_t* __restrict__ vals, int64_t n, int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw,
         double inv_h, int k, int part, int n_parts, int leaf, int win, double floor2, double* __restrict__ dk) {
     extern __shared__ double s_dyn[];
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
 
     // per-lane query
     bool valid = s < n;
-    unsigned long long key = valid ? keys[s] : ~0ull;
+    unsigned long long key = valid ? (unsigned long long)keys[s] : ~0ull;
     const int pid = valid ? vals[s] : 0;
     unsigned long long image = key >> (2 * kBits);
     if (valid && image >= (unsigned long long)n_img) { dk[pid] = 0.0; valid = false; }
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
         const unsigned long long g = __shfl_sync(FULL, image, leader);
         bool mine = valid && image == g;
         todo &= ~__ballot_sync(FULL, mine);
-        KnnTree t{keys, E, Lt, g};
+        KnnTree<KeyT> t{keys, E, Lt, g};
         int g_lo, g_hi;
         node_range(t, 0, 0u, g_lo, g_hi);
         const int nsel = g_hi - g_lo;
@@ -463,20 +469,16 @@ extern "C" int64_t so_knn_workspace_bytes(int64_t n, int32_t k) {
     return l.total + 256;
 }
 
-static int knn_run(const double* X, const double* Y, const int32_t* ix, const int32_t* img, int64_t n, int64_t n_img,
-                   int32_t k, double half_width, int32_t part, int32_t n_parts, double floor, double* dk, int32_t* order_out,
-                   int64_t* range_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
-    if (n == 0) return SO_OK;
-    if (n < 0 || k < 1 || !(half_width > 0.0) || !X || !Y || !ix || !dk || n_img < 1) return SO_ERR_BAD_ARG;
-    if (n_parts < 1 || part < 0 || part >= n_parts || (n_img > 1 && (n_parts != 1 || !img))) return SO_ERR_BAD_ARG;
-    if (n >= (int64_t)1 << 31 || n_img >= (int64_t)1 << 30) return SO_ERR_TOO_LARGE;
-    bool ok = false;
-    KnnLayout l = carve_knn(workspace, workspace_bytes, n, n_img, &ok);
-    if (!ok || !workspace) return SO_ERR_WORKSPACE;
-    int threads = 128;
-    size_t smem = (size_t)k * threads * sizeof(double);
-    if (smem > 200 * 1024) { threads = 32; smem = (size_t)k * threads * sizeof(double); }
-    if (smem > 200 * 1024) return SO_ERR_UNSUPPORTED;
+// everything after the argument checks, for one key width: uint32 keys hold the 30-bit Morton code and the
+// "outside the image" flag of ONE image (halves the radix-sort traffic of the huge-image case), uint64 keys add
+// the image id of a batch
+template <typename KeyT>
+static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, const int32_t* img, int64_t n, int64_t n_img,
+                        int32_t k, double half_width, int32_t part, int32_t n_parts, double floor, double* dk,
+                        int32_t* order_out, int64_t* range_out, const KnnLayout& l, int threads, size_t smem,
+                        cudaStream_t st) {
+    KeyT* keys0 = reinterpret_cast<KeyT*>(l.keys0);
+    KeyT* keys1 = reinterpret_cast<KeyT*>(l.keys1);
     const int Lt = l.Lt;
     const int64_t ncell = n_img << (2 * Lt);
     const double inv_h = (double)(1 << kBits) / (2.0 * half_width);
@@ -485,14 +487,14 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, const in
     SO_CUDA(cudaMemsetAsync(l.counter, 0, 2 * sizeof(unsigned long long), st));
     SO_CUDA(cudaMemsetAsync(l.E, 0, sizeof(int32_t) * (size_t)ncell, st));
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    knn_key_kernel<<<blocks, 256, 0, st>>>(X, Y, ix, img, n, n_img, half_width, inv_h, l.keys0, l.vals0, l.counter);
+    knn_key_kernel<KeyT><<<blocks, 256, 0, st>>>(X, Y, ix, img, n, n_img, half_width, inv_h, keys0, l.vals0, l.counter);
     SO_LAUNCH_CHECK();
     size_t tmp = (size_t)l.cub_tmp_bytes;
-    SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, l.keys0, l.keys1, l.vals0, l.vals1, (int)n, 0,
+    SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, keys0, keys1, l.vals0, l.vals1, (int)n, 0,
                                             2 * kBits + img_bits, st));
     knn_gather_kernel<<<blocks, 256, 0, st>>>(X, Y, l.vals1, n, l.xs, l.ys);
     SO_LAUNCH_CHECK();
-    knn_mark_kernel<<<blocks, 256, 0, st>>>(l.keys1, n, n_img, 2 * (kBits - Lt), l.E);
+    knn_mark_kernel<KeyT><<<blocks, 256, 0, st>>>(keys1, n, n_img, 2 * (kBits - Lt), l.E);
     SO_LAUNCH_CHECK();
     tmp = (size_t)l.cub_tmp_bytes;
     SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), (int)ncell, st));
@@ -513,13 +515,13 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, const in
     if (win_mul == 0) { const char* e = getenv("SO_KNN_WIN"); win_mul = e ? atoi(e) : 1; if (win_mul < 1) win_mul = 1; }
     const int win = k * win_mul;
     if (private_walk || threads != kWarpsPerCta * 32) {
-        SO_CUDA(cudaFuncSetAttribute(knn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_query_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
+        SO_CUDA(cudaFuncSetAttribute(knn_query_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_query_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
+            l.xs, l.ys, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
     } else {
-        SO_CUDA(cudaFuncSetAttribute(knn_query_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_query_warp_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, l.keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
+        SO_CUDA(cudaFuncSetAttribute(knn_query_warp_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_query_warp_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
+            l.xs, l.ys, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
     }
     SO_LAUNCH_CHECK();
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
@@ -528,6 +530,27 @@ static int knn_run(const double* X, const double* Y, const int32_t* ix, const in
         SO_LAUNCH_CHECK();
     }
     return SO_OK;
+}
+
+static int knn_run(const double* X, const double* Y, const int32_t* ix, const int32_t* img, int64_t n, int64_t n_img,
+                   int32_t k, double half_width, int32_t part, int32_t n_parts, double floor, double* dk, int32_t* order_out,
+                   int64_t* range_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+    if (n == 0) return SO_OK;
+    if (n < 0 || k < 1 || !(half_width > 0.0) || !X || !Y || !ix || !dk || n_img < 1) return SO_ERR_BAD_ARG;
+    if (n_parts < 1 || part < 0 || part >= n_parts || (n_img > 1 && (n_parts != 1 || !img))) return SO_ERR_BAD_ARG;
+    if (n >= (int64_t)1 << 31 || n_img >= (int64_t)1 << 30) return SO_ERR_TOO_LARGE;
+    bool ok = false;
+    KnnLayout l = carve_knn(workspace, workspace_bytes, n, n_img, &ok);
+    if (!ok || !workspace) return SO_ERR_WORKSPACE;
+    int threads = 128;
+    size_t smem = (size_t)k * threads * sizeof(double);
+    if (smem > 200 * 1024) { threads = 32; smem = (size_t)k * threads * sizeof(double); }
+    if (smem > 200 * 1024) return SO_ERR_UNSUPPORTED;
+    if (n_img == 1)
+        return knn_run_keys<uint32_t>(X, Y, ix, img, n, n_img, k, half_width, part, n_parts, floor, dk, order_out, range_out,
+                                      l, threads, smem, st);
+    return knn_run_keys<unsigned long long>(X, Y, ix, img, n, n_img, k, half_width, part, n_parts, floor, dk, order_out,
+                                            range_out, l, threads, smem, st);
 }
 
 extern "C" int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
