@@ -73,12 +73,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // index = #{thr <= v} (ascending thresholds); NaN / +inf -> 0 like np.argmin over all-NaN/inf distances
 __device__ __forceinline__ int locate(const double* __restrict__ thr, const unsigned char* __restrict__ lut, int n,
                                       int base, double v) {
-    if (!(v < __longlong_as_double(0x7ff0000000000000LL))) return 0;
     int b = (__double2hiint(v) >> kLutShift) - base;     // negative v -> negative -> bin 0
-    b = max(0, min(kLut - 1, b));
+    b = max(0, min(kLut - 1, b));                        // +inf / NaN -> last bin; both end bins are flagged
     const int e = lut[b];
     int g = e & 127;
     if (e & 128) {      // a threshold lies inside this bin: decide with the exact float64 values
+        if (!(v < __longlong_as_double(0x7ff0000000000000LL))) return 0;
         while (g > 0 && !(v >= thr[g - 1])) --g;
         while (g < n && v >= thr[g]) ++g;
     }
@@ -164,22 +164,28 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
     const float fesc = p.fesc, ofe = 1.0f - p.fesc;
     const int nf = p.n_filters;
 
+    // L2 prefetch: thread t < 5 * kLines owns line (t % kLines) of input array (t / kLines) of a later item
+    constexpr int kLines = kItem * 8 / 128;              // 128-byte lines per array per item
+    static_assert(5 * kLines <= kThreads, "one prefetch line per thread");
+    const double* pf_line = nullptr;
+    int64_t pf_off = 0;
+    if (p.prefetch > 0 && tid < 5 * kLines) {
+        const int arr = tid / kLines, line = tid - arr * kLines;
+        const double* base = arr == 0 ? p.ages : arr == 1 ? p.metals : arr == 2 ? p.masses : arr == 3 ? p.tau_ism : p.tau_bc;
+        pf_off = (int64_t)p.prefetch * kItem + line * 16;
+        if (base) pf_line = base + pf_off;
+    }
+
     for (int64_t item = item_lo; item < item_hi; ++item) {
         const int count = (int)min((int64_t)kItem, s1 - begin);
 
         double age[kPerThread], zz[kPerThread];
         float mm[kPerThread], ti[kPerThread], tb[kPerThread];
-        if (p.prefetch > 0 && item + p.prefetch < item_hi) {
+        if (pf_line && item + p.prefetch < item_hi) {
             // pull a later item's 128-byte lines towards L2 while this one is being processed (contiguous in
             // memory unless a galaxy boundary intervenes: then the hint is merely wasted).  One line per thread,
             // spread over 320 threads: issuing the five lines of a column from 64 threads only was slower.
-            constexpr int kLines = kItem * 8 / 128;          // lines per array per item
-            for (int t = tid; t < 5 * kLines; t += kThreads) {
-                const int arr = t / kLines, line = t - arr * kLines;
-                const double* base = arr == 0 ? p.ages : arr == 1 ? p.metals : arr == 2 ? p.masses : arr == 3 ? p.tau_ism : p.tau_bc;
-                const int64_t idx = begin + (int64_t)p.prefetch * kItem + line * 16;
-                if (base && idx < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + idx));
-            }
+            if (begin + pf_off < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_line + begin));
         }
         if (count == kItem) {
             // full item (all but the last of a galaxy): plain strided loads off one base offset
