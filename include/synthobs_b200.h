@@ -267,9 +267,10 @@ int so_img_sersic(const double* G, int32_t ndim, double r_eff, double n, double 
 /* np.median of n_arrays float64 arrays of length n (array a starts at x + a*stride), the
  * recentring step of observed.particle (synthobs/morph/images.py:183-184): element n//2 for
  * odd n, mean of the two middle elements for even n, bit-identical to NumPy for finite data.
- * 8-bit radix selection on the order-preserving integer image of the doubles: eight
- * prefix-filtered histogram passes, no sort.  out: DEVICE double[n_arrays]. */
-int64_t so_median_workspace_bytes(int32_t n_arrays);
+ * Radix selection on the order-preserving integer image of the doubles, no sort: two
+ * histogram passes over 11-bit digits, one pass that copies the keys sharing those 22 bits
+ * into the workspace, the remaining 42 bits on that (small) copy.  out: DEVICE double[n_arrays]. */
+int64_t so_median_workspace_bytes(int64_t n, int32_t n_arrays);
 int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out,
                   void* workspace, int64_t workspace_bytes, void* stream);
 

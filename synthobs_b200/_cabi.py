@@ -54,7 +54,7 @@ SIGNATURES = {
     'so_img_deposit_batch': (c_int, [P, P, P, I64, I32, I32, I32, I64, P, P, P, P, P, P, I64, P]),
     'so_img_rebin': (c_int, [P, P, I32, I32, I32, P]),
     'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, I32, P]),
-    'so_median_workspace_bytes': (I64, [I32]),
+    'so_median_workspace_bytes': (I64, [I64, I32]),
     'so_median_f64': (c_int, [P, I64, I32, I64, P, P, I64, P]),
     'so_median_segmented': (c_int, [P, P, I64, P, P]),
     'so_recentre_segmented': (c_int, [P, P, I64, P, D, P]),

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
         }
 }
 
-// ---- np.median of float64 arrays by 8-bit radix selection (no sort) --------------------------------
+// ---- np.median of float64 arrays by radix selection (no sort) ---------------------------------------
 // order-preserving map double -> uint64 (negative values: all bits flipped, others: sign bit set)
 __device__ __forceinline__ unsigned long long f64_key(double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -53,89 +53,196 @@ __device__ __forceinline__ double key_f64(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
+// Selection state of one array.  The first two passes histogram 11-bit digits of ALL keys (sign +
+// exponent, then the top mantissa bits), the third pass copies the few keys that share those 22
+// bits into a buffer, and one CTA finishes the remaining 42 bits on that buffer.
+constexpr int kSelBits = 11;
+constexpr int kSelBins = 1 << kSelBits;
+constexpr int kSelThreads = 512;
+constexpr int kSelTailThreads = 1024;
+
 struct SelectState {
-    unsigned long long prefix;      // high bytes of the selected key found so far
+    unsigned long long prefix;      // high digits of the selected key found so far
     unsigned long long rank;        // rank of the wanted element among the keys that match the prefix
-    unsigned long long below_max;   // largest key below the selected one (0 if none)
+    unsigned long long below_max;   // largest key below the selected prefix group (0 if none)
+    unsigned long long count;       // keys copied to the buffer
     unsigned int ticket;            // blocks of the current pass that have added their histogram
-    unsigned int hist[256];
+    unsigned int pad;
+    unsigned int hist[kSelBins];
 };
 
-// pass p: histogram of byte (7 - p) over the keys whose p high bytes equal the prefix; the block that adds
-// its histogram last (ticket counter) picks the byte value whose bin holds the wanted rank, descends into
-// it and clears the histogram for the next pass
-__global__ void __launch_bounds__(512) select_hist_kernel(const double* __restrict__ x, int64_t n, int64_t stride,
-                                                          SelectState* __restrict__ st, int pass) {
-    __shared__ unsigned int s_h[256];
-    __shared__ bool s_last;
-    const double* xa = x + (size_t)blockIdx.y * stride;
-    SelectState* sa = st + blockIdx.y;
-    if (threadIdx.x < 256) s_h[threadIdx.x] = 0;
+// All threads of the CTA: the bin of s_h[0 .. nbins) that holds rank r -> (*bin, *rank inside the bin)
+// written by the one thread that owns it.  nbins <= 4 * blockDim.x.
+__device__ __forceinline__ void select_pick(const unsigned int* s_h, int nbins, unsigned long long r,
+                                            unsigned int* s_scan, int* bin, unsigned long long* rank_in) {
+    const int t = threadIdx.x, per = (nbins + blockDim.x - 1) / blockDim.x;
+    unsigned int mine = 0;
+    for (int j = 0; j < per; ++j) { const int bi = t * per + j; if (bi < nbins) mine += s_h[bi]; }
+    // inclusive scan of the per-thread sums (warp shuffles + one shared pass over the warp totals)
+    unsigned int x = mine;
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_scan[warp] = x;
     __syncthreads();
-    const unsigned long long prefix = sa->prefix;
-    const int hs = 64 - 8 * pass;                   // bits above the byte of this pass
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long k = f64_key(xa[i]);
-        if (pass == 0 || (k >> hs) == (prefix >> hs)) atomicAdd(&s_h[(k >> (hs - 8)) & 255], 1u);
+    if (warp == 0) {
+        unsigned int w = (lane < (int)(blockDim.x >> 5)) ? s_scan[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        s_scan[lane] = w;
     }
     __syncthreads();
-    if (threadIdx.x < 256 && s_h[threadIdx.x]) atomicAdd(&sa->hist[threadIdx.x], s_h[threadIdx.x]);
+    unsigned long long before = (unsigned long long)(x - mine) + (warp > 0 ? s_scan[warp - 1] : 0);
+    if (r >= before && r < before + mine) {
+        for (int j = 0; j < per; ++j) {
+            const int bi = t * per + j;
+            const unsigned int c = s_h[bi];
+            if (r < before + c) { *bin = bi; *rank_in = r - before; break; }
+            before += c;
+        }
+    }
+    __syncthreads();
+}
+
+// pass p (0 or 1): histogram of digit p over the keys whose higher digits equal the prefix; the block that
+// adds its histogram last (ticket counter) picks the digit whose bin holds the wanted rank and clears the
+// histogram for the next pass
+__global__ void __launch_bounds__(kSelThreads) select_hist_kernel(const double* __restrict__ x, int64_t n, int64_t stride,
+                                                                  SelectState* __restrict__ st, int pass) {
+    __shared__ unsigned int s_h[kSelBins];
+    __shared__ unsigned int s_scan[32];
+    __shared__ bool s_last;
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_rank;
+    const double* xa = x + (size_t)blockIdx.y * stride;
+    SelectState* sa = st + blockIdx.y;
+    for (int i = threadIdx.x; i < kSelBins; i += kSelThreads) s_h[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = sa->prefix;
+    const int hs = 64 - kSelBits * pass;            // bits above the digit of this pass
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = f64_key(xa[i]);
+        if (pass == 0 || (k >> hs) == (prefix >> hs)) atomicAdd(&s_h[(k >> (hs - kSelBits)) & (kSelBins - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSelBins; i += kSelThreads)
+        if (s_h[i]) atomicAdd(&sa->hist[i], s_h[i]);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&sa->ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < 256) s_h[threadIdx.x] = *(volatile unsigned int*)&sa->hist[threadIdx.x];
+    for (int i = threadIdx.x; i < kSelBins; i += kSelThreads) {
+        s_h[i] = *(volatile unsigned int*)&sa->hist[i];
+        sa->hist[i] = 0;
+    }
     __syncthreads();
+    select_pick(s_h, kSelBins, sa->rank, s_scan, &s_bin, &s_rank);
     if (threadIdx.x == 0) {
-        unsigned long long r = sa->rank, acc = 0;
-        int b = 0;
-        for (; b < 255; ++b) {
-            if (acc + s_h[b] > r) break;
-            acc += s_h[b];
-        }
-        sa->rank = r - acc;
-        sa->prefix = prefix | ((unsigned long long)b << (56 - 8 * pass));
+        sa->rank = s_rank;
+        sa->prefix = prefix | ((unsigned long long)s_bin << (hs - kSelBits));
         sa->ticket = 0;
     }
-    if (threadIdx.x < 256) sa->hist[threadIdx.x] = 0;
 }
 
-// largest key strictly below the selected one (the lower middle element when n is even and distinct)
-__global__ void __launch_bounds__(512) select_below_kernel(const double* __restrict__ x, int64_t n, int64_t stride,
-                                                           SelectState* __restrict__ st) {
+// pass 2: the keys that share the 22 selected bits go to the buffer (any order); the largest key below
+// that group is the lower middle element when the selected key turns out to be the smallest of its group
+__global__ void __launch_bounds__(kSelThreads) select_compact_kernel(const double* __restrict__ x, int64_t n, int64_t stride,
+                                                                     SelectState* __restrict__ st,
+                                                                     unsigned long long* __restrict__ buf) {
     const double* xa = x + (size_t)blockIdx.y * stride;
     SelectState* sa = st + blockIdx.y;
-    const unsigned long long sel = sa->prefix;
-    unsigned long long m = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long k = f64_key(xa[i]);
-        if (k < sel && k > m) m = k;
+    unsigned long long* out = buf + (size_t)blockIdx.y * n;
+    constexpr int hs = 64 - 2 * kSelBits;
+    const unsigned long long want = sa->prefix >> hs;
+    unsigned long long below = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n + step - 1) / step * step;            // whole warps stay in the loop together
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += step) {
+        unsigned long long k = 0;
+        bool hit = false;
+        if (i < n) {
+            k = f64_key(xa[i]);
+            const unsigned long long top = k >> hs;
+            hit = (top == want);
+            if (top < want && k > below) below = k;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            unsigned long long base = 0;
+            if (lane == (__ffs(bal) - 1)) base = atomicAdd(&sa->count, (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+            if (hit) out[base + __popc(bal & ((1u << lane) - 1u))] = k;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
-        m = t > m ? t : m;
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, below, o);
+        below = t > below ? t : below;
     }
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(&sa->below_max, m);
+    if (lane == 0 && below) atomicMax(&sa->below_max, below);
 }
 
-// np.median: element n//2 for odd n, mean of elements n//2 - 1 and n//2 for even n.  After the
-// eight passes sa->rank is the rank of the selected value among its duplicates: when it is > 0
-// (or n is odd) the lower middle element equals the upper one
-__global__ void select_finish_kernel(const SelectState* __restrict__ st, int64_t n, double* __restrict__ out) {
-    const SelectState* sa = st + threadIdx.x;
-    const double hi = key_f64(sa->prefix);
-    double lo = hi;
-    if ((n & 1) == 0 && sa->rank == 0) lo = key_f64(sa->below_max);
-    out[threadIdx.x] = (n & 1) ? hi : __dmul_rn(__dadd_rn(lo, hi), 0.5);
-}
-
-__global__ void select_init_kernel(SelectState* __restrict__ st, int64_t n) {
+// the remaining 42 bits on the buffered keys (one CTA per array), then np.median: element n//2 for odd n,
+// mean of elements n//2 - 1 and n//2 for even n.  rank > 0 after the last digit = the selected value has
+// duplicates below the wanted rank: then the lower middle element equals the upper one
+__global__ void __launch_bounds__(kSelTailThreads) select_tail_kernel(SelectState* __restrict__ st, int64_t n,
+                                                                       const unsigned long long* __restrict__ buf,
+                                                                       double* __restrict__ out) {
+    __shared__ unsigned int s_h[kSelBins];
+    __shared__ unsigned int s_scan[32];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_rank, s_prefix, s_below;
     SelectState* sa = st + blockIdx.x;
-    if (threadIdx.x == 0) { sa->prefix = 0; sa->rank = (unsigned long long)(n / 2); sa->below_max = 0; sa->ticket = 0; }
-    sa->hist[threadIdx.x] = 0;
+    const unsigned long long* keys = buf + (size_t)blockIdx.x * n;
+    const int64_t m = (int64_t)sa->count;
+    if (threadIdx.x == 0) { s_rank = sa->rank; s_prefix = sa->prefix; s_below = sa->below_max; }
+    __syncthreads();
+    int hs = 64 - 2 * kSelBits;                      // bits above the next digit: 42 left
+    while (hs > 0) {
+        const int bits = hs >= kSelBits ? kSelBits : hs;
+        for (int i = threadIdx.x; i < kSelBins; i += kSelTailThreads) s_h[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int64_t i = threadIdx.x; i < m; i += kSelTailThreads) {
+            const unsigned long long k = keys[i];
+            if ((k >> hs) == (prefix >> hs)) atomicAdd(&s_h[(k >> (hs - bits)) & ((1u << bits) - 1u)], 1u);
+        }
+        __syncthreads();
+        select_pick(s_h, 1 << bits, s_rank, s_scan, &s_bin, &s_rank);
+        if (threadIdx.x == 0) s_prefix = prefix | ((unsigned long long)s_bin << (hs - bits));
+        __syncthreads();
+        hs -= bits;
+    }
+    const unsigned long long sel = s_prefix;
+    unsigned long long below = 0;
+    for (int64_t i = threadIdx.x; i < m; i += kSelTailThreads) {
+        const unsigned long long k = keys[i];
+        if (k < sel && k > below) below = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, below, o);
+        below = t > below ? t : below;
+    }
+    if ((threadIdx.x & 31) == 0 && below) atomicMax(&s_below, below);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double hi = key_f64(sel);
+        double lo = hi;
+        if ((n & 1) == 0 && s_rank == 0) lo = key_f64(s_below);
+        out[blockIdx.x] = (n & 1) ? hi : __dmul_rn(__dadd_rn(lo, hi), 0.5);
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_init_kernel(SelectState* __restrict__ st, int64_t n) {
+    SelectState* sa = st + blockIdx.x;
+    if (threadIdx.x == 0) {
+        sa->prefix = 0; sa->rank = (unsigned long long)(n / 2); sa->below_max = 0; sa->count = 0; sa->ticket = 0;
+    }
+    for (int i = threadIdx.x; i < kSelBins; i += kSelThreads) sa->hist[i] = 0;
 }
 
 // np.median per CSR segment: one CTA walks its segment nine times (eight digit passes + the lower middle)
@@ -218,8 +325,9 @@ extern "C" int so_recentre_segmented(double* x, const int64_t* seg_offsets, int6
     return SO_OK;
 }
 
-extern "C" int64_t so_median_workspace_bytes(int32_t n_arrays) {
-    return so_align_up((int64_t)n_arrays * (int64_t)sizeof(SelectState), 256) + 256;
+extern "C" int64_t so_median_workspace_bytes(int64_t n, int32_t n_arrays) {
+    return so_align_up((int64_t)n_arrays * (int64_t)sizeof(SelectState), 256) +
+           so_align_up((int64_t)n_arrays * n * (int64_t)sizeof(unsigned long long), 256) + 512;
 }
 
 extern "C" int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out,
@@ -228,20 +336,21 @@ extern "C" int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64
     if (!x || !out || n < 1 || n_arrays < 1 || n_arrays > 1024 || stride < n) return SO_ERR_BAD_ARG;
     SoArena a(workspace, workspace_bytes);
     SelectState* state = a.take<SelectState>(n_arrays);
+    unsigned long long* buf = a.take<unsigned long long>((size_t)n_arrays * n);
     if (!workspace || !a.ok()) return SO_ERR_WORKSPACE;
-    int64_t blocks = (n + 512 * 8 - 1) / (512 * 8);
+    int64_t blocks = (n + kSelThreads * 8 - 1) / (kSelThreads * 8);
     if (blocks > 2 * so_num_sms()) blocks = 2 * so_num_sms();
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, (unsigned)n_arrays);
-    select_init_kernel<<<n_arrays, 256, 0, st>>>(state, n);
+    select_init_kernel<<<n_arrays, kSelThreads, 0, st>>>(state, n);
     SO_LAUNCH_CHECK();
-    for (int pass = 0; pass < 8; ++pass) {
-        select_hist_kernel<<<grid, 512, 0, st>>>(x, n, stride, state, pass);
+    for (int pass = 0; pass < 2; ++pass) {
+        select_hist_kernel<<<grid, kSelThreads, 0, st>>>(x, n, stride, state, pass);
         SO_LAUNCH_CHECK();
     }
-    select_below_kernel<<<grid, 512, 0, st>>>(x, n, stride, state);
+    select_compact_kernel<<<grid, kSelThreads, 0, st>>>(x, n, stride, state, buf);
     SO_LAUNCH_CHECK();
-    select_finish_kernel<<<1, n_arrays, 0, st>>>(state, n, out);
+    select_tail_kernel<<<n_arrays, kSelTailThreads, 0, st>>>(state, n, buf, out);
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

@@ -70,19 +70,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// index = #{thr <= v} (ascending thresholds); NaN / +inf -> 0 like np.argmin over all-NaN/inf distances
-__device__ __forceinline__ int locate(const double* __restrict__ thr, const unsigned char* __restrict__ lut, int n,
-                                      int base, double v) {
+// index = #{thr <= v} (ascending thresholds); NaN / +inf -> 0 like np.argmin over all-NaN/inf distances.
+// Split in two so a thread can issue the table loads of all its particles back to back and take the
+// (rare) exact branch once: lut_entry() is the load, locate_exact() the float64 decision for flagged bins.
+__device__ __forceinline__ int lut_entry(const unsigned char* __restrict__ lut, int base, double v) {
     int b = (__double2hiint(v) >> kLutShift) - base;     // negative v -> negative -> bin 0
     b = max(0, min(kLut - 1, b));                        // +inf / NaN -> last bin; both end bins are flagged
-    const int e = lut[b];
-    int g = e & 127;
-    if (e & 128) {      // a threshold lies inside this bin: decide with the exact float64 values
-        if (!(v < __longlong_as_double(0x7ff0000000000000LL))) return 0;
-        while (g > 0 && !(v >= thr[g - 1])) --g;
-        while (g < n && v >= thr[g]) ++g;
-    }
+    return lut[b];
+}
+
+__device__ __noinline__ int locate_exact(const double* __restrict__ thr, int n, int g, double v) {
+    if (!(v < __longlong_as_double(0x7ff0000000000000LL))) return 0;
+    while (g > 0 && !(v >= thr[g - 1])) --g;
+    while (g < n && v >= thr[g]) ++g;
     return g;
+}
+
+__device__ __forceinline__ int locate(const double* __restrict__ thr, const unsigned char* __restrict__ lut, int n,
+                                      int base, double v) {
+    const int e = lut_entry(lut, base, v);
+    return (e & 128) ? locate_exact(thr, n, e & 127, v) : e;
 }
 
 __device__ __forceinline__ float2 ex2_approx2(float2 x) { return make_float2(ex2_approx(x.x), ex2_approx(x.y)); }
@@ -231,12 +238,26 @@ __global__ void __launch_bounds__(kThreads, 2) sed_broadband_kernel(const __grid
             // sums only.  Phase A: NGP cells of the thread's particles, young ones appended to the warp's buffer
             int cellj[kPerThread];
             float wj[kPerThread];
+            int iaj[kPerThread], izj[kPerThread];
+            int flagged = 0;
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                iaj[j] = lut_entry(s_age_lut, p.age.base, age[j]);
+                izj[j] = lut_entry(s_z_lut, p.z.base, zz[j]);
+                flagged |= iaj[j] | izj[j];
+            }
+            if (flagged & 128) {        // a threshold lies inside one of the bins hit: exact float64 compares
+#pragma unroll
+                for (int j = 0; j < kPerThread; ++j) {
+                    if (iaj[j] & 128) iaj[j] = locate_exact(s_age_thr, p.age.n, iaj[j] & 127, age[j]);
+                    if (izj[j] & 128) izj[j] = locate_exact(s_z_thr, p.z.n, izj[j] & 127, zz[j]);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) {
                 const int64_t i = begin + j * kThreads + tid;
                 const bool on = (j * kThreads + tid) < count;
-                const int ia = locate(s_age_thr, s_age_lut, p.age.n, p.age.base, age[j]);
-                const int iz = locate(s_z_thr, s_z_lut, p.z.n, p.z.base, zz[j]);
+                const int ia = iaj[j], iz = izj[j];
                 const bool young = (age[j] < p.young_thr) && (age[j] >= 0.0);
                 const int cell = ia * p.nz + iz;
                 if (p.out_cell && on) p.out_cell[i] = cell + (young ? 65536 : 0);

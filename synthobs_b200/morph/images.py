@@ -386,7 +386,7 @@ def median_device(x):
     x2 = x2.to(torch.float64).contiguous()
     m, n = x2.shape
     out = torch.empty(m, dtype=torch.float64, device=x2.device)
-    wsb = _cabi.lib.so_median_workspace_bytes(m)
+    wsb = _cabi.lib.so_median_workspace_bytes(n, m)
     ws = dv.workspace(wsb)
     _cabi.check(_cabi.lib.so_median_f64(_cabi.ptr(x2), n, m, x2.stride(0), _cabi.ptr(out), _cabi.ptr(ws), wsb,
                                         _cabi.stream()), 'so_median_f64')
@@ -395,7 +395,7 @@ def median_device(x):
 
 def median_device_pair(a, b):
     """np.median of two CUDA float64 vectors of equal length in ONE selection (the two arrays are
-    addressed as rows of a strided 2-row matrix: nine launches instead of eighteen)."""
+    addressed as rows of a strided 2-row matrix: one set of launches for both)."""
     if (a.dim() != 1 or b.dim() != 1 or a.numel() != b.numel() or a.dtype != torch.float64 or b.dtype != torch.float64
             or not a.is_contiguous() or not b.is_contiguous() or a.data_ptr() == b.data_ptr()):
         return median_device(a), median_device(b)
@@ -405,7 +405,7 @@ def median_device_pair(a, b):
     if diff % 8 or diff // 8 < n:
         return median_device(a), median_device(b)
     out = torch.empty(2, dtype=torch.float64, device=a.device)
-    wsb = _cabi.lib.so_median_workspace_bytes(2)
+    wsb = _cabi.lib.so_median_workspace_bytes(n, 2)
     ws = dv.workspace(wsb)
     _cabi.check(_cabi.lib.so_median_f64(_cabi.ptr(lo), n, 2, diff // 8, _cabi.ptr(out), _cabi.ptr(ws), wsb,
                                         _cabi.stream()), 'so_median_f64')

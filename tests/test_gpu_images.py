@@ -270,7 +270,12 @@ def test_median_matches_numpy_bitwise():
              np.concatenate([np.full(50, 0.25), rng.normal(0.25, 1e-3, 49)]),
              np.concatenate([np.full(40, -1.5), np.full(40, 2.0)]),
              np.round(rng.normal(0, 2, 5000), 1), -np.abs(rng.normal(5, 1, 4096)) * 1e-300,
-             rng.normal(0, 1, 300001) * 1e200]
+             rng.normal(0, 1, 300001) * 1e200,
+             np.full(70000, 3.75), np.zeros(1000), np.concatenate([np.zeros(500), -np.zeros(500)]),
+             np.concatenate([np.full(1000, 1.0), np.full(1000, np.nextafter(1.0, 2.0))]),      # the two middle elements differ in the last bit
+             np.concatenate([np.full(1000, 1.0 - 2.0 ** -30), np.full(1000, 1.0)]),            # ... and lie in different 22-bit groups
+             np.concatenate([rng.normal(0, 1, 999), [np.inf, -np.inf]]),
+             rng.standard_cauchy(1000000)]
     for a in cases:
         got = float(images.median_device(torch.from_numpy(a).cuda()).cpu())
         assert got == np.median(a), (a.size, got, np.median(a))
