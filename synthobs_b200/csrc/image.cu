@@ -38,19 +38,28 @@ __device__ __forceinline__ float gauss_factor(float cpx, int k, float u) {
     return ex2_ftz(-cpx * fk * (fk - 2.f * u));
 }
 
+// per-particle deposit plan: one 32-byte record = one memory sector per gather
+struct __align__(32) PlanRec {
+    float ux, uy;     // (x - G[ix]) / pitch, (y - G[iy]) / pitch
+    float cpx;        // log2(e) * pitch^2 / (2 sigma^2)
+    float wnorm;      // 1 / (Sx * Sy), 0 for dropped particles
+    int32_t ix, iy;   // nearest pixel (ix < 0: not selected)
+    int32_t W;        // support half width in pixels
+    int32_t pad;
+};
+
 struct PlanView {
-    float* ux;        // (x - G[ix]) / pitch
-    float* uy;
-    float* cpx;       // log2(e) * pitch^2 / (2 sigma^2)
-    float* wnorm;     // 1 / (Sx * Sy), 0 for dropped particles
-    int32_t* ix;
-    int32_t* iy;
-    int32_t* W;       // support half width in pixels
+    PlanRec* rec;     // [n]
     int64_t* offs;    // [n+1] pair offsets (exclusive scan of the tile counts)
     unsigned long long* stats;  // [4] pairs, deposits, selected, dropped
     void* cub_tmp;
     int64_t cub_tmp_bytes;
 };
+
+__device__ __forceinline__ void plan_load(const PlanRec* __restrict__ rec, int64_t p, float4& a, int4& b) {
+    a = __ldg(reinterpret_cast<const float4*>(rec + p));
+    b = __ldg(reinterpret_cast<const int4*>(rec + p) + 1);
+}
 
 static int64_t scan_tmp_bytes(int64_t n) {
     size_t b = 0;
@@ -61,13 +70,7 @@ static int64_t scan_tmp_bytes(int64_t n) {
 static PlanView carve_plan(void* ws, int64_t bytes, int64_t n, bool* ok) {
     SoArena a(ws, bytes);
     PlanView v;
-    v.ux = a.take<float>(n);
-    v.uy = a.take<float>(n);
-    v.cpx = a.take<float>(n);
-    v.wnorm = a.take<float>(n);
-    v.ix = a.take<int32_t>(n);
-    v.iy = a.take<int32_t>(n);
-    v.W = a.take<int32_t>(n);
+    v.rec = a.take<PlanRec>(n);
     v.offs = a.take<int64_t>(n + 1);
     v.stats = a.take<unsigned long long>(4);
     v.cub_tmp_bytes = scan_tmp_bytes(n);
@@ -167,8 +170,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ i
             my_drop = dropped ? 1 : 0;
             my_pairs = (unsigned long long)count;
         }
-        pv.ux[p] = ux; pv.uy[p] = uy; pv.cpx[p] = cpx; pv.wnorm[p] = wn;
-        pv.ix[p] = ip; pv.iy[p] = jp; pv.W[p] = W;
+        float4* out = reinterpret_cast<float4*>(pv.rec + p);
+        out[0] = make_float4(ux, uy, cpx, wn);
+        reinterpret_cast<int4*>(out)[1] = make_int4(ip, jp, W, 0);
         pv.offs[p] = count;
         if (p == n - 1) pv.offs[n] = 0;
     }
@@ -193,12 +197,13 @@ __global__ void __launch_bounds__(256) plan_wide_kernel(int64_t n, int ndim, Pla
     const int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
     if (base >= n) return;
     const int64_t mine = base + lane;
-    unsigned todo = __ballot_sync(0xffffffffu, mine < n && pv.wnorm[mine] < 0.f);
+    unsigned todo = __ballot_sync(0xffffffffu, mine < n && pv.rec[mine].wnorm < 0.f);
     while (todo) {
         const int64_t p = base + (__ffs(todo) - 1);
         todo &= todo - 1;
-        const int ip = pv.ix[p], jp = pv.iy[p], W = pv.W[p];
-        const float cpx = pv.cpx[p], ux = pv.ux[p], uy = pv.uy[p];
+        const PlanRec r = pv.rec[p];
+        const int ip = r.ix, jp = r.iy, W = r.W;
+        const float cpx = r.cpx, ux = r.ux, uy = r.uy;
         const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
         const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
         float sx = 0.f, sy = 0.f;
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(256) plan_wide_kernel(int64_t n, int ndim, Pla
         sx = warp_sum(sx);
         sy = warp_sum(sy);
         __syncwarp();
-        if (lane == 0) pv.wnorm[p] = 1.0f / (sx * sy);
+        if (lane == 0) pv.rec[p].wnorm = 1.0f / (sx * sy);
     }
 }
 
@@ -223,10 +228,11 @@ __global__ void __launch_bounds__(256) expand_kernel(PlanView pv, int64_t n, int
     int tx0 = 0, ty0 = 0, nx = 0, cnt = 0, kb = 0;     // kb: first tile key of the particle's image
     int64_t o = 0;
     if (p < n) {
-        const int ip = pv.ix[p];
+        const int4 r = __ldg(reinterpret_cast<const int4*>(pv.rec + p) + 1);
+        const int ip = r.x;
         if (ip >= 0) {
             kb = img ? img[p] * ntiles_img : 0;
-            const int jp = pv.iy[p], W = pv.W[p];
+            const int jp = r.y, W = r.z;
             const int kx0 = max(-W, -ip), kx1 = min(W, ndim - 1 - ip);
             const int ky0 = max(-W, -jp), ky1 = min(W, ndim - 1 - jp);
             tx0 = (ip + kx0) / kT;
@@ -324,6 +330,7 @@ __global__ void item_tile_kernel(const int64_t* __restrict__ item_start, int nti
 struct DepositParams {
     PlanView pv;
     const double* L;          // [C_total, n]
+    const float* wts;         // [n, C_total] float32 weights L * wnorm (written by weights_kernel)
     int64_t n;
     int ndim, ntx, ntiles;
     const int32_t* pids;      // sorted pair list
@@ -338,7 +345,21 @@ struct DepositParams {
     int ntiles_img;           // sub-tiles per image; tile key = image * ntiles_img + tile (batch of images)
 };
 
+// wts[p][c] = (float)(L[c][p] * wnorm[p]): the weights of a particle in one sector, so the deposit gathers
+// two sectors per (particle, sub-tile) pair (plan record + weights) instead of one per array and channel
+__global__ void __launch_bounds__(256) weights_kernel(const double* __restrict__ L, const PlanRec* __restrict__ rec,
+                                                      int64_t n, int n_chan, float* __restrict__ wts) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double wn = (double)rec[p].wnorm;
+    for (int c = 0; c < n_chan; ++c) wts[(size_t)p * n_chan + c] = (float)(L[(size_t)c * n + p] * wn);
+}
+
 // One warp = one work item (sub-tile, slice of its particle list), C channels in registers.
+// Per particle the 16 column factors and 16 row factors of the sub-tile are evaluated one per lane and
+// exchanged through shared memory (double-buffered, one __syncwarp per particle); a lane owns a 2 x 4
+// pixel block, so it reads 4 column factors and 2 row factors, and all multiply-adds are packed
+// (FMUL2 / FFMA2).
 template <int C>
 __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,73 +373,110 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
     const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
 
-    __shared__ float s_u[kDepWarps][2][kP], s_c[kDepWarps][kP], s_w[kDepWarps][C][kP];
-    __shared__ int s_i[kDepWarps][2][kP], s_W[kDepWarps][kP];
+    __shared__ float4 s_rec[kDepWarps][2][kP];                 // per axis: {-2u, -cpx, tile origin - nearest pixel, W}
+    __shared__ __align__(16) float s_w[kDepWarps][kP][C];      // weights
+    __shared__ __align__(16) float s_f[kDepWarps][2][2 * kT];  // factors: 16 columns, then 16 rows
 
     // lane -> one factor to evaluate (lanes 0-15: column px0+lane, lanes 16-31: row py0+lane-16) and
-    // 8 owned pixels (row lane/2, columns 8*(lane%2) ..)
-    const int axis = lane >> 4;                  // 0: x (columns), 1: y (rows)
-    const int fpix = (axis ? py0 : px0) + (lane & 15);
-    const int row = lane >> 1, col0 = (lane & 1) * 8;
-    float acc[C][8];
+    // a block of 2 rows x 4 columns of owned pixels
+    const int axis = lane >> 4, fl = lane & 15;                // 0: x (columns), 1: y (rows)
+    const bool fvalid = (axis ? py0 : px0) + fl < p.ndim;
+    const float flf = (float)fl;
+    const int br = lane >> 2, bc = lane & 3;                   // rows 2 br, 2 br + 1; columns 4 bc .. 4 bc + 3
+    float2 acc[C][4];                                          // [channel][2 * row + column pair]
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
     for (int64_t base = start; base < end; base += kP) {
         const int np = (int)min((int64_t)kP, end - base);
         __syncwarp();
         if (lane < np) {
             const int pid = p.pids[base + lane];
-            s_u[warp][0][lane] = p.pv.ux[pid];
-            s_u[warp][1][lane] = p.pv.uy[pid];
-            s_c[warp][lane] = p.pv.cpx[pid];
-            s_i[warp][0][lane] = p.pv.ix[pid];
-            s_i[warp][1][lane] = p.pv.iy[pid];
-            s_W[warp][lane] = p.pv.W[pid];
-            const double wn = (double)p.pv.wnorm[pid];
+            float4 ra;
+            int4 rb;
+            plan_load(p.pv.rec, pid, ra, rb);
+            const float Wf = (float)rb.z;
+            s_rec[warp][0][lane] = make_float4(-2.f * ra.x, -ra.z, (float)(px0 - rb.x), Wf);
+            s_rec[warp][1][lane] = make_float4(-2.f * ra.y, -ra.z, (float)(py0 - rb.y), Wf);
+            const float* wp = p.wts + (size_t)pid * p.n_chan + p.chan0;
+            if constexpr (C % 4 == 0) {
+                if ((p.n_chan & 3) == 0) {          // chan0 is a multiple of 4 then: 16-byte loads
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-                s_w[warp][c][lane] = (float)(p.L[(size_t)(p.chan0 + c) * p.n + pid] * wn);
+                    for (int c = 0; c < C; c += 4)
+                        *reinterpret_cast<float4*>(&s_w[warp][lane][c]) = __ldg(reinterpret_cast<const float4*>(wp + c));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) s_w[warp][lane][c] = __ldg(wp + c);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) s_w[warp][lane][c] = __ldg(wp + c);
+            }
         }
         __syncwarp();
         for (int q = 0; q < np; ++q) {
-            const int k = fpix - s_i[warp][axis][q];
-            float f = 0.f;
-            if (abs(k) <= s_W[warp][q] && fpix < p.ndim) f = gauss_factor(s_c[warp][q], k, s_u[warp][axis][q]);
-            const float ey = __shfl_sync(0xffffffffu, f, 16 + row);
-            float g[8];
+            // gauss_factor(cpx, k, u) with k = pixel - nearest pixel, zero outside the support / the image
+            const float4 r = s_rec[warp][axis][q];
+            const float fk = r.z + flf;
+            float f = ex2_ftz((r.y * fk) * (fk + r.x));
+            f = (fabsf(fk) <= r.w && fvalid) ? f : 0.f;
+            const int b = q & 1;
+            s_f[warp][b][lane] = f;
+            __syncwarp();
+            // shared-memory bandwidth (bytes per lane) is what limits this loop: operands are loaded once and
+            // paired up in registers
+            const float4 fx = *reinterpret_cast<const float4*>(&s_f[warp][b][4 * bc]);
+            const float2 fy = *reinterpret_cast<const float2*>(&s_f[warp][b][kT + 2 * br]);
+            float2 g[4];
+            g[0] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.x, fx.y));
+            g[1] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.z, fx.w));
+            g[2] = __fmul2_rn(make_float2(fy.y, fy.y), make_float2(fx.x, fx.y));
+            g[3] = __fmul2_rn(make_float2(fy.y, fy.y), make_float2(fx.z, fx.w));
+            float w[C];
+            if constexpr (C % 4 == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = ey * __shfl_sync(0xffffffffu, f, col0 + j);
+                for (int c = 0; c < C; c += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&s_w[warp][q][c]);
+                    w[c] = w4.x; w[c + 1] = w4.y; w[c + 2] = w4.z; w[c + 3] = w4.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) w[c] = s_w[warp][q][c];
+            }
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float w = s_w[warp][c][q];
+                const float2 w2 = make_float2(w[c], w[c]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(w, g[j], acc[c][j]);
+                for (int j = 0; j < 4; ++j) acc[c][j] = __ffma2_rn(w2, g[j], acc[c][j]);
             }
         }
     }
 
-    const int r = py0 + row;
+    const int col = px0 + 4 * bc;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        if (single) {
-            if (r < p.ndim) {
-                float* out = p.data + (((size_t)image * p.n_chan + p.chan0 + c) * p.ndim + r) * p.ndim + px0 + col0;
-                if (px0 + col0 + 8 <= p.ndim && (p.ndim & 3) == 0) {
-                    *reinterpret_cast<float4*>(out) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
-                    *reinterpret_cast<float4*>(out + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
-                } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (px0 + col0 + j < p.ndim) out[j] = acc[c][j];
+        for (int rr = 0; rr < 2; ++rr) {
+            const float4 v = make_float4(acc[c][2 * rr].x, acc[c][2 * rr].y, acc[c][2 * rr + 1].x, acc[c][2 * rr + 1].y);
+            const int r = py0 + 2 * br + rr;
+            if (single) {
+                if (r < p.ndim) {
+                    float* out = p.data + (((size_t)image * p.n_chan + p.chan0 + c) * p.ndim + r) * p.ndim + col;
+                    if (col + 4 <= p.ndim && (p.ndim & 3) == 0) {
+                        *reinterpret_cast<float4*>(out) = v;
+                    } else {
+                        if (col < p.ndim) out[0] = v.x;
+                        if (col + 1 < p.ndim) out[1] = v.y;
+                        if (col + 2 < p.ndim) out[2] = v.z;
+                        if (col + 3 < p.ndim) out[3] = v.w;
+                    }
                 }
+            } else {
+                float* out = p.partial + ((size_t)item * p.n_chan + p.chan0 + c) * (kT * kT) + (2 * br + rr) * kT + 4 * bc;
+                *reinterpret_cast<float4*>(out) = v;
             }
-        } else {
-            float* out = p.partial + ((size_t)item * p.n_chan + p.chan0 + c) * (kT * kT) + row * kT + col0;
-            *reinterpret_cast<float4*>(out) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
-            *reinterpret_cast<float4*>(out + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
         }
     }
 }
@@ -452,7 +510,8 @@ __global__ void __launch_bounds__(64) ngp_tile_kernel(const DepositParams p, int
         const double* Lc = p.L ? p.L + (size_t)chan * p.n : nullptr;
         for (int64_t q = t0 + threadIdx.x; q < t1; q += 64) {
             const int pid = p.pids[q];
-            const int lx = p.pv.ix[pid] - px0, ly = p.pv.iy[pid] - py0;
+            const int4 r = __ldg(reinterpret_cast<const int4*>(p.pv.rec + pid) + 1);
+            const int lx = r.x - px0, ly = r.y - py0;
             if (lx >= 0 && lx < kT && ly >= 0 && ly < kT) {   // the particle's own sub-tile only
                 if (simple) atomicAdd(&s_sum[ly * kT + lx], Lc[pid]);
                 atomicAdd(&s_cnt[ly * kT + lx], 1u);
@@ -546,6 +605,7 @@ struct DepositLayout {
     int64_t *tile_start, *item_start;
     int32_t* item_tile;
     float* partial;
+    float* wts;
     void* cub_tmp;
     int64_t cub_tmp_bytes;
     int64_t chunk, max_items;
@@ -559,12 +619,13 @@ static int64_t sort_tmp_bytes(int64_t n_pairs) {
     return (int64_t)b;
 }
 
-static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n_pairs, int ndim, int n_chan, int n_img, bool* ok) {
+static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n, int64_t n_pairs, int ndim, int n_chan, int n_img,
+                                   bool* ok) {
     DepositLayout d;
     d.ntx = (ndim + kT - 1) / kT;
     d.ntiles = d.ntx * d.ntx * n_img;       // over the whole batch of images
     // one warp per work item: aim for ~32 items (warps) per SM, never below two staging phases
-    const int64_t target = 32 * 148;
+    const int64_t target = 32 * 148;        // measured flat between 16 and 64 items per SM
     int64_t chunk = (n_pairs + target - 1) / target;
     chunk = (chunk + kP - 1) / kP * kP;
     if (chunk < 2 * kP) chunk = 2 * kP;
@@ -579,6 +640,7 @@ static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n_pairs, int
     d.item_start = a.take<int64_t>(d.ntiles + 1);
     d.item_tile = a.take<int32_t>(d.max_items);
     d.partial = a.take<float>(d.max_items * n_chan * kT * kT);
+    d.wts = a.take<float>(n * n_chan);
     d.cub_tmp_bytes = sort_tmp_bytes(n_pairs > 0 ? n_pairs : 1);
     d.cub_tmp = a.take<char>(d.cub_tmp_bytes);
     if (ok) *ok = a.ok();
@@ -602,8 +664,7 @@ extern "C" int64_t so_img_plan_workspace_bytes(int64_t n) {
     bool ok;
     (void)ok;
     // replicate carve_plan's accounting with a null base
-    a.take<float>(n); a.take<float>(n); a.take<float>(n); a.take<float>(n);
-    a.take<int32_t>(n); a.take<int32_t>(n); a.take<int32_t>(n);
+    a.take<PlanRec>(n);
     a.take<int64_t>(n + 1);
     a.take<unsigned long long>(4);
     a.take<char>(scan_tmp_bytes(n));
@@ -646,8 +707,7 @@ extern "C" int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X
 
 extern "C" int64_t so_img_deposit_batch_workspace_bytes(int64_t n, int64_t n_pairs, int32_t ndim, int32_t n_chan,
                                                         int32_t n_img) {
-    (void)n;
-    DepositLayout d = carve_deposit(nullptr, 0, n_pairs, ndim, n_chan, n_img < 1 ? 1 : n_img, nullptr);
+    DepositLayout d = carve_deposit(nullptr, 0, n, n_pairs, ndim, n_chan, n_img < 1 ? 1 : n_img, nullptr);
     return d.cub_tmp_bytes + 256;
 }
 
@@ -669,7 +729,7 @@ extern "C" int so_img_deposit_batch(const void* plan_workspace, const double* L,
     if (ntx0 * ntx0 * (int64_t)n_img >= ((int64_t)1 << 31) - 1) return SO_ERR_TOO_LARGE;
     bool ok = false;
     PlanView pv = carve_plan(const_cast<void*>(plan_workspace), (int64_t)1 << 60, n, &ok);
-    DepositLayout d = carve_deposit(workspace, workspace_bytes, n_pairs, ndim, n_chan, n_img, &ok);
+    DepositLayout d = carve_deposit(workspace, workspace_bytes, n, n_pairs, ndim, n_chan, n_img, &ok);
     if (!ok || !workspace) return SO_ERR_WORKSPACE;
     const size_t img_bytes = (size_t)ndim * ndim * sizeof(float) * n_img;
     if (n_pairs == 0) {
@@ -693,8 +753,10 @@ extern "C" int so_img_deposit_batch(const void* plan_workspace, const double* L,
     DepositParams p{};
     p.pv = pv; p.L = L; p.n = n; p.ndim = ndim; p.ntx = d.ntx; p.ntiles = d.ntiles; p.ntiles_img = ntiles_img;
     p.pids = d.vals1; p.tile_start = d.tile_start; p.item_start = d.item_start; p.item_tile = d.item_tile;
-    p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0;
+    p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0; p.wts = d.wts;
     if (data) {
+        weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, pv.rec, n, n_chan, d.wts);
+        SO_LAUNCH_CHECK();
         tile_item_scan_kernel<<<1, 1024, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start);
         SO_LAUNCH_CHECK();
         item_tile_kernel<<<(unsigned)((d.max_items + 255) / 256), 256, 0, st>>>(d.item_start, d.ntiles, d.max_items,
