@@ -184,10 +184,16 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ i
         my_drop += __shfl_xor_sync(0xffffffffu, my_drop, o);
         my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
     }
+    // one update of the four counters per CTA (same-address atomics from every warp serialise)
+    __shared__ unsigned long long s_stats[4];
+    if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
+    __syncthreads();
     if ((threadIdx.x & 31) == 0 && my_sel) {
-        atomicAdd(&pv.stats[0], my_pairs); atomicAdd(&pv.stats[1], my_dep);
-        atomicAdd(&pv.stats[2], my_sel); atomicAdd(&pv.stats[3], my_drop);
+        atomicAdd(&s_stats[0], my_pairs); atomicAdd(&s_stats[1], my_dep);
+        atomicAdd(&s_stats[2], my_sel); atomicAdd(&s_stats[3], my_drop);
     }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_stats[threadIdx.x]) atomicAdd(&pv.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
 // supports wider than kWideW (marked wnorm < 0): each warp looks at 32 consecutive particles and sums the
