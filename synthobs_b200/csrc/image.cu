@@ -282,43 +282,12 @@ __global__ void tile_start_kernel(const int32_t* __restrict__ keys, int64_t n_pa
     tile_start[t] = lo;
 }
 
-// items per tile -> exclusive scan (single CTA) ; item -> tile map
-__global__ void __launch_bounds__(1024) tile_item_scan_kernel(const int64_t* __restrict__ tile_start, int ntiles,
-                                                              int64_t chunk, int64_t* __restrict__ item_start) {
-    __shared__ int64_t s_warp[32];
-    __shared__ int64_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < ntiles; base += 1024) {
-        const int t = base + tid;
-        int64_t v = 0;
-        if (t < ntiles) v = (tile_start[t + 1] - tile_start[t] + chunk - 1) / chunk;
-        int64_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int64_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            int64_t w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int64_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const int64_t incl = x + (warp > 0 ? s_warp[warp - 1] : 0) + s_carry;
-        if (t < ntiles) item_start[t] = incl - v;
-        __syncthreads();
-        if (tid == 1023) s_carry = incl;
-        __syncthreads();
-    }
-    if (tid == 0) item_start[ntiles] = s_carry;
+// items per tile -> exclusive scan (device-wide; [ntiles + 1] entries, the last one = number of items) ; item -> tile map
+__global__ void tile_item_count_kernel(const int64_t* __restrict__ tile_start, int ntiles, int64_t chunk,
+                                       int64_t* __restrict__ item_start) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    item_start[t] = t < ntiles ? (tile_start[t + 1] - tile_start[t] + chunk - 1) / chunk : 0;
 }
 
 __global__ void item_tile_kernel(const int64_t* __restrict__ item_start, int ntiles, int64_t max_items,
@@ -648,6 +617,11 @@ static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n, int64_t n
     d.partial = a.take<float>(d.max_items * n_chan * kT * kT);
     d.wts = a.take<float>(n * n_chan);
     d.cub_tmp_bytes = sort_tmp_bytes(n_pairs > 0 ? n_pairs : 1);
+    {
+        size_t b = 0;
+        cub::DeviceScan::ExclusiveSum((void*)nullptr, b, (int64_t*)nullptr, (int64_t*)nullptr, d.ntiles + 1);
+        if ((int64_t)b > d.cub_tmp_bytes) d.cub_tmp_bytes = (int64_t)b;
+    }
     d.cub_tmp = a.take<char>(d.cub_tmp_bytes);
     if (ok) *ok = a.ok();
     if (!ws) d.cub_tmp_bytes = a.used;   // total, for the size query
@@ -763,8 +737,10 @@ extern "C" int so_img_deposit_batch(const void* plan_workspace, const double* L,
     if (data) {
         weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, pv.rec, n, n_chan, d.wts);
         SO_LAUNCH_CHECK();
-        tile_item_scan_kernel<<<1, 1024, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start);
+        tile_item_count_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start);
         SO_LAUNCH_CHECK();
+        size_t stmp = (size_t)d.cub_tmp_bytes;
+        SO_CUDA(cub::DeviceScan::ExclusiveSum(d.cub_tmp, stmp, d.item_start, d.item_start, d.ntiles + 1, st));
         item_tile_kernel<<<(unsigned)((d.max_items + 255) / 256), 256, 0, st>>>(d.item_start, d.ntiles, d.max_items,
                                                                               d.item_tile);
         SO_LAUNCH_CHECK();

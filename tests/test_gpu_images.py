@@ -155,6 +155,17 @@ def test_multi_channel_and_empty():
             assert_image_close(r['data'][c].cpu().numpy().astype(np.float64), o['data'])
         else:
             assert float(r['data'][c].abs().max()) == 0.0
+    # channel groups of 8 / 4 / 2 / 1 with and without 16-byte aligned weight rows (12 = 8 + 4, 13 = 8 + 4 + 1, 7 = 4 + 2 + 1),
+    # odd image size: every channel is a multiple of the first one (the deposit is linear in the weights)
+    o = image_oracle.core(p['X'], p['Y'], p['Masses'], resolution=0.05, ndim=157, smoothing=('adaptive', 8))
+    for C in (12, 13, 7):
+        f = 0.25 + np.arange(C)
+        r = images.deposit_device(dv.to_dev(p['X']), dv.to_dev(p['Y']), dv.to_dev(p['Masses'][None, :] * f[:, None]), 0.05, 157,
+                                  adaptive_k=8)
+        d = r['data'].cpu().numpy().astype(np.float64)
+        assert_image_close(d[0] / f[0], o['data'])
+        for c in range(1, C):
+            assert np.abs(d[c] / f[c] - d[0] / f[0]).max() <= 2e-6 * np.abs(o['data']).max(), (C, c)
     # nothing selected
     img = images.core(np.array([100.0, -100.0]), np.array([0.0, 0.0]), np.array([1.0, 1.0]), ndim=30,
                       smoothing=('adaptive', 4))
