@@ -285,9 +285,9 @@ def run_ours(args):
                        'parallelism': 'galaxies sharded by rank, no collective'},
             'particles_per_s': world * n_part / (ms_step * 1e-3),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': 1.0356e9 if n_part == 25600000 else None,
+                         'frac': achieved / hbm_peak, 'traffic': 1.0397e9 if n_part == 25600000 else None,
                          'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
-                                           '(profiles/r01_ncu_kernels.md): 1.03 GB read + 5.6 MB written vs 1.024 GB algorithmic',
+                                           '(profiles/r01_ncu_kernels.md): 1.031 GB read + 8.3 MB written vs 1.024 GB algorithmic',
                          'peak_source': peak_src,
                          'kernel': 'sed_broadband_kernel<12,0>', 'algorithmic_bytes_per_particle': 40,
                          'note': 'duration = whole step (3 launches chained by programmatic dependent launch: item scan, '
@@ -393,8 +393,8 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
                              'executed_tf32_tflops': 3 * flops / gms / 1e9,
                              'roofline': {'bound': 'tensor', 'achieved': 3 * flops / gms / 1e9, 'peak': tf32_peak,
                                           'unit': 'TFLOP/s', 'frac': 3 * flops / gms / 1e9 / tf32_peak,
-                                          'traffic': 2.02e9 if (M, n_lam, K) == (20000, 9000, 1326) else None,
-                                          'traffic_note': 'ncu dram read 1.32 GB + write 0.70 GB per launch vs 1.03 GB of '
+                                          'traffic': 1.96e9 if (M, n_lam, K) == (20000, 9000, 1326) else None,
+                                          'traffic_note': 'ncu dram read 1.26 GB + write 0.70 GB per launch vs 1.03 GB of '
                                                           'operands (hi+lo) and result (profiles/r01_ncu_kernels.md)',
                                           'peak_source': src,
                                           'cublas_tf32_8192_tflops': cublas_tf32,
