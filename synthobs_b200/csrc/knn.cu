@@ -33,7 +33,7 @@ constexpr int kMaxTableBits = 26;   // at most 2^26 table cells over all images 
 struct KnnLayout {
     void *keys0, *keys1;            // uint32 keys for one image (31 bits), uint64 for a batch of images
     int32_t *vals0, *vals1;
-    double *xs, *ys;
+    double2* pts;                   // positions in sorted (Morton) order
     double2* xy;                    // positions packed in input order: one sector per particle for the sorted gather
     int32_t* E;                    // [4^Lt] upper bounds per table cell
     unsigned long long* counter;   // [0] selected count
@@ -60,8 +60,7 @@ static KnnLayout carve_knn(void* ws, int64_t bytes, int64_t n, int64_t n_img, bo
     l.vals0 = a.take<int32_t>(n);
     l.keys1 = a.take<unsigned long long>(n);
     l.vals1 = a.take<int32_t>(n);
-    l.xs = a.take<double>(n);
-    l.ys = a.take<double>(n);
+    l.pts = a.take<double2>(n);
     l.xy = a.take<double2>(n);
     l.E = a.take<int32_t>(ncell);
     l.counter = a.take<unsigned long long>(2);
@@ -129,12 +128,10 @@ __global__ void __launch_bounds__(kKeyThreads) knn_key_kernel(
 }
 
 __global__ void knn_gather_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ vals, int64_t n,
-                                  double* __restrict__ xs, double* __restrict__ ys) {
+                                  double2* __restrict__ pts) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double2 v = __ldg(xy + vals[i]);
-    xs[i] = v.x;
-    ys[i] = v.y;
+    pts[i] = __ldg(xy + vals[i]);
 }
 
 // E[c] = i + 1 at the last sorted element of table cell c (others stay 0); a max-scan then makes
@@ -150,14 +147,15 @@ __global__ void knn_mark_kernel(const KeyT* __restrict__ keys, int64_t n, int64_
 }
 
 // scan sorted positions [a, b) minus the window [wa, wb) that is already in the list
-__device__ __forceinline__ void knn_scan_range(const double* __restrict__ xs, const double* __restrict__ ys,
+__device__ __forceinline__ void knn_scan_range(const double2* __restrict__ pts,
                                                int a, int b, int wa, int wb, double x, double y, double* best, int k,
                                                int stride) {
     double kth = best[(k - 1) * stride];
     if (a >= wa && a < wb) a = wb;                        // range starts inside the pre-scanned window
     for (int q = a; q < b; ++q) {
         if (q == wa) { q = wb; if (q >= b) break; }       // skip the pre-scanned window
-        const double dx = xs[q] - x, dy = ys[q] - y;
+        const double2 c = __ldg(pts + q);
+        const double dx = c.x - x, dy = c.y - y;
         const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         if (d2 < kth) {
             int j = k - 1;
@@ -228,8 +226,10 @@ __device__ __forceinline__ void node_range(const KnnTree<KeyT>& t, int level, ui
 //     or finest level) are scanned, skipping the window of step 1.
 // The tree is 15 levels deep whatever the particle number, so the dense cores of a clustered
 // catalogue (hundreds of particles per table cell) are resolved instead of being scanned linearly.
+// (a register-resident list for k == 8 — compile-time K, compare-exchange insertion — was slower: 60 registers, 0.71 vs
+// 0.65 ms per 1e6 queries)
 template <typename KeyT>
-__global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __restrict__ xs, const double* __restrict__ ys,
+__global__ void __launch_bounds__(128, 12) knn_query_kernel(const double2* __restrict__ pts,
                                  const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
                                  int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw, double inv_h, int k,
                                  int part, int n_parts, int leaf, int win, double floor2, double* __restrict__ dk) {
@@ -251,7 +251,10 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
     const int stride = blockDim.x;
     double* best = s_best + threadIdx.x;
     for (int j = 0; j < k; ++j) best[j * stride] = INF;
-    const double x = xs[s], y = ys[s];
+    auto kth = [&]() -> double { return best[(k - 1) * stride]; };
+    const double2 self = pts[s];
+    const double x = self.x, y = self.y;
+    auto scan = [&](int a, int b, int sa, int sb) { knn_scan_range(pts, a, b, sa, sb, x, y, best, k, stride); };
     const double ud = (x + hw) * inv_h, vd = (y + hw) * inv_h;   // fine-cell units, as used for the keys
     const float u = (float)ud, v = (float)vd;
     const double h = 1.0 / inv_h;                                 // fine-cell units -> length
@@ -260,15 +263,15 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
     int wb = min(g_hi, (int)s + win + 1);
     const int wa = max(g_lo, wb - (2 * win + 1));
     wb = min(g_hi, wa + 2 * win + 1);
-    knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
+    scan(wa, wb, -1, -1);
     // the caller only needs max(dk, floor): k neighbours inside the floor radius settle the answer
-    if (best[(k - 1) * stride] <= floor2) { dk[pid] = sqrt(best[(k - 1) * stride]); return; }
+    if (kth() <= floor2) { dk[pid] = sqrt(kth()); return; }
 
     // 2. start nodes
     uint32_t stack[kStack];       // node = (1 << 2 level) | code: the leading one marks the level
     int sp = 0;
     {
-        const double rc = sqrt(best[(k - 1) * stride]) * inv_h * (1.0 + 1e-9) + 1e-9;   // fine-cell units
+        const double rc = sqrt(kth()) * inv_h * (1.0 + 1e-9) + 1e-9;   // fine-cell units
         int e = 0;
         if (rc >= 0.5) e = ilogb(2.0 * rc) + 1;                 // 2^e >= 2 rc
         if (!(rc < (double)(1 << kBits)) || e >= kBits) {
@@ -293,12 +296,12 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
         const uint32_t code = node ^ (1u << (2 * level));
         const uint32_t ncx = compact_bits(code), ncy = compact_bits(code >> 1);
         const double dm = (double)node_dmin(kBits - level, ncx, ncy, u, v) * h;
-        if (dm * dm >= best[(k - 1) * stride]) continue;
+        if (dm * dm >= kth()) continue;
         int a, b;
         node_range(t, level, code, a, b);
         if (a == b) continue;
         if (b - a <= leaf || level == kBits) {
-            knn_scan_range(xs, ys, a, b, wa, wb, x, y, best, k, stride);
+            scan(a, b, wa, wb);
             continue;
         }
         // children, pushed farthest first so the nearest is expanded next
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(128, 12) knn_query_kernel(const double* __rest
 #pragma unroll
         for (int c = 0; c < 4; ++c) stack[sp++] = (1u << (2 * level + 2)) | cc[c];
     }
-    dk[pid] = sqrt(best[(k - 1) * stride]);
+    dk[pid] = sqrt(kth());
 }
 
 // Warp-cooperative variant (default): one warp answers 32 consecutive queries of the Morton order, which
@@ -333,7 +336,7 @@ constexpr int kWarpsPerCta = 4;
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
-        const double* __restrict__ xs, const double* __restrict__ ys, const KeyT* __restrict__ keys,
+        const double2* __restrict__ pts, const KeyT* __restrict__ keys,
         const int32_t* __restrict__ vals, int64_t n, int64_t n_img, const int32_t* __restrict__ E, int Lt, double hw,
         double inv_h, int k, int part, int n_parts, int leaf, int win, double floor2, double* __restrict__ dk) {
     extern __shared__ double s_dyn[];
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
     unsigned long long image = key >> (2 * kBits);
     if (valid && image >= (unsigned long long)n_img) { dk[pid] = 0.0; valid = false; }
     double x = 0.0, y = 0.0;
-    if (valid) { x = xs[s]; y = ys[s]; }
+    if (valid) { const double2 self = pts[s]; x = self.x; y = self.y; }
     const double ud = (x + hw) * inv_h, vd = (y + hw) * inv_h;   // fine-cell units, as used for the keys
     const float u = (float)ud, v = (float)vd;
     const double h = 1.0 / inv_h;
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
             wb = min(g_hi, (int)s + win + 1);
             wa = max(g_lo, wb - (2 * win + 1));
             wb = min(g_hi, wa + 2 * win + 1);
-            knn_scan_range(xs, ys, wa, wb, -1, -1, x, y, best, k, stride);
+            knn_scan_range(pts, wa, wb, -1, -1, x, y, best, k, stride);
         }
         double kth = best[(k - 1) * stride];
         if (mine && kth <= floor2) { dk[pid] = sqrt(kth); mine = false; }   // settled below the caller's floor
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
             if (b - a <= leaf || level == kBits) {
                 for (int base = a; base < b; base += 32) {
                     const int m = min(32, b - base);
-                    if (lane < m) { s_px[warp][lane] = xs[base + lane]; s_py[warp][lane] = ys[base + lane]; }
+                    if (lane < m) { const double2 c = pts[base + lane]; s_px[warp][lane] = c.x; s_py[warp][lane] = c.y; }
                     __syncwarp();
                     if (need) {
                         for (int c = 0; c < m; ++c) {
@@ -507,7 +510,7 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     size_t tmp = (size_t)l.cub_tmp_bytes;
     SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, keys0, keys1, l.vals0, l.vals1, (int)n, 0,
                                             2 * kBits + img_bits, st));
-    knn_gather_kernel<<<blocks, 256, 0, st>>>(l.xy, l.vals1, n, l.xs, l.ys);
+    knn_gather_kernel<<<blocks, 256, 0, st>>>(l.xy, l.vals1, n, l.pts);
     SO_LAUNCH_CHECK();
     knn_mark_kernel<KeyT><<<blocks, 256, 0, st>>>(keys1, n, n_img, 2 * (kBits - Lt), l.E);
     SO_LAUNCH_CHECK();
@@ -532,11 +535,11 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     if (private_walk || threads != kWarpsPerCta * 32) {
         SO_CUDA(cudaFuncSetAttribute(knn_query_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_query_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
+            l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
     } else {
         SO_CUDA(cudaFuncSetAttribute(knn_query_warp_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_query_warp_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.xs, l.ys, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
+            l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
     }
     SO_LAUNCH_CHECK();
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
