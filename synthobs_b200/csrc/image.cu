@@ -10,9 +10,11 @@
 // Design: the Gaussian is separable, so one particle's contribution to a
 // block of pixels is a rank-1 update  block += (w * ey) (x) ex.  Particles are binned per 16x16
 // sub-tile with a stable radix sort (deterministic lists).  One WARP owns one work item (sub-tile,
-// slice of its list): lane l owns row l/2, columns 8*(l%2)..+7 for all C channels in registers;
-// per particle the 16 column factors and 16 row factors are evaluated once (one ex2 per lane),
-// exchanged with warp shuffles, and every lane does 8*C FMAs.  Each sub-tile is written exactly
+// slice of its list): lane l owns rows 2*(l/4), +1 and columns 4*(l%4)..+3 for all C channels in
+// registers; per particle the 16 column factors and 16 row factors are evaluated once (one ex2 per
+// lane), exchanged through shared memory, and every lane does 8*C packed multiply-adds.  The
+// particle data of a list entry is gathered as two 32-byte sectors (plan record, float32 weight
+// row).  Each sub-tile is written exactly
 // once with plain stores; sub-tiles split over several items are summed by a second kernel in
 // fixed order.  No global atomics touch pixels; results are bitwise reproducible.
 #include <cub/cub.cuh>
