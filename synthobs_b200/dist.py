@@ -188,8 +188,8 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None):
     Xd, Yd, Ld = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L)
     one = Ld.dim() == 1
     Ld = Ld.reshape(1, -1) if one else Ld
-    width, G = images.pixel_grid(resolution, ndim)
-    ix, iy = images.ngp_index_device(Xd, Yd, dv.to_dev(G), ndim, width / 2.)
+    width, G, Gd = images.pixel_grid_device(resolution, ndim)
+    ix, iy = images.ngp_index_device(Xd, Yd, Gd, ndim, width / 2.)
     dk, pids = images.knn_device_part(Xd, Yd, ix, int(k), width / 2., rank, ws, floor=images.FWHM_FLOOR)
     r = images.deposit_device(Xd[pids], Yd[pids], Ld[:, pids], resolution, ndim, adaptive_k=int(k), want_ngp=False,
                               support_sigmas=support_sigmas, dk=dk[pids])

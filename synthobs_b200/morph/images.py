@@ -64,6 +64,23 @@ def pixel_grid(resolution, ndim):
     return width, np.linspace(-width / 2., width / 2., ndim)    # images.py:53
 
 
+_grid_cache = {}
+
+
+def pixel_grid_device(resolution, ndim):
+    """(width, G, G on the device).  The device copy is cached per (resolution, ndim, device): a pageable
+    host-to-device copy synchronises the stream, which would stall every call behind the previous one."""
+    dev = dv.device()
+    key = (float(resolution), int(ndim), dev.index)
+    hit = _grid_cache.get(key)
+    if hit is None:
+        if len(_grid_cache) >= 64:
+            _grid_cache.clear()
+        width, G = pixel_grid(resolution, ndim)
+        hit = _grid_cache[key] = (width, G, dv.to_dev(G))
+    return hit
+
+
 def rebin_device(img, n_out):
     """[..., n*s, n*s] float32 CUDA -> [..., n, n] block sums (K11)."""
     _cabi.require_device()
@@ -225,8 +242,7 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
         Ld = Ld.reshape(1, -1)
     Ld = Ld.contiguous()
     C, n = Ld.shape
-    width, G = pixel_grid(resolution, ndim)
-    Gd = dv.to_dev(G)
+    width, G, Gd = pixel_grid_device(resolution, ndim)
     ix, iy = ngp_index_device(Xd, Yd, Gd, ndim, width / 2.)
     adaptive = adaptive_k is not None
     if adaptive and dk is None:
