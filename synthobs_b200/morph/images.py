@@ -108,22 +108,30 @@ def rebin(arr, new_shape):
 KERNEL_CROP_EPS = 1e-14     # kernel elements below this fraction of the peak are outside the cropped support
 
 
+def _smooth7(m):
+    for f in (2, 3, 5, 7):
+        while m % f == 0:
+            m //= f
+    return m == 1
+
+
 def _fft_len(n):
-    """smallest 2^a 3^b 5^c 7^d >= n (the radices cuFFT runs at full speed)"""
-    best = 1 << (int(n) - 1).bit_length()
-    p7 = 1
-    while p7 < best:
-        p5 = p7
-        while p5 < best:
-            p3 = p5
-            while p3 < best:
-                m = p3
-                while m < n:
-                    m *= 2
-                best = min(best, m)
-                p3 *= 3
-            p5 *= 5
-        p7 *= 7
+    """Transform length >= n with radices 2, 3, 5, 7 only (the ones cuFFT runs at full speed).  Among the
+    candidates within 6 % of the smallest one, lengths with a large power of two are preferred: measured on
+    B200 for 8 images of 1024^2 plus a 57^2 kernel, rfft2 + product + irfft2 take 0.259 ms at 1080 = 2^3 3^3 5
+    and 0.221 ms at 1120 = 2^5 5 7.  The choice is a fixed rule (not a run-time timing), so results stay
+    reproducible."""
+    n = max(int(n), 1)
+    first = n
+    while not _smooth7(first):
+        first += 1
+    best, best_cost = first, None
+    for c in range(first, int(first * 1.06) + 1):
+        if not _smooth7(c):
+            continue
+        cost = float(c) * c * (1.0 if c % 32 == 0 else 1.1 if c % 16 == 0 else 1.25)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = c, cost
     return best
 
 
