@@ -423,8 +423,8 @@ def imaging_stage_times(obs, Xd, Yd, Ld):
         mx, my = images.median_device_pair(Xd, Yd)
         X, Y = Xd - mx, Yd - my
         t.append(ev())
-        width, G = images.pixel_grid(o0.resolution, o0.ndim_super)
-        ix, iy = images.ngp_index_device(X, Y, images.dv.to_dev(G), o0.ndim_super, width / 2.)
+        width, G, Gd = images.pixel_grid_device(o0.resolution, o0.ndim_super)
+        ix, iy = images.ngp_index_device(X, Y, Gd, o0.ndim_super, width / 2.)
         t.append(ev())
         dk = images.knn_device(X, Y, ix, IMG_K, width / 2., floor=images.FWHM_FLOOR)
         t.append(ev())
