@@ -334,9 +334,9 @@ __global__ void __launch_bounds__(256) weights_kernel(const double* __restrict__
 
 // One warp = one work item (sub-tile, slice of its particle list), C channels in registers.
 // Per particle the 16 column factors and 16 row factors of the sub-tile are evaluated one per lane and
-// exchanged through shared memory (double-buffered, one __syncwarp per particle); a lane owns a 2 x 4
-// pixel block, so it reads 4 column factors and 2 row factors, and all multiply-adds are packed
-// (FMUL2 / FFMA2).
+// exchanged through shared memory (all 32 staged particles at once, one __syncwarp per phase); a lane
+// owns a 2 x 4 pixel block, so it reads 4 column factors and 2 row factors per particle, and all
+// multiply-adds are packed (FMUL2 / FFMA2).
 template <int C>
 __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
 
     __shared__ float4 s_rec[kDepWarps][2][kP];                 // per axis: {-2u, -cpx, tile origin - nearest pixel, W}
     __shared__ __align__(16) float s_w[kDepWarps][kP][C];      // weights
-    __shared__ __align__(16) float s_f[kDepWarps][2][2 * kT];  // factors: 16 columns, then 16 rows
+    __shared__ __align__(16) float s_f[kDepWarps][kP][2 * kT]; // factors per staged particle: 16 columns, then 16 rows
 
     // lane -> one factor to evaluate (lanes 0-15: column px0+lane, lanes 16-31: row py0+lane-16) and
     // a block of 2 rows x 4 columns of owned pixels
@@ -393,19 +393,24 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
             }
         }
         __syncwarp();
+        // all factors of the phase first (independent iterations: the ex2 chain is pipelined), one __syncwarp, then
+        // the multiply-adds with nothing but loads in between: neither loop waits on a per-particle exchange
+#pragma unroll 4
         for (int q = 0; q < np; ++q) {
             // gauss_factor(cpx, k, u) with k = pixel - nearest pixel, zero outside the support / the image
             const float4 r = s_rec[warp][axis][q];
             const float fk = r.z + flf;
             float f = ex2_ftz((r.y * fk) * (fk + r.x));
             f = (fabsf(fk) <= r.w && fvalid) ? f : 0.f;
-            const int b = q & 1;
-            s_f[warp][b][lane] = f;
-            __syncwarp();
+            s_f[warp][q][lane] = f;
+        }
+        __syncwarp();
+#pragma unroll 2
+        for (int q = 0; q < np; ++q) {
             // shared-memory bandwidth (bytes per lane) is what limits this loop: operands are loaded once and
             // paired up in registers
-            const float4 fx = *reinterpret_cast<const float4*>(&s_f[warp][b][4 * bc]);
-            const float2 fy = *reinterpret_cast<const float2*>(&s_f[warp][b][kT + 2 * br]);
+            const float4 fx = *reinterpret_cast<const float4*>(&s_f[warp][q][4 * bc]);
+            const float2 fy = *reinterpret_cast<const float2*>(&s_f[warp][q][kT + 2 * br]);
             float2 g[4];
             g[0] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.x, fx.y));
             g[1] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.z, fx.w));
