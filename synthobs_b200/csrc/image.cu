@@ -366,11 +366,13 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
+    int pid_next = (start + lane < end) ? p.pids[start + lane] : 0;     // list entries are fetched one phase ahead
     for (int64_t base = start; base < end; base += kP) {
         const int np = (int)min((int64_t)kP, end - base);
+        const int pid = pid_next;
+        if (base + kP + lane < end) pid_next = p.pids[base + kP + lane];
         __syncwarp();
         if (lane < np) {
-            const int pid = p.pids[base + lane];
             float4 ra;
             int4 rb;
             plan_load(p.pv.rec, pid, ra, rb);
