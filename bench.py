@@ -428,9 +428,10 @@ def imaging_stage_times(obs, Xd, Yd, Ld):
         t.append(ev())
         dk = images.knn_device(X, Y, ix, IMG_K, width / 2., floor=images.FWHM_FLOOR)
         t.append(ev())
-        r = images.deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=IMG_K, want_ngp=False, dk=dk)
+        r = images.deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=IMG_K, want_ngp=False, dk=dk,
+                                  pad_to=(spec.py, spec.px))
         t.append(ev())
-        conv = images.convolve_fft_device(r['data'], spec)
+        conv = images.convolve_fft_device(r['data'], spec, padded=r['data_padded'], crop_copy=False)
         t.append(ev())
         images.rebin_device(r['data'], o0.ndim)
         images.rebin_device(conv, o0.ndim)

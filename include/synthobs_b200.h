@@ -242,9 +242,22 @@ int so_img_deposit_batch(const void* plan_workspace, const double* L, const int3
                          int32_t* tile_ids, int32_t* pair_pids,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* so_img_deposit_batch writing `data` into a larger buffer: image (i, c) starts at
+ * data + (i * n_chan + c) * data_plane and its rows are data_ld floats apart (data_ld >= ndim).  Used to
+ * deposit straight into the zero-padded buffer of the PSF transform (no pad copy); the caller zeroes the
+ * padding. */
+int so_img_deposit_batch_ld(const void* plan_workspace, const double* L, const int32_t* img, int64_t n,
+                            int32_t n_chan, int32_t n_img, int32_t ndim, int64_t n_pairs,
+                            float* data, int64_t data_ld, int64_t data_plane, float* simple, float* hist,
+                            int32_t* tile_ids, int32_t* pair_pids,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
 /* K11 — rebin by block SUM (synthobs/morph/images.py:19-22): in [n_img, n*s, n*s]
- * -> out [n_img, n, n]. */
+ * -> out [n_img, n, n].  _ld: the input images are windows of a larger buffer (rows in_ld floats apart,
+ * images in_plane floats apart), e.g. the uncropped result of the PSF convolution. */
 int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int32_t s, void* stream);
+int so_img_rebin_ld(const float* in, int64_t in_ld, int64_t in_plane, float* out, int32_t n_img,
+                    int32_t n_out, int32_t s, void* stream);
 
 /* elementwise helper for the PSF step (K10): out = a * b on interleaved complex
  * float32 spectra; a, out: [n_img, n_complex]; b: [n_complex] broadcast over the

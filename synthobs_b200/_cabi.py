@@ -53,6 +53,8 @@ SIGNATURES = {
     'so_img_deposit_batch_workspace_bytes': (I64, [I64, I64, I32, I32, I32]),
     'so_img_deposit_batch': (c_int, [P, P, P, I64, I32, I32, I32, I64, P, P, P, P, P, P, I64, P]),
     'so_img_rebin': (c_int, [P, P, I32, I32, I32, P]),
+    'so_img_rebin_ld': (c_int, [P, I64, I64, P, I32, I32, I32, P]),
+    'so_img_deposit_batch_ld': (c_int, [P, P, P, I64, I32, I32, I32, I64, P, I64, I64, P, P, P, P, P, I64, P]),
     'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, I32, P]),
     'so_median_workspace_bytes': (I64, [I64, I32]),
     'so_median_f64': (c_int, [P, I64, I32, I64, P, P, I64, P]),

@@ -315,7 +315,8 @@ struct DepositParams {
     const int64_t* item_start;
     const int32_t* item_tile;
     int64_t chunk;
-    float* data;              // [C_total, ndim, ndim]
+    float* data;              // [n_img, C_total] images of ndim x ndim, row stride ld, image stride plane (floats)
+    int64_t ld, plane;
     float* partial;           // [max_items, C_total, kT*kT]
     int n_chan;               // C_total
     int chan0;                // first channel of this launch
@@ -447,8 +448,8 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
             const int r = py0 + 2 * br + rr;
             if (single) {
                 if (r < p.ndim) {
-                    float* out = p.data + (((size_t)image * p.n_chan + p.chan0 + c) * p.ndim + r) * p.ndim + col;
-                    if (col + 4 <= p.ndim && (p.ndim & 3) == 0) {
+                    float* out = p.data + ((size_t)image * p.n_chan + p.chan0 + c) * p.plane + (size_t)r * p.ld + col;
+                    if (col + 4 <= p.ndim && ((p.ld | p.plane) & 3) == 0) {
                         *reinterpret_cast<float4*>(out) = v;
                     } else {
                         if (col < p.ndim) out[0] = v.x;
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParam
     float s = 0.f;
     for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
     const int row = py0 + e / kT, col = px0 + e % kT;
-    if (row < p.ndim && col < p.ndim) p.data[(((size_t)image * n_chan + chan) * p.ndim + row) * p.ndim + col] = s;
+    if (row < p.ndim && col < p.ndim) p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = s;
 }
 
 // NGP products: one CTA per sub-tile; shared-memory accumulation (float64 sums, integer counts)
@@ -513,12 +514,12 @@ __global__ void __launch_bounds__(64) ngp_tile_kernel(const DepositParams p, int
     }
 }
 
-__global__ void rebin_kernel(const float* __restrict__ in, float* __restrict__ out, int n_out, int s) {
+__global__ void rebin_kernel(const float* __restrict__ in, int64_t nin, int64_t plane, float* __restrict__ out,
+                             int n_out, int s) {
     const int img = blockIdx.z;
     const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
     if (ox >= n_out || oy >= n_out) return;
-    const size_t nin = (size_t)n_out * s;
-    const float* src = in + (size_t)img * nin * nin;
+    const float* src = in + (size_t)img * plane;          // nin = row stride of the input (>= n_out * s)
     // images.py:22 sums the last axis first (columns within the block), then the rows
     float tot = 0.f;
     for (int r = 0; r < s; ++r) {
@@ -709,8 +710,19 @@ extern "C" int so_img_deposit_batch(const void* plan_workspace, const double* L,
                                     float* data, float* simple, float* hist,
                                     int32_t* tile_ids, int32_t* pair_pids,
                                     void* workspace, int64_t workspace_bytes, void* stream) {
+    return so_img_deposit_batch_ld(plan_workspace, L, img, n, n_chan, n_img, ndim, n_pairs, data, ndim,
+                                   (int64_t)ndim * ndim, simple, hist, tile_ids, pair_pids, workspace, workspace_bytes, stream);
+}
+
+extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double* L, const int32_t* img, int64_t n,
+                                       int32_t n_chan, int32_t n_img, int32_t ndim, int64_t n_pairs,
+                                       float* data, int64_t data_ld, int64_t data_plane, float* simple, float* hist,
+                                       int32_t* tile_ids, int32_t* pair_pids,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n < 0 || ndim < 1 || n_chan < 1 || n_pairs < 0 || !plan_workspace || n_img < 1) return SO_ERR_BAD_ARG;
+    if (data && (data_ld < ndim || data_plane < data_ld * ndim)) return SO_ERR_BAD_ARG;
+    const bool dense = data_ld == ndim && data_plane == (int64_t)ndim * ndim;
     if (n_img > 1 && !img && n > 0) return SO_ERR_BAD_ARG;
     if (n_pairs >= (int64_t)1 << 31) return SO_ERR_TOO_LARGE;
     if (n > 0 && (data || simple) && !L) return SO_ERR_BAD_ARG;
@@ -722,7 +734,12 @@ extern "C" int so_img_deposit_batch(const void* plan_workspace, const double* L,
     if (!ok || !workspace) return SO_ERR_WORKSPACE;
     const size_t img_bytes = (size_t)ndim * ndim * sizeof(float) * n_img;
     if (n_pairs == 0) {
-        if (data) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
+        if (data) {
+            if (dense) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
+            else
+                for (int64_t i = 0; i < (int64_t)n_img * n_chan; ++i)
+                    SO_CUDA(cudaMemset2DAsync(data + i * data_plane, data_ld * sizeof(float), 0, ndim * sizeof(float), ndim, st));
+        }
         if (simple) SO_CUDA(cudaMemsetAsync(simple, 0, img_bytes * n_chan, st));
         if (hist) SO_CUDA(cudaMemsetAsync(hist, 0, img_bytes, st));
         return SO_OK;
@@ -742,6 +759,7 @@ extern "C" int so_img_deposit_batch(const void* plan_workspace, const double* L,
     DepositParams p{};
     p.pv = pv; p.L = L; p.n = n; p.ndim = ndim; p.ntx = d.ntx; p.ntiles = d.ntiles; p.ntiles_img = ntiles_img;
     p.pids = d.vals1; p.tile_start = d.tile_start; p.item_start = d.item_start; p.item_tile = d.item_tile;
+    p.ld = data_ld; p.plane = data_plane;
     p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0; p.wts = d.wts;
     if (data) {
         weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, pv.rec, n, n_chan, d.wts);
@@ -784,9 +802,14 @@ extern "C" int so_img_deposit(const void* plan_workspace, const double* L, int64
 }
 
 extern "C" int so_img_rebin(const float* in, float* out, int32_t n_img, int32_t n_out, int32_t s, void* stream) {
-    if (n_img < 1 || n_out < 1 || s < 1) return SO_ERR_BAD_ARG;
+    return so_img_rebin_ld(in, (int64_t)n_out * s, (int64_t)n_out * s * n_out * s, out, n_img, n_out, s, stream);
+}
+
+extern "C" int so_img_rebin_ld(const float* in, int64_t in_ld, int64_t in_plane, float* out, int32_t n_img,
+                               int32_t n_out, int32_t s, void* stream) {
+    if (n_img < 1 || n_out < 1 || s < 1 || in_ld < (int64_t)n_out * s) return SO_ERR_BAD_ARG;
     dim3 block(32, 8), grid((n_out + 31) / 32, (n_out + 7) / 8, n_img);
-    rebin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, n_out, s);
+    rebin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, in_ld, in_plane, out, n_out, s);
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

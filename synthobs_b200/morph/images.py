@@ -89,6 +89,12 @@ def rebin_device(img, n_out):
     s = nin // n_out
     if shape[-2] != nin or s * n_out != nin:
         raise ValueError('cannot rebin %s to (%d, %d)' % (tuple(shape), n_out, n_out))
+    if img.dim() == 3 and img.dtype == torch.float32 and img.stride(-1) == 1 and not img.is_contiguous():
+        # a window of a larger buffer (padded deposit, uncropped convolution): read it in place
+        out = torch.empty((shape[0], n_out, n_out), dtype=torch.float32, device=img.device)
+        _cabi.check(_cabi.lib.so_img_rebin_ld(_cabi.ptr(img), img.stride(-2), img.stride(-3), _cabi.ptr(out), shape[0], n_out,
+                                              s, _cabi.stream()), 'so_img_rebin_ld')
+        return out
     x = img.reshape(-1, nin, nin).contiguous()
     out = torch.empty((x.shape[0], n_out, n_out), dtype=torch.float32, device=x.device)
     _cabi.check(_cabi.lib.so_img_rebin(_cabi.ptr(x), _cabi.ptr(out), x.shape[0], n_out, s, _cabi.stream()),
@@ -167,13 +173,16 @@ class KernelSpectrum:
         self.K = torch.fft.rfft2(k, s=(self.py, self.px)).contiguous()   # 2-D rfft2 returns a strided view
 
 
-def convolve_fft_device(img, kernel):
+def convolve_fft_device(img, kernel, padded=None, crop_copy=True):
     """astropy.convolution.convolve_fft with its defaults (zero fill, kernel
     normalised to unit sum and centred on element n//2, output cropped to the
     image; see oracle/ref_loader.py for the restated identity) as a batched
     cuFFT step (K10).  img: [..., n, n] float32 CUDA; kernel: [nk, nk] (shared by
     all images) or [C, nk, nk] (one per image) as host float64 array or CUDA
-    tensor, or a prepared KernelSpectrum."""
+    tensor, or a prepared KernelSpectrum.  padded: the zero-padded buffer
+    [C, py, px] that already holds img in its top-left corner (no pad copy);
+    crop_copy=False returns the result as a window of the full transform
+    (no crop copy)."""
     _cabi.require_device()
     n_y, n_x = img.shape[-2], img.shape[-1]
     ks = kernel if isinstance(kernel, KernelSpectrum) else KernelSpectrum(kernel, n_y, n_x)
@@ -182,14 +191,21 @@ def convolve_fft_device(img, kernel):
     x = img.reshape(-1, n_y, n_x)
     if ks.per_image and ks.n_kernels != x.shape[0]:
         raise ValueError('one kernel per image expected')
-    A = torch.fft.rfft2(x, s=(ks.py, ks.px)).contiguous()
+    if padded is not None:
+        if tuple(padded.shape[-2:]) != (ks.py, ks.px) or not padded.is_contiguous():
+            raise ValueError('padded buffer does not match the kernel spectrum')
+        A = torch.fft.rfft2(padded.reshape(-1, ks.py, ks.px)).contiguous()
+    else:
+        A = torch.fft.rfft2(x, s=(ks.py, ks.px)).contiguous()
     _cabi.check(_cabi.lib.so_complex_mul_bcast(_cabi.ptr(torch.view_as_real(A)), _cabi.ptr(torch.view_as_real(ks.K)),
                                                _cabi.ptr(torch.view_as_real(A)), A.shape[-2] * A.shape[-1],
                                                A.shape[0], 1 if ks.per_image else 0, _cabi.stream()),
                 'so_complex_mul_bcast')
     full = torch.fft.irfft2(A, s=(ks.py, ks.px))
-    out = full[:, ks.oy:ks.oy + n_y, ks.ox:ks.ox + n_x].contiguous()
-    return out.reshape(img.shape)
+    out = full[:, ks.oy:ks.oy + n_y, ks.ox:ks.ox + n_x]
+    if not crop_copy and img.dim() == 3:
+        return out
+    return out.contiguous().reshape(img.shape)
 
 
 def convolve_fft(array, kernel):
@@ -240,11 +256,13 @@ def knn_device_part(Xd, Yd, ix, k, half_width, part, n_parts, floor=0.0):
 
 
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
-                   support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1, exact_dk=False):
+                   support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1, exact_dk=False,
+                   pad_to=None):
     """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
     CUDA (C images sharing positions).  Returns dict of float32 CUDA tensors:
     data [C, ndim, ndim] (adaptive only), simple [C, ndim, ndim], hist [ndim, ndim],
-    plus ix, iy, dk and the stats (pairs, deposits, selected, dropped)."""
+    plus ix, iy, dk and the stats (pairs, deposits, selected, dropped).  pad_to=(py, px): `data` is the
+    top-left window of a zero-padded buffer [C, py, px] (returned as 'data_padded') ready for the PSF transform."""
     _cabi.require_device()
     if Ld.dim() == 1:
         Ld = Ld.reshape(1, -1)
@@ -271,9 +289,9 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
         h = n // 2
         sub = lambda t, a, b: None if t is None else t[..., a:b]   # noqa: E731
         r1 = deposit_device(Xd[:h], Yd[:h], Ld[:, :h], resolution, ndim, adaptive_k, want_data, want_ngp,
-                            support_sigmas, sub(dk, 0, h), False, img=sub(img, 0, h), n_img=n_img)
+                            support_sigmas, sub(dk, 0, h), False, img=sub(img, 0, h), n_img=n_img, pad_to=pad_to)
         r2 = deposit_device(Xd[h:], Yd[h:], Ld[:, h:], resolution, ndim, adaptive_k, want_data, want_ngp,
-                            support_sigmas, sub(dk, h, n), False, img=sub(img, h, n), n_img=n_img)
+                            support_sigmas, sub(dk, h, n), False, img=sub(img, h, n), n_img=n_img, pad_to=pad_to)
         for key in ('data', 'simple', 'hist'):
             if r1[key] is not None:
                 r1[key] += r2[key]
@@ -282,7 +300,12 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
         return r1
     dev = Xd.device
     lead = () if img is None else (int(n_img),)     # a batch of images adds a leading axis
-    data = torch.empty(lead + (C, ndim, ndim), dtype=torch.float32, device=dev) if (adaptive and want_data) else None
+    padded = None
+    if adaptive and want_data and pad_to is not None and img is None:
+        padded = torch.zeros((C, int(pad_to[0]), int(pad_to[1])), dtype=torch.float32, device=dev)
+        data = padded[:, :ndim, :ndim]
+    else:
+        data = torch.empty(lead + (C, ndim, ndim), dtype=torch.float32, device=dev) if (adaptive and want_data) else None
     simple = torch.empty(lead + (C, ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
     hist = torch.empty(lead + (ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
     tiles = torch.empty(npairs, dtype=torch.int32, device=dev) if return_pairs else None
@@ -291,11 +314,13 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
     ws = dv.workspace(wsb)
     if L_event is not None:        # the weights may still be arriving on a copy stream (k-NN and binning need positions only)
         torch.cuda.current_stream().wait_event(L_event)
-    _cabi.check(_cabi.lib.so_img_deposit_batch(_cabi.ptr(pws), _cabi.ptr(Ld), _cabi.ptr(img), n, C, int(n_img), ndim,
-                                               npairs, _cabi.ptr(data), _cabi.ptr(simple), _cabi.ptr(hist),
-                                               _cabi.ptr(tiles), _cabi.ptr(pids), _cabi.ptr(ws), wsb, _cabi.stream()),
-                'so_img_deposit_batch')
-    return {'data': data, 'simple': simple, 'hist': hist, 'ix': ix, 'iy': iy, 'dk': dk, 'G': G,
+    ld, plane = (padded.shape[-1], padded.shape[-1] * padded.shape[-2]) if padded is not None else (ndim, ndim * ndim)
+    _cabi.check(_cabi.lib.so_img_deposit_batch_ld(_cabi.ptr(pws), _cabi.ptr(Ld), _cabi.ptr(img), n, C, int(n_img), ndim,
+                                                  npairs, _cabi.ptr(padded if padded is not None else data), ld, plane,
+                                                  _cabi.ptr(simple), _cabi.ptr(hist), _cabi.ptr(tiles), _cabi.ptr(pids),
+                                                  _cabi.ptr(ws), wsb, _cabi.stream()),
+                'so_img_deposit_batch_ld')
+    return {'data': data, 'data_padded': padded, 'simple': simple, 'hist': hist, 'ix': ix, 'iy': iy, 'dk': dk, 'G': G,
             'stats': {'pairs': stats[0], 'deposits': stats[1], 'selected': stats[2], 'dropped': stats[3]},
             'tiles': tiles, 'pids': pids}
 
@@ -451,19 +476,23 @@ def particle_device_multi(obs_list, Xd, Yd, Ld, L_event=None):
     method, scale = _parse_smoothing(o0.smoothing)
     X = Xd + o0.xoffset if o0.xoffset else Xd
     Y = Yd + o0.yoffset if o0.yoffset else Yd
-    if method == 'adaptive':
-        r = deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=int(scale), want_ngp=False,
-                           L_event=L_event)
-        no_psf = r['data']
-    else:
-        if L_event is not None:
-            torch.cuda.current_stream().wait_event(L_event)
-        no_psf, _, _, r = core_device(X, Y, Ld, o0.resolution, o0.ndim_super, o0.smoothing)
     key = tuple(id(o) for o in obs_list)
     if getattr(o0, '_multi_spec', (None, None))[0] != key:
         o0._multi_spec = (key, KernelSpectrum(np.stack([o.psf_kernel() for o in obs_list]), o0.ndim_super,
                                               o0.ndim_super))
-    conv = convolve_fft_device(no_psf, o0._multi_spec[1])
+    spec = o0._multi_spec[1]
+    if method == 'adaptive':
+        # deposit straight into the zero-padded buffer of the PSF transform; the convolved images stay windows of
+        # the full inverse transform (rebin reads them in place): no pad copy, no crop copy
+        r = deposit_device(X, Y, Ld, o0.resolution, o0.ndim_super, adaptive_k=int(scale), want_ngp=False,
+                           L_event=L_event, pad_to=(spec.py, spec.px))
+        no_psf = r['data']
+        conv = convolve_fft_device(no_psf, spec, padded=r['data_padded'], crop_copy=False)
+    else:
+        if L_event is not None:
+            torch.cuda.current_stream().wait_event(L_event)
+        no_psf, _, _, r = core_device(X, Y, Ld, o0.resolution, o0.ndim_super, o0.smoothing)
+        conv = convolve_fft_device(no_psf, spec)
     return {'super_no_PSF': no_psf, 'super_data': conv, 'no_PSF': rebin_device(no_psf, o0.ndim),
             'data': rebin_device(conv, o0.ndim), 'stats': r['stats']}
 
