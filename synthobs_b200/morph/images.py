@@ -611,13 +611,15 @@ class observed():
         """Device pipeline after recentring: deposit -> PSF FFT convolution -> rebin.
         Ld: [C, n].  Returns dict of float32 CUDA tensors."""
         method, scale = _parse_smoothing(self.smoothing)
+        spec = self.psf_spectrum()
         if method == 'adaptive':
             r = deposit_device(Xd, Yd, Ld, self.resolution, self.ndim_super, adaptive_k=int(scale), want_ngp=False,
-                               dk=dk)
+                               dk=dk, pad_to=(spec.py, spec.px))
             no_psf = r['data']
+            conv = convolve_fft_device(no_psf, spec, padded=r['data_padded'], crop_copy=False)      # images.py:202
         else:
             no_psf, _, _, r = core_device(Xd, Yd, Ld, self.resolution, self.ndim_super, self.smoothing)
-        conv = convolve_fft_device(no_psf, self.psf_spectrum())                                     # images.py:202
+            conv = convolve_fft_device(no_psf, spec)                                                # images.py:202
         return {'super_no_PSF': no_psf, 'super_data': conv,
                 'no_PSF': rebin_device(no_psf, self.ndim), 'data': rebin_device(conv, self.ndim),  # images.py:210-211
                 'info': r}
