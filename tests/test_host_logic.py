@@ -100,3 +100,17 @@ def test_core_loaders_roundtrip(tmp_path):
 def ref_t(n, seed):
     from synthobs_b200 import synthetic
     return synthetic.particles(n, seed=seed)
+
+
+def test_fft_length_rule():
+    """transform lengths: >= n, radices 2/3/5/7 only, within 6 % of the smallest such length, a large power of
+    two preferred (the measured 1080 -> 1120 case), fixed (no run-time timing)"""
+    from synthobs_b200.morph.images import _fft_len, _smooth7
+    assert _fft_len(1080) == 1120 and _fft_len(1024) == 1024 and _fft_len(1) == 1 and _fft_len(100) == 100
+    for n in list(range(1, 400)) + [513, 1000, 2047, 2049, 4099, 8192 + 56, 12345]:
+        m = _fft_len(n)
+        first = n
+        while not _smooth7(first):
+            first += 1
+        assert m >= n and _smooth7(m) and m <= first * 1.06 + 1, (n, m, first)
+        assert _fft_len(n) == m
