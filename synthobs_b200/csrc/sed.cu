@@ -566,6 +566,23 @@ static void fill_axis(Axis& ax, const double* thr, int n) {
     }
 }
 
+// The index table of an axis takes ~50 us of host time to build and only depends on the thresholds: keep the
+// last one per axis and thread (a model is normally used for many calls in a row).
+static void fill_axis_cached(int which, Axis& ax, const double* thr, int n) {
+    struct Slot { bool valid; int n; double thr[kMaxThr + 1]; Axis ax; };
+    static thread_local Slot slots[2] = {};
+    Slot& c = slots[which];
+    if (c.valid && c.n == n && (n == 0 || memcmp(c.thr, thr, sizeof(double) * (size_t)n) == 0)) {
+        ax = c.ax;
+        return;
+    }
+    fill_axis(ax, thr, n);
+    c.valid = true;
+    c.n = n;
+    if (n > 0) memcpy(c.thr, thr, sizeof(double) * (size_t)n);
+    c.ax = ax;
+}
+
 __global__ void hist_kernel(const double* __restrict__ masses, const int32_t* __restrict__ cell,
                             const int64_t* __restrict__ seg, int64_t n, int32_t ncell, int32_t chunks_per_seg,
                             double* __restrict__ partial) {
@@ -660,8 +677,8 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
     p.masses = masses; p.ages = ages; p.metals = metals; p.tau_ism = tau_ism; p.tau_bc = tau_bc; p.n = n;
     p.seg_offsets = seg_offsets; p.n_seg = n_seg;
     p.na = na; p.nz = nz; p.young_thr = young_thr;
-    fill_axis(p.age, age_thr, na - 1);
-    fill_axis(p.z, z_thr, nz - 1);
+    fill_axis_cached(0, p.age, age_thr, na - 1);
+    fill_axis_cached(1, p.z, z_thr, nz - 1);
     p.tab_inc = tab_inc; p.tab_tn = tab_tn; p.n_filters_total = n_filters;
     // the per-particle-output variant is store-bound and loses with the prefetch (measured): off there
     { const char* e = getenv("SO_SED_PREFETCH"); p.prefetch = e ? atoi(e) : (out_pf ? 0 : kPrefetchItems); }
