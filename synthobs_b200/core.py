@@ -72,7 +72,11 @@ class all_test_data():
         return self.get(self.j - 1)
 
 
-Euclid_test_data = all_test_data      # core.py:94-131: same class body, another default path
+class Euclid_test_data(all_test_data):
+    """reference: core.py:90-131 -- same walk and loader as all_test_data, default root EuclidPredictions"""
+
+    def __init__(self, snap, path_to_example_data=FLARE_dir + '/data/project_data/EuclidPredictions/'):
+        all_test_data.__init__(self, snap, path_to_example_data)
 
 
 def write_object(path, X, Y, MetSurfaceDensities, Ages, Metallicities):

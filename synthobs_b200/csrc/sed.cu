@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -609,8 +611,8 @@ __global__ void hist_kernel(const double* __restrict__ masses, const int32_t* __
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 __global__ void hist_finish_kernel(const double* __restrict__ partial, int32_t ncell2, int32_t chunks_per_seg,
-                                   float* __restrict__ H, float* __restrict__ H_lo, int64_t ld) {
-    const int64_t g = blockIdx.y;
+                                   float* __restrict__ H, float* __restrict__ H_lo, int64_t ld, int64_t g_base) {
+    const int64_t g = g_base + blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncell2) return;
     double a = 0.0;
@@ -774,9 +776,11 @@ extern "C" int so_sed_hist(const double* masses, const int32_t* cell, int64_t n,
     SO_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hist_kernel<<<(unsigned)(n_seg * chunks), 256, smem, st>>>(masses, cell, seg_offsets, n, ncell, chunks, partial);
     SO_LAUNCH_CHECK();
-    dim3 grid((2 * ncell + 255) / 256, (unsigned)n_seg);
-    hist_finish_kernel<<<grid, 256, 0, st>>>(partial, 2 * ncell, chunks, H, H_lo, ld_h);
-    SO_LAUNCH_CHECK();
+    for (int64_t g0 = 0; g0 < n_seg; g0 += 65535) {       // gridDim.y <= 65535
+        dim3 grid((2 * ncell + 255) / 256, (unsigned)std::min<int64_t>(65535, n_seg - g0));
+        hist_finish_kernel<<<grid, 256, 0, st>>>(partial, 2 * ncell, chunks, H, H_lo, ld_h, g0);
+        SO_LAUNCH_CHECK();
+    }
     return SO_OK;
 }
 

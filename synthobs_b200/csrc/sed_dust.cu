@@ -13,6 +13,8 @@
 // read once per (run, particle block) instead of once per particle.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -36,6 +38,7 @@ struct DustParams {
     float* partial;          // [n_seg * pblocks, 3, n_lam]
     int32_t pblocks;         // particle blocks per galaxy
     const int64_t* seg;      // CSR offsets of the galaxies in the sorted order, or null (one galaxy)
+    int64_t y_base;          // first (galaxy, particle block) pair of this launch (gridDim.y <= 65535)
 };
 
 __device__ __forceinline__ float ex2a(float x) {
@@ -82,7 +85,8 @@ __global__ void __launch_bounds__(kDustThreads) dust_spectra_kernel(const DustPa
     __shared__ float4 s_rec[kStage];
     __shared__ unsigned s_end[kStage / 32];
     const int lam0 = blockIdx.x * (kDustThreads * kLamPerThread) + threadIdx.x;
-    const int gal = blockIdx.y / p.pblocks, pb = blockIdx.y % p.pblocks;
+    const int64_t yb = p.y_base + blockIdx.y;
+    const int gal = (int)(yb / p.pblocks), pb = (int)(yb % p.pblocks);
     const int64_t g0 = p.seg ? p.seg[gal] : 0, g1 = p.seg ? p.seg[gal + 1] : p.n;
     const int64_t per = (g1 - g0 + p.pblocks - 1) / p.pblocks;
     const int64_t p0 = min(g1, g0 + (int64_t)pb * per), p1 = min(g1, p0 + per);
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kDustThreads) dust_spectra_kernel(const DustPa
         }
     }
     flush();
-    float* out = p.partial + (size_t)blockIdx.y * 3 * p.n_lam;
+    float* out = p.partial + (size_t)yb * 3 * p.n_lam;
 #pragma unroll
     for (int j = 0; j < kLamPerThread; ++j) {
         if (!ok[j]) continue;
@@ -222,9 +226,10 @@ __global__ void __launch_bounds__(kDustThreads) dust_spectra_kernel(const DustPa
 }
 
 __global__ void dust_reduce_kernel(const float* __restrict__ partial, int pblocks, int n_lam,
-                                   float* __restrict__ o_bc, float* __restrict__ o_tot, float* __restrict__ o_noh) {
+                                   float* __restrict__ o_bc, float* __restrict__ o_tot, float* __restrict__ o_noh,
+                                   int64_t gal_base) {
     const int lam = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gal = blockIdx.y;
+    const int64_t gal = gal_base + blockIdx.y;
     if (lam >= n_lam) return;
     double a = 0, b = 0, c = 0;
     for (int pb = 0; pb < pblocks; ++pb) {
@@ -284,12 +289,18 @@ extern "C" int so_sed_dust_spectra(const double* masses, const double* tau_ism, 
     p.masses = masses; p.tau_ism = tau_ism; p.tau_bc = tau_bc; p.key = cell_sorted; p.order = order; p.n = n;
     p.inc = grid_inc; p.tn = grid_tn; p.ncell = ncell; p.n_lam = n_lam; p.k_ism = k_ism_lam; p.k_bc = k_bc_lam;
     p.fesc = (float)fesc; p.partial = partial; p.pblocks = pb; p.seg = seg_offsets;
-    dim3 grid((n_lam + kDustThreads * kLamPerThread - 1) / (kDustThreads * kLamPerThread), (unsigned)(n_seg * pb));
-    if (so_dust_hybrid()) dust_spectra_kernel<true><<<grid, kDustThreads, 0, st>>>(p);
-    else dust_spectra_kernel<false><<<grid, kDustThreads, 0, st>>>(p);
-    SO_LAUNCH_CHECK();
-    dim3 rgrid((n_lam + 255) / 256, (unsigned)n_seg);
-    dust_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, pb, n_lam, out_bc, out_total, out_nohii);
-    SO_LAUNCH_CHECK();
+    const unsigned gx = (n_lam + kDustThreads * kLamPerThread - 1) / (kDustThreads * kLamPerThread);
+    for (int64_t y0 = 0; y0 < n_seg * pb; y0 += 65535) {        // gridDim.y <= 65535: (galaxy, particle block) pairs in slabs
+        p.y_base = y0;
+        dim3 grid(gx, (unsigned)std::min<int64_t>(65535, n_seg * pb - y0));
+        if (so_dust_hybrid()) dust_spectra_kernel<true><<<grid, kDustThreads, 0, st>>>(p);
+        else dust_spectra_kernel<false><<<grid, kDustThreads, 0, st>>>(p);
+        SO_LAUNCH_CHECK();
+    }
+    for (int64_t g0 = 0; g0 < n_seg; g0 += 65535) {
+        dim3 rgrid((n_lam + 255) / 256, (unsigned)std::min<int64_t>(65535, n_seg - g0));
+        dust_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, pb, n_lam, out_bc, out_total, out_nohii, g0);
+        SO_LAUNCH_CHECK();
+    }
     return SO_OK;
 }

@@ -127,10 +127,13 @@ def reduce_image(img):
 def generate_Fnu_sharded(model, F, batch, kind='Fnu', **kw):
     """Broadband fluxes of a batch of galaxies, sharded by galaxy over the ranks.  `batch` is a
     dict with Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, offsets (host arrays)."""
+    from . import device as dv
     from .sed import models
     keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
 
     def compute(indices):
+        if len(indices) == 0:      # fewer galaxies than ranks: this rank only takes part in the gather
+            return torch.zeros((0, len(F['filters'])), dtype=torch.float64, device=dv.device())
         sub, off = subset_csr({k: batch[k] for k in keys if k in batch}, batch['offsets'], indices)
         out = models.generate_Lnu_batch(model, F, sub['Masses'], sub['Ages'], sub['Metallicities'], off,
                                         tauVs_ISM=sub.get('tauVs_ISM', False), tauVs_BC=sub.get('tauVs_BC', False),
@@ -143,11 +146,14 @@ def generate_Fnu_sharded(model, F, batch, kind='Fnu', **kw):
 def generate_SED_sharded(model, batch, **kw):
     """The five spectra of generate_SED for a batch of galaxies, sharded by galaxy (config 4): returns a dict of
     [G, n_lam] float32 CUDA tensors, complete on every rank (one gather per spectrum)."""
+    from . import device as dv
     from .sed import models
     keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
     names = ('stellar', 'intrinsic', 'BC', 'total', 'no_HII_no_BC')
 
     def compute(indices):
+        if len(indices) == 0:
+            return torch.zeros((0, len(names), model.lam.size), dtype=torch.float32, device=dv.device())
         sub, off = subset_csr({k: batch[k] for k in keys if k in batch}, batch['offsets'], indices)
         out = models.sed_spectra_device(model, sub['Masses'], sub['Ages'], sub['Metallicities'],
                                         sub.get('tauVs_ISM', False), sub.get('tauVs_BC', False),

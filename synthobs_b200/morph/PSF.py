@@ -61,18 +61,20 @@ HubblePSF = _needs_data('HubblePSF')
 EuclidPSF = _needs_data('EuclidPSF')
 
 
-def PSF(f):
-    """reference: PSF.py:26-35 — dispatch on the observatory prefix of the filter name."""
-    if f.split('.')[0] == 'Spitzer':
-        return SpitzerPSF(f)
-    if f.split('.')[0] == 'Webb':
-        return WebbPSF(f)
-    if f.split('.')[0] == 'Hubble':
-        return HubblePSF(f)
-    if f.split('.')[0] == 'Euclid':
-        return EuclidPSF(f)
-    raise KeyError(f)
+def PSF(f, **kwargs):
+    """reference: PSF.py:26-35 — dispatch on the observatory prefix of the filter name
+    (HST / Hubble, JWST / Webb, Euclid, Spitzer)."""
+    obs = f.split('.')[0]
+    if obs == 'Spitzer':
+        return SpitzerPSF(f, **kwargs)
+    if obs in ('JWST', 'Webb'):
+        return WebbPSF(f, **kwargs)
+    if obs in ('HST', 'Hubble'):
+        return HubblePSF(f, **kwargs)
+    if obs == 'Euclid':
+        return EuclidPSF(f, **kwargs)
+    raise KeyError(f)       # upstream: UnboundLocalError on `psf`
 
 
-def PSFs(filters):
-    return {f: PSF(f) for f in filters}
+def PSFs(filters, **kwargs):
+    return {f: PSF(f, **kwargs) for f in filters}

@@ -64,11 +64,16 @@ def _bisect_bits(pred, m):
 def ngp_thresholds(nodes, offset):
     """thr[i] = smallest v > 0 for which the reference's
     argmin|nodes - (log10(v) + offset)| (models.py:108-114) is >= i+1.
-    The index is then  #{i : v >= thr[i]}  — float64 compares only."""
+    The index is then  #{i : v >= thr[i]}  — float64 compares only.
+    The node axis must be strictly ascending (every SSP grid is); np.argmin itself would accept any
+    order, the threshold form does not, so anything else is refused instead of silently mis-indexed."""
     nodes = np.asarray(nodes, dtype=np.float64)
     n = nodes.size
     if n < 2:
         return np.zeros(0)
+    if not (np.all(np.isfinite(nodes)) and np.all(np.diff(nodes) > 0)):
+        raise ValueError('the SSP grid axes (log10age, log10Z) must be finite and strictly ascending for the '
+                         'exact nearest-grid-point thresholds; got %r' % (nodes,))
     want = np.arange(1, n)
 
     def index_of(v):
@@ -84,6 +89,11 @@ def ngp_thresholds(nodes, offset):
         if np.any(index_of(up)[fin] < want[fin]) or np.any(index_of(dn)[fin & (dn > 0)] >= want[fin & (dn > 0)]):
             raise RuntimeError('NGP index is not monotone around a threshold; cannot build exact thresholds')
         up, dn = np.nextafter(up, np.inf), np.nextafter(dn, 0.0)
+    # and end to end on a sample spanning the axis: the reference's argmin == the number of thresholds passed
+    lo, hi = nodes[0] - offset - 1.0, nodes[-1] - offset + 1.0
+    sample = 10.0 ** np.linspace(lo, hi, 4096)
+    if not np.array_equal(index_of(sample), (sample[:, None] >= thr[None, :]).sum(axis=1)):
+        raise RuntimeError('NGP thresholds do not reproduce argmin on the sample; cannot build exact thresholds')
     return thr
 
 
@@ -136,6 +146,13 @@ class _NGPGrid():
         if key not in c:
             c[key] = young_threshold(key)
         return c[key]
+
+    def invalidate(self):
+        """Drop every device-side cache (thresholds, filter tables, SSP-grid operands, dust-curve values).
+        The reference reads model.grid / model.Lnu / model.Fnu / F[f].T at call time; here they are uploaded
+        once and keyed by object identity, so call this after editing any of them IN PLACE (replacing the
+        objects, e.g. by create_Lnu_grid, is noticed without it)."""
+        self._dev.clear()
 
 
 class define_model(_NGPGrid):
@@ -320,9 +337,14 @@ def _tables(model, kind, filters):
     """Device tables [F, ncell] float32 built from whatever model.Lnu / model.Fnu
     currently hold (the reference reads them at call time, models.py:131-133)."""
     src = model.Lnu if kind == 'Lnu' else model.Fnu
-    key = (kind, tuple(filters), tuple(id(getattr(src[f], c)) for f in filters for c in COMPONENTS))
+    arrays = [getattr(src[f], c) for f in filters for c in COMPONENTS]
+    key = (kind, tuple(filters), tuple(id(a) for a in arrays))
     cache = model._dev.setdefault('tabs', {})
     if key not in cache:
+        # the cache keeps the keyed arrays alive, so an id() cannot be recycled while its entry exists; arrays
+        # REPLACED on model.Lnu / model.Fnu are picked up at the next call, arrays edited IN PLACE need
+        # model.invalidate()
+        model._dev['tabs_keep'] = arrays
         inc = np.stack([np.asarray(src[f].stellar_incident, dtype=np.float64).reshape(-1) for f in filters])
         tn = np.stack([(np.asarray(src[f].stellar_transmitted, dtype=np.float64)
                         + np.asarray(src[f].nebular, dtype=np.float64)).reshape(-1) for f in filters])
@@ -347,6 +369,7 @@ def _broadband(model, kind, F, filters, Masses, Ages, Metallicities, tauVs_ISM, 
     if ckey not in kcache:     # pivot wavelengths cost two trapz per filter: do them once per (F, dust) setup
         piv = [F[f].pivwv() / zshift for f in filters]
         kcache.clear()
+        model._dev['dustk_keep'] = F     # keeps id(F) from being recycled while the entry exists
         kcache[ckey] = (None if not model.dust_ISM else [float(_dust_k(model, 'ISM', p)) for p in piv],
                         None if not model.dust_BC else [float(_dust_k(model, 'BC', p)) for p in piv])
     kI, kB = kcache[ckey]
@@ -677,6 +700,7 @@ def _filter_weight_operand(model, F, kind, z=None, cosmo=None, include_IGM=True)
         Wp[:, :nl] = Wt / scale[:, None]
         Wd = dv.to_dev(Wp, torch.float32)
         cache.clear()
+        model._dev['specW_keep'] = (F, cosmo)
         cache[key] = (Wd, split_tf32(Wd), dv.to_dev(scale, torch.float64))
     return cache[key]
 

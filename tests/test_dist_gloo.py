@@ -81,6 +81,11 @@ def _worker(rank, ws, port, q):
         full3 = sdist.sharded_galaxy_map(compute3, offsets)
         ref3 = np.array([[[g, sizes[g]], [2 * g, 1], [0, -g]] for g in range(37)], dtype=np.float32)
         ok1 = ok1 and full3.shape == (37, 3, 2) and np.array_equal(full3.numpy(), ref3)
+        # fewer galaxies than ranks: the rank without a share returns an empty block and still takes part in the gather
+        one_off = np.array([0, 5])
+        mine = sdist.shard_galaxies(np.diff(one_off), ws)[rank]
+        full1 = sdist.sharded_galaxy_map(lambda idx: torch.full((len(idx), 3), 7.0, dtype=torch.float64), one_off)
+        ok1 = ok1 and full1.shape == (1, 3) and bool((full1 == 7.0).all()) and len(mine) == (1 if rank == 0 else 0)
         # one giant galaxy in particle blocks: per-rank partial sums + all-reduce == the whole
         blk = torch.tensor([vals[slice(*sdist.particle_block(vals.size))].sum()], dtype=torch.float64)
         dist.all_reduce(blk)

@@ -114,3 +114,14 @@ def test_fft_length_rule():
             first += 1
         assert m >= n and _smooth7(m) and m <= first * 1.06 + 1, (n, m, first)
         assert _fft_len(n) == m
+
+
+def test_ngp_thresholds_refuse_unsorted_axes():
+    """np.argmin works for any node order; the threshold form does not and must say so"""
+    from synthobs_b200.sed import models
+    la = 6.0 + 0.1 * np.arange(51)
+    thr = models.ngp_thresholds(la, 6.0)
+    assert thr.size == 50 and np.all(np.diff(thr) > 0)
+    for bad in (la[::-1], np.r_[la[:10], la[9:]], np.r_[la[:5], np.nan, la[6:]]):
+        with pytest.raises(ValueError):
+            models.ngp_thresholds(bad, 6.0)

@@ -92,14 +92,37 @@ def test_histogram_gemm_formulation_equals_loop():
 def test_image_oracle_matches_reference(tag):
     g = _cases.load('img_' + tag)
     sm = _cases.smoothing_of(g)
-    for literal in ([True, False] if sm and sm[0] == 'adaptive' else [False]):
+    adaptive = bool(sm) and sm[0] == 'adaptive'
+    # literal per-particle loop, separable form, and the windowed/tiled form the full-size GPU parity tests use
+    for literal, tiled in ([(True, False), (False, False), (False, True)] if adaptive else [(False, False)]):
         with np.errstate(all='ignore'):
             o = image_oracle.core(g['X'], g['Y'], g['L'], resolution=float(g['resolution']), ndim=int(g['ndim']),
-                                  smoothing=sm, literal=literal)
+                                  smoothing=sm, literal=literal, tiled=tiled)
         assert np.array_equal(o['hist'], g['hist'])
         np.testing.assert_allclose(o['simple'], g['simple'], rtol=RT)
         peak = np.abs(g['data']).max()
         np.testing.assert_allclose(o['data'], g['data'], rtol=1e-9, atol=1e-13 * peak)
+
+
+def test_windowed_oracle_equals_separable():
+    """adaptive_window / adaptive_tiled (terms that are exactly 0.0 in float64 skipped) == adaptive_separable, incl.
+    multi-channel weights, a window of a larger image, dk = inf (k > N) and the FWHM floor."""
+    rng = np.random.default_rng(5)
+    for n, ndim, res, k in ((4000, 96, 0.1, 8), (9000, 200, 0.02, 5), (20, 40, 0.1, 64)):
+        p = synthetic.particles(n, seed=n)
+        width, G = image_oracle.pixel_grid(res, ndim)
+        sel = image_oracle.select(p['X'], p['Y'], width)
+        X, Y = p['X'][sel], p['Y'][sel]
+        L = np.stack([p['Masses'][sel] * rng.random(X.size), rng.random(X.size)])
+        dk = image_oracle.kth_neighbour_distance(X, Y, k)
+        dk[::7] = 0.0          # FWHM floor (images.py:89)
+        full = np.stack([image_oracle.adaptive_separable(G, X, Y, L[c], dk) for c in range(2)])
+        tiled = image_oracle.adaptive_tiled(G, X, Y, L, dk, block=37)
+        win = image_oracle.adaptive_window(G, X, Y, L, dk, (5, 33), (11, 40))
+        for c in range(2):
+            peak = full[c].max()
+            np.testing.assert_allclose(tiled[c], full[c], rtol=1e-12, atol=1e-15 * peak)
+            np.testing.assert_allclose(win[c], full[c][5:33, 11:40], rtol=1e-12, atol=1e-15 * peak)
 
 
 def test_pixel_indices_match_reference():
