@@ -1,21 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the two SynthObs hot paths on B200.
+"""bench.py -- the two SynthObs hot paths on B200, every BASELINE.json configuration.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--sections a,b,...]
 
-Prints ONE JSON line (rank 0).  Primary record: BASELINE.json config[1]
-(SED_fluxes-style: galaxies of 1e5 particles, BPASS-shape grid 51x13x9000, ISM+BC LOS
-dust, 10 broadband filters), batched so one step streams more than L2 from HBM.
-`value` = galaxy SEDs x filters / s with inputs resident in HBM; `e2e` = the same through
-the public API with pinned HOST inputs (H2D + D2H inside the timed region).
-Secondary record under "imaging": BASELINE.json config[2] (1e6 particles, 8 filters,
-512x512 observed-frame images, super-sampling 2, adaptive smoothing, PSF convolution).
-Multi-GPU: one process per GPU, galaxies/objects sharded by rank, no data-path collective
-(weak scaling); time = max over ranks.
+Prints ONE JSON line (rank 0).  Primary record = BASELINE.json config[1] (SED_fluxes-style: galaxies of 1e5
+particles, BPASS-shape grid 51x13x9000, ISM+BC LOS dust, 10 broadband filters), batched so one step streams more
+than L2 from HBM.  `value` = galaxy SEDs x filters / s with inputs resident in HBM; `e2e` = the same through the
+public API with pinned HOST inputs (H2D + D2H inside the timed region); `roofline` = the streaming kernel's own
+launch duration (CUDA events around the launch, on its stream) against the measured HBM bandwidth.
 
---impl reference times the CPU restatement of the reference (oracle/, NumPy, the reference is
-pure Python so there is nothing to compile into oracle/_ref) on bounded samples of the same
-workload on the host cores.
+Nested records (same line): `peaks` (TF32 / FP32-FMA / MUFU measured on this GPU), `latency_c2` (the single-galaxy
+reference call), `spectra` (generate_SED + the tcgen05 contractions), `imaging` (config[2]: 1e6 particles, 8 filters,
+512^2 + PSF; per-kernel rooflines, e2e through images.particle, SED -> image pipeline), `config1` (1e4 particles ->
+100^2), `config4` (ONE ragged catalogue of 1e4 galaxies through the galaxy-sharded entry points, STRONG scaling,
+the all_gather inside the timed region), `config5` (1e8 particles -> 8192^2 through dist.image_huge, STRONG scaling,
+the NCCL reduce inside the timed region).
+
+--impl reference times the CPU restatement of the reference (oracle/, NumPy: the reference is pure Python, there is
+nothing to compile into oracle/_ref) on the same config[1] step on all host cores.
 """
 
 import argparse
@@ -23,7 +25,6 @@ import contextlib
 import io
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -44,19 +45,26 @@ IMG_NDIM = 512
 IMG_SS = 2
 IMG_K = 8
 Z = 8.0
+C4_GALAXIES = 10000
+C5_PARTICLES = 100000000
+C5_NDIM = 8192
+ALL_SECTIONS = ('peaks', 'sed', 'latency', 'spectra', 'imaging', 'c1', 'c4', 'c5')
+SED_WORKLOAD = ('config[1] SED_fluxes: %d galaxies per step (and per GPU) x 1e5 particles, BPASS-shape grid 51x13x%d, '
+                'ISM+BC LOS dust, %d filters' % (GALAXIES_PER_GPU, N_LAM, N_FILTERS))
 
 
-def peaks():
+def peaks_file():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
             p = json.load(fh)
-        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        return {'hbm_gbs': float(p['hbm_gbs']), 'bf16_tflops': float(p.get('bf16_tflops', 0.0)),
+                'source': 'measured (MEASURED_PEAKS.json)'}
     except Exception:
-        return 6650.0, 'fallback (B200_PROFILING.md)'
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback (B200_PROFILING.md)'}
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML, 20 ms period;
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, 5 ms period;
     same fields as the nvidia-smi clocks line of B200_PROFILING.md)."""
 
     def __init__(self, index):
@@ -119,11 +127,81 @@ class ClockSampler:
                 'power_w_max': max([x[3] for x in sel]) if sel else None}
 
 
-def timed_steps(step, steps, barrier, flush=None):
+class Ctx:
+    """what every section needs: rank / world, barrier, max over ranks, the measured peaks"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.args = args
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            # NCCL prints its version banner on stdout when the communicator is created: point fd 1 at stderr until
+            # the first collective has run, so that stdout carries the one JSON line only
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group('nccl', device_id=self.dev)
+                t = torch.zeros(1, device=self.dev)
+                dist.all_reduce(t)
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+        self.peaks = peaks_file()
+        self.measured = {}
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return float(ms)
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def timed_loop(ctx, step, steps):
+    """K back-to-back steps between two CUDA events, bracketed by barrier + synchronize; ms per step, max over ranks"""
+    import torch
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    ctx.barrier()
+    return ctx.max_over_ranks(e0.elapsed_time(e1) / steps)
+
+
+def timed_steps(ctx, step, steps, flush=None):
     """Mean device time of `steps` runs of `step`, each bracketed by its own CUDA events; when `flush` (a buffer
     larger than L2) is given it is rewritten between the runs, outside the timed intervals."""
     import torch
-    barrier()
+    ctx.barrier()
     tot = 0.0
     for _ in range(steps):
         if flush is not None:
@@ -134,11 +212,37 @@ def timed_steps(step, steps, barrier, flush=None):
         e1.record()
         e1.synchronize()
         tot += e0.elapsed_time(e1)
-    barrier()
-    return tot / steps
+    ctx.barrier()
+    return ctx.max_over_ranks(tot / steps)
 
 
-def setup_model(n_lam=N_LAM, n_filters=N_FILTERS):
+def wall_loop(ctx, step, steps):
+    """host wall clock per step (end-to-end calls synchronise themselves), max over ranks"""
+    ctx.barrier()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    ctx.barrier()
+    return ctx.max_over_ranks((time.time() - t0) * 1e3 / steps)
+
+
+def kernel_profile(step, reps=3):
+    """{label: (launches per step, ms per launch)} from CUDA events recorded around every labelled launch inside the
+    library (so_prof_*), on the stream the kernels run on; a separate pass, never inside a timed loop"""
+    import torch
+    from synthobs_b200 import _cabi
+    step()
+    torch.cuda.synchronize()
+    _cabi.prof_enable(True)
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize()
+    rep = _cabi.prof_report()
+    _cabi.prof_enable(False)
+    return {k: {'launches_per_step': c / reps, 'ms_per_launch': ms / c, 'ms_per_step': ms / reps} for k, (c, ms) in rep.items()}
+
+
+def setup_model(n_lam=N_LAM, n_filters=N_FILTERS, names=None):
     from synthobs_b200 import synthetic
     from synthobs_b200.sed import models
     grid = synthetic.ssp_grid(n_lam=n_lam, seed=0)
@@ -148,174 +252,176 @@ def setup_model(n_lam=N_LAM, n_filters=N_FILTERS):
     model.dust_BC = ('simple', {'slope': -1.0})
     F = synthetic.filter_set(model.lam * (1. + Z), n_filters=n_filters, kind='gauss', lo=12000., hi=50000.,
                              prefix='JWST.FAKE.')
+    if names is not None:       # rename the filters (the imaging pipeline uses the imaging filter names)
+        F = {'filters': list(names), **{new: F[old] for new, old in zip(names, F['filters'])}}
     cosmo = synthetic.FixedCosmology()
     model.create_Fnu_grid(F, Z, cosmo)
     return model, F, cosmo
 
 
-# ------------------------------------------------------------------ ours (GPU)
+# ------------------------------------------------------------------ measured peaks
 
-def run_ours(args):
+def run_peaks(ctx):
+    """TF32 dense (cuBLAS, 8192^3), FP32 FFMA / FFMA2, MUFU.EX2 and the dust kernel's own arithmetic, measured on this
+    GPU with CUDA events (same method as MEASURED_PEAKS.json: best of 5 after warm-up)."""
     import torch
-    import torch.distributed as dist
-    from synthobs_b200 import _cabi, synthetic
-    from synthobs_b200.morph import images
+    from ctypes import byref, c_double
+    from synthobs_b200 import _cabi
+    dev = ctx.dev
+    out = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def best_of(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    res = {}
+    for kind, key, scale in ((0, 'fp32_ffma_tflops', 2e-12), (1, 'fp32_ffma2_tflops', 2e-12), (2, 'mufu_ex2_per_s', 1.0),
+                             (3, 'dust_arith_mufu_exp_per_s', 1.0), (4, 'dust_arith_hybrid_exp_per_s', 1.0)):
+        ops = c_double(0.0)
+
+        def fn():
+            _cabi.check(_cabi.lib.so_peak_kernel(kind, 4096, 8, _cabi.ptr(out), byref(ops), _cabi.stream()), 'so_peak_kernel')
+        ms = best_of(fn)
+        res[key] = ops.value / (ms * 1e-3) * scale
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.rand((8192, 8192), device=dev)
+    b = torch.rand((8192, 8192), device=dev)
+    ms = best_of(lambda: torch.matmul(a, b))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    res['tf32_dense_tflops'] = 2.0 * 8192 ** 3 / (ms * 1e-3) / 1e12
+    del a, b
+    res['hbm_gbs'] = ctx.peaks['hbm_gbs']
+    res['how'] = ('so_peak_kernel: 8 CTAs x 256 threads per SM, 16 independent register chains per thread, best of 5 '
+                  '(CUDA events); tf32_dense = cuBLAS torch.matmul 8192^3 with allow_tf32, best of 5; hbm_gbs from '
+                  + ctx.peaks['source'])
+    ctx.measured = res
+    return res
+
+
+# ------------------------------------------------------------------ SED (primary record)
+
+def run_sed(ctx):
+    import torch
+    from synthobs_b200 import synthetic
     from synthobs_b200.sed import models
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL prints its version banner on stdout when the communicator is created: point fd 1 at stderr until
-        # the first collective has run, so that stdout carries the one JSON line only
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-            t = torch.zeros(1, device=torch.device('cuda', local))
-            dist.all_reduce(t)
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    _cabi.require_device()
-    dev = torch.device('cuda', local)
-    hbm_peak, peak_src = peaks()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---------------- SED workload (primary)
+    args, dev = ctx.args, ctx.dev
     model, F, cosmo = setup_model()
     G = GALAXIES_PER_GPU
-    batch = synthetic.galaxy_batch(G, fixed_n=N_PER_GALAXY, seed=100 + rank)
+    batch = synthetic.galaxy_batch(G, fixed_n=N_PER_GALAXY, seed=100 + ctx.rank)
     keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in keys}
     offsets = torch.from_numpy(batch['offsets'])
     d = {k: host[k].to(dev) for k in keys}
     d_off = offsets.to(dev)
     n_part = d['Masses'].numel()
-    kw_names = dict(fesc=0.0, log10t_BC=7.0)
+    kw = dict(fesc=0.0, log10t_BC=7.0)
 
-    def sed_step_device():
+    def step_device():
         return models.generate_Fnu_batch(model, F, d['Masses'], d['Ages'], d['Metallicities'], d_off,
-                                         tauVs_ISM=d['tauVs_ISM'], tauVs_BC=d['tauVs_BC'], **kw_names)
+                                         tauVs_ISM=d['tauVs_ISM'], tauVs_BC=d['tauVs_BC'], **kw)
 
-    def sed_step_e2e():
+    def step_e2e():
         # public API with HOST (pinned) inputs: H2D of the five particle arrays + kernels + D2H of [G, F]
-        out = models.generate_Fnu_batch(model, F, host['Masses'], host['Ages'], host['Metallicities'], offsets,
-                                        tauVs_ISM=host['tauVs_ISM'], tauVs_BC=host['tauVs_BC'], **kw_names)
-        return out
+        return models.generate_Fnu_batch(model, F, host['Masses'], host['Ages'], host['Metallicities'], offsets,
+                                         tauVs_ISM=host['tauVs_ISM'], tauVs_BC=host['tauVs_BC'], **kw)
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    sed_steps = 1 if args.no_sed else args.steps
-    for _ in range(1 if args.no_sed else max(args.warmup, 3)):
-        out = sed_step_device()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_device()
     t_wall0 = time.time()
-    e0.record()
-    for _ in range(sed_steps):
-        out = sed_step_device()
-    e1.record()
-    barrier()
+    ms_step = timed_loop(ctx, step_device, args.steps)
     t_wall1 = time.time()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / sed_steps)
-    sed_value = world * G * N_FILTERS / (ms_step * 1e-3)
-    algo_bytes = 40.0 * n_part                     # 5 float64 arrays read once
-    achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    value = ctx.world * G * N_FILTERS / (ms_step * 1e-3)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = wall_loop(ctx, step_e2e, e2e_steps)
+    prof = kernel_profile(step_device)
+    kname = 'sed_broadband_kernel'
+    kms = prof.get(kname, {}).get('ms_per_launch', ms_step)
+    algo_bytes = 40.0 * n_part                     # 5 float64 arrays read once (SURVEY 8d)
+    achieved = algo_bytes / (kms * 1e-3) / 1e9
+    hbm = ctx.peaks['hbm_gbs']
+    rec = {
+        'metric': 'galaxy SEDs x filters / s', 'value': value, 'unit': 'galaxy_SEDs_x_filters/s',
+        'n_gpus': ctx.world, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 values, f64 index compares',
+        'data': 'synthetic',
+        'config': {'workload': SED_WORKLOAD, 'entry_point': 'models.generate_Fnu_batch (one segmented so_sed_broadband pass)',
+                   'particles_per_step_per_gpu': n_part, 'l2_policy': 'inputs (1.02 GB/step) larger than L2',
+                   'parallelism': 'galaxies sharded by rank, no collective'},
+        'particles_per_s': ctx.world * n_part / (ms_step * 1e-3),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
+                     'traffic': 1.0397e9 if n_part == 25600000 else None,
+                     'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
+                                       '(profiles/): 1.031 GB read + 8.3 MB written vs 1.024 GB algorithmic',
+                     'peak_source': ctx.peaks['source'], 'kernel': kname, 'kernel_ms_per_launch': kms,
+                     'algorithmic_bytes_per_particle': 40, 'algorithmic_bytes_per_launch': algo_bytes,
+                     'step_frac': algo_bytes / (ms_step * 1e-3) / 1e9 / hbm,
+                     'note': 'achieved = 40 B x particles of one launch / the broadband kernel\'s own launch duration '
+                             '(CUDA events around the launch on its stream, profiling pass: the events break the '
+                             'programmatic-dependent-launch overlap with the item scan and the per-galaxy reduce); '
+                             'step_frac = the same bytes / the whole 3-launch step as timed for `value`'},
+        'e2e': {'value': ctx.world * G * N_FILTERS / (e2e_ms * 1e-3), 'unit': 'galaxy_SEDs_x_filters/s',
+                'h2d_bytes_per_step': int(sum(host[k].numel() * 8 for k in keys) + offsets.numel() * 8),
+                'd2h_bytes_per_step': int(G * N_FILTERS * 8), 'ms_per_step': e2e_ms,
+                'note': 'PCIe-bound: 1.02 GB per step over one Gen5 x16 link; see imaging.pipeline_e2e for the call '
+                        'chain that uploads a catalogue once and keeps the per-particle fluxes on the GPU'},
+        'gpu_launches': 3 * args.steps,
+        'kernels': prof,
+    }
+    return rec, (t_wall0, t_wall1), (batch, model, F)
 
-    # e2e
-    e2e_steps = 1 if args.no_sed else max(3, min(args.steps, 10))
-    for _ in range(0 if args.no_sed else 2):
-        sed_step_e2e()
-    barrier()
+
+def run_latency(ctx):
+    """config[1] exactly as examples/SED_fluxes.py:45 makes the call: ONE galaxy of 1e5 particles, NumPy arrays in,
+    {filter: float} out (launch- and host-latency bound: 4 MB of inputs)."""
+    from synthobs_b200 import synthetic
+    from synthobs_b200.sed import models
+    model, F, cosmo = setup_model()
+    p = synthetic.particles(N_PER_GALAXY, seed=41)
+    a = (p['Masses'], p['Ages'], p['Metallicities'])
+    kw = dict(tauVs_ISM=p['tauVs_ISM'], tauVs_BC=p['tauVs_BC'], fesc=0.0)
+    for _ in range(5):
+        models.generate_Fnu(model, F, *a, **kw)
+    n = 50
     t0 = time.time()
-    for _ in range(e2e_steps):
-        res = sed_step_e2e()
-    barrier()
-    e2e_ms = max_over_ranks((time.time() - t0) * 1e3 / e2e_steps)
-    e2e_value = world * G * N_FILTERS / (e2e_ms * 1e-3)
-    h2d = int(sum(host[k].numel() * 8 for k in keys) + offsets.numel() * 8)
-    d2h = int(G * N_FILTERS * 8)
-
-    # ---------------- full spectra (generate_SED) + the two tensor-core contractions (secondary)
-    spectra = None
-    if not args.no_spectra:
-        spectra = run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks)
-
-    # ---------------- imaging workload (secondary, config[2])
-    imaging = None
-    if not args.no_imaging:
-        imaging = run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak)
-    sampler.stop()
-    clocks = sampler.summary(t_wall0, time.time())     # all timed regions of this run (SED, e2e, spectra, imaging)
-
-    # ---------------- CPU baseline (rank 0, N=1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_sed(batch, model, F, budget_s=12.0)
-        if imaging is not None:
-            imaging['cpu_baseline'] = cpu_baseline_imaging(budget_s=12.0)
-
-    if rank == 0:
-        rec = {
-            'metric': 'galaxy SEDs x filters / s', 'value': sed_value, 'unit': 'galaxy_SEDs_x_filters/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 values, f64 index compares',
-            'data': 'synthetic',
-            'config': {'workload': 'config[1] SED_fluxes: %d galaxies/GPU x 1e5 particles, BPASS-shape grid 51x13x%d, '
-                                   'ISM+BC LOS dust, %d filters; one segmented so_sed_broadband pass per step' %
-                                   (G, N_LAM, N_FILTERS),
-                       'particles_per_step_per_gpu': n_part, 'l2_policy': 'inputs (1.02 GB/step) larger than L2',
-                       'parallelism': 'galaxies sharded by rank, no collective'},
-            'particles_per_s': world * n_part / (ms_step * 1e-3),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': 1.0397e9 if n_part == 25600000 else None,
-                         'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
-                                           '(profiles/r01_ncu_kernels.md): 1.031 GB read + 8.3 MB written vs 1.024 GB algorithmic',
-                         'peak_source': peak_src,
-                         'kernel': 'sed_broadband_kernel<12,0>', 'algorithmic_bytes_per_particle': 40,
-                         'note': 'duration = whole step (3 launches chained by programmatic dependent launch: item scan, '
-                                 'broadband, per-galaxy reduce), so the fraction is a lower bound for the '
-                                 'streaming kernel'},
-            'e2e': {'value': e2e_value, 'unit': 'galaxy_SEDs_x_filters/s', 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
-            'gpu_launches': 3 * sed_steps,
-            'clocks': clocks,
-            'cpu_baseline': cpu,
-            'spectra': spectra,
-            'imaging': imaging,
-        }
-        print(json.dumps(rec))
-    if world > 1:
-        dist.destroy_process_group()
+    for _ in range(n):
+        models.generate_Fnu(model, F, *a, **kw)
+    ms = (time.time() - t0) * 1e3 / n
+    t0 = time.time()
+    for _ in range(n):
+        models.generate_Fnu_array(model, F, F['filters'][0], *a, **kw)
+    ms_arr = (time.time() - t0) * 1e3 / n
+    return {'call': 'models.generate_Fnu(model, F, Masses, Ages, Metallicities, tauVs_ISM=, tauVs_BC=) with NumPy inputs, '
+                    '1e5 particles, 10 filters', 'ms_per_call': ms, 'galaxy_SEDs_x_filters_per_s': N_FILTERS / (ms * 1e-3),
+            'generate_Fnu_array_ms_per_call': ms_arr,
+            'h2d_bytes_per_call': 5 * 8 * N_PER_GALAXY, 'note': 'pageable NumPy inputs: the 4 MB upload and the host-side '
+            'call overhead are the step; reference: ~10 us per particle and filter in a Python loop (SURVEY 8a)'}
 
 
-def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
-    """generate_SED for a batch of galaxies (five spectra over 9000 wavelengths each: segmented
-    histogram -> 3xTF32 tcgen05 GEMM against the SSP grid, per-particle dust kernel) followed by the
-    second contraction spectra x filter weights; plus the histogram x grid GEMM alone at FLARES batch
-    size (1e4 galaxies -> M = 2e4 rows) with its tensor-pipe roofline."""
+# ------------------------------------------------------------------ spectra + GEMM
+
+def run_spectra(ctx, model, F):
+    """generate_SED for a batch of galaxies (five spectra over 9000 wavelengths each: segmented histogram -> 3xTF32
+    tcgen05 GEMM against the SSP grid, per-particle dust kernel) followed by the second contraction spectra x filter
+    weights; plus the histogram x grid GEMM alone at FLARES batch size (1e4 galaxies -> M = 2e4 rows)."""
     import torch
     from synthobs_b200 import _cabi, synthetic
     from synthobs_b200.sed import models
+    args, dev = ctx.args, ctx.dev
     G = 32
-    batch = synthetic.galaxy_batch(G, fixed_n=N_PER_GALAXY, seed=300 + rank)
+    batch = synthetic.galaxy_batch(G, fixed_n=N_PER_GALAXY, seed=300 + ctx.rank)
     keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
     d = {k: torch.from_numpy(batch[k]).to(dev) for k in keys}
     off = torch.from_numpy(batch['offsets']).to(dev)
@@ -326,13 +432,12 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
                                       0.0, 7.0, offsets=off)
         return models.spectra_Fnu(model, F, o['total'], Z, cosmo)      # [G, F] band fluxes from the spectra
 
-    for _ in range(2):
+    for _ in range(3):
         step()
-    barrier()
     steps = max(3, min(args.steps, 5))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # 256 MB > 126 MB of L2
-    ms = max_over_ranks(timed_steps(step, steps, barrier, flush))
+    ms = timed_steps(ctx, step, steps, flush)
+    prof = kernel_profile(step, reps=2)
     n_lam = model.lam.size
     n_part = G * N_PER_GALAXY
     # the hist x grid GEMM alone, FLARES batch size
@@ -350,57 +455,66 @@ def run_spectra(args, model, F, rank, world, dev, barrier, max_over_ranks):
                     'so_gemm_3xtf32')
     for _ in range(3):
         gemm_only()
-    barrier()
-    e0.record()
-    for _ in range(10):
-        gemm_only()
-    e1.record()
-    barrier()
-    gms = max_over_ranks(e0.elapsed_time(e1) / 10)
+    gms = timed_loop(ctx, gemm_only, 10)
     flops = 2.0 * M * n_lam * K
-    try:
-        bf16_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops'])
-        src = 'measured bf16 burst / 2 (no TF32 entry in MEASURED_PEAKS.json)'
-    except Exception:
-        bf16_peak, src = 1590.0, 'fallback bf16 / 2'
-    tf32_peak = bf16_peak / 2
-    # context for the denominator: cuBLAS TF32 (one pass, no error compensation) on 8192^3, measured live
-    old_tf32 = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    a32 = torch.rand((8192, 8192), device=dev)
-    b32 = torch.rand((8192, 8192), device=dev)
-    for _ in range(3):
-        c32 = a32 @ b32
-    barrier()
-    e0.record()
-    for _ in range(10):
-        c32 = a32 @ b32
-    e1.record()
-    barrier()
-    cublas_tf32 = 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) / 10) / 1e9
-    torch.backends.cuda.matmul.allow_tf32 = old_tf32
-    del a32, b32, c32
+    tf32_peak = ctx.measured.get('tf32_dense_tflops') or ctx.peaks['bf16_tflops'] / 2
+    src = 'measured: cuBLAS TF32 8192^3 in this run (peaks.tf32_dense_tflops)' if ctx.measured.get('tf32_dense_tflops') \
+        else 'bf16 peak / 2 (peaks section skipped)'
+    young = float((batch['Ages'] < 10.0).mean())
+    exps = n_part * n_lam * (1.0 + young)
+    dms = prof.get('dust_spectra_kernel', {}).get('ms_per_step', ms)
+    exp_peak = ctx.measured.get('dust_arith_hybrid_exp_per_s') or 148 * 16 * 1.965e9
     return {
         'metric': 'galaxy SEDs/sec (5 spectra x %d wavelengths, ISM+BC dust) + %d band fluxes' % (n_lam, len(F['filters'])),
-        'value': world * G / (ms * 1e-3), 'unit': 'galaxy_SEDs/s', 'ms_per_step': ms,
-        'galaxy_SEDs_x_filters_per_s': world * G * len(F['filters']) / (ms * 1e-3),
-        'particle_wavelengths_per_s': world * n_part * n_lam / (ms * 1e-3),
+        'value': ctx.world * G / (ms * 1e-3), 'unit': 'galaxy_SEDs/s', 'ms_per_step': ms,
+        'galaxy_SEDs_x_filters_per_s': ctx.world * G * len(F['filters']) / (ms * 1e-3),
+        'particle_wavelengths_per_s': ctx.world * n_part * n_lam / (ms * 1e-3),
         'config': {'workload': '%d galaxies x 1e5 particles per GPU, generate_SED_batch + spectra x filters' % G,
                    'l2_policy': 'L2 flushed (256 MB write) between steps, outside the timed intervals'},
-        'ex2_roofline': _ex2_roofline(batch, n_part, n_lam, ms),
+        'kernels': prof,
+        'dust_roofline': {'bound': 'mufu_ex2 + fma polynomial', 'kernel': 'dust_spectra_kernel<hybrid>',
+                          'achieved': exps / (dms * 1e-3), 'peak': exp_peak, 'unit': 'exp/s', 'frac': exps / (dms * 1e-3) / exp_peak,
+                          'kernel_ms_per_step': dms, 'young_fraction': young,
+                          'mufu_only_peak': ctx.measured.get('dust_arith_mufu_exp_per_s'),
+                          'raw_mufu_ex2_per_s': ctx.measured.get('mufu_ex2_per_s'),
+                          'peak_source': 'measured in this run: the kernel\'s own per-particle-wavelength arithmetic (3 MUFU '
+                                         'exponentials + 1 FMA-pipe polynomial per 4) on register operands, so_peak_kernel(4)'
+                                         if ctx.measured else 'nominal 148 x 16 ex2/clk x 1.965 GHz (peaks section skipped)',
+                          'note': 'algorithmic exponentials: 1 per (old particle, wavelength), 2 per young one '
+                                  '(models.py:285-304); duration = the dust kernel\'s own launches (CUDA events)'},
         'gemm_hist_x_grid': {'M': M, 'N': n_lam, 'K': K, 'ms': gms,
-                             'l2_policy': 'operands and result (1.03 GB per launch) larger than L2', 'algorithmic_tflops': flops / gms / 1e9,
-                             'executed_tf32_tflops': 3 * flops / gms / 1e9,
-                             'roofline': {'bound': 'tensor', 'achieved': 3 * flops / gms / 1e9, 'peak': tf32_peak,
-                                          'unit': 'TFLOP/s', 'frac': 3 * flops / gms / 1e9 / tf32_peak,
+                             'l2_policy': 'operands and result (1.03 GB per launch) larger than L2',
+                             'algorithmic_tflops': flops / gms / 1e9, 'executed_tf32_tflops': 3 * flops / gms / 1e9,
+                             'roofline': {'bound': 'tensor', 'achieved': flops / gms / 1e9, 'peak': tf32_peak,
+                                          'unit': 'TFLOP/s', 'frac': flops / gms / 1e9 / tf32_peak,
+                                          'executed_frac': 3 * flops / gms / 1e9 / tf32_peak,
                                           'traffic': 1.96e9 if (M, n_lam, K) == (20000, 9000, 1326) else None,
-                                          'traffic_note': 'ncu dram read 1.26 GB + write 0.70 GB per launch vs 1.03 GB of '
-                                                          'operands (hi+lo) and result (profiles/r01_ncu_kernels.md)',
+                                          'algorithmic_bytes': 4.0 * (M * K + n_lam * K + M * n_lam),
+                                          'traffic_note': 'ncu dram read 1.26 GB + write 0.70 GB per launch '
+                                                          '(profiles/r01_ncu_kernels.md)',
                                           'peak_source': src,
-                                          'cublas_tf32_8192_tflops': cublas_tf32,
-                                          'note': 'achieved counts the three TF32 MMAs actually executed per '
-                                                  'algorithmic product (3xTF32); algorithmic fraction is a third'}},
+                                          'note': 'achieved = ALGORITHMIC flops 2*M*N*K (SURVEY 8d: the x3 of 3xTF32 is '
+                                                  'implementation overhead); executed_frac counts the three TF32 MMAs '
+                                                  'per product'}},
     }
+
+
+# ------------------------------------------------------------------ imaging (config[2])
+
+def imaging_inputs(ctx, seed_shift=0):
+    import torch
+    from synthobs_b200 import synthetic
+    from synthobs_b200.morph import images
+    p = synthetic.particles(IMG_PARTICLES, seed=200 + ctx.rank + seed_shift, scale_kpc=3.0)
+    filters = ['JWST.NIRCAM.B%d' % i for i in range(IMG_FILTERS)]
+    for f in filters:
+        images.filter_info[f] = {'pixel_scale': 0.031}
+    cosmo = synthetic.FixedCosmology()
+    width_arcsec = IMG_NDIM * 0.031 + 1e-9
+    rng = np.random.default_rng(7 + ctx.rank)
+    Lh = np.stack([p['Masses'] * (0.5 + rng.random(IMG_PARTICLES)) for _ in filters])
+    PSFs = {f: synthetic.GaussianPSF(1.5 + 0.2 * i) for i, f in enumerate(filters)}
+    return p, filters, cosmo, width_arcsec, Lh, PSFs
 
 
 def imaging_stage_times(obs, Xd, Yd, Ld):
@@ -409,7 +523,7 @@ def imaging_stage_times(obs, Xd, Yd, Ld):
     import torch
     from synthobs_b200.morph import images
     o0 = obs[0]
-    spec = images.KernelSpectrum(np.stack([o.psf_kernel() for o in obs]), o0.ndim_super, o0.ndim_super)
+    spec = images._group_spectrum(obs)
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
@@ -442,100 +556,274 @@ def imaging_stage_times(obs, Xd, Yd, Ld):
     return {n: float(v / reps) for n, v in zip(names, acc)}
 
 
-def _ex2_roofline(batch, n_part, n_lam, ms):
-    """The dust-spectra kernel is bound by exponentials: one per (old particle, wavelength), two per young one
-    (models.py:285-304).  Peak = 16 MUFU.EX2 per clock and SM at the maximum SM clock; the step time (which also
-    holds the histogram, sort and GEMM launches) is used, so the fraction is a lower bound for the kernel.  The
-    kernel evaluates a quarter of them on the FMA pipe instead, which is how it can pass the MUFU-only roof."""
-    young = float((batch['Ages'] < 10.0).mean())
-    exps = n_part * n_lam * (1.0 + young)
-    peak = 148 * 16 * 1.965e9
-    return {'bound': 'mufu_ex2', 'achieved': exps / (ms * 1e-3), 'peak': peak, 'unit': 'ex2/s',
-            'frac': exps / (ms * 1e-3) / peak, 'young_fraction': young,
-            'peak_source': '148 SMs x 16 MUFU.EX2/clk x 1.965 GHz (nominal XU rate; no measured entry)'}
-
-
-def run_imaging(args, rank, world, dev, barrier, max_over_ranks, hbm_peak):
+def count_launches(step):
+    """kernel launches of one step, all libraries (torch profiler / CUPTI); None when the profiler is unavailable"""
     import torch
-    from synthobs_b200 import synthetic
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        step()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        return int(sum(1 for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
+                       and 'memcpy' not in e.name.lower() and 'memset' not in e.name.lower()))
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def run_imaging(ctx):
+    import torch
     from synthobs_b200.morph import images
-    p = synthetic.particles(IMG_PARTICLES, seed=200 + rank, scale_kpc=3.0)
-    filters = ['JWST.NIRCAM.B%d' % i for i in range(IMG_FILTERS)]
-    for f in filters:
-        images.filter_info[f] = {'pixel_scale': 0.031}
-    cosmo = synthetic.FixedCosmology()
-    width_arcsec = IMG_NDIM * 0.031 + 1e-9
-    rng = np.random.default_rng(7 + rank)
-    Lh = np.stack([p['Masses'] * (0.5 + rng.random(IMG_PARTICLES)) for _ in filters])
-    PSFs = {f: synthetic.GaussianPSF(1.5 + 0.2 * i) for i, f in enumerate(filters)}
+    from synthobs_b200.sed import models
+    args, dev = ctx.args, ctx.dev
+    p, filters, cosmo, width_arcsec, Lh, PSFs = imaging_inputs(ctx)
     Xh = torch.from_numpy(p['X']).pin_memory()
     Yh = torch.from_numpy(p['Y']).pin_memory()
     Lh_t = torch.from_numpy(Lh).pin_memory()
     Xd, Yd, Ld = Xh.to(dev), Yh.to(dev), Lh_t.to(dev)
-    obs = [images.observed(f, cosmo, Z, width_arcsec, smoothing=('adaptive', float(IMG_K)), PSF=PSFs[f],
-                           super_sampling=IMG_SS) for f in filters]
+    kw = dict(smoothing=('adaptive', float(IMG_K)), super_sampling=IMG_SS)
+    obs = [images.observed(f, cosmo, Z, width_arcsec, PSF=PSFs[f], **kw) for f in filters]
     assert obs[0].ndim == IMG_NDIM, obs[0].ndim
     stats = {}
 
-    def step_device(Xd, Yd, Ld):
+    def step_device():
         mx, my = images.median_device_pair(Xd, Yd)    # recentring (images.py:183-184, np.median semantics)
-        X = Xd - mx                                   # on device copies
-        Y = Yd - my
-        r = images.particle_device_multi(obs, X, Y, Ld)
+        r = images.particle_device_multi(obs, Xd - mx, Yd - my, Ld)
         stats.update(r['stats'])
         return r['data']
 
+    Ldict = {f: Lh_t[i] for i, f in enumerate(filters)}
+    Xw, Yw = Xh.clone().pin_memory(), Yh.clone().pin_memory()
+
     def step_e2e():
-        # public host-input entry point: pinned X, Y, L in, final images out (H2D of L overlaps the k-NN)
-        out, _ = images.particle_host_multi(obs, Xh, Yh, Lh_t)
-        return out
+        # THE reference-named call (images.py:263): pinned host X, Y, {filter: L} in, {filter: img} (NumPy) out; the
+        # call recentres X, Y in place, so every step starts from a fresh copy of the catalogue (host memcpy, inside
+        # the timed region like everything else the call does)
+        Xw.copy_(Xh)
+        Yw.copy_(Yh)
+        return images.particle(Xw, Yw, Ldict, filters, cosmo, Z, width_arcsec, PSFs=PSFs, **kw)
 
     for _ in range(3):
-        step_device(Xd, Yd, Ld)
-    barrier()
+        step_device()
     steps = max(3, min(args.steps, 10))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # inputs (80 MB) fit in L2: flush between steps
-    ms = max_over_ranks(timed_steps(lambda: step_device(Xd, Yd, Ld), steps, barrier, flush))
+    ms = timed_steps(ctx, step_device, steps, flush)
     del flush
     for _ in range(2):
         step_e2e()
-    barrier()
-    t0 = time.time()
-    for _ in range(steps):
-        step_e2e()
-    barrier()
-    e2e_ms = max_over_ranks((time.time() - t0) * 1e3 / steps)
+    e2e_ms = wall_loop(ctx, step_e2e, steps)
     stages = imaging_stage_times(obs, Xd, Yd, Ld)
-    deposits = stats.get('deposits', 0.0) * IMG_FILTERS
+    prof = kernel_profile(step_device)
+
+    # SED -> images pipeline (examples/morph_image_observed.py:93-95): the catalogue goes up ONCE (56 B/particle), the
+    # per-particle fluxes of the 8 filters never leave the GPU, 8 images come back
+    pmodel, pF, _ = setup_model(n_filters=IMG_FILTERS, names=filters)
+    cat = {k: torch.from_numpy(p[k]).pin_memory() for k in ('X', 'Y', 'Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')}
+
+    def step_pipeline():
+        c = {k: v.to(dev, non_blocking=True) for k, v in cat.items()}
+        Lp = models.generate_Fnu_arrays(pmodel, pF, c['Masses'], c['Ages'], c['Metallicities'], tauVs_ISM=c['tauVs_ISM'],
+                                        tauVs_BC=c['tauVs_BC'])
+        out = images.particle(c['X'], c['Y'], Lp, filters, cosmo, Z, width_arcsec, PSFs=PSFs, **kw)
+        return torch.stack([out[f].data for f in filters]).cpu()
+    for _ in range(2):
+        step_pipeline()
+    pipe_ms = wall_loop(ctx, step_pipeline, steps)
+    launches = count_launches(step_device)
+
+    deposits = stats.get('deposits', 0.0)
+    pairs = stats.get('pairs', 0.0)
     nsel = stats.get('selected', 0.0)
     ref_equiv = nsel * (IMG_NDIM * IMG_SS) ** 2 * IMG_FILTERS
-    # algorithmic bytes of one step (SURVEY.md 8d): positions and weights as the API hands them over (float64),
-    # every super-sampled and final pixel written once
+    hbm = ctx.peaks['hbm_gbs']
+    ffma = ctx.measured.get('fp32_ffma2_tflops') or ctx.measured.get('fp32_ffma_tflops')
+
+    def kms(name):
+        return prof.get(name, {}).get('ms_per_step')
+    kern = {}
+    dep_ms = kms('deposit_kernel')
+    if dep_ms:
+        useful = 2.0 * deposits * IMG_FILTERS                      # 2 flop per in-support (particle, pixel, channel) deposit
+        executed = 2.0 * pairs * 256 * IMG_FILTERS                 # every pair evaluates its whole 16 x 16 sub-tile
+        kern['deposit_kernel'] = {
+            'bound': 'fp32_fma', 'ms_per_step': dep_ms, 'algorithmic_flops': useful, 'executed_flops': executed,
+            'achieved': useful / (dep_ms * 1e-3) / 1e12, 'executed_tflops': executed / (dep_ms * 1e-3) / 1e12,
+            'peak': ffma, 'unit': 'TFLOP/s', 'frac': (useful / (dep_ms * 1e-3) / 1e12 / ffma) if ffma else None,
+            'executed_frac': (executed / (dep_ms * 1e-3) / 1e12 / ffma) if ffma else None,
+            'useful_fma_fraction': useful / executed if executed else None,
+            'algorithmic_bytes': IMG_PARTICLES * (8 + 8 + 4 + 4 * IMG_FILTERS) + 4 * IMG_FILTERS * (IMG_NDIM * IMG_SS) ** 2,
+            'hbm_frac': (IMG_PARTICLES * (20 + 4 * IMG_FILTERS) + 4 * IMG_FILTERS * (IMG_NDIM * IMG_SS) ** 2) / (dep_ms * 1e-3) / 1e9 / hbm,
+            'peak_source': 'measured FFMA2 throughput (peaks.fp32_ffma2_tflops)' if ffma else None,
+            'note': 'SURVEY 8d: binding roof = max(bytes/HBM, flops/FP32-FMA, exps/MUFU); at ~18 pixels per particle '
+                    'the algorithmic work is tiny against either roof, the kernel\'s time is the evaluated sub-tiles'}
+    for name in ('knn_query_kernel', 'knn_group_kernel'):
+        q_ms = kms(name)
+        if q_ms:
+            kern[name] = {'bound': 'hbm (algorithmic) / latency (actual)', 'ms_per_step': q_ms,
+                          'algorithmic_bytes': 20.0 * nsel, 'achieved': 20.0 * nsel / (q_ms * 1e-3) / 1e9, 'peak': hbm,
+                          'unit': 'GB/s', 'frac': 20.0 * nsel / (q_ms * 1e-3) / 1e9 / hbm,
+                          'queries_per_s': nsel / (q_ms * 1e-3),
+                          'note': 'SURVEY 8d: 16 B in + 4 B out per particle; a tree search is latency- and '
+                                  'instruction-bound, the HBM fraction is reported because 8d asks for it'}
     algo_bytes = IMG_PARTICLES * (16 + 8 * IMG_FILTERS) + 4 * IMG_FILTERS * ((IMG_NDIM * IMG_SS) ** 2 + IMG_NDIM ** 2)
-    ach = algo_bytes / (ms * 1e-3) / 1e9
+    top = max(kern.items(), key=lambda kv: kv[1]['ms_per_step'])[0] if kern else None
     return {
-        'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                     'traffic': None, 'algorithmic_bytes_per_step': algo_bytes,
-                     'note': 'whole imaging step (recentring, k-NN, tile binning, deposit, PSF FFT, rebin: ~60 '
-                             'launches), not one kernel: at ~18 pixels per particle the step is a chain of '
-                             'latency-bound stages (tree walk, radix sorts, FFT) and sits far below the HBM roof; '
-                             'per-kernel figures are in profiles/'},
-        'stages_ms': stages,
         'metric': 'particles/sec imaged', 'unit': 'particles/s (all %d filter images)' % IMG_FILTERS,
-        'value': world * IMG_PARTICLES / (ms * 1e-3), 'ms_per_step': ms,
-        'particle_filter_images_per_s': world * IMG_PARTICLES * IMG_FILTERS / (ms * 1e-3),
-        'deposits_evaluated_per_s': world * deposits / (ms * 1e-3),
-        'reference_equivalent_deposits_per_s': world * ref_equiv / (ms * 1e-3),
+        'value': ctx.world * IMG_PARTICLES / (ms * 1e-3), 'ms_per_step': ms,
+        'particle_filter_images_per_s': ctx.world * IMG_PARTICLES * IMG_FILTERS / (ms * 1e-3),
+        'deposits_evaluated_per_s': ctx.world * deposits * IMG_FILTERS / (ms * 1e-3),
+        'reference_equivalent_deposits_per_s': ctx.world * ref_equiv / (ms * 1e-3),
+        'roofline': dict(kern[top], kernel=top) if top else None,
+        'kernel_rooflines': kern,
+        'whole_step_hbm_frac': algo_bytes / (ms * 1e-3) / 1e9 / hbm,
+        'stages_ms': stages, 'kernels': prof, 'launches_per_step': launches,
         'config': {'workload': 'config[2] observed-frame: %d particles, %d filters, %dx%d, super_sampling %d, '
                                "('adaptive', %d), Gaussian PSF FFT convolution, rebin" %
                                (IMG_PARTICLES, IMG_FILTERS, IMG_NDIM, IMG_NDIM, IMG_SS, IMG_K),
                    'l2_policy': 'L2 flushed (256 MB write) between steps, outside the timed intervals',
-                   'support_sigmas': images.SUPPORT_SIGMAS, 'pairs_particle_tile': stats.get('pairs'),
-                   'selected': nsel, 'deposits_per_filter': stats.get('deposits')},
-        'e2e': {'value': world * IMG_PARTICLES / (e2e_ms * 1e-3), 'unit': 'particles/s', 'ms_per_step': e2e_ms,
+                   'support_sigmas': images.SUPPORT_SIGMAS, 'pairs_particle_tile': pairs,
+                   'selected': nsel, 'deposits_per_filter': deposits},
+        'e2e': {'value': ctx.world * IMG_PARTICLES / (e2e_ms * 1e-3), 'unit': 'particles/s', 'ms_per_step': e2e_ms,
+                'entry_point': 'images.particle(X, Y, {filter: L}, filters, cosmo, z, width, smoothing=, PSFs=, super_sampling=) '
+                               'with pinned CPU tensors; returns {filter: img} NumPy; X, Y recentred in place',
                 'h2d_bytes_per_step': int(IMG_PARTICLES * 8 * (2 + IMG_FILTERS)),
-                'd2h_bytes_per_step': int(IMG_FILTERS * IMG_NDIM * IMG_NDIM * 4)},
+                'd2h_bytes_per_step': int(2 * IMG_FILTERS * IMG_NDIM * IMG_NDIM * 4 + 16 * IMG_PARTICLES)},
+        'pipeline_e2e': {'value': ctx.world * IMG_PARTICLES / (pipe_ms * 1e-3), 'unit': 'particles/s', 'ms_per_step': pipe_ms,
+                         'chain': 'pinned catalogue (X, Y, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC) -> H2D once -> '
+                                  'models.generate_Fnu_arrays (8 filters, stays on the GPU) -> images.particle -> 8 images D2H',
+                         'h2d_bytes_per_step': int(IMG_PARTICLES * 56),
+                         'd2h_bytes_per_step': int(IMG_FILTERS * IMG_NDIM * IMG_NDIM * 4)},
     }
+
+
+def run_c1(ctx):
+    """config[0]: examples/morph_image_physical.py-style, 1e4 particles onto a 100 x 100 physical image through
+    images.core, the three smoothing modes; NumPy in / NumPy out, ms per call."""
+    from synthobs_b200 import synthetic
+    from synthobs_b200.morph import images
+    p = synthetic.particles(10000, seed=5)
+    out = {}
+    for name, sm in (('ngp', False), ('convolved_gaussian', ('convolved_gaussian', 0.2)), ('adaptive16', ('adaptive', 16))):
+        for _ in range(3):
+            images.core(p['X'], p['Y'], p['Masses'], resolution=0.1, ndim=100, smoothing=sm)
+        n = 20
+        t0 = time.time()
+        for _ in range(n):
+            img = images.core(p['X'], p['Y'], p['Masses'], resolution=0.1, ndim=100, smoothing=sm)
+        ms = (time.time() - t0) * 1e3 / n
+        out[name] = {'ms_per_call': ms, 'particles_per_s': 10000 / (ms * 1e-3)}
+        if name == 'adaptive16':
+            out[name]['deposits_evaluated_per_s'] = img.info['deposits'] / (ms * 1e-3)
+            out[name]['reference_equivalent_deposits_per_s'] = img.info['selected'] * 1e4 / (ms * 1e-3)
+    rec = {'workload': 'config[0]: 1e4 particles -> 100 x 100 physical image, images.core (host arrays in and out)', **out}
+    if ctx.rank == 0 and ctx.world == 1 and not ctx.args.no_cpu:
+        from oracle import image_oracle
+        t0 = time.time()
+        image_oracle.core(p['X'], p['Y'], p['Masses'], resolution=0.1, ndim=100, smoothing=('adaptive', 16))
+        rec['cpu_baseline'] = {'value': 10000 / (time.time() - t0), 'unit': 'particles/s', 'cores': 1, 'kind': 'port',
+                               'sample': 'the whole config: oracle image_oracle.core adaptive 16 (cKDTree + separable NumPy deposit)'}
+    return rec
+
+
+# ------------------------------------------------------------------ config 4: one ragged catalogue, galaxy-sharded
+
+def run_c4(ctx, model, F):
+    """ONE catalogue of 1e4 galaxies (sizes 10^U(3,5), counter-based particles: every rank generates exactly its share)
+    through dist.generate_Fnu_sharded and dist.core_batch_sharded: LPT shares, the all_gather inside the timed
+    region; total work fixed as N grows (strong scaling)."""
+    import torch
+    from synthobs_b200 import dist as sdist, synthetic
+    args, dev = ctx.args, ctx.dev
+    G = args.c4_galaxies
+    sizes, offsets = synthetic.ragged_sizes(G, 1000, 100000, seed=2)
+    mine, local_off = sdist.shard_plan(offsets)
+    ids = torch.cat([torch.arange(offsets[g], offsets[g + 1], dtype=torch.int64, device=dev) for g in mine]) \
+        if len(mine) else torch.zeros(0, dtype=torch.int64, device=dev)
+    cat = synthetic.hashed_catalogue(ids)
+    del ids
+    share = {'indices': mine, 'offsets': local_off, 'n_total': G}
+    share.update({k: cat[k] for k in sdist.SED_KEYS})
+    n_local = int(local_off[-1])
+    n_total = int(offsets[-1])
+
+    def sed_step():
+        return sdist.generate_Fnu_sharded(model, F, None, share=share)
+    for _ in range(3):
+        rows = sed_step()
+    assert tuple(rows.shape) == (G, len(F['filters']))
+    steps = max(3, min(args.steps, 10))
+    sed_ms = timed_loop(ctx, sed_step, steps)
+    # end to end: the share as pinned host arrays, uploaded inside the call
+    hshare = {'indices': mine, 'offsets': local_off, 'n_total': G}
+    hshare.update({k: cat[k].cpu().pin_memory() for k in sdist.SED_KEYS})
+
+    def sed_e2e():
+        return sdist.generate_Fnu_sharded(model, F, None, share=hshare).cpu()
+    sed_e2e()
+    sed_e2e_ms = wall_loop(ctx, sed_e2e, 3)
+    del hshare
+    # images: 100 x 100 physical, ('adaptive', 16), every object of the share in segmented passes
+    ishare = {'indices': mine, 'offsets': local_off, 'n_total': G, 'X': cat['X'], 'Y': cat['Y'],
+              'L': cat['Masses'] * cat['weight']}
+
+    def img_step():
+        return sdist.core_batch_sharded(None, None, None, None, resolution=0.1, ndim=100, smoothing=('adaptive', 16),
+                                        share=ishare, gather=False)
+    img_step()
+    img_ms = timed_loop(ctx, img_step, 2)
+    loads = ctx.max_over_ranks(n_local)
+    return {'workload': 'config[3] FLARES-scale batch: ONE catalogue of %d galaxies x 1e3..1e5 particles (%d particles), LPT '
+                        'shares, %d filters + 100x100 adaptive-16 images' % (G, n_total, len(F['filters'])),
+            'scaling': 'strong', 'n_gpus': ctx.world, 'galaxies': G, 'particles': n_total,
+            'max_share_particles': loads, 'share_imbalance': loads / (n_total / ctx.world),
+            'sed': {'entry_point': 'dist.generate_Fnu_sharded (segmented so_sed_broadband on the share + all_gather of [G, F])',
+                    'ms_per_step': sed_ms, 'value': G * len(F['filters']) / (sed_ms * 1e-3), 'unit': 'galaxy_SEDs_x_filters/s',
+                    'particles_per_s': n_total / (sed_ms * 1e-3),
+                    'hbm_frac_of_n_gpus': 40.0 * n_total / (sed_ms * 1e-3) / 1e9 / (ctx.peaks['hbm_gbs'] * ctx.world),
+                    'e2e': {'ms_per_step': sed_e2e_ms, 'value': G * len(F['filters']) / (sed_e2e_ms * 1e-3),
+                            'h2d_bytes_per_step_per_rank': 40 * n_local, 'd2h_bytes_per_step': G * len(F['filters']) * 8}},
+            'images': {'entry_point': 'dist.core_batch_sharded(..., gather=False): images.core of every object of the share',
+                       'ms_per_step': img_ms, 'value': n_total / (img_ms * 1e-3), 'unit': 'particles/s',
+                       'galaxies_per_s': G / (img_ms * 1e-3)}}
+
+
+# ------------------------------------------------------------------ config 5: one huge image, particle shares + NCCL
+
+def run_c5(ctx):
+    """1e8 particles onto 8192 x 8192, ('adaptive', 8), through dist.image_huge: every rank answers the k-NN and
+    deposits for its Morton-range share, the partial images are reduced over NVLink inside the timed region."""
+    import torch
+    from synthobs_b200 import dist as sdist
+    args, dev = ctx.args, ctx.dev
+    N, ndim, S = args.c5_particles, C5_NDIM, 10.0
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)                      # same stream on every rank: every rank holds the whole catalogue
+    X = S * torch.randn(N, dtype=torch.float64, device=dev, generator=g)
+    Y = S * torch.randn(N, dtype=torch.float64, device=dev, generator=g)
+    m = N // 20
+    X[:m] = 3.0 + 0.5 * torch.randn(m, dtype=torch.float64, device=dev, generator=g)      # a dense clump
+    Y[:m] = -7.0 + 0.5 * torch.randn(m, dtype=torch.float64, device=dev, generator=g)
+    L = 8.47e5 * (0.5 + torch.rand(N, dtype=torch.float64, device=dev, generator=g))
+    res = 8.0 * S / ndim
+
+    def step():
+        return sdist.image_huge(X, Y, L, res, ndim, IMG_K)
+    for _ in range(2):
+        img = step()
+    flux = float(img.double().sum())
+    ms = timed_loop(ctx, step, max(3, min(args.steps, 5)))
+    stages = {}
+    for _ in range(2):
+        sdist.image_huge(X, Y, L, res, ndim, IMG_K, stages=stages)
+    stages = {k: ctx.max_over_ranks(v / 2) for k, v in stages.items()}
+    sel = float(((X.abs() < 4 * S) & (Y.abs() < 4 * S)).sum())
+    return {'workload': 'config[4] single huge object: %d particles -> %d x %d, (\'adaptive\', %d), Morton-range particle '
+                        'shares, NCCL sum of the partial images' % (N, ndim, ndim, IMG_K),
+            'entry_point': 'dist.image_huge', 'scaling': 'strong', 'n_gpus': ctx.world, 'ms_per_step': ms,
+            'value': N / (ms * 1e-3), 'unit': 'particles/s', 'selected': sel,
+            'flux_conservation': flux / float(L[(X.abs() < 4 * S) & (Y.abs() < 4 * S)].sum()) - 1.0,
+            'stages_ms_max_over_ranks': stages, 'reduce_bytes': 4 * ndim * ndim}
 
 
 # ------------------------------------------------------------------ CPU baselines (oracle port)
@@ -594,15 +882,68 @@ def cpu_baseline_imaging(budget_s=12.0, n_sample=4000):
                        IMG_FILTERS)}
 
 
+# ------------------------------------------------------------------ ours (GPU)
+
+def run_ours(args):
+    import torch.distributed as dist
+    from synthobs_b200 import _cabi
+    ctx = Ctx(args)
+    _cabi.require_device()
+    sections = set(args.sections.split(',')) if args.sections else set(ALL_SECTIONS)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    t_start = time.time()
+    rec = {}
+    peaks = run_peaks(ctx) if 'peaks' in sections else None
+    batch = model = F = None
+    if 'sed' in sections:
+        rec, _, (batch, model, F) = run_sed(ctx)
+    else:
+        rec = {'metric': 'galaxy SEDs x filters / s', 'value': None, 'unit': 'galaxy_SEDs_x_filters/s', 'n_gpus': ctx.world,
+               'note': 'SED section skipped (--sections)'}
+        model, F, _ = setup_model()
+    rec['peaks'] = peaks
+    if 'latency' in sections and ctx.rank == 0:
+        rec['latency_c2'] = run_latency(ctx)
+    ctx.barrier()
+    if 'spectra' in sections:
+        rec['spectra'] = run_spectra(ctx, model, F)
+    if 'imaging' in sections:
+        rec['imaging'] = run_imaging(ctx)
+    if 'c1' in sections and ctx.rank == 0:
+        rec['config1'] = run_c1(ctx)
+    ctx.barrier()
+    if 'c4' in sections:
+        rec['config4'] = run_c4(ctx, model, F)
+    if 'c5' in sections:
+        rec['config5'] = run_c5(ctx)
+    sampler.stop()
+    rec['clocks'] = sampler.summary(t_start, time.time())     # all timed regions of this run
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:
+        if batch is not None:
+            rec['cpu_baseline'] = cpu_baseline_sed(batch, model, F, budget_s=12.0)
+        if rec.get('imaging'):
+            rec['imaging']['cpu_baseline'] = cpu_baseline_imaging(budget_s=12.0)
+    else:
+        rec.setdefault('cpu_baseline', None)
+    if ctx.rank == 0:
+        print(json.dumps(rec))
+    if ctx.world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ reference arm
 
 _REF = {}
 
 
-def _ref_one_galaxy(gi):
+def _ref_task(task):
     from oracle import sed_oracle
+    gi, half = task
     b, off = _REF['batch'], _REF['batch']['offsets']
     s, e = off[gi], off[gi + 1]
+    mid = (s + e) // 2
+    s, e = (s, mid) if half == 0 else (mid, e)
     out = sed_oracle.broadband(_REF['tabs'], _REF['filters'], _REF['grid']['log10age'], _REF['grid']['log10Z'],
                                b['Masses'][s:e], b['Ages'][s:e], b['Metallicities'][s:e], tauVs_ISM=b['tauVs_ISM'][s:e],
                                tauVs_BC=b['tauVs_BC'][s:e], k_ISM=_REF['k'], k_BC=_REF['k'], fesc=0.0)
@@ -611,8 +952,9 @@ def _ref_one_galaxy(gi):
 
 def run_reference(args):
     """The reference's own CPU path for the headline metric, on the host cores of the box: the oracle port
-    (vectorised NumPy restatement of generate_Fnu; the reference is pure Python, so there is no oracle/_ref
-    to compile), one galaxy per task over a pool of worker processes (galaxies are independent)."""
+    (vectorised NumPy restatement of generate_Fnu; the reference is pure Python, so there is no oracle/_ref to
+    compile), half a galaxy per task over a pool of worker processes on all host cores.  Same config[1] step as the
+    GPU arm (GALAXIES_PER_GPU galaxies of 1e5 particles) unless --ref-galaxies bounds it; --steps / --warmup honoured."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -629,40 +971,41 @@ def run_reference(args):
     tabs = sed_oracle.fnu_grid(grid, F, Z, cosmo.dl_cm, providers.madau)
     t_setup = time.time() - t0
     k = {f: float(providers.simple({'slope': -1.0}).tau(F[f].pivwv() / (1. + Z))) for f in F['filters']}
-    procs = max(1, min(os.cpu_count() or 1, 32))
-    per_step = max(4, procs)      # galaxies per step: bounded sample of the 256-galaxy step, one per worker
+    procs = max(1, os.cpu_count() or 1)
+    per_step = args.ref_galaxies
     batch = synthetic.galaxy_batch(per_step, fixed_n=N_PER_GALAXY, seed=100)
     _REF.update(batch=batch, tabs=tabs, filters=F['filters'], grid={'log10age': grid['log10age'], 'log10Z': grid['log10Z']}, k=k)
+    tasks = [(g, h) for g in range(per_step) for h in (0, 1)]
     pool = mp.get_context('fork').Pool(procs) if procs > 1 else None
 
     def step():
         if pool is None:
-            return [_ref_one_galaxy(g) for g in range(per_step)]
-        return pool.map(_ref_one_galaxy, range(per_step), chunksize=1)
+            return [_ref_task(t) for t in tasks]
+        return pool.map(_ref_task, tasks, chunksize=max(1, len(tasks) // (4 * procs)))
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(args.warmup):
         step()
-    steps = min(args.steps, 10)
     t0 = time.time()
-    for _ in range(steps):
+    for _ in range(args.steps):
         step()
-    dt = (time.time() - t0) / steps
+    dt = (time.time() - t0) / args.steps
     if pool is not None:
         pool.close()
     value = per_step * N_FILTERS / dt
+    sample = ('the whole %d-galaxy step' % per_step) if per_step == GALAXIES_PER_GPU else \
+        ('%d of the %d galaxies of the step (throughput-normalised)' % (per_step, GALAXIES_PER_GPU))
     rec = {
         'impl': 'reference', 'metric': 'galaxy SEDs x filters / s', 'value': value,
-        'unit': 'galaxy_SEDs_x_filters/s', 'n_gpus': world, 'steps': steps, 'warmup': max(1, min(args.warmup, 2)),
+        'unit': 'galaxy_SEDs_x_filters/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': 'config[1] SED_fluxes: galaxies of 1e5 particles, BPASS-shape grid 51x13x%d, ISM+BC '
-                               'LOS dust, %d filters; each step = %d galaxies (bounded sample of the GPU arm\'s '
-                               '%d-galaxy step)' % (N_LAM, N_FILTERS, per_step, GALAXIES_PER_GPU),
-                   'table_setup_s': t_setup},
+        'config': {'workload': SED_WORKLOAD, 'entry_point': 'oracle/sed_oracle.broadband (kind: port)',
+                   'galaxies_per_step': per_step, 'table_setup_s': t_setup},
         'cpu_baseline': {'value': value, 'unit': 'galaxy_SEDs_x_filters/s', 'cores': procs, 'kind': 'port',
-                         'sample': 'oracle/sed_oracle.broadband (vectorised NumPy restatement of generate_Fnu), one '
-                                   'galaxy per task on a pool of %d worker processes, %d galaxies per step; host has '
-                                   '%d cores' % (procs, per_step, os.cpu_count())},
+                         'sample': '%s; oracle/sed_oracle.broadband (vectorised NumPy restatement of generate_Fnu -- the '
+                                   'builder\'s port, not code from the reference tree, which is a per-particle Python loop '
+                                   '~100x slower), half a galaxy per task on a pool of %d worker processes; host has %d '
+                                   'cores' % (sample, procs, os.cpu_count())},
         'e2e': {'value': value, 'unit': 'galaxy_SEDs_x_filters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(rec))
@@ -674,11 +1017,12 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-imaging', action='store_true')
-    ap.add_argument('--no-spectra', action='store_true')
-    ap.add_argument('--no-sed', action='store_true', help='profiling aid: skip the SED timed loops')
+    ap.add_argument('--sections', default='', help='comma list of %s (default: all)' % ','.join(ALL_SECTIONS))
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--no-sed-e2e', action='store_true')
+    ap.add_argument('--c4-galaxies', type=int, default=C4_GALAXIES)
+    ap.add_argument('--c5-particles', type=int, default=C5_PARTICLES)
+    ap.add_argument('--ref-galaxies', type=int, default=GALAXIES_PER_GPU,
+                    help='galaxies per reference-arm step (default: the whole GPU step)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

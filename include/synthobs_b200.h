@@ -286,6 +286,21 @@ int so_img_sersic(const double* G, int32_t ndim, double r_eff, double n, double 
 int64_t so_median_workspace_bytes(int64_t n, int32_t n_arrays);
 int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out,
                   void* workspace, int64_t workspace_bytes, void* stream);
+/* same, and mid[2a], mid[2a+1] (DEVICE double[2 n_arrays], may be null) receive the two middle elements of
+ * array a (both the median element for odd n) */
+int so_median_f64_mid(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out, double* mid,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The per-filter recentring of images.particle (synthobs/morph/images.py:277-284 calling :183-187 once per
+ * filter): X_f = (X_{f-1} - np.median(X_{f-1})) + off_x[f], likewise Y, for f = 1..n_steps, bit-identical to the
+ * reference's repeated in-place updates.  mid = the two middle elements of x and of y (so_median_f64_mid on the
+ * two arrays): every later median follows from them by scalar arithmetic, so the arrays are read once.  The
+ * positions after step out_step[j] (1-based, ascending) are written to out_x[j], out_y[j] (n_out <= 8).
+ * off_x, off_y, out_step, out_x, out_y are HOST arrays (out_x[j], out_y[j] DEVICE pointers). */
+int so_recentre_chain(const double* x, const double* y, int64_t n, const double* mid, int32_t n_steps,
+                      const double* off_x, const double* off_y, int32_t n_out, const int32_t* out_step,
+                      double* const* out_x, double* const* out_y, void* stream);
+
 
 /* np.median per CSR segment (one object of a batch per segment; out: DEVICE double[n_seg], NaN for
  * an empty segment) and the in-place recentring x[i] += shift - med[segment(i)] of
@@ -293,6 +308,23 @@ int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, 
 int so_median_segmented(const double* x, const int64_t* seg_offsets, int64_t n_seg, double* out, void* stream);
 int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, const double* med, double shift,
                           void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* measurement support (bench.py); no upstream equivalent                      */
+/* ------------------------------------------------------------------------- */
+
+/* Register-only micro-benchmark of one pipe on every SM (ctas_per_sm CTAs of 256 threads per SM, `iters`
+ * iterations): kind 0 = FP32 FFMA, 1 = packed FFMA2, 2 = MUFU.EX2, 3 / 4 = the per-particle-wavelength arithmetic
+ * of so_sed_dust_spectra with MUFU only / with its FMA-pipe polynomial share.  *ops_host (HOST pointer) receives the
+ * operations one launch executes (multiply-adds for kinds 0-1, exponentials for 2-4); time the launch with CUDA
+ * events on `stream`.  `out` is a device float the kernels never actually write. */
+int so_peak_kernel(int32_t kind, int64_t iters, int32_t ctas_per_sm, float* out, double* ops_host, void* stream);
+
+/* Per-kernel timing: while enabled, every labelled launch inside the library is bracketed by CUDA events on its
+ * own stream.  so_prof_enable(0/1) also discards the marks collected so far.  so_prof_report synchronises on the
+ * recorded events and writes "label<TAB>launches<TAB>total_ms" lines into buf (HOST); returns the bytes needed. */
+int so_prof_enable(int32_t on);
+int64_t so_prof_report(char* buf, int64_t buf_bytes);
 
 #ifdef __cplusplus
 }

@@ -58,10 +58,16 @@ SIGNATURES = {
     'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, I32, P]),
     'so_median_workspace_bytes': (I64, [I64, I32]),
     'so_median_f64': (c_int, [P, I64, I32, I64, P, P, I64, P]),
+    'so_median_f64_mid': (c_int, [P, I64, I32, I64, P, P, P, I64, P]),
+    'so_recentre_chain': (c_int, [P, P, I64, P, I32, POINTER(c_double), POINTER(c_double), I32, POINTER(c_int32),
+                                  POINTER(c_void_p), POINTER(c_void_p), P]),
     'so_median_segmented': (c_int, [P, P, I64, P, P]),
     'so_recentre_segmented': (c_int, [P, P, I64, P, D, P]),
     'so_img_sersic_workspace_bytes': (I64, [I32]),
     'so_img_sersic': (c_int, [P, I32, D, D, D, D, D, D, D, P, I32, P, P, I64, P]),
+    'so_peak_kernel': (c_int, [I32, I64, I32, P, POINTER(c_double), P]),
+    'so_prof_enable': (c_int, [I32]),
+    'so_prof_report': (I64, [c_char_p, I64]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -118,3 +124,20 @@ def host_doubles(values):
 
 def version():
     return lib.so_version().decode()
+
+
+def prof_enable(on=True):
+    """per-kernel timing of every labelled launch inside the library (bench.py's profiling pass)"""
+    check(lib.so_prof_enable(1 if on else 0), 'so_prof_enable')
+
+
+def prof_report():
+    """{label: (launches, total_ms)} collected since prof_enable(True); synchronises"""
+    n = lib.so_prof_report(None, 0)
+    buf = ctypes.create_string_buffer(int(n) + 16)
+    lib.so_prof_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        label, cnt, ms = line.split('\t')
+        out[label] = (int(cnt), float(ms))
+    return out

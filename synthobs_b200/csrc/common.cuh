@@ -18,6 +18,21 @@
         if (_e != cudaSuccess) return (int)_e;         \
     } while (0)
 
+// optional per-kernel timing (peaks.cu; bench.py switches it on for one profiling pass): a labelled scope records
+// CUDA events on the launching stream before and after the launches it encloses
+int so_prof_is_on();
+int so_prof_open(const char* label, cudaStream_t st);
+void so_prof_close(int id, cudaStream_t st);
+struct SoProfScope {
+    int id;
+    cudaStream_t st;
+    SoProfScope(const char* label, cudaStream_t s) : id(-1), st(s) { if (so_prof_is_on()) id = so_prof_open(label, s); }
+    ~SoProfScope() { if (id >= 0) so_prof_close(id, st); }
+};
+#define SO_PROF_CAT2(a, b) a##b
+#define SO_PROF_CAT(a, b) SO_PROF_CAT2(a, b)
+#define SO_PROF(label, st) SoProfScope SO_PROF_CAT(so_prof_scope_, __LINE__)(label, st)
+
 static inline int64_t so_align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // bump allocator over a caller-provided workspace

@@ -421,6 +421,7 @@ extern "C" int so_gemm_3xtf32(const float* A_hi, const float* A_lo, int64_t lda,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    SO_PROF("gemm_3xtf32_kernel", cfg.stream);
     if (pair) {
         cfg.dynamicSmemBytes = smem_bytes<2>();
         SO_CUDA(cudaFuncSetAttribute(gemm_3xtf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<2>()));

@@ -644,7 +644,7 @@ extern "C" int so_img_ngp_index(const double* X, const double* Y, int64_t n, con
                                 double half_width, int32_t* ix, int32_t* iy, void* stream) {
     if (n < 0 || ndim < 1 || !G) return SO_ERR_BAD_ARG;
     if (n == 0) return SO_OK;
-    ngp_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, Y, n, G, ndim, half_width, ix, iy);
+    { SO_PROF("ngp_index_kernel", (cudaStream_t)stream); ngp_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, Y, n, G, ndim, half_width, ix, iy); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
@@ -677,10 +677,10 @@ extern "C" int so_img_plan(const int32_t* ix, const int32_t* iy, const double* X
         if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0.0;
         return SO_OK;
     }
-    plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix, iy, X, Y, dk, n, G, ndim, support_sigmas, pv);
+    { SO_PROF("plan_kernel", st); plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix, iy, X, Y, dk, n, G, ndim, support_sigmas, pv); }
     SO_LAUNCH_CHECK();
     if (dk) {
-        plan_wide_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ndim, pv);
+        { SO_PROF("plan_wide_kernel", st); plan_wide_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ndim, pv); }
         SO_LAUNCH_CHECK();
     }
     size_t tmp = (size_t)pv.cub_tmp_bytes;
@@ -745,13 +745,13 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
         return SO_OK;
     }
     const int ntiles_img = d.ntx * d.ntx;
-    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, img, ntiles_img, d.keys0, d.vals0);
+    { SO_PROF("expand_kernel", st); expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, img, ntiles_img, d.keys0, d.vals0); }
     SO_LAUNCH_CHECK();
     int bits = 1;
     while (((int64_t)1 << bits) < d.ntiles) ++bits;
     size_t tmp = (size_t)d.cub_tmp_bytes;
-    SO_CUDA(cub::DeviceRadixSort::SortPairs(d.cub_tmp, tmp, d.keys0, d.keys1, d.vals0, d.vals1, (int)n_pairs, 0, bits, st));
-    tile_start_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.keys1, n_pairs, d.ntiles, d.tile_start);
+    { SO_PROF("cub sort (tile, particle) pairs", st); SO_CUDA(cub::DeviceRadixSort::SortPairs(d.cub_tmp, tmp, d.keys0, d.keys1, d.vals0, d.vals1, (int)n_pairs, 0, bits, st)); }
+    { SO_PROF("tile_start_kernel", st); tile_start_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.keys1, n_pairs, d.ntiles, d.tile_start); }
     SO_LAUNCH_CHECK();
     if (tile_ids) SO_CUDA(cudaMemcpyAsync(tile_ids, d.keys1, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToDevice, st));
     if (pair_pids) SO_CUDA(cudaMemcpyAsync(pair_pids, d.vals1, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToDevice, st));
@@ -762,17 +762,18 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
     p.ld = data_ld; p.plane = data_plane;
     p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0; p.wts = d.wts;
     if (data) {
-        weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, pv.rec, n, n_chan, d.wts);
+        { SO_PROF("weights_kernel", st); weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, pv.rec, n, n_chan, d.wts); }
         SO_LAUNCH_CHECK();
-        tile_item_count_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start);
+        { SO_PROF("tile_item_count_kernel", st); tile_item_count_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start); }
         SO_LAUNCH_CHECK();
         size_t stmp = (size_t)d.cub_tmp_bytes;
         SO_CUDA(cub::DeviceScan::ExclusiveSum(d.cub_tmp, stmp, d.item_start, d.item_start, d.ntiles + 1, st));
-        item_tile_kernel<<<(unsigned)((d.max_items + 255) / 256), 256, 0, st>>>(d.item_start, d.ntiles, d.max_items,
-                                                                              d.item_tile);
+        { SO_PROF("item_tile_kernel", st); item_tile_kernel<<<(unsigned)((d.max_items + 255) / 256), 256, 0, st>>>(d.item_start, d.ntiles, d.max_items,
+                                                                              d.item_tile); }
         SO_LAUNCH_CHECK();
         const unsigned grid = (unsigned)((d.max_items + kDepWarps - 1) / kDepWarps);
         for (int c0 = 0; c0 < n_chan;) {       // channel groups of 8 / 4 / 2 / 1 share one pass over the lists
+            SO_PROF("deposit_kernel", st);
             p.chan0 = c0;
             const int left = n_chan - c0;
             if (left >= 8) { deposit_kernel<8><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 8; }
@@ -782,11 +783,11 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
             SO_LAUNCH_CHECK();
         }
         dim3 rgrid((unsigned)d.ntiles, (unsigned)n_chan);
-        tile_reduce_kernel<<<rgrid, kT * kT, 0, st>>>(p, n_chan);
+        { SO_PROF("tile_reduce_kernel", st); tile_reduce_kernel<<<rgrid, kT * kT, 0, st>>>(p, n_chan); }
         SO_LAUNCH_CHECK();
     }
     if (simple || hist) {
-        ngp_tile_kernel<<<(unsigned)d.ntiles, 64, 0, st>>>(p, n_chan, simple, hist);
+        { SO_PROF("ngp_tile_kernel", st); ngp_tile_kernel<<<(unsigned)d.ntiles, 64, 0, st>>>(p, n_chan, simple, hist); }
         SO_LAUNCH_CHECK();
     }
     return SO_OK;
@@ -809,7 +810,7 @@ extern "C" int so_img_rebin_ld(const float* in, int64_t in_ld, int64_t in_plane,
                                int32_t n_out, int32_t s, void* stream) {
     if (n_img < 1 || n_out < 1 || s < 1 || in_ld < (int64_t)n_out * s) return SO_ERR_BAD_ARG;
     dim3 block(32, 8), grid((n_out + 31) / 32, (n_out + 7) / 8, n_img);
-    rebin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, in_ld, in_plane, out, n_out, s);
+    { SO_PROF("rebin_kernel", (cudaStream_t)stream); rebin_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, in_ld, in_plane, out, n_out, s); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
@@ -818,8 +819,8 @@ extern "C" int so_complex_mul_bcast(const float* a, const float* b, float* out, 
                                     int32_t b_per_image, void* stream) {
     if (n_complex < 1 || n_img < 1) return SO_ERR_BAD_ARG;
     dim3 grid((unsigned)((n_complex + 255) / 256), (unsigned)n_img);
-    complex_mul_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)a, (const float2*)b, (float2*)out, n_complex,
-                                                               b_per_image);
+    { SO_PROF("complex_mul_kernel", (cudaStream_t)stream); complex_mul_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)a, (const float2*)b, (float2*)out, n_complex,
+                                                               b_per_image); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
@@ -840,9 +841,9 @@ extern "C" int so_img_sersic(const double* G, int32_t ndim, double r_eff, double
     double* prof = a.take<double>(npix);
     double* sums = a.take<double>(nblk);
     if (!workspace || !a.ok()) return SO_ERR_WORKSPACE;
-    sersic_kernel<<<(unsigned)nblk, 256, 0, st>>>(G, ndim, r_eff, n, x0, y0, ellip, theta, bn, prof, sums);
+    { SO_PROF("sersic_kernel", st); sersic_kernel<<<(unsigned)nblk, 256, 0, st>>>(G, ndim, r_eff, n, x0, y0, ellip, theta, bn, prof, sums); }
     SO_LAUNCH_CHECK();
-    sersic_scale_kernel<<<(unsigned)nblk, 256, 0, st>>>(prof, sums, (int)nblk, L, n_chan, npix, out);
+    { SO_PROF("sersic_scale_kernel", st); sersic_scale_kernel<<<(unsigned)nblk, 256, 0, st>>>(prof, sums, (int)nblk, L, n_chan, npix, out); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

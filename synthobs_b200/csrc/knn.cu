@@ -504,15 +504,15 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     const unsigned blocks = (unsigned)((n + 255) / 256);
     int64_t key_blocks = (n + kKeyThreads - 1) / kKeyThreads;
     if (key_blocks > 8 * so_num_sms()) key_blocks = 8 * so_num_sms();
-    knn_key_kernel<KeyT><<<(unsigned)key_blocks, kKeyThreads, 0, st>>>(X, Y, ix, img, n, n_img, half_width, inv_h, keys0,
-                                                                     l.vals0, l.xy, l.counter);
+    { SO_PROF("knn_key_kernel", st); knn_key_kernel<KeyT><<<(unsigned)key_blocks, kKeyThreads, 0, st>>>(X, Y, ix, img, n, n_img, half_width, inv_h, keys0,
+                                                                     l.vals0, l.xy, l.counter); }
     SO_LAUNCH_CHECK();
     size_t tmp = (size_t)l.cub_tmp_bytes;
-    SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, keys0, keys1, l.vals0, l.vals1, (int)n, 0,
-                                            2 * kBits + img_bits, st));
-    knn_gather_kernel<<<blocks, 256, 0, st>>>(l.xy, l.vals1, n, l.pts);
+    { SO_PROF("cub sort Morton keys", st); SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, keys0, keys1, l.vals0, l.vals1, (int)n, 0,
+                                            2 * kBits + img_bits, st)); }
+    { SO_PROF("knn_gather_kernel", st); knn_gather_kernel<<<blocks, 256, 0, st>>>(l.xy, l.vals1, n, l.pts); }
     SO_LAUNCH_CHECK();
-    knn_mark_kernel<KeyT><<<blocks, 256, 0, st>>>(keys1, n, n_img, 2 * (kBits - Lt), l.E);
+    { SO_PROF("knn_mark_kernel", st); knn_mark_kernel<KeyT><<<blocks, 256, 0, st>>>(keys1, n, n_img, 2 * (kBits - Lt), l.E); }
     SO_LAUNCH_CHECK();
     tmp = (size_t)l.cub_tmp_bytes;
     SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), (int)ncell, st));
@@ -534,17 +534,17 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     const int win = k * win_mul;
     if (private_walk || threads != kWarpsPerCta * 32) {
         SO_CUDA(cudaFuncSetAttribute(knn_query_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_query_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
+        { SO_PROF("knn_query_kernel", st); knn_query_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
+            l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk); }
     } else {
         SO_CUDA(cudaFuncSetAttribute(knn_query_warp_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_query_warp_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
-            l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk);
+        { SO_PROF("knn_query_warp_kernel", st); knn_query_warp_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
+            l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, dk); }
     }
     SO_LAUNCH_CHECK();
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
     if (range_out) {
-        knn_range_kernel<<<1, 1, 0, st>>>(l.counter, part, n_parts, range_out);
+        { SO_PROF("knn_range_kernel", st); knn_range_kernel<<<1, 1, 0, st>>>(l.counter, part, n_parts, range_out); }
         SO_LAUNCH_CHECK();
     }
     return SO_OK;

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kSelThreads) select_compact_kernel(const doubl
 // duplicates below the wanted rank: then the lower middle element equals the upper one
 __global__ void __launch_bounds__(kSelTailThreads) select_tail_kernel(SelectState* __restrict__ st, int64_t n,
                                                                        const unsigned long long* __restrict__ buf,
-                                                                       double* __restrict__ out) {
+                                                                       double* __restrict__ out, double* __restrict__ mid) {
     __shared__ unsigned int s_h[kSelBins];
     __shared__ unsigned int s_scan[32];
     __shared__ int s_bin;
@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(kSelTailThreads) select_tail_kernel(SelectStat
         double lo = hi;
         if ((n & 1) == 0 && s_rank == 0) lo = key_f64(s_below);
         out[blockIdx.x] = (n & 1) ? hi : __dmul_rn(__dadd_rn(lo, hi), 0.5);
+        if (mid) { mid[2 * blockIdx.x] = (n & 1) ? hi : lo; mid[2 * blockIdx.x + 1] = hi; }
     }
 }
 
@@ -308,11 +309,70 @@ __global__ void __launch_bounds__(256) recentre_segmented_kernel(double* __restr
     for (int64_t i = a + threadIdx.x; i < b; i += 256) x[i] = __dadd_rn(__dsub_rn(x[i], m), shift);
 }
 
+// The reference's images.particle recentres the caller's X, Y once per filter (images.py:183-187 inside the loop of
+// :277-284): X_f = (X_{f-1} - median(X_{f-1})) + offset_f.  Every step is a monotone map, so the two middle elements
+// of X_f are the images of the two middle elements of X: the whole chain of medians follows from (lo, hi) of the
+// original array by scalar arithmetic, and all steps are applied to an element in one pass.
+constexpr int kChainMax = 32;
+struct ChainParams {
+    const double* in[2];
+    const double* mid;              // [4]: x_lo, x_hi, y_lo, y_hi
+    double off[2][kChainMax];
+    int n_steps, n_out, odd;
+    int out_step[8];                // 1-based, ascending
+    double* out[2][8];
+    int64_t n;
+};
+
+__global__ void __launch_bounds__(256) recentre_chain_kernel(const ChainParams p) {
+    const int axis = blockIdx.y;
+    double lo = p.mid[2 * axis], hi = p.mid[2 * axis + 1];
+    double med[kChainMax];
+#pragma unroll 1
+    for (int s = 0; s < p.n_steps; ++s) {
+        const double m = p.odd ? hi : __dmul_rn(__dadd_rn(lo, hi), 0.5);
+        med[s] = m;
+        lo = __dadd_rn(__dsub_rn(lo, m), p.off[axis][s]);
+        hi = __dadd_rn(__dsub_rn(hi, m), p.off[axis][s]);
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = p.in[axis][i];
+        int j = 0;
+#pragma unroll 1
+        for (int s = 0; s < p.n_steps; ++s) {
+            v = __dadd_rn(__dsub_rn(v, med[s]), p.off[axis][s]);       // A -= np.median(A); A += offset
+            if (j < p.n_out && p.out_step[j] == s + 1) { p.out[axis][j][i] = v; ++j; }
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int so_recentre_chain(const double* x, const double* y, int64_t n, const double* mid, int32_t n_steps,
+                                 const double* off_x, const double* off_y, int32_t n_out, const int32_t* out_step,
+                                 double* const* out_x, double* const* out_y, void* stream) {
+    if (!x || !y || !mid || n < 0 || n_steps < 1 || n_steps > kChainMax || n_out < 1 || n_out > 8 || !off_x || !off_y ||
+        !out_step || !out_x || !out_y)
+        return SO_ERR_BAD_ARG;
+    if (n == 0) return SO_OK;
+    ChainParams p{};
+    p.in[0] = x; p.in[1] = y; p.mid = mid; p.n_steps = n_steps; p.n_out = n_out; p.odd = (int)(n & 1); p.n = n;
+    for (int s = 0; s < n_steps; ++s) { p.off[0][s] = off_x[s]; p.off[1][s] = off_y[s]; }
+    for (int j = 0; j < n_out; ++j) {
+        if (out_step[j] < 1 || out_step[j] > n_steps || (j > 0 && out_step[j] <= out_step[j - 1]) || !out_x[j] || !out_y[j])
+            return SO_ERR_BAD_ARG;
+        p.out_step[j] = out_step[j]; p.out[0][j] = out_x[j]; p.out[1][j] = out_y[j];
+    }
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 8 * so_num_sms()) blocks = 8 * so_num_sms();
+    { SO_PROF("recentre_chain_kernel", (cudaStream_t)stream); recentre_chain_kernel<<<dim3((unsigned)blocks, 2), 256, 0, (cudaStream_t)stream>>>(p); }
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
 
 extern "C" int so_median_segmented(const double* x, const int64_t* seg_offsets, int64_t n_seg, double* out, void* stream) {
     if (!x || !seg_offsets || !out || n_seg < 1 || n_seg >= ((int64_t)1 << 31)) return SO_ERR_BAD_ARG;
-    median_segmented_kernel<<<(unsigned)n_seg, 256, 0, (cudaStream_t)stream>>>(x, seg_offsets, out);
+    { SO_PROF("median_segmented_kernel", (cudaStream_t)stream); median_segmented_kernel<<<(unsigned)n_seg, 256, 0, (cudaStream_t)stream>>>(x, seg_offsets, out); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
@@ -320,7 +380,7 @@ extern "C" int so_median_segmented(const double* x, const int64_t* seg_offsets, 
 extern "C" int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, const double* med, double shift,
                                      void* stream) {
     if (!x || !seg_offsets || !med || n_seg < 1 || n_seg >= ((int64_t)1 << 31)) return SO_ERR_BAD_ARG;
-    recentre_segmented_kernel<<<(unsigned)n_seg, 256, 0, (cudaStream_t)stream>>>(x, seg_offsets, med, shift);
+    { SO_PROF("recentre_segmented_kernel", (cudaStream_t)stream); recentre_segmented_kernel<<<(unsigned)n_seg, 256, 0, (cudaStream_t)stream>>>(x, seg_offsets, med, shift); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
@@ -332,6 +392,11 @@ extern "C" int64_t so_median_workspace_bytes(int64_t n, int32_t n_arrays) {
 
 extern "C" int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out,
                              void* workspace, int64_t workspace_bytes, void* stream) {
+    return so_median_f64_mid(x, n, n_arrays, stride, out, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int so_median_f64_mid(const double* x, int64_t n, int32_t n_arrays, int64_t stride, double* out, double* mid,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !out || n < 1 || n_arrays < 1 || n_arrays > 1024 || stride < n) return SO_ERR_BAD_ARG;
     SoArena a(workspace, workspace_bytes);
@@ -342,15 +407,15 @@ extern "C" int so_median_f64(const double* x, int64_t n, int32_t n_arrays, int64
     if (blocks > 2 * so_num_sms()) blocks = 2 * so_num_sms();
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, (unsigned)n_arrays);
-    select_init_kernel<<<n_arrays, kSelThreads, 0, st>>>(state, n);
+    { SO_PROF("select_init_kernel", st); select_init_kernel<<<n_arrays, kSelThreads, 0, st>>>(state, n); }
     SO_LAUNCH_CHECK();
     for (int pass = 0; pass < 2; ++pass) {
-        select_hist_kernel<<<grid, kSelThreads, 0, st>>>(x, n, stride, state, pass);
+        { SO_PROF("select_hist_kernel", st); select_hist_kernel<<<grid, kSelThreads, 0, st>>>(x, n, stride, state, pass); }
         SO_LAUNCH_CHECK();
     }
-    select_compact_kernel<<<grid, kSelThreads, 0, st>>>(x, n, stride, state, buf);
+    { SO_PROF("select_compact_kernel", st); select_compact_kernel<<<grid, kSelThreads, 0, st>>>(x, n, stride, state, buf); }
     SO_LAUNCH_CHECK();
-    select_tail_kernel<<<n_arrays, kSelTailThreads, 0, st>>>(state, n, buf, out);
+    { SO_PROF("select_tail_kernel", st); select_tail_kernel<<<n_arrays, kSelTailThreads, 0, st>>>(state, n, buf, out, mid); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
@@ -370,7 +435,7 @@ extern "C" int so_gemm_f32(const float* A, int64_t lda, const float* B, int64_t 
                            float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream) {
     if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return SO_ERR_BAD_ARG;
     dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
-    gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, C, ldc, M, N, K);
+    { SO_PROF("gemm_f32_kernel", (cudaStream_t)stream); gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, C, ldc, M, N, K); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

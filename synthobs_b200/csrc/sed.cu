@@ -519,7 +519,7 @@ int launch_broadband_impl(const BroadbandParams& p, cudaStream_t st) {
     // only behind our own item-scan kernel (segmented path): the table staging must not overtake a foreign
     // predecessor that might still be writing the tables
     cfg.numAttrs = p.item_start ? 1 : 0;
-    SO_CUDA(cudaLaunchKernelEx(&cfg, sed_broadband_kernel<FP, WRITE_PF>, p));
+    { SO_PROF("sed_broadband_kernel", cfg.stream); SO_CUDA(cudaLaunchKernelEx(&cfg, sed_broadband_kernel<FP, WRITE_PF>, p)); }
     return SO_OK;
 }
 
@@ -687,7 +687,7 @@ extern "C" int so_sed_broadband(const double* masses, const double* ages, const 
     p.fesc = (float)fesc; p.out_pf = out_pf; p.partial = out_sums ? partial : nullptr; p.out_cell = out_cell;
 
     if (segmented) {
-        item_scan_kernel<<<1, 1024, 0, st>>>(seg_offsets, n_seg, item_start);
+        { SO_PROF("item_scan_kernel", st); item_scan_kernel<<<1, 1024, 0, st>>>(seg_offsets, n_seg, item_start); }
         SO_LAUNCH_CHECK();
         p.item_start = item_start;
         p.n_items = max_items;  // upper bound for the grid; the exact count is read on the device
@@ -774,11 +774,11 @@ extern "C" int so_sed_hist(const double* masses, const int32_t* cell, int64_t n,
     const size_t smem = (size_t)2 * ncell * sizeof(double);
     if (smem > 200 * 1024) return SO_ERR_TOO_LARGE;
     SO_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hist_kernel<<<(unsigned)(n_seg * chunks), 256, smem, st>>>(masses, cell, seg_offsets, n, ncell, chunks, partial);
+    { SO_PROF("hist_kernel", st); hist_kernel<<<(unsigned)(n_seg * chunks), 256, smem, st>>>(masses, cell, seg_offsets, n, ncell, chunks, partial); }
     SO_LAUNCH_CHECK();
     for (int64_t g0 = 0; g0 < n_seg; g0 += 65535) {       // gridDim.y <= 65535
         dim3 grid((2 * ncell + 255) / 256, (unsigned)std::min<int64_t>(65535, n_seg - g0));
-        hist_finish_kernel<<<grid, 256, 0, st>>>(partial, 2 * ncell, chunks, H, H_lo, ld_h, g0);
+        { SO_PROF("hist_finish_kernel", st); hist_finish_kernel<<<grid, 256, 0, st>>>(partial, 2 * ncell, chunks, H, H_lo, ld_h, g0); }
         SO_LAUNCH_CHECK();
     }
     return SO_OK;
@@ -786,7 +786,7 @@ extern "C" int so_sed_hist(const double* masses, const int32_t* cell, int64_t n,
 
 extern "C" int so_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
     if (n <= 0) return SO_OK;
-    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+    { SO_PROF("split_tf32_kernel", (cudaStream_t)stream); split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

@@ -16,6 +16,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exp2.cuh"
 
 namespace {
 
@@ -40,35 +41,6 @@ struct DustParams {
     const int64_t* seg;      // CSR offsets of the galaxies in the sorted order, or null (one galaxy)
     int64_t y_base;          // first (galaxy, particle block) pair of this launch (gridDim.y <= 65535)
 };
-
-__device__ __forceinline__ float ex2a(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float2 ex2_mufu2(float2 x) { return make_float2(ex2a(x.x), ex2a(x.y)); }
-
-// 2^x for x <= 0 on the FMA/ALU pipes (packed FP32): the XU pipe (16 ex2/clk/SM) is this kernel's
-// roof, so half of the exponentials are evaluated here instead.  Round-to-nearest split x = n + f
-// via the 1.5*2^23 magic constant, degree-5 minimax polynomial of 2^f on [-0.5, 0.5] (max relative
-// error 2.3e-7 in FP32 Horner form, the same order as ex2.approx), exponent add on the bit pattern.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-    const float kMagic = 12582912.f;
-    x.x = fmaxf(x.x, -125.f);
-    x.y = fmaxf(x.y, -125.f);
-    const float2 r = __fadd2_rn(x, make_float2(kMagic, kMagic));
-    const float2 rn = __fadd2_rn(r, make_float2(-kMagic, -kMagic));
-    const float2 f = __ffma2_rn(rn, make_float2(-1.f, -1.f), x);
-    float2 q = make_float2(0.0013276471518578379f, 0.0013276471518578379f);
-    q = __ffma2_rn(q, f, make_float2(0.009675541330665999f, 0.009675541330665999f));
-    q = __ffma2_rn(q, f, make_float2(0.05550713274963921f, 0.05550713274963921f));
-    q = __ffma2_rn(q, f, make_float2(0.24022119723934243f, 0.24022119723934243f));
-    q = __ffma2_rn(q, f, make_float2(0.6931469670638628f, 0.6931469670638628f));
-    q = __ffma2_rn(q, f, make_float2(1.0000000716546567f, 1.0000000716546567f));
-    q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
-    q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
-    return q;
-}
 
 // kLamPerThread wavelengths per thread (strided by the CTA width, so grid rows are read coalesced).
 // Particles are staged in shared memory as 16-byte records {M, tauV_ISM, tauV_BC, key} (one
@@ -293,13 +265,13 @@ extern "C" int so_sed_dust_spectra(const double* masses, const double* tau_ism, 
     for (int64_t y0 = 0; y0 < n_seg * pb; y0 += 65535) {        // gridDim.y <= 65535: (galaxy, particle block) pairs in slabs
         p.y_base = y0;
         dim3 grid(gx, (unsigned)std::min<int64_t>(65535, n_seg * pb - y0));
-        if (so_dust_hybrid()) dust_spectra_kernel<true><<<grid, kDustThreads, 0, st>>>(p);
-        else dust_spectra_kernel<false><<<grid, kDustThreads, 0, st>>>(p);
+        if (so_dust_hybrid()) { SO_PROF("dust_spectra_kernel", st); dust_spectra_kernel<true><<<grid, kDustThreads, 0, st>>>(p); }
+        else { SO_PROF("dust_spectra_kernel", st); dust_spectra_kernel<false><<<grid, kDustThreads, 0, st>>>(p); }
         SO_LAUNCH_CHECK();
     }
     for (int64_t g0 = 0; g0 < n_seg; g0 += 65535) {
         dim3 rgrid((n_lam + 255) / 256, (unsigned)std::min<int64_t>(65535, n_seg - g0));
-        dust_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, pb, n_lam, out_bc, out_total, out_nohii, g0);
+        { SO_PROF("dust_reduce_kernel", st); dust_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, pb, n_lam, out_bc, out_total, out_nohii, g0); }
         SO_LAUNCH_CHECK();
     }
     return SO_OK;

@@ -124,82 +124,139 @@ def reduce_image(img):
     return img
 
 
-def generate_Fnu_sharded(model, F, batch, kind='Fnu', **kw):
-    """Broadband fluxes of a batch of galaxies, sharded by galaxy over the ranks.  `batch` is a
-    dict with Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC, offsets (host arrays)."""
+SED_KEYS = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
+MAX_PASS_PARTICLES = 40000000      # particles per images.core_batch pass of a share (core_batch_sharded)
+
+
+def shard_plan(offsets, rank=None, n_ranks=None):
+    """This rank's galaxies of a catalogue with CSR `offsets`: (ascending galaxy indices, their local CSR offsets)."""
+    r, ws = world()
+    rank = r if rank is None else rank
+    n_ranks = ws if n_ranks is None else n_ranks
+    offsets = np.asarray(offsets, dtype=np.int64)
+    sizes = np.diff(offsets)
+    mine = np.asarray(shard_galaxies(sizes, n_ranks)[rank], dtype=np.int64)
+    local = np.zeros(mine.size + 1, dtype=np.int64)
+    np.cumsum(sizes[mine], out=local[1:])
+    return mine, local
+
+
+def local_share(batch, keys=SED_KEYS):
+    """Extract this rank's share of a host catalogue (dict of arrays + 'offsets') ONCE: {'indices', 'offsets'
+    (local CSR), 'n_total', arrays...}.  The sharded entry points take it as `share=` so a resident share is
+    not re-extracted (or re-uploaded, if its arrays are CUDA tensors) per call."""
+    mine, _ = shard_plan(batch['offsets'])
+    sub, off = subset_csr({k: np.asarray(batch[k]) for k in keys if k in batch}, batch['offsets'], mine)
+    sub.update(indices=mine, offsets=off, n_total=int(np.asarray(batch['offsets']).size - 1))
+    return sub
+
+
+def _gather_share(rows, share):
+    return gather_rows(rows, share['indices'], share['n_total'])
+
+
+def generate_Fnu_sharded(model, F, batch, kind='Fnu', share=None, **kw):
+    """Broadband fluxes of a batch of galaxies, sharded by galaxy over the ranks (LPT by particle count, no
+    collective on the compute path, one all_gather of the [G, F] result).  `batch` is a dict with Masses, Ages,
+    Metallicities, tauVs_ISM, tauVs_BC, offsets (host arrays); `share` = local_share(batch) (or a dict of the same
+    layout whose arrays already live on the device) skips the extraction."""
     from . import device as dv
     from .sed import models
-    keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
-
-    def compute(indices):
-        if len(indices) == 0:      # fewer galaxies than ranks: this rank only takes part in the gather
-            return torch.zeros((0, len(F['filters'])), dtype=torch.float64, device=dv.device())
-        sub, off = subset_csr({k: batch[k] for k in keys if k in batch}, batch['offsets'], indices)
-        out = models.generate_Lnu_batch(model, F, sub['Masses'], sub['Ages'], sub['Metallicities'], off,
-                                        tauVs_ISM=sub.get('tauVs_ISM', False), tauVs_BC=sub.get('tauVs_BC', False),
+    sh = local_share(batch) if share is None else share
+    if len(sh['indices']) == 0:      # fewer galaxies than ranks: this rank only takes part in the gather
+        rows = torch.zeros((0, len(F['filters'])), dtype=torch.float64, device=dv.device())
+    else:
+        out = models.generate_Lnu_batch(model, F, sh['Masses'], sh['Ages'], sh['Metallicities'], sh['offsets'],
+                                        tauVs_ISM=sh.get('tauVs_ISM', False), tauVs_BC=sh.get('tauVs_BC', False),
                                         kind=kind, **kw)
-        return torch.as_tensor(out).cuda()
+        rows = torch.as_tensor(out).to(dv.device())
+    return _gather_share(rows, sh)
 
-    return sharded_galaxy_map(compute, batch['offsets'])
 
-
-def generate_SED_sharded(model, batch, **kw):
+def generate_SED_sharded(model, batch, share=None, **kw):
     """The five spectra of generate_SED for a batch of galaxies, sharded by galaxy (config 4): returns a dict of
-    [G, n_lam] float32 CUDA tensors, complete on every rank (one gather per spectrum)."""
+    [G, n_lam] float32 CUDA tensors, complete on every rank (one gather of the [g, 5, n_lam] block)."""
     from . import device as dv
     from .sed import models
-    keys = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
     names = ('stellar', 'intrinsic', 'BC', 'total', 'no_HII_no_BC')
-
-    def compute(indices):
-        if len(indices) == 0:
-            return torch.zeros((0, len(names), model.lam.size), dtype=torch.float32, device=dv.device())
-        sub, off = subset_csr({k: batch[k] for k in keys if k in batch}, batch['offsets'], indices)
-        out = models.sed_spectra_device(model, sub['Masses'], sub['Ages'], sub['Metallicities'],
-                                        sub.get('tauVs_ISM', False), sub.get('tauVs_BC', False),
-                                        kw.get('fesc', 0.0), kw.get('log10t_BC', 7.), offsets=off)
-        return torch.stack([out[k] for k in names], dim=1)          # [g, 5, n_lam]
-
-    full = sharded_galaxy_map(compute, batch['offsets'])
+    sh = local_share(batch) if share is None else share
+    if len(sh['indices']) == 0:
+        rows = torch.zeros((0, len(names), model.lam.size), dtype=torch.float32, device=dv.device())
+    else:
+        out = models.sed_spectra_device(model, sh['Masses'], sh['Ages'], sh['Metallicities'],
+                                        sh.get('tauVs_ISM', False), sh.get('tauVs_BC', False),
+                                        kw.get('fesc', 0.0), kw.get('log10t_BC', 7.), offsets=sh['offsets'])
+        rows = torch.stack([out[k] for k in names], dim=1)          # [g, 5, n_lam]
+    full = _gather_share(rows, sh)
     return {k: full[:, i] for i, k in enumerate(names)}
 
 
-def core_batch_sharded(X, Y, L, offsets, resolution=0.1, ndim=100, smoothing=False):
+def core_batch_sharded(X, Y, L, offsets, resolution=0.1, ndim=100, smoothing=False, share=None, gather=True):
     """images.core for a batch of objects, sharded by object over the ranks (config 4): every rank images its
-    share in one pass (images.core_batch) and the [G, ndim, ndim] stack is gathered on every rank."""
+    share in one pass (images.core_batch) and the [G, ndim, ndim] stack is gathered on every rank (gather=False:
+    the local [g, ndim, ndim] block and its galaxy indices are returned instead -- 1e4 images of 100 x 100 are
+    400 MB per rank once gathered).  `share` = local_share({'X', 'Y', 'L', 'offsets'}, keys=('X', 'Y', 'L'))."""
     from . import device as dv
     from .morph import images
+    sh = local_share({'X': X, 'Y': Y, 'L': L, 'offsets': offsets}, keys=('X', 'Y', 'L')) if share is None else share
+    if len(sh['indices']) == 0:
+        rows = torch.zeros((0, ndim, ndim), dtype=torch.float32, device=dv.device())
+    else:
+        # passes of at most MAX_PASS_PARTICLES particles: bounded workspace whatever the share holds
+        off = np.asarray(sh['offsets'], dtype=np.int64)
+        Xd, Yd, Ld = dv.to_dev(sh['X']), dv.to_dev(sh['Y']), dv.to_dev(sh['L'])
+        parts, g0 = [], 0
+        while g0 < off.size - 1:
+            g1 = int(np.searchsorted(off, off[g0] + MAX_PASS_PARTICLES, side='right')) - 1
+            g1 = min(max(g1, g0 + 1), off.size - 1)
+            a, b = int(off[g0]), int(off[g1])
+            data, _, _, _ = images.core_device(Xd[a:b], Yd[a:b], Ld[a:b], resolution, ndim, smoothing,
+                                               img=images._image_ids(off[g0:g1 + 1] - off[g0], dv.device())[1],
+                                               n_img=g1 - g0)
+            parts.append(data[:, 0])
+            g0 = g1
+        rows = torch.cat(parts) if len(parts) > 1 else parts[0]
+    if not gather:
+        return rows, sh['indices']
+    return _gather_share(rows, sh)
 
-    def compute(indices):
-        sub, off = subset_csr({'X': np.asarray(X), 'Y': np.asarray(Y), 'L': np.asarray(L)}, offsets, indices)
-        if len(indices) == 0:
-            return torch.zeros((0, ndim, ndim), dtype=torch.float32, device=dv.device())
-        data, _, _, _ = images.core_device(dv.to_dev(sub['X']), dv.to_dev(sub['Y']), dv.to_dev(sub['L']), resolution, ndim,
-                                           smoothing, img=images._image_ids(off, dv.device())[1], n_img=len(indices))
-        return data[:, 0]
 
-    return sharded_galaxy_map(compute, offsets)
-
-
-def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None):
+def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None):
     """One huge adaptive-smoothed image split over the ranks (BASELINE config 5).  Every rank holds all
     positions (neighbours cross any partition) and builds the same search tree, but answers the k-NN
     queries and deposits only for ITS share of the particles: a contiguous range of the Morton order,
     i.e. a spatially compact block, so the work per rank is 1/N and each partial image touches a
     fraction of the tiles.  The partial images are summed with one all-reduce (NCCL over NVLink).
-    Returns the full [C, ndim, ndim] (or [ndim, ndim] for 1-D L) float32 CUDA image on every rank."""
+    Returns the full [C, ndim, ndim] (or [ndim, ndim] for 1-D L) float32 CUDA image on every rank.
+    `stages` (dict): filled with the device time [ms] of the stages of this call (CUDA events)."""
     from . import device as dv
     from .morph import images
     rank, ws = world()
+    marks = []
+
+    def mark(name):
+        if stages is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
     Xd, Yd, Ld = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(L)
     one = Ld.dim() == 1
     Ld = Ld.reshape(1, -1) if one else Ld
+    mark('start')
     width, G, Gd = images.pixel_grid_device(resolution, ndim)
     ix, iy = images.ngp_index_device(Xd, Yd, Gd, ndim, width / 2.)
+    mark('nearest-pixel index')
     dk, pids = images.knn_device_part(Xd, Yd, ix, int(k), width / 2., rank, ws, floor=images.FWHM_FLOOR)
+    mark('k-NN (tree of all particles, queries of the share)')
     r = images.deposit_device(Xd[pids], Yd[pids], Ld[:, pids], resolution, ndim, adaptive_k=int(k), want_ngp=False,
                               support_sigmas=support_sigmas, dk=dk[pids])
+    mark('gather share + plan + binning + deposit')
     img = reduce_image(r['data'])
+    mark('all-reduce of the image')
+    if stages is not None:
+        torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            stages[name] = stages.get(name, 0.0) + a.elapsed_time(b)
     return img[0] if one else img
 
 

@@ -461,7 +461,70 @@ def median_device_pair(a, b):
     return (out[1], out[0]) if swap else (out[0], out[1])
 
 
-def particle_device_multi(obs_list, Xd, Yd, Ld, L_event=None):
+_psf_spec_cache = {}
+
+
+def clear_caches():
+    """Drop the cached PSF spectra and pixel grids (PSF providers are treated as immutable objects: a provider
+    edited in place after its first use needs this)."""
+    _psf_spec_cache.clear()
+    _grid_cache.clear()
+
+
+def _group_spectrum(obs_list):
+    """KernelSpectrum of the PSFs of several observed() set-ups sharing one geometry.  The PSF image only depends on
+    the provider object and the geometry (images.py:198-200), so it is evaluated and transformed once per
+    (provider, geometry) and kept: images.particle() builds fresh observed() objects on every call."""
+    o0 = obs_list[0]
+    key = (dv.device().index,) + tuple((id(o.PSF), o.ndim_super, o.width_arcsec, o.native_pixel_scale) for o in obs_list)
+    hit = _psf_spec_cache.get(key)
+    if hit is None:
+        if len(_psf_spec_cache) >= 16:
+            _psf_spec_cache.clear()
+        spec = KernelSpectrum(np.stack([o.psf_kernel() for o in obs_list]), o0.ndim_super, o0.ndim_super)
+        hit = _psf_spec_cache[key] = (spec, [o.PSF for o in obs_list])      # the providers stay alive with their ids
+    return hit[0]
+
+
+def median_pair_mid(a, b):
+    """np.median of two CUDA float64 vectors of equal length plus their two middle elements: (med [2], mid [4] =
+    a_lo, a_hi, b_lo, b_hi) as CUDA tensors, one selection for both arrays when they sit in one allocation order."""
+    n = a.numel()
+    out = torch.empty(2, dtype=torch.float64, device=a.device)
+    mid = torch.empty(4, dtype=torch.float64, device=a.device)
+    diff = b.data_ptr() - a.data_ptr()
+    if a.is_contiguous() and b.is_contiguous() and diff > 0 and diff % 8 == 0 and diff // 8 >= n:
+        wsb = _cabi.lib.so_median_workspace_bytes(n, 2)
+        ws = dv.workspace(wsb)
+        _cabi.check(_cabi.lib.so_median_f64_mid(_cabi.ptr(a), n, 2, diff // 8, _cabi.ptr(out), _cabi.ptr(mid), _cabi.ptr(ws),
+                                                wsb, _cabi.stream()), 'so_median_f64_mid')
+        return out, mid
+    wsb = _cabi.lib.so_median_workspace_bytes(n, 1)
+    ws = dv.workspace(wsb)
+    for i, t in enumerate((a.contiguous(), b.contiguous())):
+        _cabi.check(_cabi.lib.so_median_f64_mid(_cabi.ptr(t), n, 1, n, _cabi.ptr(out[i:]), _cabi.ptr(mid[2 * i:]),
+                                                _cabi.ptr(ws), wsb, _cabi.stream()), 'so_median_f64_mid')
+    return out, mid
+
+
+def recentre_chain_device(Xd, Yd, off_x, off_y, out_steps):
+    """The positions after steps `out_steps` (1-based, ascending) of the reference's per-filter recentring
+    X_f = (X_{f-1} - np.median(X_{f-1})) + off_x[f] (images.py:183-187 inside the loop of :277-284), bit-identical
+    to the repeated in-place updates; Xd, Yd are read once (so_recentre_chain).  Returns [(X_t, Y_t), ...]."""
+    from ctypes import c_int32, c_void_p
+    n = Xd.numel()
+    _, mid = median_pair_mid(Xd, Yd)
+    outs = [(torch.empty_like(Xd), torch.empty_like(Yd)) for _ in out_steps]
+    nst = len(off_x)
+    _cabi.check(_cabi.lib.so_recentre_chain(
+        _cabi.ptr(Xd), _cabi.ptr(Yd), n, _cabi.ptr(mid), nst, (c_double * nst)(*[float(v) for v in off_x]),
+        (c_double * nst)(*[float(v) for v in off_y]), len(out_steps), (c_int32 * len(out_steps))(*[int(v) for v in out_steps]),
+        (c_void_p * len(outs))(*[o[0].data_ptr() for o in outs]), (c_void_p * len(outs))(*[o[1].data_ptr() for o in outs]),
+        _cabi.stream()), 'so_recentre_chain')
+    return outs
+
+
+def particle_device_multi(obs_list, Xd, Yd, Ld, L_event=None, offsets_applied=False):
     """Several observed() set-ups that share one geometry (same pixel scale, width,
     super-sampling, offsets, smoothing) imaged in one pass: one k-NN, one tile
     binning, a C-channel deposit, one batched FFT with a PSF per channel, one
@@ -474,13 +537,9 @@ def particle_device_multi(obs_list, Xd, Yd, Ld, L_event=None):
         if not same:
             raise ValueError('particle_device_multi needs identical geometry; group the filters by pixel scale')
     method, scale = _parse_smoothing(o0.smoothing)
-    X = Xd + o0.xoffset if o0.xoffset else Xd
-    Y = Yd + o0.yoffset if o0.yoffset else Yd
-    key = tuple(id(o) for o in obs_list)
-    if getattr(o0, '_multi_spec', (None, None))[0] != key:
-        o0._multi_spec = (key, KernelSpectrum(np.stack([o.psf_kernel() for o in obs_list]), o0.ndim_super,
-                                              o0.ndim_super))
-    spec = o0._multi_spec[1]
+    X = Xd + o0.xoffset if (o0.xoffset and not offsets_applied) else Xd
+    Y = Yd + o0.yoffset if (o0.yoffset and not offsets_applied) else Yd
+    spec = _group_spectrum(obs_list)
     if method == 'adaptive':
         # deposit straight into the zero-padded buffer of the PSF transform; the convolved images stay windows of
         # the full inverse transform (rebin reads them in place): no pad copy, no crop copy
@@ -718,9 +777,25 @@ def _observed_particle_batch(self, X, Y, L, offsets):
 observed.particle_batch = _observed_particle_batch
 
 
+def _as_cpu_tensor(a):
+    return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+
+
 def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=False, pixel_scale=False,
              smoothing=False, PSFs=False, super_sampling=10, verbose=False, offsets=False):
-    """reference: images.py:263-286 — one observed image per filter."""
+    """reference: images.py:263-286 -- one observed image per filter; returns {filter: img} with
+    img.pixel_scale, img.pixel_scale_kpc, img.no_PSF, img.data.
+
+    The reference runs observed(...).particle(X, Y, L[filter]) filter by filter, i.e. it repeats the median
+    recentring, the k-NN and the deposit on identical positions (images.py:277-284).  Here filters whose
+    geometry is identical (same pixel scale, hence same grid, offsets and smoothing) are imaged TOGETHER: one
+    recentring, one k-NN, one tile binning, a multi-channel deposit, one batched PSF FFT (particle_device_multi).
+    X, Y, L[f]: NumPy arrays (as upstream), CPU tensors (pinned ones upload asynchronously) or CUDA tensors;
+    host inputs give NumPy float64 images, CUDA inputs CUDA float32 tensors.
+    The caller's X and Y are left exactly as upstream leaves them (recentred once per filter; all those steps are
+    applied in one pass, so_recentre_chain).  Deviation, stated: a group is imaged at the positions its FIRST
+    filter sees; upstream re-takes the median for every filter, which moves the later filters' positions by the
+    rounding residue of the previous shift (<= 1 ulp-level of the coordinates, exactly 0 for odd N)."""
     if offsets:
         xoffset_pix_base = np.random.random() - 0.5
         yoffset_pix_base = np.random.random() - 0.5
@@ -729,16 +804,98 @@ def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=
 
     max_pixel_scale = np.max([filter_info[filter]['pixel_scale'] for filter in filters])
 
-    IMGs = {}
+    obs = {}
     for filter in filters:
         xoffset_pix = xoffset_pix_base * (max_pixel_scale / filter_info[filter]['pixel_scale'])
         yoffset_pix = yoffset_pix_base * (max_pixel_scale / filter_info[filter]['pixel_scale'])  # noqa: F841 (unused upstream too)
-        imgs = observed(filter, cosmo, z, target_width_arcsec, resampling_factor=resampling_factor,
-                        pixel_scale=pixel_scale, smoothing=smoothing, PSF=PSFs[filter],
-                        super_sampling=super_sampling, verbose=verbose, xoffset_pix=xoffset_pix,
-                        yoffset_pix=xoffset_pix).particle(X, Y, L[filter])
-        IMGs[filter] = imgs.img
-    return IMGs
+        obs[filter] = observed(filter, cosmo, z, target_width_arcsec, resampling_factor=resampling_factor,
+                               pixel_scale=pixel_scale, smoothing=smoothing, PSF=PSFs[filter],
+                               super_sampling=super_sampling, verbose=verbose, xoffset_pix=xoffset_pix,
+                               yoffset_pix=xoffset_pix)               # images.py:282 passes xoffset_pix twice
+    groups = {}
+    for filter in filters:
+        o = obs[filter]
+        key = (o.ndim, o.ndim_super, o.resolution, o.xoffset, o.yoffset, repr(o.smoothing))
+        groups.setdefault(key, []).append(filter)
+
+    host = not any(dv.is_device_tensor(a) for a in [X, Y] + [L[f] for f in filters])
+    dev = dv.device()
+    main = torch.cuda.current_stream()
+    n = len(X)
+    if host:
+        # positions first (the k-NN and the binning only need them), the weights follow on a copy stream
+        side = _copy_stream.setdefault(dev.index, torch.cuda.Stream(device=dev))
+        XY = torch.empty((2, n), dtype=torch.float64, device=dev)     # one block: both medians in one selection
+        XY[0].copy_(_as_cpu_tensor(X), non_blocking=True)
+        XY[1].copy_(_as_cpu_tensor(Y), non_blocking=True)
+        Xd, Yd = XY[0], XY[1]
+        xy_up = torch.cuda.Event()
+        xy_up.record(main)
+        Ld, L_ev = {}, {}
+        with torch.cuda.stream(side):
+            side.wait_event(xy_up)
+            for key, fs in groups.items():
+                buf = torch.empty((len(fs), n), dtype=torch.float64, device=dev)
+                for c, f in enumerate(fs):
+                    buf[c].copy_(_as_cpu_tensor(L[f]), non_blocking=True)
+                buf.record_stream(main)
+                Ld[key] = buf
+                L_ev[key] = torch.cuda.Event()
+                L_ev[key].record(side)
+    else:
+        Xd, Yd = dv.to_dev(X), dv.to_dev(Y)
+        Ld = {key: torch.stack([dv.to_dev(L[f]) for f in fs]) for key, fs in groups.items()}
+        L_ev = {key: None for key in groups}
+    # the reference's per-filter in-place recentring (images.py:183-187 once per filter), all steps in one pass;
+    # a group is imaged at the positions its FIRST filter sees
+    first_step = {key: filters.index(fs[0]) + 1 for key, fs in groups.items()}
+    out_steps = sorted(set(first_step.values()) | {len(filters)})
+    pos = dict(zip(out_steps, recentre_chain_device(Xd, Yd, [obs[f].xoffset for f in filters],
+                                                    [obs[f].yoffset for f in filters], out_steps)))
+
+    IMGs = {}
+    pending = []
+    for key, fs in groups.items():
+        Xg, Yg = pos[first_step[key]]
+        r = particle_device_multi([obs[f] for f in fs], Xg, Yg, Ld[key], L_event=L_ev[key], offsets_applied=True)
+        if host:
+            # one page-locked block per group: [2, C, ndim, ndim] (no_PSF, data)
+            out = torch.empty((2,) + tuple(r['data'].shape), dtype=torch.float32, pin_memory=True)
+            out[0].copy_(r['no_PSF'], non_blocking=True)
+            out[1].copy_(r['data'], non_blocking=True)
+            pending.append((fs, out))
+        else:
+            for c, f in enumerate(fs):
+                img = empty()
+                img.pixel_scale, img.pixel_scale_kpc = obs[f].pixel_scale, obs[f].pixel_scale_kpc
+                img.no_PSF, img.data = r['no_PSF'][c], r['data'][c]
+                IMGs[f] = img
+    # the caller's arrays end up exactly as the reference leaves them (recentred once per filter)
+    Xf, Yf = pos[len(filters)]
+    if host:
+        Xh = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        Yh = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        Xh.copy_(Xf, non_blocking=True)
+        Yh.copy_(Yf, non_blocking=True)
+        main.synchronize()
+        for A, Ah in ((X, Xh), (Y, Yh)):
+            if isinstance(A, torch.Tensor):
+                A.copy_(Ah)
+            else:
+                A[...] = Ah.numpy()
+        for fs, out in pending:
+            arr = out.numpy().astype(np.float64)
+            for c, f in enumerate(fs):
+                img = empty()
+                img.pixel_scale, img.pixel_scale_kpc = obs[f].pixel_scale, obs[f].pixel_scale_kpc
+                img.no_PSF, img.data = arr[0, c], arr[1, c]
+                IMGs[f] = img
+    else:
+        if isinstance(X, torch.Tensor) and X.is_cuda and X.dtype == torch.float64:
+            X.copy_(Xf)
+        if isinstance(Y, torch.Tensor) and Y.is_cuda and Y.dtype == torch.float64:
+            Y.copy_(Yf)
+    return {f: IMGs[f] for f in filters}
 
 
 def Sersic(L, p, filters, cosmo, z, target_width_arcsec, resampling_factor=False, pixel_scale=False, smoothing=False,

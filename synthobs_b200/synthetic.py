@@ -6,7 +6,8 @@ from here.  Everything is float64 NumPy on the host, because that is what the
 reference API receives (reference: synthobs/core.py:13-24 defines the particle
 schema X, Y, MetSurfaceDensities, Ages [Myr], Metallicities, Masses [Msol]).
 
-Nothing in this module touches the GPU or the oracle.
+Nothing in this module touches the oracle; only `hashed_catalogue` uses torch (on whatever device it is
+given), everything else is NumPy on the host.
 """
 
 import os
@@ -253,3 +254,56 @@ def adversarial_ages(log10age_grid, ulps=(0, 1, 2)):
             dn = np.nextafter(dn, -np.inf)
         out += [up, dn]
     return np.concatenate(out)
+
+
+# ---------------------------------------------------------------------------
+# counter-based catalogue: every particle's attributes are a pure function of its GLOBAL id, so any rank can
+# generate exactly its own share of ONE fixed catalogue (bench.py config 4: 1e4 galaxies sharded over the GPUs)
+# ---------------------------------------------------------------------------
+
+def _wrap64(c):
+    c &= (1 << 64) - 1
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _lsr(z, k):
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def hashed_uniform(ids, stream):
+    """U(0,1) float64 per element of the int64 tensor `ids` (splitmix64 of id and stream number; torch int64
+    arithmetic wraps like uint64)."""
+    import torch
+    z = ids * _wrap64(0x9E3779B97F4A7C15) + _wrap64((stream + 1) * 0xD1B54A32D192ED03)
+    z = (z ^ _lsr(z, 30)) * _wrap64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _wrap64(0x94D049BB133111EB)
+    z = z ^ _lsr(z, 31)
+    return (_lsr(z, 11).to(torch.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def hashed_catalogue(ids, scale_kpc=1.5):
+    """Particle attributes for the global particle ids `ids` (int64 tensor, any device): the same distributions
+    as particles(..., clumps=0) -- Gaussian positions, Ages = 10^U(0, 4.2) Myr, Z = 10^U(-4.5, -1.5), constant
+    mass, log-normal metal surface density, tauVs as in examples/SED_luminosities.py:69-70."""
+    import math
+    import torch
+    u = [hashed_uniform(ids, k) for k in range(7)]
+    r = torch.sqrt(-2.0 * torch.log(u[0]))
+    X = scale_kpc * r * torch.cos(2.0 * math.pi * u[1])
+    Y = scale_kpc * r * torch.sin(2.0 * math.pi * u[1])
+    Ages = torch.pow(10.0, 4.2 * u[2])
+    Z = torch.pow(10.0, -4.5 + 3.0 * u[3])
+    g = torch.sqrt(-2.0 * torch.log(u[4])) * torch.cos(2.0 * math.pi * u[5])
+    msd = torch.exp(math.log(0.3 / 10 ** 5.2) + 0.8 * g)
+    M = torch.full_like(X, BLUETIDES_MASS)
+    return {'X': X, 'Y': Y, 'Ages': Ages, 'Metallicities': Z, 'Masses': M, 'MetSurfaceDensities': msd,
+            'tauVs_ISM': (10 ** 5.2) * msd, 'tauVs_BC': 2.0 * (Z / 0.01), 'weight': 0.5 + u[6]}
+
+
+def ragged_sizes(n_galaxies, n_min=1000, n_max=100000, seed=2):
+    """galaxy sizes 10^U(log n_min, log n_max) and their CSR offsets"""
+    rng = np.random.default_rng(seed)
+    sizes = (10.0 ** rng.uniform(np.log10(n_min), np.log10(n_max), n_galaxies)).astype(np.int64)
+    offsets = np.zeros(n_galaxies + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    return sizes, offsets

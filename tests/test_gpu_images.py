@@ -214,6 +214,50 @@ def test_observed_matches_reference():
         assert_image_close(IMGs[f].no_PSF, g['multi_%d_no_PSF' % i])
 
 
+def test_particle_fast_path_equals_per_filter_loop():
+    """images.particle images the filters of one geometry together (one k-NN, one binning, multi-channel deposit,
+    batched FFT).  Against the reference's own structure -- a loop of observed(...).particle per filter
+    (images.py:277-284) -- the caller's X, Y must end up bit-identical (one in-place recentring per filter) and the
+    images equal; random sub-pixel offsets (global np.random, images.py:265-267), two pixel scales, even N (the
+    median residue of the second recentring is then not zero)."""
+    import torch
+    from synthobs_b200.morph import images
+    p = synthetic.particles(6000, seed=31, scale_kpc=1.0)
+    filters = ['T.A', 'T.B', 'T.C', 'T.D']
+    scales = {'T.A': 0.031, 'T.B': 0.063, 'T.C': 0.031, 'T.D': 0.031}
+    for f in filters:
+        images.filter_info[f] = {'pixel_scale': scales[f]}
+    cosmo = synthetic.FixedCosmology()
+    PSFs = {f: synthetic.GaussianPSF(1.4 + 0.3 * i) for i, f in enumerate(filters)}
+    rng = np.random.default_rng(2)
+    L = {f: p['Masses'] * (0.5 + rng.random(6000)) for f in filters}
+    kw = dict(smoothing=('adaptive', 8.), super_sampling=2)
+    X1, Y1 = p['X'].copy(), p['Y'].copy()
+    np.random.seed(11)
+    got = images.particle(X1, Y1, L, filters, cosmo, 8.0, 3.0, PSFs=PSFs, offsets=True, **kw)
+    # the reference's loop, spelled out with observed.particle
+    X2, Y2 = p['X'].copy(), p['Y'].copy()
+    np.random.seed(11)
+    bx = np.random.random() - 0.5
+    np.random.random()
+    mps = max(scales.values())
+    for f in filters:
+        off = bx * (mps / scales[f])
+        ref = images.observed(f, cosmo, 8.0, 3.0, PSF=PSFs[f], xoffset_pix=off, yoffset_pix=off, **kw).particle(X2, Y2, L[f])
+        assert got[f].pixel_scale == ref.img.pixel_scale and got[f].data.shape == ref.img.data.shape
+        assert_image_close(got[f].data, ref.img.data, 2e-6)
+        assert_image_close(got[f].no_PSF, ref.img.no_PSF, 2e-6)
+    assert np.array_equal(X1, X2) and np.array_equal(Y1, Y2)
+    # CUDA tensors in -> CUDA tensors out, same values, tensors recentred in place
+    Xd, Yd = torch.from_numpy(p['X']).cuda(), torch.from_numpy(p['Y']).cuda()
+    np.random.seed(11)
+    gd = images.particle(Xd, Yd, {f: torch.from_numpy(L[f]).cuda() for f in filters}, filters, cosmo, 8.0, 3.0,
+                         PSFs=PSFs, offsets=True, **kw)
+    assert gd['T.B'].data.is_cuda and np.array_equal(Xd.cpu().numpy(), X2)
+    for f in filters:
+        assert np.array_equal(gd[f].data.double().cpu().numpy(), got[f].data)
+
+
 def test_image_huge_single_rank_equals_core():
     """particle-block path (BASELINE config 5) on one rank == images.core adaptive"""
     from synthobs_b200 import dist as sdist
