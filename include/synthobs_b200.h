@@ -309,6 +309,25 @@ int so_median_segmented(const double* x, const int64_t* seg_offsets, int64_t n_s
 int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, const double* med, double shift,
                           void* stream);
 
+/* One huge image over several GPUs (BASELINE config 5; the reference images one object in one Python loop,
+ * synthobs/morph/images.py:83-97): split the selected particles (|x|, |y| < half_width) into n_parts spatially compact
+ * shares of equal size (+- one coarse cell) -- contiguous Morton ranges of a 2^cb x 2^cb grid over the image -- and flag
+ * every particle for share `part`: bit 1 (value 2) = OWN (this share answers its k-NN query and deposits it),
+ * bit 0 = LOCAL (own or halo: member of this share's search tree).  The halo is sized from the coarse histogram so
+ * that the k-th neighbour distance among the LOCAL particles is exact for every OWN particle (share.cu header).
+ * counts: DEVICE uint64[2] = number of local / own particles.  Identical on every rank given identical positions. */
+int64_t so_share_plan_workspace_bytes(int32_t cb);
+int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, int32_t k,
+                  int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
+/* so_knn_kth_distance_ex for one image where only the particles whose query_mask byte has bit 1 set are answered
+ * (query_mask: DEVICE uint8[n] or null = all); every selected particle is a member of the tree.  dk of the others
+ * is left untouched. */
+int so_knn_kth_distance_q(const double* X, const double* Y, const int32_t* ix, int64_t n, int32_t k, double half_width,
+                          const uint8_t* query_mask, double floor, double* dk, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* measurement support (bench.py); no upstream equivalent                      */
 /* ------------------------------------------------------------------------- */

@@ -1,0 +1,215 @@
+// Particle shares of ONE huge image over several GPUs (BASELINE config 5; no upstream equivalent: the reference images
+// one object in one Python loop, synthobs/morph/images.py:83-97).
+//
+// Every rank holds all positions, but a rank only needs the search tree AROUND its own share.  so_share_plan splits the
+// selected particles into n_parts spatially compact shares of (almost) equal size and tells each particle whether it
+// is OWN (this rank answers its k-NN query and deposits it) and/or LOCAL (own or halo: a member of this rank's search
+// tree), such that the k-th neighbour distance computed among the LOCAL particles is EXACT for every OWN particle:
+//
+//   1. histogram of the selected particles on a coarse 2^cb x 2^cb grid over the image (one pass, integer atomics
+//      on counters -- never on pixels -- so it is order-independent and identical on every rank);
+//   2. shares = contiguous ranges of the coarse cells in Morton order with equal cumulative counts;
+//   3. halo: a query in coarse cell c has at least k particles inside the smallest block B_m(c) of cells within
+//      Chebyshev distance m of c that holds >= k particles (summed-area table), so its k-th neighbour is at most
+//      diag(B_m) = sqrt(2) (2m + 1) cells away: every cell within ceil(sqrt(2) (2m + 1)) of c is marked LOCAL;
+//   4. one pass over the particles writes the flags.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxCb = 9;
+
+__host__ __device__ __forceinline__ uint32_t sh_spread(uint32_t v) {
+    v &= 0xffff;
+    v = (v | (v << 8)) & 0x00ff00ff;
+    v = (v | (v << 4)) & 0x0f0f0f0f;
+    v = (v | (v << 2)) & 0x33333333;
+    v = (v | (v << 1)) & 0x55555555;
+    return v;
+}
+__device__ __forceinline__ uint32_t sh_compact(uint32_t c) {
+    c &= 0x55555555u;
+    c = (c | (c >> 1)) & 0x33333333u; c = (c | (c >> 2)) & 0x0f0f0f0fu;
+    c = (c | (c >> 4)) & 0x00ff00ffu; c = (c | (c >> 8)) & 0xffffu;
+    return c;
+}
+
+// coarse cell (Morton index) of a position, -1 when the particle is not selected (images.py:47, strict)
+__device__ __forceinline__ int coarse_cell(double x, double y, double hw, double inv_c, int nc) {
+    if (!(fabs(x) < hw) || !(fabs(y) < hw)) return -1;
+    int cx = (int)((x + hw) * inv_c), cy = (int)((y + hw) * inv_c);
+    cx = max(0, min(nc - 1, cx));
+    cy = max(0, min(nc - 1, cy));
+    return (int)(sh_spread((uint32_t)cx) | (sh_spread((uint32_t)cy) << 1));
+}
+
+__global__ void __launch_bounds__(512) share_hist_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n,
+                                                         double hw, double inv_c, int nc, unsigned int* __restrict__ hist) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = coarse_cell(X[i], Y[i], hw, inv_c, nc);
+        if (c >= 0) atomicAdd(&hist[c], 1u);
+    }
+}
+
+// row-major counts -> summed-area table sat[(y + 1) * (nc + 1) + (x + 1)] = sum of cells (<= x, <= y); one CTA
+__global__ void __launch_bounds__(1024) share_sat_kernel(const unsigned int* __restrict__ hist, int nc,
+                                                         unsigned long long* __restrict__ sat) {
+    const int w = nc + 1;
+    for (int i = threadIdx.x; i < w; i += blockDim.x) { sat[i] = 0; sat[(size_t)i * w] = 0; }
+    __syncthreads();
+    // row prefix sums (thread per row), then column prefix sums (thread per column)
+    for (int y = threadIdx.x; y < nc; y += blockDim.x) {
+        unsigned long long acc = 0;
+        for (int x = 0; x < nc; ++x) {
+            acc += hist[sh_spread((uint32_t)x) | (sh_spread((uint32_t)y) << 1)];
+            sat[(size_t)(y + 1) * w + x + 1] = acc;
+        }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < nc; x += blockDim.x) {
+        unsigned long long acc = 0;
+        for (int y = 0; y < nc; ++y) {
+            acc += sat[(size_t)(y + 1) * w + x + 1];
+            sat[(size_t)(y + 1) * w + x + 1] = acc;
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long sat_block(const unsigned long long* sat, int w, int x0, int y0, int x1, int y1) {
+    // cells [x0, x1] x [y0, y1], clipped by the caller
+    return sat[(size_t)(y1 + 1) * w + x1 + 1] - sat[(size_t)y0 * w + x1 + 1] - sat[(size_t)(y1 + 1) * w + x0] + sat[(size_t)y0 * w + x0];
+}
+
+// cum = inclusive Morton-order prefix of hist.  The share of Morton cell c is the part whose count interval holds the
+// MIDDLE of the cell's interval: contiguous ranges of cells, equal counts up to one cell.
+__device__ __forceinline__ int cell_share(const unsigned long long* cum, int c, unsigned long long total, int n_parts) {
+    const unsigned long long lo = c ? cum[c - 1] : 0, hi = cum[c];
+    if (hi == lo) return -1;                                  // empty cell: nobody's
+    const unsigned long long mid2 = lo + hi;                  // twice the middle
+    int p = (int)((mid2 * (unsigned long long)n_parts) / (2 * total));
+    return p >= n_parts ? n_parts - 1 : p;
+}
+
+// every cell of share `part` marks the cells its queries may need (see header); mark: 1 = local, 2 = own
+__global__ void __launch_bounds__(256) share_mark_kernel(const unsigned int* __restrict__ hist, const unsigned long long* __restrict__ cum,
+                                                         const unsigned long long* __restrict__ sat, int nc, int k, int part,
+                                                         int n_parts, unsigned char* __restrict__ mark) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc * nc) return;
+    const unsigned long long total = cum[nc * nc - 1];
+    if (total == 0 || cell_share(cum, c, total, n_parts) != part) return;
+    const int cx = (int)sh_compact((uint32_t)c), cy = (int)sh_compact((uint32_t)c >> 1);
+    const int w = nc + 1;
+    int m = 0;
+    if (total < (unsigned long long)k) {
+        m = nc;                                               // fewer than k particles at all: every distance is inf
+    } else {
+        while (sat_block(sat, w, max(0, cx - m), max(0, cy - m), min(nc - 1, cx + m), min(nc - 1, cy + m)) < (unsigned long long)k) ++m;
+    }
+    // k-th neighbour within diag(B_m) = sqrt(2) (2m + 1) cell edges: Chebyshev ring M = ceil of that
+    const int M = min(nc, (int)ceil(1.41421356237309515 * (double)(2 * m + 1)));
+    for (int y = max(0, cy - M); y <= min(nc - 1, cy + M); ++y)
+        for (int x = max(0, cx - M); x <= min(nc - 1, cx + M); ++x)
+            mark[sh_spread((uint32_t)x) | (sh_spread((uint32_t)y) << 1)] |= 1;      // racing writers all set bit 0
+    __threadfence();
+}
+
+__global__ void __launch_bounds__(256) share_own_kernel(const unsigned long long* __restrict__ cum, int nc, int part, int n_parts,
+                                                        unsigned char* __restrict__ mark) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc * nc) return;
+    const unsigned long long total = cum[nc * nc - 1];
+    if (total && cell_share(cum, c, total, n_parts) == part) mark[c] |= 3;
+}
+
+__global__ void __launch_bounds__(512) share_flag_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n,
+                                                         double hw, double inv_c, int nc, const unsigned char* __restrict__ mark,
+                                                         unsigned char* __restrict__ flags, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int loc = 0, own = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = coarse_cell(X[i], Y[i], hw, inv_c, nc);
+        const unsigned char f = c >= 0 ? mark[c] : 0;
+        flags[i] = f;
+        loc += f & 1;
+        own += (f >> 1) & 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { loc += __shfl_xor_sync(0xffffffffu, loc, o); own += __shfl_xor_sync(0xffffffffu, own, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], loc); atomicAdd(&s_cnt[1], own); }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+struct ShareLayout {
+    unsigned int* hist;
+    unsigned long long* cum;
+    unsigned long long* sat;
+    unsigned char* mark;
+    void* cub_tmp;
+    size_t cub_bytes;
+    int64_t total;
+};
+
+static ShareLayout carve_share(void* ws, int64_t bytes, int cb, bool* ok) {
+    ShareLayout l;
+    const int nc = 1 << cb;
+    const int64_t cells = (int64_t)nc * nc;
+    SoArena a(ws, bytes);
+    l.hist = a.take<unsigned int>(cells);
+    l.cum = a.take<unsigned long long>(cells);
+    l.sat = a.take<unsigned long long>((int64_t)(nc + 1) * (nc + 1));
+    l.mark = a.take<unsigned char>(cells);
+    l.cub_bytes = 0;
+    cub::DeviceScan::InclusiveSum((void*)nullptr, l.cub_bytes, (unsigned int*)nullptr, (unsigned long long*)nullptr, (int)cells);
+    l.cub_tmp = a.take<char>((int64_t)l.cub_bytes);
+    l.total = a.used;
+    if (ok) *ok = a.ok();
+    return l;
+}
+
+}  // namespace
+
+extern "C" int64_t so_share_plan_workspace_bytes(int32_t cb) {
+    if (cb < 1 || cb > kMaxCb) return 0;
+    return carve_share(nullptr, 0, cb, nullptr).total + 256;
+}
+
+extern "C" int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, int32_t k,
+                             int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0 || !(half_width > 0.0) || cb < 1 || cb > kMaxCb || k < 1 || n_parts < 1 || part < 0 || part >= n_parts || !counts)
+        return SO_ERR_BAD_ARG;
+    if (n > 0 && (!X || !Y || !flags)) return SO_ERR_BAD_ARG;
+    bool ok = false;
+    ShareLayout l = carve_share(workspace, workspace_bytes, cb, &ok);
+    if (!ok || !workspace) return SO_ERR_WORKSPACE;
+    const int nc = 1 << cb;
+    const int cells = nc * nc;
+    const double inv_c = (double)nc / (2.0 * half_width);
+    SO_CUDA(cudaMemsetAsync(l.hist, 0, sizeof(unsigned int) * (size_t)cells, st));
+    SO_CUDA(cudaMemsetAsync(l.mark, 0, (size_t)cells, st));
+    SO_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(uint64_t), st));
+    if (n == 0) return SO_OK;
+    int64_t blocks = (n + 511) / 512;
+    if (blocks > 16 * so_num_sms()) blocks = 16 * so_num_sms();
+    { SO_PROF("share_hist_kernel", st); share_hist_kernel<<<(unsigned)blocks, 512, 0, st>>>(X, Y, n, half_width, inv_c, nc, l.hist); }
+    SO_LAUNCH_CHECK();
+    size_t tmp = l.cub_bytes;
+    SO_CUDA(cub::DeviceScan::InclusiveSum(l.cub_tmp, tmp, l.hist, l.cum, cells, st));
+    { SO_PROF("share_sat_kernel", st); share_sat_kernel<<<1, 1024, 0, st>>>(l.hist, nc, l.sat); }
+    SO_LAUNCH_CHECK();
+    { SO_PROF("share_mark_kernel", st); share_mark_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.hist, l.cum, l.sat, nc, k, part, n_parts, l.mark); }
+    SO_LAUNCH_CHECK();
+    { SO_PROF("share_own_kernel", st); share_own_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.cum, nc, part, n_parts, l.mark); }
+    SO_LAUNCH_CHECK();
+    { SO_PROF("share_flag_kernel", st); share_flag_kernel<<<(unsigned)blocks, 512, 0, st>>>(X, Y, n, half_width, inv_c, nc, l.mark, flags,
+                                                                                          (unsigned long long*)counts); }
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}

@@ -221,17 +221,21 @@ def core_batch_sharded(X, Y, L, offsets, resolution=0.1, ndim=100, smoothing=Fal
     return _gather_share(rows, sh)
 
 
-def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None):
-    """One huge adaptive-smoothed image split over the ranks (BASELINE config 5).  Every rank holds all
-    positions (neighbours cross any partition) and builds the same search tree, but answers the k-NN
-    queries and deposits only for ITS share of the particles: a contiguous range of the Morton order,
-    i.e. a spatially compact block, so the work per rank is 1/N and each partial image touches a
-    fraction of the tiles.  The partial images are summed with one all-reduce (NCCL over NVLink).
+def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, rank=None, n_ranks=None, reduce=True):
+    """One huge adaptive-smoothed image split over the ranks (BASELINE config 5).  Every rank holds all positions,
+    but works on a spatially compact SHARE of the particles (a contiguous Morton range of a coarse grid over the
+    image, equal counts): it builds the search tree only for its share plus the halo that makes the k-th neighbour
+    distances of the share exact (so_share_plan), answers the k-NN queries of the share, deposits the share onto a
+    private image, and the partial images are summed with one all-reduce (NCCL over NVLink).  Work per rank is
+    ~1/N (+ the halo, + two passes over all positions for the coarse histogram and the flags).
     Returns the full [C, ndim, ndim] (or [ndim, ndim] for 1-D L) float32 CUDA image on every rank.
-    `stages` (dict): filled with the device time [ms] of the stages of this call (CUDA events)."""
+    rank / n_ranks override the process group (reduce=False: the partial image of that share, e.g. to add the shares
+    on one GPU); `stages` (dict) is filled with the device time [ms] of the stages of this call (CUDA events)."""
     from . import device as dv
     from .morph import images
-    rank, ws = world()
+    r0, w0 = world()
+    rank = r0 if rank is None else int(rank)
+    ws = w0 if n_ranks is None else int(n_ranks)
     marks = []
 
     def mark(name):
@@ -244,15 +248,32 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None):
     Ld = Ld.reshape(1, -1) if one else Ld
     mark('start')
     width, G, Gd = images.pixel_grid_device(resolution, ndim)
-    ix, iy = images.ngp_index_device(Xd, Yd, Gd, ndim, width / 2.)
-    mark('nearest-pixel index')
-    dk, pids = images.knn_device_part(Xd, Yd, ix, int(k), width / 2., rank, ws, floor=images.FWHM_FLOOR)
-    mark('k-NN (tree of all particles, queries of the share)')
-    r = images.deposit_device(Xd[pids], Yd[pids], Ld[:, pids], resolution, ndim, adaptive_k=int(k), want_ngp=False,
-                              support_sigmas=support_sigmas, dk=dk[pids])
-    mark('gather share + plan + binning + deposit')
-    img = reduce_image(r['data'])
-    mark('all-reduce of the image')
+    hw = width / 2.
+    if ws == 1:
+        Xo, Yo, Lo = Xd, Yd, Ld
+        ix, iy = images.ngp_index_device(Xo, Yo, Gd, ndim, hw)
+        mark('nearest-pixel index')
+        dko = images.knn_device(Xo, Yo, ix, int(k), hw, floor=images.FWHM_FLOOR)
+        mark('k-NN')
+    else:
+        flags, counts = images.share_plan_device(Xd, Yd, hw, int(k), rank, ws)
+        loc = torch.nonzero(flags).reshape(-1)               # local = own + halo (synchronises: sizes of the share)
+        fl = flags[loc]
+        Xl, Yl = Xd[loc], Yd[loc]
+        mark('share plan (coarse histogram, halo) + gather of the local particles')
+        ix, iy = images.ngp_index_device(Xl, Yl, Gd, ndim, hw)
+        mark('nearest-pixel index')
+        dkl = images.knn_device_masked(Xl, Yl, ix, int(k), hw, fl, floor=images.FWHM_FLOOR)
+        mark('k-NN (tree of the local particles, queries of the share)')
+        own = torch.nonzero(fl & 2).reshape(-1)
+        Xo, Yo, dko, Lo = Xl[own], Yl[own], dkl[own], Ld[:, loc[own]]
+    r = images.deposit_device(Xo, Yo, Lo, resolution, ndim, adaptive_k=int(k), want_ngp=False,
+                              support_sigmas=support_sigmas, dk=dko)
+    mark('plan + binning + deposit of the share')
+    img = r['data']
+    if reduce and ws > 1:
+        img = reduce_image(img)
+        mark('all-reduce of the image')
     if stages is not None:
         torch.cuda.synchronize()
         for (_, a), (name, b) in zip(marks[:-1], marks[1:]):

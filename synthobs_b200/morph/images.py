@@ -255,6 +255,40 @@ def knn_device_part(Xd, Yd, ix, k, half_width, part, n_parts, floor=0.0):
     return knn_device(Xd, Yd, ix, k, half_width, floor=floor, part=part, n_parts=n_parts, want_order=True)
 
 
+def knn_device_masked(Xd, Yd, ix, k, half_width, query_mask, floor=0.0):
+    """k-th neighbour distance (self = first) among ALL selected particles, answered only for the particles whose
+    query_mask byte has bit 1 set (uint8 CUDA tensor; the others keep 0): so_knn_kth_distance_q."""
+    n = Xd.numel()
+    dk = torch.zeros(n, dtype=torch.float64, device=Xd.device)
+    wsb = _cabi.lib.so_knn_batch_workspace_bytes(n, 1, int(k))
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_knn_kth_distance_q(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(ix), n, int(k), float(half_width),
+                                                _cabi.ptr(query_mask), float(floor), _cabi.ptr(dk), _cabi.ptr(ws), wsb,
+                                                _cabi.stream()), 'so_knn_kth_distance_q')
+    return dk
+
+
+def share_grid_bits(n):
+    """coarse grid (2^cb cells per axis) of the particle shares: ~256 particles per cell, 8 <= cells per axis <= 512"""
+    cb = int(np.floor(np.log2(max(np.sqrt(max(n, 1) / 256.0), 1.0))))
+    return int(min(max(cb, 3), 9))
+
+
+def share_plan_device(Xd, Yd, half_width, k, part, n_parts, cb=None):
+    """Flags of share `part` of `n_parts` of one huge image (so_share_plan): uint8 CUDA tensor, bit 0 = local (member
+    of the share's search tree: own + halo), bit 1 = own; plus the device counts [local, own]."""
+    n = Xd.numel()
+    cb = share_grid_bits(n) if cb is None else int(cb)
+    flags = torch.empty(n, dtype=torch.uint8, device=Xd.device)
+    counts = torch.zeros(2, dtype=torch.int64, device=Xd.device)
+    wsb = _cabi.lib.so_share_plan_workspace_bytes(cb)
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_share_plan(_cabi.ptr(Xd), _cabi.ptr(Yd), n, float(half_width), cb, int(k), int(part), int(n_parts),
+                                        _cabi.ptr(flags), _cabi.ptr(counts), _cabi.ptr(ws), wsb, _cabi.stream()),
+                'so_share_plan')
+    return flags, counts
+
+
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
                    support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1, exact_dk=False,
                    pad_to=None):
@@ -859,10 +893,11 @@ def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=
         Xg, Yg = pos[first_step[key]]
         r = particle_device_multi([obs[f] for f in fs], Xg, Yg, Ld[key], L_event=L_ev[key], offsets_applied=True)
         if host:
-            # one page-locked block per group: [2, C, ndim, ndim] (no_PSF, data)
-            out = torch.empty((2,) + tuple(r['data'].shape), dtype=torch.float32, pin_memory=True)
-            out[0].copy_(r['no_PSF'], non_blocking=True)
-            out[1].copy_(r['data'], non_blocking=True)
+            # one page-locked float64 block per group: [2, C, ndim, ndim] (no_PSF, data); widened on the device (a
+            # host-side astype of the block costs more than the whole imaging step)
+            out = torch.empty((2,) + tuple(r['data'].shape), dtype=torch.float64, pin_memory=True)
+            out[0].copy_(r['no_PSF'].to(torch.float64), non_blocking=True)
+            out[1].copy_(r['data'].to(torch.float64), non_blocking=True)
             pending.append((fs, out))
         else:
             for c, f in enumerate(fs):
@@ -873,18 +908,23 @@ def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=
     # the caller's arrays end up exactly as the reference leaves them (recentred once per filter)
     Xf, Yf = pos[len(filters)]
     if host:
-        Xh = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        Yh = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        Xh.copy_(Xf, non_blocking=True)
-        Yh.copy_(Yf, non_blocking=True)
+        # D2H of the recentred positions: straight into the caller's buffer when it is page-locked
+        back = []
+        for A, Af in ((X, Xf), (Y, Yf)):
+            if isinstance(A, torch.Tensor) and A.is_pinned() and A.dtype == torch.float64 and A.is_contiguous():
+                A.copy_(Af, non_blocking=True)
+            else:
+                Ah = torch.empty(n, dtype=torch.float64, pin_memory=True)
+                Ah.copy_(Af, non_blocking=True)
+                back.append((A, Ah))
         main.synchronize()
-        for A, Ah in ((X, Xh), (Y, Yh)):
+        for A, Ah in back:
             if isinstance(A, torch.Tensor):
                 A.copy_(Ah)
             else:
                 A[...] = Ah.numpy()
         for fs, out in pending:
-            arr = out.numpy().astype(np.float64)
+            arr = out.numpy()          # views of the page-locked block
             for c, f in enumerate(fs):
                 img = empty()
                 img.pixel_scale, img.pixel_scale_kpc = obs[f].pixel_scale, obs[f].pixel_scale_kpc

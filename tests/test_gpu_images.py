@@ -258,6 +258,39 @@ def test_particle_fast_path_equals_per_filter_loop():
         assert np.array_equal(gd[f].data.double().cpu().numpy(), got[f].data)
 
 
+@pytest.mark.parametrize('n_parts', [2, 5, 8])
+def test_share_plan_keeps_knn_exact(n_parts):
+    """so_share_plan: the shares are disjoint, cover every selected particle, are balanced, and the k-th neighbour
+    distance of every OWN particle computed among the LOCAL particles only (own + halo) is bit-identical to the
+    one computed among all particles -- clustered catalogue, sparse outskirts, k larger than many coarse cells hold"""
+    import torch
+    from synthobs_b200 import device as dv
+    from synthobs_b200.morph import images
+    p = synthetic.particles(400000, seed=77, scale_kpc=2.0)
+    X, Y = dv.to_dev(p['X']), dv.to_dev(p['Y'])
+    hw, k = 9.0, 12
+    width, G, Gd = images.pixel_grid_device(2 * hw / 2000, 2000)
+    ix, _ = images.ngp_index_device(X, Y, Gd, 2000, hw)
+    full = images.knn_device(X, Y, ix, k, hw)
+    sel = ix >= 0
+    owned = torch.zeros_like(sel, dtype=torch.int32)
+    for part in range(n_parts):
+        for cb in (None, 7):
+            flags, counts = images.share_plan_device(X, Y, hw, k, part, n_parts, cb=cb)
+            loc = torch.nonzero(flags).reshape(-1)
+            own = (flags & 2) != 0
+            assert int(counts[0]) == loc.numel() and int(counts[1]) == int(own.sum())
+            assert bool(((flags & 1) != 0)[own].all()) and not bool(own[~sel].any())
+            ixl, _ = images.ngp_index_device(X[loc], Y[loc], Gd, 2000, hw)
+            dkl = images.knn_device_masked(X[loc], Y[loc], ixl, k, hw, flags[loc])
+            o = own[loc]
+            assert torch.equal(dkl[o], full[loc][o])
+            if cb is None:
+                owned += own.to(torch.int32)
+                assert abs(int(own.sum()) / (int(sel.sum()) / n_parts) - 1.0) < 0.1
+    assert torch.equal(owned, sel.to(torch.int32))
+
+
 def test_image_huge_single_rank_equals_core():
     """particle-block path (BASELINE config 5) on one rank == images.core adaptive"""
     from synthobs_b200 import dist as sdist

@@ -7,7 +7,7 @@ against itself -- at BASELINE.json's configurations:
              (synthobs/morph/images.py:83-97, 181-213): images 1e-5 (peak and L2), flux 2e-6;
   config[3]  20 ragged galaxies of 1e3..1e5 particles in ONE batched pass vs a loop of oracle calls;
   config[4]  a 3e6-particle, 8192^2 image with two dense clumps (tens of thousands of FP32 contributions per pixel)
-             vs the oracle on 512^2 windows, for one particle share and for two shares added.
+             vs the oracle on 512^2 windows, for one particle share and for three shares added.
 
 The oracle reaches these sizes because (i) its spectra are summed over particle blocks on all host cores (NumPy
 releases the GIL) and (ii) image_oracle.adaptive_window skips the terms that are exactly 0.0 in float64 (pinned
@@ -232,7 +232,7 @@ def test_config4_ragged_batch_vs_oracle_loop(full_model):
 
 def test_config5_huge_image_windows_vs_oracle():
     """3e6 particles onto 8192 x 8192 with a moderate and an extreme clump (the extreme one stacks tens of thousands of
-    FP32 contributions per pixel at the FWHM floor): one particle share and two Morton-range shares added, each
+    FP32 contributions per pixel at the FWHM floor): one particle share and three spatial shares added, each
     against the float64 oracle on 512 x 512 windows around the clumps and in the field."""
     import torch
     from synthobs_b200 import device as dv
@@ -258,12 +258,12 @@ def test_config5_huge_image_windows_vs_oracle():
     # exact k-NN at this size (floor shortcut off): equal to cKDTree to rounding
     got_dk = images.knn_device(Xd, Yd, ix, 8, width / 2.).cpu().numpy()[sel]
     np.testing.assert_allclose(got_dk, dk, rtol=4e-16, atol=0)
+    from synthobs_b200 import dist as sdist
     whole = images.deposit_device(Xd, Yd, Ld.reshape(1, -1), res, ndim, adaptive_k=8, want_ngp=False)['data'][0]
+    # the multi-GPU path on one GPU: the partial images of the 3 shares (what 3 ranks would deposit), added
     shares = torch.zeros_like(whole)
-    for part in range(2):
-        dkp, pids = images.knn_device_part(Xd, Yd, ix, 8, width / 2., part, 2, floor=images.FWHM_FLOOR)
-        shares += images.deposit_device(Xd[pids], Yd[pids], Ld[pids].reshape(1, -1), res, ndim, adaptive_k=8,
-                                        want_ngp=False, dk=dkp[pids])['data'][0]
+    for part in range(3):
+        shares += sdist.image_huge(Xd, Yd, Ld, res, ndim, 8, rank=part, n_ranks=3, reduce=False)
     flux = Ls.sum()
     assert float(whole.double().sum()) == pytest.approx(flux, rel=2e-6)
     assert float(shares.double().sum()) == pytest.approx(flux, rel=2e-6)
