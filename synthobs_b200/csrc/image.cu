@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ i
                 const double two_s2 = __dmul_rn(2.0, __dmul_rn(sigma, sigma));
                 // the reference drops the particle when every float64 term underflows (images.py:95-97)
                 const double amin = __ddiv_rn(__dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0)), two_s2);
-                dropped = exp(-amin) <= 0.0;
+                // np.exp(-a) == 0.0 exactly for a >= 0x1.74910d52d3052p+9 (745.1332191019412: below half the smallest
+                // denormal); established by bisection against NumPy, so no device exp is needed (or trusted) here
+                dropped = !(amin < 745.1332191019412);
                 const double c = 1.4426950408889634 * pitch * pitch / two_s2;
                 cpx = (float)c;
                 if (R > 0.0) {
@@ -466,18 +468,32 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     }
 }
 
-// sub-tiles with 0 items -> zeros, 1 item -> already written, >1 -> ordered sum of the partial sub-tiles
-__global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParams p, int n_chan) {
-    const int tile = blockIdx.x, chan = blockIdx.y;
-    const int64_t i0 = p.item_start[tile], i1 = p.item_start[tile + 1];
-    if (i1 - i0 == 1) return;
+// sub-tiles with 0 items -> zeros, 1 item -> already written, >1 -> ordered sum of the partial sub-tiles.
+// One CTA per WORK ITEM (+ one per sub-tile for the empty ones): only the first item of a split sub-tile does work, so
+// the launch is a few thousand CTAs, most of which exit at once, instead of sub-tiles x channels
+__global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParams p, int n_chan, int64_t max_items) {
+    int tile;
+    int64_t i0, i1;
+    if ((int64_t)blockIdx.x < max_items) {
+        const int64_t item = blockIdx.x;
+        if (item >= p.item_start[p.ntiles]) return;
+        tile = p.item_tile[item];
+        i0 = p.item_start[tile]; i1 = p.item_start[tile + 1];
+        if (item != i0 || i1 - i0 == 1) return;            // not the first item of its sub-tile, or written directly
+    } else {
+        tile = (int)((int64_t)blockIdx.x - max_items);
+        i0 = p.item_start[tile]; i1 = p.item_start[tile + 1];
+        if (i1 != i0) return;                              // only the empty sub-tiles are zeroed here
+    }
     const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
     const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
     const int e = threadIdx.x;
-    float s = 0.f;
-    for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
     const int row = py0 + e / kT, col = px0 + e % kT;
-    if (row < p.ndim && col < p.ndim) p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = s;
+    for (int chan = 0; chan < n_chan; ++chan) {
+        float s = 0.f;
+        for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
+        if (row < p.ndim && col < p.ndim) p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = s;
+    }
 }
 
 // NGP products: one CTA per sub-tile; shared-memory accumulation (float64 sums, integer counts)
@@ -782,8 +798,8 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
             else { deposit_kernel<1><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 1; }
             SO_LAUNCH_CHECK();
         }
-        dim3 rgrid((unsigned)d.ntiles, (unsigned)n_chan);
-        { SO_PROF("tile_reduce_kernel", st); tile_reduce_kernel<<<rgrid, kT * kT, 0, st>>>(p, n_chan); }
+        { SO_PROF("tile_reduce_kernel", st);
+          tile_reduce_kernel<<<(unsigned)(d.max_items + d.ntiles), kT * kT, 0, st>>>(p, n_chan, d.max_items); }
         SO_LAUNCH_CHECK();
     }
     if (simple || hist) {

@@ -125,3 +125,42 @@ def test_ngp_thresholds_refuse_unsorted_axes():
     for bad in (la[::-1], np.r_[la[:10], la[9:]], np.r_[la[:5], np.nan, la[6:]]):
         with pytest.raises(ValueError):
             models.ngp_thresholds(bad, 6.0)
+
+
+def test_core_sed_known_answers():
+    """interrogator's core.sed is not vendored, so its post-processing (examples/SED_spectra.py:103,
+    112; SED_Lion.py:38) is restated in synthobs_b200.providers.sed.  The formulas restated are
+        get_Lnu(F)[f]  = trapz(lnu T_f, lam) / trapz(T_f, lam)
+        get_fnu(cosmo, z): fnu = 1e23 * 1e9 * lnu * (1 + z) / (4 pi dL^2) [nJy] (x IGM transmission), lamz = lam (1 + z)
+        get_Fnu(F)[f]  = trapz(fnu T_f, lam_f) / trapz(T_f, lam_f)
+        return_log10Q  = log10 integral_{lam < 912} lnu / (h lam) dlam
+    and they are pinned here by answers derived by hand: a flat spectrum through any filter, a power law through a
+    top hat, the z -> flux scale, and the ionising photon rate of a flat Lyman continuum."""
+    from synthobs_b200 import providers
+    lam = np.linspace(100.0, 20000.0, 199001)           # 0.1 A steps: trapz error of the power law ~1e-10
+    c0 = 3.7e28
+    sed = providers.sed(lam)
+    F = {'filters': ['th', 'ga']}
+    F['th'] = synthetic.Filter(lam, ((lam >= 4000.0) & (lam <= 6000.0)).astype(float))
+    F['ga'] = synthetic.Filter(lam, np.exp(-0.5 * ((lam - 9000.0) / 700.0) ** 2))
+    sed.lnu = np.full(lam.size, c0)
+    L = sed.get_Lnu(F)
+    assert L['th'] == pytest.approx(c0, rel=1e-14) and L['ga'] == pytest.approx(c0, rel=1e-14)
+    a = -1.5                                            # lnu = lam^a through the top hat [4000, 6000]
+    sed.lnu = lam ** a
+    exact = (6000.0 ** (a + 1) - 4000.0 ** (a + 1)) / ((a + 1) * 2000.0)
+    assert sed.get_Lnu(F)['th'] == pytest.approx(exact, rel=2e-5)      # edge pixels of the top hat: O(h / width)
+    z, cosmo = 8.0, synthetic.FixedCosmology()
+    sed.lnu = np.full(lam.size, c0)
+    fnu = sed.get_fnu(cosmo, z, include_IGM=False)
+    scale = 1e23 * 1e9 * (1.0 + z) / (4.0 * np.pi * cosmo.dl_cm ** 2)
+    np.testing.assert_allclose(fnu, c0 * scale, rtol=1e-15)
+    np.testing.assert_allclose(sed.lamz, lam * 9.0, rtol=0)
+    Fz = {'filters': ['th'], 'th': synthetic.Filter(lam * 9.0, F['th'].T)}
+    assert sed.get_Fnu(Fz)['th'] == pytest.approx(c0 * scale, rel=1e-14)
+    h = 6.626e-27
+    top = lam[lam < 912.][-1]                            # strict cut (lam < 912): the integral ends at the last node below
+    assert sed.return_log10Q() == pytest.approx(np.log10(c0 / h * np.log(top / 100.0)), abs=1e-7)   # trapz of 1/lam on 0.1 A steps
+    # IGM: transparent redward of Lyman alpha in the observed frame, opaque far blueward
+    t = providers.madau(np.array([500.0 * 9, 1300.0 * 9, 20000.0]), 8.0)
+    assert t[1] == 1.0 and t[2] == 1.0 and t[0] < 1e-3
