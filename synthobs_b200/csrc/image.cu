@@ -335,13 +335,32 @@ __global__ void __launch_bounds__(256) weights_kernel(const double* __restrict__
     for (int c = 0; c < n_chan; ++c) wts[(size_t)p * n_chan + c] = (float)(L[(size_t)c * n + p] * wn);
 }
 
+// 32 x 32 bit-matrix transpose across the lanes of a warp: bit j of the result in lane i = bit i of x in lane j
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const unsigned m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    }
+    return x;
+}
+
 // One warp = one work item (sub-tile, slice of its particle list), C channels in registers.
 // Per particle the 16 column factors and 16 row factors of the sub-tile are evaluated one per lane and
 // exchanged through shared memory (all 32 staged particles at once, one __syncwarp per phase); a lane
-// owns a 2 x 4 pixel block, so it reads 4 column factors and 2 row factors per particle, and all
-// multiply-adds are packed (FMUL2 / FFMA2).
+// owns a 2 x 4 pixel block, so it reads 4 column and 2 row factors per particle, and all multiply-adds are
+// packed (FMUL2 / FFMA2).
+// A narrow particle (support of a few pixels: the bulk of a dense image) overlaps only a few of the 32 pixel
+// blocks, so each lane walks ITS OWN list of the staged particles whose support box meets its block: the lane
+// that stages particle q computes the 32-bit set of lanes the particle touches from its support box, a bit-matrix
+// transpose turns the 32 sets into one particle mask per lane, and the multiply-add loop runs until the longest
+// list is done (about 14 instead of 32 rounds at ~18 pixels per particle; all 32 for wide supports).  The order
+// in which a pixel receives its contributions is still the order of the list: bitwise reproducible.
 template <int C>
 __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositParams p) {
+    constexpr int CP = (C == 8) ? 12 : C;                      // padded weight row: lanes read different rows at once
+    constexpr int FP = 2 * kT + 4;                             // padded factor row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * kDepWarps + warp;
     if (item >= p.item_start[p.ntiles]) return;
@@ -354,8 +373,8 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
 
     __shared__ float4 s_rec[kDepWarps][2][kP];                 // per axis: {-2u, -cpx, tile origin - nearest pixel, W}
-    __shared__ __align__(16) float s_w[kDepWarps][kP][C];      // weights
-    __shared__ __align__(16) float s_f[kDepWarps][kP][2 * kT]; // factors per staged particle: 16 columns, then 16 rows
+    __shared__ __align__(16) float s_w[kDepWarps][kP][CP];     // weights
+    __shared__ __align__(16) float s_f[kDepWarps][kP][FP];     // factors per staged particle: 16 columns, then 16 rows
 
     // lane -> one factor to evaluate (lanes 0-15: column px0+lane, lanes 16-31: row py0+lane-16) and
     // a block of 2 rows x 4 columns of owned pixels
@@ -375,6 +394,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
         const int pid = pid_next;
         if (base + kP + lane < end) pid_next = p.pids[base + kP + lane];
         __syncwarp();
+        unsigned touched = 0;                                  // lanes (pixel blocks) the particle of this lane overlaps
         if (lane < np) {
             float4 ra;
             int4 rb;
@@ -396,7 +416,17 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
 #pragma unroll
                 for (int c = 0; c < C; ++c) s_w[warp][lane][c] = __ldg(wp + c);
             }
+            // support box [nearest - W, nearest + W]^2 in sub-tile coordinates -> pixel blocks (2 rows x 4 columns)
+            const int W = rb.z, cx = rb.x - px0, cy = rb.y - py0;      // (the nearest pixel may be far outside this sub-tile)
+            const int cA = max(0, cx - W), cB = min(kT - 1, cx + W), rA = max(0, cy - W), rB = min(kT - 1, cy + W);
+            if (cA <= cB && rA <= rB) {
+                const unsigned cols = ((2u << (cB >> 2)) - 1u) & ~((1u << (cA >> 2)) - 1u);           // 4-bit pattern
+                const int bA = rA >> 1, bB = rB >> 1;
+                const unsigned hi = bB == 7 ? 0xffffffffu : ((1u << (4 * (bB + 1))) - 1u);
+                touched = cols * (hi & ~((1u << (4 * bA)) - 1u) & 0x11111111u);
+            }
         }
+        unsigned mine = warp_transpose32(touched, lane);       // bit q: staged particle q overlaps my pixel block
         __syncwarp();
         // all factors of the phase first (independent iterations: the ex2 chain is pipelined), one __syncwarp, then
         // the multiply-adds with nothing but loads in between: neither loop waits on a per-particle exchange
@@ -410,33 +440,34 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
             s_f[warp][q][lane] = f;
         }
         __syncwarp();
-#pragma unroll 2
-        for (int q = 0; q < np; ++q) {
-            // shared-memory bandwidth (bytes per lane) is what limits this loop: operands are loaded once and
-            // paired up in registers
-            const float4 fx = *reinterpret_cast<const float4*>(&s_f[warp][q][4 * bc]);
-            const float2 fy = *reinterpret_cast<const float2*>(&s_f[warp][q][kT + 2 * br]);
-            float2 g[4];
-            g[0] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.x, fx.y));
-            g[1] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.z, fx.w));
-            g[2] = __fmul2_rn(make_float2(fy.y, fy.y), make_float2(fx.x, fx.y));
-            g[3] = __fmul2_rn(make_float2(fy.y, fy.y), make_float2(fx.z, fx.w));
-            float w[C];
-            if constexpr (C % 4 == 0) {
+        while (__any_sync(0xffffffffu, mine != 0)) {
+            if (mine) {
+                const int q = __ffs(mine) - 1;
+                mine &= mine - 1;
+                const float4 fx = *reinterpret_cast<const float4*>(&s_f[warp][q][4 * bc]);
+                const float2 fy = *reinterpret_cast<const float2*>(&s_f[warp][q][kT + 2 * br]);
+                float2 g[4];
+                g[0] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.x, fx.y));
+                g[1] = __fmul2_rn(make_float2(fy.x, fy.x), make_float2(fx.z, fx.w));
+                g[2] = __fmul2_rn(make_float2(fy.y, fy.y), make_float2(fx.x, fx.y));
+                g[3] = __fmul2_rn(make_float2(fy.y, fy.y), make_float2(fx.z, fx.w));
+                float w[C];
+                if constexpr (C % 4 == 0) {
 #pragma unroll
-                for (int c = 0; c < C; c += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(&s_w[warp][q][c]);
-                    w[c] = w4.x; w[c + 1] = w4.y; w[c + 2] = w4.z; w[c + 3] = w4.w;
+                    for (int c = 0; c < C; c += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[warp][q][c]);
+                        w[c] = w4.x; w[c + 1] = w4.y; w[c + 2] = w4.z; w[c + 3] = w4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) w[c] = s_w[warp][q][c];
                 }
-            } else {
 #pragma unroll
-                for (int c = 0; c < C; ++c) w[c] = s_w[warp][q][c];
-            }
+                for (int c = 0; c < C; ++c) {
+                    const float2 w2 = make_float2(w[c], w[c]);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float2 w2 = make_float2(w[c], w[c]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[c][j] = __ffma2_rn(w2, g[j], acc[c][j]);
+                    for (int j = 0; j < 4; ++j) acc[c][j] = __ffma2_rn(w2, g[j], acc[c][j]);
+                }
             }
         }
     }

@@ -13,7 +13,6 @@
 // sparse outskirts and isolated particles all cost O(log) node visits plus a few leaf scans.
 // The squared distance is formed with separately rounded products and sum (no FMA contraction) and
 // an IEEE sqrt, i.e. the same float64 arithmetic as a straightforward C loop.
-#include <stdio.h>
 #include <stdlib.h>
 
 #include <cub/cub.cuh>
@@ -38,9 +37,6 @@ struct KnnLayout {
     double2* xy;                    // positions packed in input order: one sector per particle for the sorted gather
     int32_t* E;                    // [4^Lt] upper bounds per table cell
     unsigned long long* counter;   // [0] selected count
-    uint8_t* gflag;                // [n] 1 where a node of the query partition starts (sorted order)
-    int32_t* gstart;               // [n + 1] compacted group starts
-    int32_t* gcount;               // [0] number of groups, [1] work ticket of the group kernel
     void* cub_tmp;
     int64_t cub_tmp_bytes;
     int Lt;
@@ -68,16 +64,10 @@ static KnnLayout carve_knn(void* ws, int64_t bytes, int64_t n, int64_t n_img, bo
     l.xy = a.take<double2>(n);
     l.E = a.take<int32_t>(ncell);
     l.counter = a.take<unsigned long long>(2);
-    l.gflag = a.take<uint8_t>(n);
-    l.gstart = a.take<int32_t>(n + 1);
-    l.gcount = a.take<int32_t>(4);
-    size_t b1 = 0, b2 = 0, b3 = 0;
+    size_t b1 = 0, b2 = 0;
     cub::DeviceRadixSort::SortPairs((void*)nullptr, b1, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                     (const int32_t*)nullptr, (int32_t*)nullptr, (int)(n > 0 ? n : 1), 0, 64);
     cub::DeviceScan::InclusiveScan((void*)nullptr, b2, (int32_t*)nullptr, (int32_t*)nullptr, cub::Max(), (int)ncell);
-    cub::DeviceSelect::Flagged((void*)nullptr, b3, cub::CountingInputIterator<int32_t>(0), (const uint8_t*)nullptr,
-                               (int32_t*)nullptr, (int32_t*)nullptr, (int)(n > 0 ? n : 1));
-    if (b3 > b2) b2 = b3;
     l.cub_tmp_bytes = (int64_t)(b1 > b2 ? b1 : b2);
     l.cub_tmp = a.take<char>(l.cub_tmp_bytes);
     l.total = a.used;
@@ -482,361 +472,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_query_warp_kernel(
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Query groups.  The queries are partitioned by NODE: the deepest quadtree node with at most kNodeMax points whose
-// parent has more (a finest-level cell with more points is cut into runs of kNodeMax).  In Morton order a node is a
-// run of consecutive positions; one warp takes a node and answers it in balanced chunks of <= 32 consecutive
-// queries (about a quadrant each): lane = query.  The queries of a chunk sit in one small rectangle, so their
-// candidate sets nearly coincide: candidates are staged once in shared memory and broadcast to all lanes, the tree
-// is walked once per chunk with the range look-ups of up to 32 nodes done in parallel, one per lane.
-//
-// Node level without a tree: the node of level l that holds sorted position i has more than kNodeMax points iff some
-// window [j, j + kNodeMax] with i - kNodeMax <= j <= i lies inside it, i.e. iff
-// max_j common_level(key[j], key[j + kNodeMax]) >= l.  depth(i) = that maximum, node level = depth + 1.
-constexpr int kNodeMax = 128;
-constexpr int kGroupWarps = 4;
-constexpr int kGroupStack = 320;     // shared walk stack per warp (nodes); overflow degrades to scanning, never fails
-constexpr int kLeafCap = 8;          // nodes with at most this many points are staged whole
-constexpr int kStageCap = 32 * kLeafCap;
-
-template <typename KeyT>
-__device__ __forceinline__ int common_level(KeyT a, KeyT b) {
-    const unsigned long long x = (unsigned long long)a ^ (unsigned long long)b;
-    if (x >> (2 * kBits)) return -1;                       // different images (or one of them outside its image)
-    if (x == 0) return kBits;
-    return (2 * kBits - 1 - (63 - __clzll((long long)x))) >> 1;
-}
-
-template <typename KeyT>
-__global__ void __launch_bounds__(256) knn_group_flag_kernel(const KeyT* __restrict__ keys, int64_t n,
-                                                             const unsigned long long* __restrict__ n_valid_ptr,
-                                                             uint8_t* __restrict__ gflag) {
-    __shared__ int8_t s_c[2][256 + kNodeMax + 1];
-    const int64_t nv = (int64_t)*n_valid_ptr;
-    const int64_t i0 = (int64_t)blockIdx.x * 256;
-    if (i0 >= nv) {
-        const int64_t i = i0 + threadIdx.x;
-        if (i < n) gflag[i] = 0;
-        return;
-    }
-    constexpr int kTile = 256 + kNodeMax;                  // entries t <-> j = i0 - kNodeMax + t
-    for (int t = threadIdx.x; t < kTile + 1; t += 256) {
-        const int64_t j = i0 - kNodeMax + t;
-        int c = -1;
-        if (t < kTile && j >= 0 && j + kNodeMax < nv) c = common_level<KeyT>(keys[j], keys[j + kNodeMax]);
-        s_c[0][t] = (int8_t)c;
-    }
-    __syncthreads();
-    // sliding maximum over kNodeMax + 1 = 2^7 + 1 entries: seven doubling steps (window 2^s), then one more entry
-    int cur = 0;
-#pragma unroll
-    for (int st = 1; st < kNodeMax; st <<= 1) {
-        for (int t = threadIdx.x; t < kTile + 1; t += 256) {
-            const int o = t + st;
-            s_c[cur ^ 1][t] = max(s_c[cur][t], o < kTile + 1 ? s_c[cur][o] : (int8_t)-1);
-        }
-        cur ^= 1;
-        __syncthreads();
-    }
-    const int64_t i = i0 + threadIdx.x;
-    if (i >= n) return;
-    if (i >= nv) { gflag[i] = 0; return; }
-    // window of position i: j in [i - kNodeMax, i] <-> t in [threadIdx.x, threadIdx.x + kNodeMax]
-    const int depth = max((int)s_c[cur][threadIdx.x], (int)s_c[0][threadIdx.x + kNodeMax]);
-    const int level = min(depth + 1, kBits);
-    const int sh = 2 * (kBits - level);
-    bool start = (i == 0);
-    if (!start) {
-        const unsigned long long a = keys[i - 1], b = keys[i];
-        start = (a >> sh) != (b >> sh);
-    }
-    if (depth >= kBits && (i % kNodeMax) == 0) start = true;       // an over-full finest cell: runs of kNodeMax
-    gflag[i] = start ? 1 : 0;
-}
-
-// conservative lower bound (fine-cell units, FP32) of the distance between the square of node (cx, cy, edge
-// 2^shift) and the rectangle [gx0, gx1] x [gy0, gy1]
-__device__ __forceinline__ float node_box_dmin(int shift, uint32_t cx, uint32_t cy, float gx0, float gx1, float gy0, float gy1) {
-    const float s = (float)(1u << shift);
-    const float x0 = (float)cx * s, y0 = (float)cy * s;
-    const float dx = fmaxf(fmaxf(x0 - gx1, gx0 - (x0 + s)), 0.f);
-    const float dy = fmaxf(fmaxf(y0 - gy1, gy0 - (y0 + s)), 0.f);
-    return fmaxf(sqrtf(dx * dx + dy * dy) * (1.f - 1e-5f) - 3.2e-2f, 0.f);
-}
-
-// One warp per node (work-ticket order), chunks of <= 32 queries.  Exactness: every open lane tests every point of
-// every node whose square is closer to the chunk's bounding box than the largest current k-th distance of the chunk
-// (node-parallel pruning, conservative FP32).  A candidate is first screened in FP32 on coordinates relative to the
-// chunk (threshold widened by the rounding bound), then decided in float64 without FMA contraction.
-template <typename KeyT, bool STATS>
-__global__ void __launch_bounds__(kGroupWarps * 32, 5) knn_group_kernel(
-        const double2* __restrict__ pts, const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
-        const int32_t* __restrict__ gstart, int32_t* __restrict__ gcount,
-        const unsigned long long* __restrict__ n_valid_ptr, int64_t n_img, const int32_t* __restrict__ E, int Lt,
-        double hw, double inv_h, int k, int part, int n_parts, double floor2, const uint8_t* __restrict__ qmask,
-        double* __restrict__ dk, unsigned long long* __restrict__ stats) {
-    extern __shared__ double s_dyn[];                            // [kGroupWarps][k][32] k-best lists
-    __shared__ double2 s_pt[kGroupWarps][kStageCap];
-    __shared__ float2 s_pf[kGroupWarps][kStageCap];
-    __shared__ uint32_t s_stack[kGroupWarps][kGroupStack];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    double* best = s_dyn + (size_t)warp * k * 32 + lane;         // element j at best[j * 32], ascending
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const float FINF = __int_as_float(0x7f800000);
-    const int ng = gcount[0];
-    const int nv = (int)*n_valid_ptr;
-    const double h = 1.0 / inv_h;
-    unsigned long long st_groups = 0, st_q = 0, st_cand = 0, st_pass = 0, st_rounds = 0, st_nodes = 0, c_win = 0, c_walk = 0,
-                       c_leaf = 0;
-
-    for (;;) {
-        int g = 0;
-        if (lane == 0) g = atomicAdd(&gcount[1], 1);
-        g = __shfl_sync(FULL, g, 0);
-        if (g >= ng) break;
-        const int na = gstart[g], nb = (g + 1 < ng) ? gstart[g + 1] : nv;
-        const unsigned long long key0 = keys[na];
-        KnnTree<KeyT> t{keys, E, Lt, key0 >> (2 * kBits)};
-        int g_lo, g_hi;
-        node_range(t, 0, 0u, g_lo, g_hi);
-        const int nsel = g_hi - g_lo;
-        const int n_chunks = (nb - na + 31) >> 5;
-        const int per = (nb - na + n_chunks - 1) / n_chunks;
-        for (int qa = na; qa < nb; qa += per) {
-            const int qb = min(nb, qa + per);
-            const int nq = qb - qa;
-            const int s = qa + lane;
-            bool mine = lane < nq;
-            const int pid = mine ? vals[s] : 0;
-            if (mine && ((int64_t)(s - g_lo) < (int64_t)nsel * part / n_parts || (int64_t)(s - g_lo) >= (int64_t)nsel * (part + 1) / n_parts))
-                mine = false;                                     // not this call's share of the queries
-            if (mine && qmask && !(qmask[pid] & 2)) mine = false; // a tree member (halo) whose answer nobody asked for
-            if (mine && k > nsel) { dk[pid] = INF; mine = false; }
-            if (!__any_sync(FULL, mine)) continue;
-            double x = 0.0, y = 0.0;
-            if (lane < nq) { const double2 self = pts[s]; x = self.x; y = self.y; }
-            const float u = (float)((x + hw) * inv_h), v = (float)((y + hw) * inv_h);   // fine-cell units, as the keys
-            // FP32 screening frame: coordinates relative to the first query of the chunk
-            const double ox = __shfl_sync(FULL, x, 0), oy = __shfl_sync(FULL, y, 0);
-            const float qx = (float)(x - ox), qy = (float)(y - oy);
-            for (int j = 0; j < k; ++j) best[j * 32] = INF;
-            double kth = INF;
-            float thr = FINF;                                     // screening threshold on the FP32 squared distance
-            float eps = 0.f;                                      // bound of the FP32 error of a coordinate difference
-            long long t0 = 0;
-            if (STATS) { ++st_groups; st_q += __popc(__ballot_sync(FULL, mine)); t0 = clock64(); }
-
-            // every open lane tests the `total` staged candidates against its list
-            auto test_staged = [&](int total) {
-                for (int c = 0; c < total; ++c) {
-                    const float2 cf = s_pf[warp][c];
-                    const float dxf = cf.x - qx, dyf = cf.y - qy;
-                    const bool pass = mine && fmaf(dxf, dxf, dyf * dyf) < thr;
-                    if (!__any_sync(FULL, pass)) continue;
-                    if (STATS) ++st_pass;
-                    if (pass) {
-                        const double2 cp = s_pt[warp][c];
-                        const double dx = cp.x - x, dy = cp.y - y;
-                        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                        if (d2 < kth) {
-                            int j = k - 1;
-                            while (j > 0 && best[(j - 1) * 32] > d2) {
-                                best[j * 32] = best[(j - 1) * 32];
-                                --j;
-                            }
-                            best[j * 32] = d2;
-                            kth = best[(k - 1) * 32];
-                            if (kth < INF) { const float r = sqrtf((float)kth) * (1.f + 1e-6f) + eps; thr = r * r * (1.f + 1e-6f); }
-                        }
-                    }
-                }
-                if (STATS) st_cand += total;
-            };
-            // stage sorted positions [a, b) (b - a <= kStageCap) at slots off.., skipping nothing
-            auto stage_range = [&](int a, int b, int off) {
-                for (int q = a + lane; q < b; q += 32) {
-                    const double2 cp = pts[q];
-                    s_pt[warp][off + q - a] = cp;
-                    s_pf[warp][off + q - a] = make_float2((float)(cp.x - ox), (float)(cp.y - oy));
-                }
-            };
-
-            // 1. the union of the lanes' windows of sorted neighbours: [qa - k, qb + k)
-            const int wa = max(g_lo, qa - k), wb = min(g_hi, qb + k);
-            // |FP32 coordinate error| <= 2^-23 max|coordinate|: bound the frame by the chunk + window extent, refined below
-            {
-                float ext = mine ? fmaxf(fabsf(qx), fabsf(qy)) : 0.f;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ext = fmaxf(ext, __shfl_xor_sync(FULL, ext, o));
-                eps = 0.f;                                        // no threshold yet: everything passes while thr = inf
-                (void)ext;
-            }
-            for (int base = wa; base < wb; base += kStageCap) {
-                const int m = min(kStageCap, wb - base);
-                __syncwarp();
-                stage_range(base, base + m, 0);
-                __syncwarp();
-                // thr stays +inf until the lists are full; afterwards it needs eps: use the extent of what is staged
-                float ext = 0.f;
-                for (int c = lane; c < m; c += 32) ext = fmaxf(ext, fmaxf(fabsf(s_pf[warp][c].x), fabsf(s_pf[warp][c].y)));
-                ext = fmaxf(ext, mine ? fmaxf(fabsf(qx), fabsf(qy)) : 0.f);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ext = fmaxf(ext, __shfl_xor_sync(FULL, ext, o));
-                eps = fmaxf(eps, 4.8e-7f * ext);
-                if (kth < INF) { const float r = sqrtf((float)kth) * (1.f + 1e-6f) + eps; thr = r * r * (1.f + 1e-6f); }
-                test_staged(m);
-            }
-            if (STATS) { c_win += clock64() - t0; t0 = clock64(); }
-            // the caller only needs max(dk, floor): k neighbours inside the floor radius settle the answer
-            if (mine && kth <= floor2) { dk[pid] = sqrt(kth); mine = false; }
-            if (!__any_sync(FULL, mine)) continue;
-
-            // 2. bounding box of the open queries, start nodes = the <= 2 x 2 nodes covering box + largest radius
-            float gx0 = mine ? u : 3.0e38f, gx1 = mine ? u : -3.0e38f, gy0 = mine ? v : 3.0e38f, gy1 = mine ? v : -3.0e38f;
-            float rc = mine ? (float)(sqrt(kth) * inv_h) * (1.f + 1e-5f) + 3.2e-2f : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                gx0 = fminf(gx0, __shfl_xor_sync(FULL, gx0, o)); gx1 = fmaxf(gx1, __shfl_xor_sync(FULL, gx1, o));
-                gy0 = fminf(gy0, __shfl_xor_sync(FULL, gy0, o)); gy1 = fmaxf(gy1, __shfl_xor_sync(FULL, gy1, o));
-                rc = fmaxf(rc, __shfl_xor_sync(FULL, rc, o));
-            }
-            // every candidate of the walk lies within the box widened by rc: the frame extent for the FP32 error bound
-            {
-                const float ext = (fmaxf(gx1 - gx0, gy1 - gy0) + rc + 2.f) * (float)h * 1.001f;
-                eps = fmaxf(eps, 4.8e-7f * ext);
-                if (mine) { const float r = sqrtf((float)kth) * (1.f + 1e-6f) + eps; thr = r * r * (1.f + 1e-6f); }
-            }
-            int sp = 0;
-            {
-                const float x0 = gx0 - rc, x1 = gx1 + rc, y0 = gy0 - rc, y1 = gy1 + rc;
-                const float ext = fmaxf(x1 - x0, y1 - y0);
-                int e = 0;
-                if (ext >= 1.f) e = ilogbf(ext) + 1;              // 2^e > ext: the box spans at most 2 cells per axis
-                if (!(ext < (float)(1 << kBits)) || e >= kBits) {
-                    if (lane == 0) s_stack[warp][0] = 1u;         // root
-                    sp = 1;
-                } else {
-                    const int level = kBits - e;
-                    const float sc = (float)(1 << e);
-                    const int top = (1 << level) - 1;
-                    const int cx0 = max(0, min(top, (int)floorf(x0 / sc))), cx1 = max(0, min(top, (int)floorf(x1 / sc)));
-                    const int cy0 = max(0, min(top, (int)floorf(y0 / sc))), cy1 = max(0, min(top, (int)floorf(y1 / sc)));
-                    for (int cy = cy0; cy <= cy1; ++cy)
-                        for (int cx = cx0; cx <= cx1; ++cx) {
-                            if (lane == 0) s_stack[warp][sp] = (1u << (2 * level)) | morton((uint32_t)cx, (uint32_t)cy);
-                            ++sp;
-                        }
-                }
-            }
-            __syncwarp();
-
-            // 3. shared walk: each round pops up to 32 nodes, one per lane (range look-ups and pruning in parallel);
-            //    the small leaves found in the round are staged TOGETHER and tested in one pass, large ones in slabs
-            while (sp > 0) {
-                int P = min(32, sp);
-                P = min(P, max(1, (kGroupStack - 64 - sp) / 3));
-                uint32_t node = 0;
-                if (lane < P) node = s_stack[warp][sp - 1 - lane];
-                sp -= P;
-                __syncwarp();
-                bool is_leaf = false, split = false;
-                int a = 0, b = 0;
-                uint32_t code = 0;
-                int level = 0;
-                if (lane < P) {
-                    level = (31 - __clz(node)) >> 1;
-                    code = node ^ (1u << (2 * level));
-                    const uint32_t ncx = compact_bits(code), ncy = compact_bits(code >> 1);
-                    if (node_box_dmin(kBits - level, ncx, ncy, gx0, gx1, gy0, gy1) < rc) {
-                        node_range(t, level, code, a, b);
-                        if (a >= wa && b <= wb) b = a;            // wholly inside the first window: already in the lists
-                        if (a < b) {
-                            if (b - a <= kLeafCap || level == kBits) is_leaf = true; else split = true;
-                        }
-                    }
-                }
-                const unsigned sm = __ballot_sync(FULL, split);
-                const int push_at = sp + 4 * __popc(sm & lt_mask);
-                if (split && push_at + 4 > kGroupStack) { split = false; is_leaf = true; }   // no room: scan the node whole
-                const unsigned sm2 = __ballot_sync(FULL, split);
-                if (split) {
-                    const int at = sp + 4 * __popc(sm2 & lt_mask);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) s_stack[warp][at + c] = (1u << (2 * level + 2)) | (code << 2) | (uint32_t)c;
-                }
-                sp += 4 * __popc(sm2);
-                long long t1 = 0;
-                if (STATS) { ++st_rounds; st_nodes += P; t1 = clock64(); c_walk += t1 - t0; }
-                // small leaves: one slot range per lane (exclusive scan of the counts), staged together
-                const bool small = is_leaf && (b - a) <= kLeafCap;
-                int cnt = small ? b - a : 0;
-                int off = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int tmp = __shfl_up_sync(FULL, off, o);
-                    if (lane >= o) off += tmp;
-                }
-                const int total = __shfl_sync(FULL, off, 31);
-                off -= cnt;
-                __syncwarp();
-                if (total > 0) {
-                    for (int j = 0; j < cnt; ++j) {
-                        const int q = a + j;
-                        double2 cp = pts[q];
-                        if (q >= wa && q < wb) cp = make_double2(INF, INF);       // already in the lists
-                        s_pt[warp][off + j] = cp;
-                        s_pf[warp][off + j] = make_float2((float)(cp.x - ox), (float)(cp.y - oy));
-                    }
-                    __syncwarp();
-                    test_staged(total);
-                }
-                // large leaves (finest-level cells, or nodes the stack had no room to split): slabs of kStageCap
-                unsigned big = __ballot_sync(FULL, is_leaf && !small);
-                while (big) {
-                    const int src = __ffs(big) - 1;
-                    big &= big - 1;
-                    const int ba = __shfl_sync(FULL, a, src), bb = __shfl_sync(FULL, b, src);
-                    for (int base = ba; base < bb; base += kStageCap) {
-                        const int m = min(kStageCap, bb - base);
-                        if (base >= wa && base + m <= wb) continue;
-                        __syncwarp();
-                        for (int q = base + lane; q < base + m; q += 32) {
-                            double2 cp = pts[q];
-                            if (q >= wa && q < wb) cp = make_double2(INF, INF);
-                            s_pt[warp][q - base] = cp;
-                            s_pf[warp][q - base] = make_float2((float)(cp.x - ox), (float)(cp.y - oy));
-                        }
-                        __syncwarp();
-                        test_staged(m);
-                    }
-                }
-                // the radius shrinks as the lists fill
-                rc = mine ? (float)(sqrt(kth) * inv_h) * (1.f + 1e-5f) + 3.2e-2f : 0.f;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) rc = fmaxf(rc, __shfl_xor_sync(FULL, rc, o));
-                __syncwarp();
-                if (STATS) { t0 = clock64(); c_leaf += t0 - t1; }
-            }
-            if (mine) dk[pid] = sqrt(kth);
-            __syncwarp();
-        }
-    }
-    if (STATS && lane == 0) {
-        atomicAdd(&stats[0], st_groups); atomicAdd(&stats[1], st_q); atomicAdd(&stats[2], st_cand); atomicAdd(&stats[3], st_pass);
-        atomicAdd(&stats[4], st_rounds); atomicAdd(&stats[5], st_nodes); atomicAdd(&stats[8], c_win); atomicAdd(&stats[9], c_walk);
-        atomicAdd(&stats[10], c_leaf);
-    }
-}
-
-template <typename KeyT>
-__global__ void knn_outside_kernel(const KeyT* __restrict__ keys, const int32_t* __restrict__ vals, int64_t n,
-                                   const unsigned long long* __restrict__ n_valid_ptr, double* __restrict__ dk) {
-    const int64_t i = (int64_t)*n_valid_ptr + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dk[vals[i]] = 0.0;
-}
-
 __global__ void knn_range_kernel(const unsigned long long* __restrict__ counter, int part, int n_parts,
                                  int64_t* __restrict__ range_out) {
     const int64_t nsel = (int64_t)*counter;
@@ -901,54 +536,7 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     static int win_mul = 0;
     if (win_mul == 0) { const char* e = getenv("SO_KNN_WIN"); win_mul = e ? atoi(e) : 1; if (win_mul < 1) win_mul = 1; }
     const int win = k * win_mul;
-    // default: one warp per group of queries sharing a quadtree leaf (knn_group_kernel); SO_KNN_GROUP=0 selects the
-    // per-query walks (A/B aid)
-    static int use_group = -1;
-    if (use_group < 0) { const char* e = getenv("SO_KNN_GROUP"); use_group = (e && e[0] == '0') ? 0 : 1; }
-    const size_t gsmem = (size_t)kGroupWarps * k * 32 * sizeof(double);
-    if (use_group && gsmem <= 180 * 1024) {
-        { SO_PROF("knn_group_flag_kernel", st); knn_group_flag_kernel<KeyT><<<blocks, 256, 0, st>>>(keys1, n, l.counter, l.gflag); }
-        SO_LAUNCH_CHECK();
-        SO_CUDA(cudaMemsetAsync(l.gcount, 0, 4 * sizeof(int32_t), st));
-        tmp = (size_t)l.cub_tmp_bytes;
-        { SO_PROF("cub select group starts", st);
-          SO_CUDA(cub::DeviceSelect::Flagged(l.cub_tmp, tmp, cub::CountingInputIterator<int32_t>(0), l.gflag, l.gstart, l.gcount,
-                                             (int)n, st)); }
-        SO_CUDA(cudaFuncSetAttribute(knn_group_kernel<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        SO_CUDA(cudaFuncSetAttribute(knn_group_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        static unsigned long long* dstats_buf = nullptr;
-        unsigned long long* dstats = nullptr;
-        if (getenv("SO_KNN_STATS")) {                       // debugging aid: per-phase counters printed to stderr
-            if (!dstats_buf) cudaMalloc(&dstats_buf, 16 * sizeof(unsigned long long));
-            cudaMemsetAsync(dstats_buf, 0, 16 * sizeof(unsigned long long), st);
-            dstats = dstats_buf;
-        }
-        int per_sm = 8;
-        if ((size_t)per_sm * (gsmem + 32 * 1024) > 200 * 1024) per_sm = (int)(200 * 1024 / (gsmem + 32 * 1024));
-        if (per_sm < 1) per_sm = 1;
-        int64_t gblocks = (int64_t)so_num_sms() * per_sm;
-        const int64_t max_blocks = (n + kGroupWarps - 1) / kGroupWarps;
-        if (gblocks > max_blocks) gblocks = max_blocks;
-        { SO_PROF("knn_group_kernel", st);
-          if (dstats)
-              knn_group_kernel<KeyT, true><<<(unsigned)gblocks, kGroupWarps * 32, gsmem, st>>>(
-                  l.pts, keys1, l.vals1, l.gstart, l.gcount, l.counter, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts,
-                  floor2, qmask, dk, dstats);
-          else
-              knn_group_kernel<KeyT, false><<<(unsigned)gblocks, kGroupWarps * 32, gsmem, st>>>(
-                  l.pts, keys1, l.vals1, l.gstart, l.gcount, l.counter, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts,
-                  floor2, qmask, dk, dstats); }
-        if (dstats) {
-            unsigned long long hs[16];
-            cudaStreamSynchronize(st);
-            cudaMemcpy(hs, dstats, sizeof hs, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[knn stats] n=%lld k=%d chunks=%llu queries=%llu candidates=%llu passed_screen=%llu rounds=%llu nodes=%llu "
-                            "cyc_window=%llu cyc_walk=%llu cyc_leaf=%llu\n", (long long)n, k, hs[0], hs[1], hs[2], hs[3], hs[4], hs[5],
-                    hs[8], hs[9], hs[10]);
-        }
-        // particles outside their image are not in any group: their answer is 0 (as the per-query kernels write)
-        { SO_PROF("knn_outside_kernel", st); knn_outside_kernel<KeyT><<<blocks, 256, 0, st>>>(keys1, l.vals1, n, l.counter, dk); }
-    } else if (private_walk || threads != kWarpsPerCta * 32) {
+    if (private_walk || threads != kWarpsPerCta * 32) {
         SO_CUDA(cudaFuncSetAttribute(knn_query_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         { SO_PROF("knn_query_kernel", st); knn_query_kernel<KeyT><<<(unsigned)((n + threads - 1) / threads), threads, smem, st>>>(
             l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, qmask, dk); }
