@@ -740,7 +740,8 @@ def run_c4(ctx, model, F):
         if len(mine) else torch.zeros(0, dtype=torch.int64, device=dev)
     cat = synthetic.hashed_catalogue(ids)
     del ids
-    share = {'indices': mine, 'offsets': local_off, 'n_total': G}
+    shards = sdist.shard_galaxies(sizes, ctx.world)
+    share = {'indices': mine, 'offsets': local_off, 'n_total': G, 'all_indices': shards}
     share.update({k: cat[k] for k in sdist.SED_KEYS})
     n_local = int(local_off[-1])
     n_total = int(offsets[-1])
@@ -753,7 +754,7 @@ def run_c4(ctx, model, F):
     steps = max(3, min(args.steps, 10))
     sed_ms = timed_loop(ctx, sed_step, steps)
     # end to end: the share as pinned host arrays, uploaded inside the call
-    hshare = {'indices': mine, 'offsets': local_off, 'n_total': G}
+    hshare = {'indices': mine, 'offsets': local_off, 'n_total': G, 'all_indices': shards}
     hshare.update({k: cat[k].cpu().pin_memory() for k in sdist.SED_KEYS})
 
     def sed_e2e():

@@ -321,6 +321,15 @@ int so_share_plan(const double* X, const double* Y, int64_t n, double half_width
                   int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* Stable compaction of the particles whose flag byte has a bit of bit_mask set: out_index[j] = index of the j-th
+ * such particle (DEVICE int32[m]), and, where the pointers are not null, their positions and flag bytes.  m = the number
+ * of flagged particles, known from so_share_plan's counts (the caller sizes the outputs with it); *count (DEVICE) receives
+ * it again. */
+int64_t so_share_compact_workspace_bytes(int64_t n);
+int so_share_compact(const double* X, const double* Y, const uint8_t* flags, int64_t n, int32_t bit_mask, int64_t m,
+                     int32_t* out_index, double* out_X, double* out_Y, uint8_t* out_flags, int64_t* count,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* so_knn_kth_distance_ex for one image where only the particles whose query_mask byte has bit 1 set are answered
  * (query_mask: DEVICE uint8[n] or null = all); every selected particle is a member of the tree.  dk of the others
  * is left untouched. */

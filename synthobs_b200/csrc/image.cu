@@ -499,9 +499,10 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     }
 }
 
-// sub-tiles with 0 items -> zeros, 1 item -> already written, >1 -> ordered sum of the partial sub-tiles.
-// One CTA per WORK ITEM (+ one per sub-tile for the empty ones): only the first item of a split sub-tile does work, so
-// the launch is a few thousand CTAs, most of which exit at once, instead of sub-tiles x channels
+// sub-tiles with 0 items -> zeros, 1 item -> already written, >1 -> sum of the partial sub-tiles in a FIXED order
+// (four interleaved running sums, combined pairwise: deterministic, and the loads of four items are in flight).
+// blockIdx.x = work item (+ one per sub-tile for the empty ones), blockIdx.y = channel: only the first item of a split
+// sub-tile does work, so most CTAs exit at once
 __global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParams p, int n_chan, int64_t max_items) {
     int tile;
     int64_t i0, i1;
@@ -516,15 +517,22 @@ __global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParam
         i0 = p.item_start[tile]; i1 = p.item_start[tile + 1];
         if (i1 != i0) return;                              // only the empty sub-tiles are zeroed here
     }
+    const int chan = blockIdx.y;
     const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
     const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
     const int e = threadIdx.x;
     const int row = py0 + e / kT, col = px0 + e % kT;
-    for (int chan = 0; chan < n_chan; ++chan) {
-        float s = 0.f;
-        for (int64_t it = i0; it < i1; ++it) s += p.partial[((size_t)it * n_chan + chan) * (kT * kT) + e];
-        if (row < p.ndim && col < p.ndim) p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = s;
+    const float* src = p.partial + ((size_t)i0 * n_chan + chan) * (kT * kT) + e;
+    const size_t stride = (size_t)n_chan * (kT * kT);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t it = i0;
+    for (; it + 4 <= i1; it += 4) {
+        s0 += src[0]; s1 += src[stride]; s2 += src[2 * stride]; s3 += src[3 * stride];
+        src += 4 * stride;
     }
+    for (; it < i1; ++it) { s0 += src[0]; src += stride; }
+    const float s = (s0 + s1) + (s2 + s3);
+    if (row < p.ndim && col < p.ndim) p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = s;
 }
 
 // NGP products: one CTA per sub-tile; shared-memory accumulation (float64 sums, integer counts)
@@ -830,7 +838,7 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
             SO_LAUNCH_CHECK();
         }
         { SO_PROF("tile_reduce_kernel", st);
-          tile_reduce_kernel<<<(unsigned)(d.max_items + d.ntiles), kT * kT, 0, st>>>(p, n_chan, d.max_items); }
+          tile_reduce_kernel<<<dim3((unsigned)(d.max_items + d.ntiles), (unsigned)n_chan), kT * kT, 0, st>>>(p, n_chan, d.max_items); }
         SO_LAUNCH_CHECK();
     }
     if (simple || hist) {

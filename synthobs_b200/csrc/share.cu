@@ -145,6 +145,24 @@ __global__ void __launch_bounds__(512) share_flag_kernel(const double* __restric
     if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
+struct FlagSet {
+    const unsigned char* flags;
+    unsigned char mask;
+    __host__ __device__ unsigned char operator()(int i) const { return (flags[i] & mask) ? 1 : 0; }
+};
+
+__global__ void __launch_bounds__(256) share_gather_kernel(const double* __restrict__ X, const double* __restrict__ Y,
+                                                           const unsigned char* __restrict__ flags, const int32_t* __restrict__ idx,
+                                                           int64_t m, double* __restrict__ oX, double* __restrict__ oY,
+                                                           unsigned char* __restrict__ oF) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int32_t i = idx[j];
+    if (oX) oX[j] = X[i];
+    if (oY) oY[j] = Y[i];
+    if (oF) oF[j] = flags[i];
+}
+
 struct ShareLayout {
     unsigned int* hist;
     unsigned long long* cum;
@@ -211,5 +229,40 @@ extern "C" int so_share_plan(const double* X, const double* Y, int64_t n, double
     { SO_PROF("share_flag_kernel", st); share_flag_kernel<<<(unsigned)blocks, 512, 0, st>>>(X, Y, n, half_width, inv_c, nc, l.mark, flags,
                                                                                           (unsigned long long*)counts); }
     SO_LAUNCH_CHECK();
+    return SO_OK;
+}
+
+static size_t compact_tmp_bytes(int64_t n) {
+    size_t b = 0;
+    cub::TransformInputIterator<unsigned char, FlagSet, cub::CountingInputIterator<int32_t>> fl(cub::CountingInputIterator<int32_t>(0),
+                                                                                                 FlagSet{nullptr, 1});
+    cub::DeviceSelect::Flagged((void*)nullptr, b, cub::CountingInputIterator<int32_t>(0), fl, (int32_t*)nullptr, (int64_t*)nullptr,
+                               (int)(n > 0 ? n : 1));
+    return b;
+}
+
+extern "C" int64_t so_share_compact_workspace_bytes(int64_t n) { return (int64_t)so_align_up((int64_t)compact_tmp_bytes(n), 256) + 256; }
+
+extern "C" int so_share_compact(const double* X, const double* Y, const uint8_t* flags, int64_t n, int32_t bit_mask, int64_t m,
+                                int32_t* out_index, double* out_X, double* out_Y, uint8_t* out_flags, int64_t* count,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0 || m < 0 || m > n || !out_index || !count || bit_mask < 1 || bit_mask > 255) return SO_ERR_BAD_ARG;
+    if (n >= ((int64_t)1 << 31)) return SO_ERR_TOO_LARGE;
+    if (n == 0) { SO_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), st)); return SO_OK; }
+    if (!flags) return SO_ERR_BAD_ARG;
+    size_t tmp = compact_tmp_bytes(n);
+    if (!workspace || (int64_t)tmp > workspace_bytes) return SO_ERR_WORKSPACE;
+    cub::TransformInputIterator<unsigned char, FlagSet, cub::CountingInputIterator<int32_t>> fl(
+        cub::CountingInputIterator<int32_t>(0), FlagSet{flags, (unsigned char)bit_mask});
+    // stable: the selected particles keep their relative order.  out_index must hold m entries and m must be the number of
+    // flagged particles (so_share_plan's counts): DeviceSelect writes exactly that many.
+    { SO_PROF("cub select share", st);
+      SO_CUDA(cub::DeviceSelect::Flagged(workspace, tmp, cub::CountingInputIterator<int32_t>(0), fl, out_index, count, (int)n, st)); }
+    if (m > 0 && (out_X || out_Y || out_flags)) {
+        { SO_PROF("share_gather_kernel", st);
+          share_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(X, Y, flags, out_index, m, out_X, out_Y, out_flags); }
+        SO_LAUNCH_CHECK();
+    }
     return SO_OK;
 }

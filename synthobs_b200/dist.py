@@ -52,10 +52,31 @@ def shard_galaxies(sizes, n_ranks):
     return [sorted(o) for o in out]
 
 
-def gather_rows(local_rows, local_index, n_total, device=None):
-    """Every rank holds rows for the galaxy indices `local_index`; returns the full
-    [n_total, F] array on every rank (all_gather of padded blocks; the only collective of
-    the galaxy-sharded path, a few MB at most)."""
+_gather_plans = {}
+
+
+def _gather_plan(all_index, n_total, device):
+    """index bookkeeping of gather_rows for one sharding (cached: the same catalogue is gathered every step)"""
+    key = (int(n_total), str(device), hash(b'|'.join(np.asarray(i, dtype=np.int64).tobytes() for i in all_index)))
+    hit = _gather_plans.get(key)
+    if hit is None:
+        if len(_gather_plans) > 32:
+            _gather_plans.clear()
+        cmax = max(1, max(len(i) for i in all_index))
+        src = np.concatenate([r * cmax + np.arange(len(i), dtype=np.int64) for r, i in enumerate(all_index)]) \
+            if n_total else np.zeros(0, np.int64)
+        dst = np.concatenate([np.asarray(i, dtype=np.int64) for i in all_index]) if n_total else np.zeros(0, np.int64)
+        order = np.empty(n_total, dtype=np.int64)
+        order[dst] = src                       # row g of the result = row order[g] of the gathered padded blocks
+        hit = _gather_plans[key] = (cmax, torch.as_tensor(order, device=device))
+    return hit
+
+
+def gather_rows(local_rows, local_index, n_total, device=None, all_index=None):
+    """Every rank holds rows for the galaxy indices `local_index`; returns the full [n_total, ...] array on every
+    rank.  ONE all_gather of the padded blocks -- the only collective of the galaxy-sharded path, a few MB at most.
+    all_index = the index lists of ALL ranks (the sharding is deterministic, so every rank knows them: no size
+    exchange and no host synchronisation); without it the sizes are exchanged first."""
     rank, ws = world()
     rows = torch.as_tensor(local_rows)
     if ws == 1:
@@ -63,24 +84,23 @@ def gather_rows(local_rows, local_index, n_total, device=None):
         out[torch.as_tensor(local_index, dtype=torch.long, device=rows.device)] = rows
         return out
     dev = rows.device if device is None else device
-    counts = torch.zeros(ws, dtype=torch.long, device=dev)
-    counts[rank] = len(local_index)
-    dist.all_reduce(counts)
-    cmax = int(counts.max().item())
+    if all_index is None:
+        counts = torch.zeros(ws, dtype=torch.long, device=dev)
+        counts[rank] = len(local_index)
+        dist.all_reduce(counts)
+        cmax = int(counts.max().item())
+        pad_idx = torch.full((cmax,), -1, dtype=torch.long, device=dev)
+        pad_idx[:len(local_index)] = torch.as_tensor(local_index, dtype=torch.long, device=dev)
+        all_idx = [torch.empty_like(pad_idx) for _ in range(ws)]
+        dist.all_gather(all_idx, pad_idx)
+        all_index = [t[:int(c)].cpu().numpy() for t, c in zip(all_idx, counts.cpu())]
+    cmax, order = _gather_plan(all_index, n_total, dev)
     F = tuple(rows.shape[1:])
     pad_rows = torch.zeros((cmax,) + F, dtype=rows.dtype, device=dev)
     pad_rows[:len(local_index)] = rows.to(dev)
-    pad_idx = torch.full((cmax,), -1, dtype=torch.long, device=dev)
-    pad_idx[:len(local_index)] = torch.as_tensor(local_index, dtype=torch.long, device=dev)
-    all_rows = [torch.empty_like(pad_rows) for _ in range(ws)]
-    all_idx = [torch.empty_like(pad_idx) for _ in range(ws)]
-    dist.all_gather(all_rows, pad_rows)
-    dist.all_gather(all_idx, pad_idx)
-    out = torch.zeros((n_total,) + F, dtype=rows.dtype, device=dev)
-    for r in range(ws):
-        c = int(counts[r].item())
-        out[all_idx[r][:c]] = all_rows[r][:c]
-    return out
+    gathered = torch.empty((ws * cmax,) + F, dtype=rows.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, pad_rows)
+    return gathered[order]
 
 
 def sharded_galaxy_map(compute, offsets, n_filters_hint=None):
@@ -89,9 +109,10 @@ def sharded_galaxy_map(compute, offsets, n_filters_hint=None):
     rank, ws = world()
     offsets = np.asarray(offsets, dtype=np.int64)
     sizes = np.diff(offsets)
-    mine = shard_galaxies(sizes, ws)[rank]
+    shards = shard_galaxies(sizes, ws)
+    mine = shards[rank]
     rows = compute(mine)
-    return gather_rows(rows, mine, sizes.size)
+    return gather_rows(rows, mine, sizes.size, all_index=shards)
 
 
 def subset_csr(arrays, offsets, indices):
@@ -128,6 +149,9 @@ SED_KEYS = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
 MAX_PASS_PARTICLES = 40000000      # particles per images.core_batch pass of a share (core_batch_sharded)
 
 
+_last_shards = [None]
+
+
 def shard_plan(offsets, rank=None, n_ranks=None):
     """This rank's galaxies of a catalogue with CSR `offsets`: (ascending galaxy indices, their local CSR offsets)."""
     r, ws = world()
@@ -135,9 +159,11 @@ def shard_plan(offsets, rank=None, n_ranks=None):
     n_ranks = ws if n_ranks is None else n_ranks
     offsets = np.asarray(offsets, dtype=np.int64)
     sizes = np.diff(offsets)
-    mine = np.asarray(shard_galaxies(sizes, n_ranks)[rank], dtype=np.int64)
+    shards = shard_galaxies(sizes, n_ranks)
+    mine = np.asarray(shards[rank], dtype=np.int64)
     local = np.zeros(mine.size + 1, dtype=np.int64)
     np.cumsum(sizes[mine], out=local[1:])
+    _last_shards[0] = shards
     return mine, local
 
 
@@ -147,12 +173,12 @@ def local_share(batch, keys=SED_KEYS):
     not re-extracted (or re-uploaded, if its arrays are CUDA tensors) per call."""
     mine, _ = shard_plan(batch['offsets'])
     sub, off = subset_csr({k: np.asarray(batch[k]) for k in keys if k in batch}, batch['offsets'], mine)
-    sub.update(indices=mine, offsets=off, n_total=int(np.asarray(batch['offsets']).size - 1))
+    sub.update(indices=mine, offsets=off, n_total=int(np.asarray(batch['offsets']).size - 1), all_indices=_last_shards[0])
     return sub
 
 
 def _gather_share(rows, share):
-    return gather_rows(rows, share['indices'], share['n_total'])
+    return gather_rows(rows, share['indices'], share['n_total'], all_index=share.get('all_indices'))
 
 
 def generate_Fnu_sharded(model, F, batch, kind='Fnu', share=None, **kw):
@@ -257,16 +283,18 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
         mark('k-NN')
     else:
         flags, counts = images.share_plan_device(Xd, Yd, hw, int(k), rank, ws)
-        loc = torch.nonzero(flags).reshape(-1)               # local = own + halo (synchronises: sizes of the share)
-        fl = flags[loc]
-        Xl, Yl = Xd[loc], Yd[loc]
-        mark('share plan (coarse histogram, halo) + gather of the local particles')
+        n_loc, n_own = (int(v) for v in counts.cpu())        # the one host synchronisation: the sizes of the share
+        mark('share plan (coarse histogram, halo flags)')
+        loc, Xl, Yl, fl = images.share_compact_device(Xd, Yd, flags, 1, n_loc)      # local = own + halo
+        mark('compaction of the local particles')
         ix, iy = images.ngp_index_device(Xl, Yl, Gd, ndim, hw)
         mark('nearest-pixel index')
         dkl = images.knn_device_masked(Xl, Yl, ix, int(k), hw, fl, floor=images.FWHM_FLOOR)
         mark('k-NN (tree of the local particles, queries of the share)')
-        own = torch.nonzero(fl & 2).reshape(-1)
-        Xo, Yo, dko, Lo = Xl[own], Yl[own], dkl[own], Ld[:, loc[own]]
+        own, Xo, Yo, _ = images.share_compact_device(Xl, Yl, fl, 2, n_own)
+        dko = dkl.index_select(0, own)
+        Lo = Ld.index_select(1, loc.index_select(0, own))
+        mark('compaction of the own particles')
     r = images.deposit_device(Xo, Yo, Lo, resolution, ndim, adaptive_k=int(k), want_ngp=False,
                               support_sigmas=support_sigmas, dk=dko)
     mark('plan + binning + deposit of the share')

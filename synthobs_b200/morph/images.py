@@ -289,6 +289,24 @@ def share_plan_device(Xd, Yd, half_width, k, part, n_parts, cb=None):
     return flags, counts
 
 
+def share_compact_device(Xd, Yd, flags, bit_mask, m):
+    """The m particles whose flag byte has a bit of bit_mask set, in their original order (so_share_compact):
+    (index int32 [m], X [m], Y [m], flags [m]) as CUDA tensors."""
+    n = Xd.numel()
+    dev = Xd.device
+    idx = torch.empty(m, dtype=torch.int32, device=dev)
+    oX = torch.empty(m, dtype=torch.float64, device=dev)
+    oY = torch.empty(m, dtype=torch.float64, device=dev)
+    oF = torch.empty(m, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    wsb = _cabi.lib.so_share_compact_workspace_bytes(n)
+    ws = dv.workspace(wsb)
+    _cabi.check(_cabi.lib.so_share_compact(_cabi.ptr(Xd), _cabi.ptr(Yd), _cabi.ptr(flags), n, int(bit_mask), int(m), _cabi.ptr(idx),
+                                           _cabi.ptr(oX), _cabi.ptr(oY), _cabi.ptr(oF), _cabi.ptr(cnt), _cabi.ptr(ws), wsb,
+                                           _cabi.stream()), 'so_share_compact')
+    return idx, oX, oY, oF
+
+
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
                    support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1, exact_dk=False,
                    pad_to=None):
