@@ -311,15 +311,21 @@ int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, 
 
 /* One huge image over several GPUs (BASELINE config 5; the reference images one object in one Python loop,
  * synthobs/morph/images.py:83-97): split the selected particles (|x|, |y| < half_width) into n_parts spatially compact
- * shares of equal size (+- one coarse cell) -- contiguous Morton ranges of a 2^cb x 2^cb grid over the image -- and flag
+ * shares of equal WORK (+- one coarse cell; a particle of a cell too sparse to hold k particles within `floor`, the
+ * FWHM floor of synthobs/morph/images.py:89, counts 2.5 times: its query walks the tree and its support is wide) --
+ * contiguous Morton ranges of a 2^cb x 2^cb grid over the image -- and flag
  * every particle for share `part`: bit 1 (value 2) = OWN (this share answers its k-NN query and deposits it),
  * bit 0 = LOCAL (own or halo: member of this share's search tree).  The halo is sized from the coarse histogram so
  * that the k-th neighbour distance among the LOCAL particles is exact for every OWN particle (share.cu header).
+ * so_share_hist counts the selected particles [begin, end) per coarse cell (DEVICE int32[4^cb], Morton order): with
+ * several ranks each counts its 1/N of the particles and the tables are summed (ncclAllReduce) before so_share_plan.
  * counts: DEVICE uint64[2] = number of local / own particles.  Identical on every rank given identical positions. */
+int so_share_hist(const double* X, const double* Y, int64_t begin, int64_t end, double half_width, int32_t cb,
+                  int32_t* hist, void* stream);
 int64_t so_share_plan_workspace_bytes(int32_t cb);
-int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, int32_t k,
-                  int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts, void* workspace,
-                  int64_t workspace_bytes, void* stream);
+int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, const int32_t* hist,
+                  int32_t k, double floor, int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts,
+                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Stable compaction of the particles whose flag byte has a bit of bit_mask set: out_index[j] = index of the j-th
  * such particle (DEVICE int32[m]), and, where the pointers are not null, their positions and flag bytes.  m = the number

@@ -6,8 +6,9 @@
 // is OWN (this rank answers its k-NN query and deposits it) and/or LOCAL (own or halo: a member of this rank's search
 // tree), such that the k-th neighbour distance computed among the LOCAL particles is EXACT for every OWN particle:
 //
-//   1. histogram of the selected particles on a coarse 2^cb x 2^cb grid over the image (one pass, integer atomics
-//      on counters -- never on pixels -- so it is order-independent and identical on every rank);
+//   1. histogram of the selected particles on a coarse 2^cb x 2^cb grid over the image (so_share_hist: integer atomics
+//      on counters -- never on pixels -- so it is order-independent; with several ranks each one counts 1/N of the
+//      particles and the counts are summed with an all-reduce of the small table, identical on every rank);
 //   2. shares = contiguous ranges of the coarse cells in Morton order with equal cumulative counts;
 //   3. halo: a query in coarse cell c has at least k particles inside the smallest block B_m(c) of cells within
 //      Chebyshev distance m of c that holds >= k particles (summed-area table), so its k-th neighbour is at most
@@ -45,35 +46,46 @@ __device__ __forceinline__ int coarse_cell(double x, double y, double hw, double
     return (int)(sh_spread((uint32_t)cx) | (sh_spread((uint32_t)cy) << 1));
 }
 
+// counts per coarse cell in MORTON order (the order of the shares); integer atomics on counters, order-independent
 __global__ void __launch_bounds__(512) share_hist_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n,
-                                                         double hw, double inv_c, int nc, unsigned int* __restrict__ hist) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = coarse_cell(X[i], Y[i], hw, inv_c, nc);
-        if (c >= 0) atomicAdd(&hist[c], 1u);
+                                                         double hw, double inv_c, int nc, int32_t* __restrict__ hist) {
+    // neighbours in memory are often neighbours in space (a simulation writes its particles clump by clump): the lanes
+    // of a warp that hit the same cell add ONE count together
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (n + stride - 1) / stride;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t r = 0; r < rounds; ++r, i += stride) {
+        const int c = i < n ? coarse_cell(X[i], Y[i], hw, inv_c, nc) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (c >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[c], __popc(peers));
     }
 }
 
-// row-major counts -> summed-area table sat[(y + 1) * (nc + 1) + (x + 1)] = sum of cells (<= x, <= y); one CTA
-__global__ void __launch_bounds__(1024) share_sat_kernel(const unsigned int* __restrict__ hist, int nc,
-                                                         unsigned long long* __restrict__ sat) {
+// Morton-ordered counts -> summed-area table sat[(y + 1) * (nc + 1) + (x + 1)] = sum of cells (<= x, <= y):
+// row prefix sums (one thread per row), then column prefix sums (one thread per column, coalesced)
+__global__ void __launch_bounds__(128) share_sat_rows_kernel(const int32_t* __restrict__ hist, int nc, unsigned long long* __restrict__ sat) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = nc + 1;
-    for (int i = threadIdx.x; i < w; i += blockDim.x) { sat[i] = 0; sat[(size_t)i * w] = 0; }
-    __syncthreads();
-    // row prefix sums (thread per row), then column prefix sums (thread per column)
-    for (int y = threadIdx.x; y < nc; y += blockDim.x) {
-        unsigned long long acc = 0;
-        for (int x = 0; x < nc; ++x) {
-            acc += hist[sh_spread((uint32_t)x) | (sh_spread((uint32_t)y) << 1)];
-            sat[(size_t)(y + 1) * w + x + 1] = acc;
-        }
+    if (y > nc) return;
+    if (y == nc) { for (int x = 0; x < w; ++x) sat[x] = 0; return; }
+    unsigned long long acc = 0;
+    const uint32_t ybits = sh_spread((uint32_t)y) << 1;
+    sat[(size_t)(y + 1) * w] = 0;
+#pragma unroll 8
+    for (int x = 0; x < nc; ++x) {
+        acc += (unsigned long long)hist[sh_spread((uint32_t)x) | ybits];
+        sat[(size_t)(y + 1) * w + x + 1] = acc;
     }
-    __syncthreads();
-    for (int x = threadIdx.x; x < nc; x += blockDim.x) {
-        unsigned long long acc = 0;
-        for (int y = 0; y < nc; ++y) {
-            acc += sat[(size_t)(y + 1) * w + x + 1];
-            sat[(size_t)(y + 1) * w + x + 1] = acc;
-        }
+}
+__global__ void __launch_bounds__(128) share_sat_cols_kernel(int nc, unsigned long long* __restrict__ sat) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = nc + 1;
+    if (x >= nc) return;
+    unsigned long long acc = 0;
+#pragma unroll 8
+    for (int y = 0; y < nc; ++y) {
+        acc += sat[(size_t)(y + 1) * w + x + 1];
+        sat[(size_t)(y + 1) * w + x + 1] = acc;
     }
 }
 
@@ -82,8 +94,8 @@ __device__ __forceinline__ unsigned long long sat_block(const unsigned long long
     return sat[(size_t)(y1 + 1) * w + x1 + 1] - sat[(size_t)y0 * w + x1 + 1] - sat[(size_t)(y1 + 1) * w + x0] + sat[(size_t)y0 * w + x0];
 }
 
-// cum = inclusive Morton-order prefix of hist.  The share of Morton cell c is the part whose count interval holds the
-// MIDDLE of the cell's interval: contiguous ranges of cells, equal counts up to one cell.
+// cum = inclusive Morton-order prefix of the cells' WORK (share_weight_kernel).  The share of Morton cell c is the part
+// whose work interval holds the MIDDLE of the cell's interval: contiguous ranges of cells, equal work up to one cell.
 __device__ __forceinline__ int cell_share(const unsigned long long* cum, int c, unsigned long long total, int n_parts) {
     const unsigned long long lo = c ? cum[c - 1] : 0, hi = cum[c];
     if (hi == lo) return -1;                                  // empty cell: nobody's
@@ -92,18 +104,29 @@ __device__ __forceinline__ int cell_share(const unsigned long long* cum, int c, 
     return p >= n_parts ? n_parts - 1 : p;
 }
 
+// work of a cell = its particles, counted 2.5 times where the density is below dense_count per cell: there the k-th
+// neighbour lies beyond the FWHM floor, so a query walks the tree instead of being settled by its sorted window
+// (knn.cu) and its support spans many pixels
+__global__ void __launch_bounds__(256) share_weight_kernel(const int32_t* __restrict__ hist, int cells, double dense_count,
+                                                           unsigned long long* __restrict__ wgt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    const unsigned long long n = (unsigned long long)hist[c];
+    wgt[c] = ((double)n < dense_count) ? 5 * n : 2 * n;
+}
+
 // every cell of share `part` marks the cells its queries may need (see header); mark: 1 = local, 2 = own
-__global__ void __launch_bounds__(256) share_mark_kernel(const unsigned int* __restrict__ hist, const unsigned long long* __restrict__ cum,
+__global__ void __launch_bounds__(256) share_mark_kernel(const int32_t* __restrict__ hist, const unsigned long long* __restrict__ cum,
                                                          const unsigned long long* __restrict__ sat, int nc, int k, int part,
                                                          int n_parts, unsigned char* __restrict__ mark) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc * nc) return;
     const unsigned long long total = cum[nc * nc - 1];
-    if (total == 0 || cell_share(cum, c, total, n_parts) != part) return;
+    if (total == 0 || hist[c] == 0 || cell_share(cum, c, total, n_parts) != part) return;
     const int cx = (int)sh_compact((uint32_t)c), cy = (int)sh_compact((uint32_t)c >> 1);
     const int w = nc + 1;
     int m = 0;
-    if (total < (unsigned long long)k) {
+    if (sat[(size_t)w * w - 1] < (unsigned long long)k) {
         m = nc;                                               // fewer than k particles at all: every distance is inf
     } else {
         while (sat_block(sat, w, max(0, cx - m), max(0, cy - m), min(nc - 1, cx + m), min(nc - 1, cy + m)) < (unsigned long long)k) ++m;
@@ -164,8 +187,8 @@ __global__ void __launch_bounds__(256) share_gather_kernel(const double* __restr
 }
 
 struct ShareLayout {
-    unsigned int* hist;
     unsigned long long* cum;
+    unsigned long long* wgt;
     unsigned long long* sat;
     unsigned char* mark;
     void* cub_tmp;
@@ -178,58 +201,16 @@ static ShareLayout carve_share(void* ws, int64_t bytes, int cb, bool* ok) {
     const int nc = 1 << cb;
     const int64_t cells = (int64_t)nc * nc;
     SoArena a(ws, bytes);
-    l.hist = a.take<unsigned int>(cells);
     l.cum = a.take<unsigned long long>(cells);
+    l.wgt = a.take<unsigned long long>(cells);
     l.sat = a.take<unsigned long long>((int64_t)(nc + 1) * (nc + 1));
     l.mark = a.take<unsigned char>(cells);
     l.cub_bytes = 0;
-    cub::DeviceScan::InclusiveSum((void*)nullptr, l.cub_bytes, (unsigned int*)nullptr, (unsigned long long*)nullptr, (int)cells);
+    cub::DeviceScan::InclusiveSum((void*)nullptr, l.cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)cells);
     l.cub_tmp = a.take<char>((int64_t)l.cub_bytes);
     l.total = a.used;
     if (ok) *ok = a.ok();
     return l;
-}
-
-}  // namespace
-
-extern "C" int64_t so_share_plan_workspace_bytes(int32_t cb) {
-    if (cb < 1 || cb > kMaxCb) return 0;
-    return carve_share(nullptr, 0, cb, nullptr).total + 256;
-}
-
-extern "C" int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, int32_t k,
-                             int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts, void* workspace,
-                             int64_t workspace_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (n < 0 || !(half_width > 0.0) || cb < 1 || cb > kMaxCb || k < 1 || n_parts < 1 || part < 0 || part >= n_parts || !counts)
-        return SO_ERR_BAD_ARG;
-    if (n > 0 && (!X || !Y || !flags)) return SO_ERR_BAD_ARG;
-    bool ok = false;
-    ShareLayout l = carve_share(workspace, workspace_bytes, cb, &ok);
-    if (!ok || !workspace) return SO_ERR_WORKSPACE;
-    const int nc = 1 << cb;
-    const int cells = nc * nc;
-    const double inv_c = (double)nc / (2.0 * half_width);
-    SO_CUDA(cudaMemsetAsync(l.hist, 0, sizeof(unsigned int) * (size_t)cells, st));
-    SO_CUDA(cudaMemsetAsync(l.mark, 0, (size_t)cells, st));
-    SO_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(uint64_t), st));
-    if (n == 0) return SO_OK;
-    int64_t blocks = (n + 511) / 512;
-    if (blocks > 16 * so_num_sms()) blocks = 16 * so_num_sms();
-    { SO_PROF("share_hist_kernel", st); share_hist_kernel<<<(unsigned)blocks, 512, 0, st>>>(X, Y, n, half_width, inv_c, nc, l.hist); }
-    SO_LAUNCH_CHECK();
-    size_t tmp = l.cub_bytes;
-    SO_CUDA(cub::DeviceScan::InclusiveSum(l.cub_tmp, tmp, l.hist, l.cum, cells, st));
-    { SO_PROF("share_sat_kernel", st); share_sat_kernel<<<1, 1024, 0, st>>>(l.hist, nc, l.sat); }
-    SO_LAUNCH_CHECK();
-    { SO_PROF("share_mark_kernel", st); share_mark_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.hist, l.cum, l.sat, nc, k, part, n_parts, l.mark); }
-    SO_LAUNCH_CHECK();
-    { SO_PROF("share_own_kernel", st); share_own_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.cum, nc, part, n_parts, l.mark); }
-    SO_LAUNCH_CHECK();
-    { SO_PROF("share_flag_kernel", st); share_flag_kernel<<<(unsigned)blocks, 512, 0, st>>>(X, Y, n, half_width, inv_c, nc, l.mark, flags,
-                                                                                          (unsigned long long*)counts); }
-    SO_LAUNCH_CHECK();
-    return SO_OK;
 }
 
 static size_t compact_tmp_bytes(int64_t n) {
@@ -239,6 +220,69 @@ static size_t compact_tmp_bytes(int64_t n) {
     cub::DeviceSelect::Flagged((void*)nullptr, b, cub::CountingInputIterator<int32_t>(0), fl, (int32_t*)nullptr, (int64_t*)nullptr,
                                (int)(n > 0 ? n : 1));
     return b;
+}
+
+}  // namespace
+
+extern "C" int so_share_hist(const double* X, const double* Y, int64_t begin, int64_t end, double half_width, int32_t cb,
+                             int32_t* hist, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (begin < 0 || end < begin || !(half_width > 0.0) || cb < 1 || cb > kMaxCb || !hist) return SO_ERR_BAD_ARG;
+    const int nc = 1 << cb;
+    SO_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * (size_t)nc * nc, st));
+    const int64_t n = end - begin;
+    if (n == 0) return SO_OK;
+    if (!X || !Y) return SO_ERR_BAD_ARG;
+    int64_t blocks = (n + 511) / 512;
+    if (blocks > 16 * so_num_sms()) blocks = 16 * so_num_sms();
+    { SO_PROF("share_hist_kernel", st);
+      share_hist_kernel<<<(unsigned)blocks, 512, 0, st>>>(X + begin, Y + begin, n, half_width, (double)nc / (2.0 * half_width), nc, hist); }
+    SO_LAUNCH_CHECK();
+    return SO_OK;
+}
+
+extern "C" int64_t so_share_plan_workspace_bytes(int32_t cb) {
+    if (cb < 1 || cb > kMaxCb) return 0;
+    return carve_share(nullptr, 0, cb, nullptr).total + 256;
+}
+
+extern "C" int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, const int32_t* hist,
+                             int32_t k, double floor, int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0 || !(half_width > 0.0) || cb < 1 || cb > kMaxCb || k < 1 || n_parts < 1 || part < 0 || part >= n_parts || !counts || !hist)
+        return SO_ERR_BAD_ARG;
+    if (n > 0 && (!X || !Y || !flags)) return SO_ERR_BAD_ARG;
+    bool ok = false;
+    ShareLayout l = carve_share(workspace, workspace_bytes, cb, &ok);
+    if (!ok || !workspace) return SO_ERR_WORKSPACE;
+    const int nc = 1 << cb;
+    const int cells = nc * nc;
+    const double inv_c = (double)nc / (2.0 * half_width);
+    SO_CUDA(cudaMemsetAsync(l.mark, 0, (size_t)cells, st));
+    SO_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(uint64_t), st));
+    if (n == 0) return SO_OK;
+    // a cell is "dense" when k particles fit inside the floor radius: count >= k * cell area / (pi floor^2)
+    const double cell = 2.0 * half_width / nc;
+    const double dense_count = floor > 0.0 ? (double)k * cell * cell / (3.14159265358979312 * floor * floor) : 0.0;
+    { SO_PROF("share_weight_kernel", st); share_weight_kernel<<<(cells + 255) / 256, 256, 0, st>>>(hist, cells, dense_count, l.wgt); }
+    SO_LAUNCH_CHECK();
+    size_t tmp = l.cub_bytes;
+    SO_CUDA(cub::DeviceScan::InclusiveSum(l.cub_tmp, tmp, l.wgt, l.cum, cells, st));
+    { SO_PROF("share_sat_kernels", st);
+      share_sat_rows_kernel<<<(nc + 1 + 127) / 128, 128, 0, st>>>(hist, nc, l.sat);
+      share_sat_cols_kernel<<<(nc + 127) / 128, 128, 0, st>>>(nc, l.sat); }
+    SO_LAUNCH_CHECK();
+    { SO_PROF("share_mark_kernel", st); share_mark_kernel<<<(cells + 255) / 256, 256, 0, st>>>(hist, l.cum, l.sat, nc, k, part, n_parts, l.mark); }
+    SO_LAUNCH_CHECK();
+    { SO_PROF("share_own_kernel", st); share_own_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.cum, nc, part, n_parts, l.mark); }
+    SO_LAUNCH_CHECK();
+    int64_t blocks = (n + 511) / 512;
+    if (blocks > 16 * so_num_sms()) blocks = 16 * so_num_sms();
+    { SO_PROF("share_flag_kernel", st); share_flag_kernel<<<(unsigned)blocks, 512, 0, st>>>(X, Y, n, half_width, inv_c, nc, l.mark, flags,
+                                                                                          (unsigned long long*)counts); }
+    SO_LAUNCH_CHECK();
+    return SO_OK;
 }
 
 extern "C" int64_t so_share_compact_workspace_bytes(int64_t n) { return (int64_t)so_align_up((int64_t)compact_tmp_bytes(n), 256) + 256; }

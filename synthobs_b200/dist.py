@@ -282,7 +282,16 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
         dko = images.knn_device(Xo, Yo, ix, int(k), hw, floor=images.FWHM_FLOOR)
         mark('k-NN')
     else:
-        flags, counts = images.share_plan_device(Xd, Yd, hw, int(k), rank, ws)
+        n = Xd.numel()
+        cb = images.share_grid_bits(n, ws)
+        if w0 == ws and w0 > 1:
+            # every rank counts its 1/N of the particles; the small table is summed over the ranks (exact integers)
+            b, e = particle_block(n, rank, ws)
+            hist = images.share_hist_device(Xd, Yd, hw, cb, b, e)
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        else:
+            hist = images.share_hist_device(Xd, Yd, hw, cb)
+        flags, counts = images.share_plan_device(Xd, Yd, hw, int(k), rank, ws, cb=cb, hist=hist)
         n_loc, n_own = (int(v) for v in counts.cpu())        # the one host synchronisation: the sizes of the share
         mark('share plan (coarse histogram, halo flags)')
         loc, Xl, Yl, fl = images.share_compact_device(Xd, Yd, flags, 1, n_loc)      # local = own + halo

@@ -268,23 +268,39 @@ def knn_device_masked(Xd, Yd, ix, k, half_width, query_mask, floor=0.0):
     return dk
 
 
-def share_grid_bits(n):
-    """coarse grid (2^cb cells per axis) of the particle shares: ~256 particles per cell, 8 <= cells per axis <= 512"""
-    cb = int(np.floor(np.log2(max(np.sqrt(max(n, 1) / 256.0), 1.0))))
+def share_grid_bits(n, n_parts=1):
+    """coarse grid (2^cb cells per axis) of the particle shares: ~1500 particles per cell (256 x 256 cells for 1e8
+    particles: a ring of two cells around a share of 1/8 adds ~10 % halo) but at least ~500 cells per share (the
+    shares are balanced to one cell), 8 <= cells per axis <= 512"""
+    cb = int(np.floor(np.log2(max(np.sqrt(max(n, 1) / 1500.0), 1.0)) + 0.5))
+    cb = max(cb, int(np.ceil(0.5 * np.log2(500.0 * max(int(n_parts), 1)))))
     return int(min(max(cb, 3), 9))
 
 
-def share_plan_device(Xd, Yd, half_width, k, part, n_parts, cb=None):
-    """Flags of share `part` of `n_parts` of one huge image (so_share_plan): uint8 CUDA tensor, bit 0 = local (member
-    of the share's search tree: own + halo), bit 1 = own; plus the device counts [local, own]."""
+def share_hist_device(Xd, Yd, half_width, cb, begin=0, end=None):
+    """counts of the selected particles [begin, end) per coarse cell (Morton order), int32 CUDA tensor [4^cb]"""
     n = Xd.numel()
-    cb = share_grid_bits(n) if cb is None else int(cb)
+    end = n if end is None else int(end)
+    hist = torch.empty(1 << (2 * cb), dtype=torch.int32, device=Xd.device)
+    _cabi.check(_cabi.lib.so_share_hist(_cabi.ptr(Xd), _cabi.ptr(Yd), int(begin), end, float(half_width), int(cb), _cabi.ptr(hist),
+                                        _cabi.stream()), 'so_share_hist')
+    return hist
+
+
+def share_plan_device(Xd, Yd, half_width, k, part, n_parts, cb=None, hist=None):
+    """Flags of share `part` of `n_parts` of one huge image (so_share_plan): uint8 CUDA tensor, bit 0 = local (member
+    of the share's search tree: own + halo), bit 1 = own; plus the device counts [local, own].  hist = the coarse
+    histogram of ALL particles (share_hist_device; summed over the ranks when each counted a part)."""
+    n = Xd.numel()
+    cb = share_grid_bits(n, n_parts) if cb is None else int(cb)
+    if hist is None:
+        hist = share_hist_device(Xd, Yd, half_width, cb)
     flags = torch.empty(n, dtype=torch.uint8, device=Xd.device)
     counts = torch.zeros(2, dtype=torch.int64, device=Xd.device)
     wsb = _cabi.lib.so_share_plan_workspace_bytes(cb)
     ws = dv.workspace(wsb)
-    _cabi.check(_cabi.lib.so_share_plan(_cabi.ptr(Xd), _cabi.ptr(Yd), n, float(half_width), cb, int(k), int(part), int(n_parts),
-                                        _cabi.ptr(flags), _cabi.ptr(counts), _cabi.ptr(ws), wsb, _cabi.stream()),
+    _cabi.check(_cabi.lib.so_share_plan(_cabi.ptr(Xd), _cabi.ptr(Yd), n, float(half_width), cb, _cabi.ptr(hist), int(k),
+                                        float(FWHM_FLOOR), int(part), int(n_parts), _cabi.ptr(flags), _cabi.ptr(counts), _cabi.ptr(ws), wsb, _cabi.stream()),
                 'so_share_plan')
     return flags, counts
 

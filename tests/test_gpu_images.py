@@ -287,7 +287,8 @@ def test_share_plan_keeps_knn_exact(n_parts):
             assert torch.equal(dkl[o], full[loc][o])
             if cb is None:
                 owned += own.to(torch.int32)
-                assert abs(int(own.sum()) / (int(sel.sum()) / n_parts) - 1.0) < 0.1
+                # equal WORK up to one coarse cell (sparse cells weigh three times): the counts stay within a factor
+                assert 0.3 < int(own.sum()) / (int(sel.sum()) / n_parts) < 2.0
     assert torch.equal(owned, sel.to(torch.int32))
 
 
