@@ -816,13 +816,26 @@ def run_c5(ctx):
     for _ in range(2):
         sdist.image_huge(X, Y, L, res, ndim, IMG_K, stages=stages)
     stages = {k: ctx.max_over_ranks(v / 2) for k, v in stages.items()}
+    # the same step with a plain ncclAllReduce of the whole image instead of the peer-memory block exchange
+    nccl_ms = None
+    if ctx.world > 1 and sdist.peer_reduce_enabled():
+        os.environ['SO_PEER_REDUCE'] = '0'
+        try:
+            for _ in range(2):
+                step()
+            nccl_ms = timed_loop(ctx, step, max(3, min(args.steps, 5)))
+        finally:
+            os.environ['SO_PEER_REDUCE'] = '1'
     sel = float(((X.abs() < 4 * S) & (Y.abs() < 4 * S)).sum())
     return {'workload': 'config[4] single huge object: %d particles -> %d x %d, (\'adaptive\', %d), Morton-range particle '
-                        'shares, NCCL sum of the partial images' % (N, ndim, ndim, IMG_K),
+                        'shares, partial images summed over NVLink' % (N, ndim, ndim, IMG_K),
             'entry_point': 'dist.image_huge', 'scaling': 'strong', 'n_gpus': ctx.world, 'ms_per_step': ms,
             'value': N / (ms * 1e-3), 'unit': 'particles/s', 'selected': sel,
             'flux_conservation': flux / float(L[(X.abs() < 4 * S) & (Y.abs() < 4 * S)].sum()) - 1.0,
-            'stages_ms_max_over_ranks': stages, 'reduce_bytes': 4 * ndim * ndim}
+            'stages_ms_max_over_ranks': stages, 'image_bytes': 4 * ndim * ndim,
+            'reduce': 'peer-memory block exchange (csrc/peer.cu)' if (ctx.world > 1 and sdist.peer_reduce_enabled()) else
+                      ('ncclAllReduce' if ctx.world > 1 else 'none (one rank)'),
+            'ms_per_step_with_nccl_allreduce': nccl_ms}
 
 
 # ------------------------------------------------------------------ CPU baselines (oracle port)

@@ -343,6 +343,30 @@ int so_knn_kth_distance_q(const double* X, const double* Y, const int32_t* ix, i
                           const uint8_t* query_mask, double floor, double* dk, void* workspace,
                           int64_t workspace_bytes, void* stream);
 
+/* Sum of the ranks' partial images over NVLink peer memory (config 5; instead of ncclAllReduce of the whole image).
+ * The image [n_planes, ndim, ndim] (dense float32) is cut into so_peer_block_edge() = 32 pixel square exchange blocks.
+ *   so_peer_alloc / so_peer_free          device buffers that other processes may map (plain cudaMalloc)
+ *   so_ipc_get_handle / so_ipc_open / so_ipc_close   cudaIpc handle (64 bytes, HOST) of such a buffer / mapping of a peer's
+ *   so_peer_block_mask   mask[b] = 1 iff block b of the image holds a non-zero pixel (DEVICE uint8[nb * nb])
+ *   so_peer_reduce       masks = the N ranks' masks, gathered (DEVICE uint8[N][nb * nb]); partial_ptrs = HOST array of the N
+ *                        partial images (DEVICE pointers, the peers' mapped).  For every block whose lowest touching rank is
+ *                        `rank`: out = sum over the touching ranks, in rank order.  Blocks of other owners are left alone.
+ *   so_peer_gather       final_ptrs = the N ranks' result images; copies the blocks owned by other ranks from their owners
+ *                        into out, zeroes the blocks nobody touched.
+ * The caller orders the steps across ranks (all partial images complete before so_peer_reduce, all reduces complete
+ * before so_peer_gather, all gathers complete before the buffers are written again). */
+int32_t so_peer_block_edge(void);
+int so_peer_alloc(int64_t bytes, void** ptr);
+int so_peer_free(void* ptr);
+int so_ipc_get_handle(const void* ptr, void* handle64);
+int so_ipc_open(const void* handle64, void** ptr);
+int so_ipc_close(void* ptr);
+int so_peer_block_mask(const float* img, int32_t n_planes, int32_t ndim, int64_t ld, int64_t plane, uint8_t* mask, void* stream);
+int so_peer_reduce(const void* const* partial_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
+                   int32_t n_planes, int32_t ndim, float* out, void* stream);
+int so_peer_gather(const void* const* final_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
+                   int32_t n_planes, int32_t ndim, float* out, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* measurement support (bench.py); no upstream equivalent                      */
 /* ------------------------------------------------------------------------- */

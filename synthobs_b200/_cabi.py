@@ -71,6 +71,15 @@ SIGNATURES = {
     'so_recentre_segmented': (c_int, [P, P, I64, P, D, P]),
     'so_img_sersic_workspace_bytes': (I64, [I32]),
     'so_img_sersic': (c_int, [P, I32, D, D, D, D, D, D, D, P, I32, P, P, I64, P]),
+    'so_peer_block_edge': (I32, []),
+    'so_peer_alloc': (c_int, [I64, POINTER(c_void_p)]),
+    'so_peer_free': (c_int, [P]),
+    'so_ipc_get_handle': (c_int, [P, P]),
+    'so_ipc_open': (c_int, [P, POINTER(c_void_p)]),
+    'so_ipc_close': (c_int, [P]),
+    'so_peer_block_mask': (c_int, [P, I32, I32, I64, I64, P, P]),
+    'so_peer_reduce': (c_int, [POINTER(c_void_p), P, I32, I32, I32, I32, P, P]),
+    'so_peer_gather': (c_int, [POINTER(c_void_p), P, I32, I32, I32, I32, P, P]),
     'so_peak_kernel': (c_int, [I32, I64, I32, P, POINTER(c_double), P]),
     'so_prof_enable': (c_int, [I32]),
     'so_prof_report': (I64, [c_char_p, I64]),

@@ -145,6 +145,91 @@ def reduce_image(img):
     return img
 
 
+class _DevicePtr:
+    """a cudaMalloc'ed buffer seen as a CUDA array (torch.as_tensor maps it without a copy)"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {'shape': tuple(int(v) for v in shape), 'typestr': '<f4', 'data': (int(ptr), False),
+                                         'version': 3, 'strides': None}
+
+
+class PeerImage:
+    """Peer-mapped buffers for the sum of the ranks' partial images [C, ndim, ndim] without an all-reduce of the whole
+    image (csrc/peer.cu): `partial` (the deposit target) and `result`, allocated with cudaMalloc, exported with cudaIpc
+    and mapped by every other rank of the node over NVLink.  Created collectively, once per image shape."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, n_planes, ndim):
+        from . import device as dv
+        rank, ws = world()
+        key = (int(n_planes), int(ndim), ws, dv.device().index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(n_planes, ndim)
+        return cls._cache[key]
+
+    def __init__(self, n_planes, ndim):
+        from ctypes import byref, c_void_p, create_string_buffer
+        from . import _cabi, device as dv
+        self.rank, self.ws = world()
+        self.n_planes, self.ndim = int(n_planes), int(ndim)
+        self.dev = dv.device()
+        nbytes = 4 * self.n_planes * self.ndim * self.ndim
+        own = []
+        for _ in range(2):
+            p = c_void_p()
+            _cabi.check(_cabi.lib.so_peer_alloc(nbytes, byref(p)), 'so_peer_alloc')
+            own.append(p.value)
+        handles = []
+        for p in own:
+            h = create_string_buffer(64)
+            _cabi.check(_cabi.lib.so_ipc_get_handle(c_void_p(p), h), 'so_ipc_get_handle')
+            handles.append(h.raw)
+        every = [None] * self.ws
+        dist.all_gather_object(every, handles)
+        self.ptrs = [[None] * self.ws, [None] * self.ws]          # [partial | result][rank]
+        for r in range(self.ws):
+            for b in range(2):
+                if r == self.rank:
+                    self.ptrs[b][r] = own[b]
+                else:
+                    q = c_void_p()
+                    _cabi.check(_cabi.lib.so_ipc_open(create_string_buffer(every[r][b], 64), byref(q)), 'so_ipc_open')
+                    self.ptrs[b][r] = q.value
+        shape = (self.n_planes, self.ndim, self.ndim)
+        self.partial = torch.as_tensor(_DevicePtr(own[0], shape), device=self.dev)
+        self.result = torch.as_tensor(_DevicePtr(own[1], shape), device=self.dev)
+        xb = int(_cabi.lib.so_peer_block_edge())
+        self.n_blocks = ((self.ndim + xb - 1) // xb) ** 2
+        self.mask = torch.empty(self.n_blocks, dtype=torch.uint8, device=self.dev)
+        self.masks = torch.empty(self.ws * self.n_blocks, dtype=torch.uint8, device=self.dev)
+        self.token = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.c_ptrs = [(c_void_p * self.ws)(*self.ptrs[b]) for b in range(2)]
+        dist.barrier()
+
+    def reduce(self):
+        """sum of the ranks' `partial` images -> `result` on every rank (see csrc/peer.cu); stream-ordered"""
+        from . import _cabi
+        n, C = self.ndim, self.n_planes
+        _cabi.check(_cabi.lib.so_peer_block_mask(_cabi.ptr(self.partial), C, n, n, n * n, _cabi.ptr(self.mask), _cabi.stream()),
+                    'so_peer_block_mask')
+        # the all-gather of the masks is also the point after which every rank's partial image is complete
+        dist.all_gather_into_tensor(self.masks, self.mask)
+        _cabi.check(_cabi.lib.so_peer_reduce(self.c_ptrs[0], _cabi.ptr(self.masks), self.ws, self.rank, C, n,
+                                             _cabi.ptr(self.result), _cabi.stream()), 'so_peer_reduce')
+        dist.all_reduce(self.token)          # every owner has finished its blocks (and reading the partial images)
+        _cabi.check(_cabi.lib.so_peer_gather(self.c_ptrs[1], _cabi.ptr(self.masks), self.ws, self.rank, C, n,
+                                             _cabi.ptr(self.result), _cabi.stream()), 'so_peer_gather')
+        dist.all_reduce(self.token)          # every rank has its copy: the buffers may be written again
+        return self.result
+
+
+def peer_reduce_enabled():
+    """SO_PEER_REDUCE=0 selects the plain NCCL all-reduce of the whole image"""
+    return os.environ.get('SO_PEER_REDUCE', '1') != '0'
+
+
 SED_KEYS = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
 MAX_PASS_PARTICLES = 40000000      # particles per images.core_batch pass of a share (core_batch_sharded)
 
@@ -304,13 +389,25 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
         dko = dkl.index_select(0, own)
         Lo = Ld.index_select(1, loc.index_select(0, own))
         mark('compaction of the own particles')
+    peer = None
+    if reduce and ws > 1 and ws == w0 and peer_reduce_enabled():
+        try:
+            peer = PeerImage.get(Ld.shape[0], ndim)
+        except Exception as e:      # noqa: BLE001  (no peer access between the GPUs of this node: NCCL does the sum)
+            import warnings
+            warnings.warn('synthobs_b200.dist: peer-memory image reduce unavailable (%r); using ncclAllReduce' % (e,))
+            os.environ['SO_PEER_REDUCE'] = '0'
     r = images.deposit_device(Xo, Yo, Lo, resolution, ndim, adaptive_k=int(k), want_ngp=False,
-                              support_sigmas=support_sigmas, dk=dko)
+                              support_sigmas=support_sigmas, dk=dko, out=None if peer is None else peer.partial)
     mark('plan + binning + deposit of the share')
     img = r['data']
     if reduce and ws > 1:
-        img = reduce_image(img)
-        mark('all-reduce of the image')
+        if peer is not None:
+            img = peer.reduce().clone()      # the peer buffers are written again by the next call
+            mark('sum of the partial images over peer memory')
+        else:
+            img = reduce_image(img)
+            mark('all-reduce of the image')
     if stages is not None:
         torch.cuda.synchronize()
         for (_, a), (name, b) in zip(marks[:-1], marks[1:]):

@@ -325,12 +325,13 @@ def share_compact_device(Xd, Yd, flags, bit_mask, m):
 
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
                    support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1, exact_dk=False,
-                   pad_to=None):
+                   pad_to=None, out=None):
     """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
     CUDA (C images sharing positions).  Returns dict of float32 CUDA tensors:
     data [C, ndim, ndim] (adaptive only), simple [C, ndim, ndim], hist [ndim, ndim],
     plus ix, iy, dk and the stats (pairs, deposits, selected, dropped).  pad_to=(py, px): `data` is the
-    top-left window of a zero-padded buffer [C, py, px] (returned as 'data_padded') ready for the PSF transform."""
+    top-left window of a zero-padded buffer [C, py, px] (returned as 'data_padded') ready for the PSF transform.
+    out: a float32 CUDA tensor [C, ndim, ndim] to deposit into (every pixel is written) instead of a new one."""
     _cabi.require_device()
     if Ld.dim() == 1:
         Ld = Ld.reshape(1, -1)
@@ -357,7 +358,7 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
         h = n // 2
         sub = lambda t, a, b: None if t is None else t[..., a:b]   # noqa: E731
         r1 = deposit_device(Xd[:h], Yd[:h], Ld[:, :h], resolution, ndim, adaptive_k, want_data, want_ngp,
-                            support_sigmas, sub(dk, 0, h), False, img=sub(img, 0, h), n_img=n_img, pad_to=pad_to)
+                            support_sigmas, sub(dk, 0, h), False, img=sub(img, 0, h), n_img=n_img, pad_to=pad_to, out=out)
         r2 = deposit_device(Xd[h:], Yd[h:], Ld[:, h:], resolution, ndim, adaptive_k, want_data, want_ngp,
                             support_sigmas, sub(dk, h, n), False, img=sub(img, h, n), n_img=n_img, pad_to=pad_to)
         for key in ('data', 'simple', 'hist'):
@@ -372,6 +373,10 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
     if adaptive and want_data and pad_to is not None and img is None:
         padded = torch.zeros((C, int(pad_to[0]), int(pad_to[1])), dtype=torch.float32, device=dev)
         data = padded[:, :ndim, :ndim]
+    elif out is not None and adaptive and want_data and img is None:
+        if tuple(out.shape) != (C, ndim, ndim) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError('out must be a contiguous float32 tensor [C, ndim, ndim]')
+        data = out
     else:
         data = torch.empty(lead + (C, ndim, ndim), dtype=torch.float32, device=dev) if (adaptive and want_data) else None
     simple = torch.empty(lead + (C, ndim, ndim), dtype=torch.float32, device=dev) if want_ngp else None
