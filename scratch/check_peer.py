@@ -24,6 +24,16 @@ for mode in ('1', '0'):
         img = sdist.image_huge(X, Y, L, res, ndim, 8)
     torch.cuda.synchronize(); dist.barrier()
     out[mode] = (img.clone(), (time.time() - t0) * 200)
+from synthobs_b200 import _cabi
+os.environ['SO_PEER_REDUCE'] = '1'
+_cabi.prof_enable(True)
+st = {}
+sdist.image_huge(X, Y, L, res, ndim, 8, stages=st)
+torch.cuda.synchronize()
+if rank == 0:
+    print({k[:40]: round(v, 3) for k, v in st.items()})
+    print({k: round(ms, 3) for k, (c, ms) in _cabi.prof_report().items() if 'peer' in k or 'mask' in k})
+_cabi.prof_enable(False)
 whole = sdist.image_huge(X, Y, L, res, ndim, 8, rank=0, n_ranks=1, reduce=False)
 peak = float(whole.max())
 d_peer = float((out['1'][0] - whole).abs().max()) / peak

@@ -30,11 +30,20 @@ __global__ void __launch_bounds__(256) block_mask_kernel(const float* __restrict
     const int b = blockIdx.x;
     const int y0 = (b / nbx) * kXB, x0 = (b % nbx) * kXB;
     bool any = false;
-    for (int c = 0; c < n_planes; ++c)
-        for (int e = threadIdx.x; e < kXB * kXB; e += 256) {
-            const int y = y0 + e / kXB, x = x0 + e % kXB;
-            if (y < ndim && x < ndim) any |= img[(size_t)c * plane + (size_t)y * ld + x] != 0.f;
-        }
+    if (((ld | plane | ndim) & 3) == 0) {
+        const int y = y0 + threadIdx.x / 8, x = x0 + (threadIdx.x % 8) * 4;
+        if (y < ndim && x < ndim)
+            for (int c = 0; c < n_planes; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(img + (size_t)c * plane + (size_t)y * ld + x);
+                any |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+            }
+    } else {
+        for (int c = 0; c < n_planes; ++c)
+            for (int e = threadIdx.x; e < kXB * kXB; e += 256) {
+                const int y = y0 + e / kXB, x = x0 + e % kXB;
+                if (y < ndim && x < ndim) any |= img[(size_t)c * plane + (size_t)y * ld + x] != 0.f;
+            }
+    }
     const int r = __syncthreads_or(any ? 1 : 0);
     if (threadIdx.x == 0) mask[b] = r ? 1 : 0;
 }
@@ -45,24 +54,44 @@ __device__ __forceinline__ int block_owner(const unsigned char* __restrict__ mas
     return -1;
 }
 
+// one 16-byte load per thread and plane (a 32 x 32 block = 256 float4): peer loads need many bytes in flight
+template <bool VEC>
 __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerPtrs part, const unsigned char* __restrict__ masks, int n_ranks, int rank,
                                                           int n_planes, int ndim, int nbx, int64_t n_blocks, float* __restrict__ out) {
     const int b = blockIdx.x;
     if (block_owner(masks, n_ranks, n_blocks, b) != rank) return;
     const int y0 = (b / nbx) * kXB, x0 = (b % nbx) * kXB;
     const size_t plane = (size_t)ndim * ndim;
-    for (int c = 0; c < n_planes; ++c)
-        for (int e = threadIdx.x; e < kXB * kXB; e += 256) {
-            const int y = y0 + e / kXB, x = x0 + e % kXB;
-            if (y >= ndim || x >= ndim) continue;
+    unsigned touch = 0;
+    for (int r = 0; r < n_ranks; ++r) touch |= (masks[(size_t)r * n_blocks + b] ? 1u : 0u) << r;
+    if (VEC) {
+        const int y = y0 + threadIdx.x / 8, x = x0 + (threadIdx.x % 8) * 4;
+        if (y >= ndim || x >= ndim) return;
+        for (int c = 0; c < n_planes; ++c) {
             const size_t o = (size_t)c * plane + (size_t)y * ndim + x;
-            float s = 0.f;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = 0; r < n_ranks; ++r)
-                if (masks[(size_t)r * n_blocks + b]) s += part.p[r][o];        // rank order: deterministic
-            out[o] = s;
+                if (touch >> r & 1u) {                                             // rank order: deterministic
+                    const float4 v = *reinterpret_cast<const float4*>(part.p[r] + o);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+            *reinterpret_cast<float4*>(out + o) = s;
         }
+    } else {
+        for (int c = 0; c < n_planes; ++c)
+            for (int e = threadIdx.x; e < kXB * kXB; e += 256) {
+                const int y = y0 + e / kXB, x = x0 + e % kXB;
+                if (y >= ndim || x >= ndim) continue;
+                const size_t o = (size_t)c * plane + (size_t)y * ndim + x;
+                float s = 0.f;
+                for (int r = 0; r < n_ranks; ++r)
+                    if (touch >> r & 1u) s += part.p[r][o];
+                out[o] = s;
+            }
+    }
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) peer_gather_kernel(PeerPtrs fin, const unsigned char* __restrict__ masks, int n_ranks, int rank,
                                                           int n_planes, int ndim, int nbx, int64_t n_blocks, float* __restrict__ out) {
     const int b = blockIdx.x;
@@ -71,13 +100,29 @@ __global__ void __launch_bounds__(256) peer_gather_kernel(PeerPtrs fin, const un
     const int y0 = (b / nbx) * kXB, x0 = (b % nbx) * kXB;
     const size_t plane = (size_t)ndim * ndim;
     const float* src = owner >= 0 ? fin.p[owner] : nullptr;
-    for (int c = 0; c < n_planes; ++c)
-        for (int e = threadIdx.x; e < kXB * kXB; e += 256) {
-            const int y = y0 + e / kXB, x = x0 + e % kXB;
-            if (y >= ndim || x >= ndim) continue;
-            const size_t o = (size_t)c * plane + (size_t)y * ndim + x;
-            out[o] = src ? src[o] : 0.f;
+    if (VEC) {
+        const int y = y0 + threadIdx.x / 8, x = x0 + (threadIdx.x % 8) * 4;
+        if (y >= ndim || x >= ndim) return;
+        float4 v[4];
+        for (int c0 = 0; c0 < n_planes; c0 += 4) {                                  // up to four planes' loads in flight
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < n_planes)
+                    v[j] = src ? *reinterpret_cast<const float4*>(src + (size_t)(c0 + j) * plane + (size_t)y * ndim + x)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < n_planes) *reinterpret_cast<float4*>(out + (size_t)(c0 + j) * plane + (size_t)y * ndim + x) = v[j];
         }
+    } else {
+        for (int c = 0; c < n_planes; ++c)
+            for (int e = threadIdx.x; e < kXB * kXB; e += 256) {
+                const int y = y0 + e / kXB, x = x0 + e % kXB;
+                if (y >= ndim || x >= ndim) continue;
+                const size_t o = (size_t)c * plane + (size_t)y * ndim + x;
+                out[o] = src ? src[o] : 0.f;
+            }
+    }
 }
 
 }  // namespace
@@ -143,8 +188,12 @@ extern "C" int so_peer_reduce(const void* const* partial_ptrs, const uint8_t* ma
     if (rc != SO_OK || !masks || !out) return SO_ERR_BAD_ARG;
     const int nbx = (ndim + kXB - 1) / kXB;
     { SO_PROF("peer_reduce_kernel", (cudaStream_t)stream);
-      peer_reduce_kernel<<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
-                                                                                 (int64_t)nbx * nbx, out); }
+      if ((ndim & 3) == 0)
+          peer_reduce_kernel<true><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
+                                                                                           (int64_t)nbx * nbx, out);
+      else
+          peer_reduce_kernel<false><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
+                                                                                            (int64_t)nbx * nbx, out); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
@@ -156,8 +205,12 @@ extern "C" int so_peer_gather(const void* const* final_ptrs, const uint8_t* mask
     if (rc != SO_OK || !masks || !out) return SO_ERR_BAD_ARG;
     const int nbx = (ndim + kXB - 1) / kXB;
     { SO_PROF("peer_gather_kernel", (cudaStream_t)stream);
-      peer_gather_kernel<<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
-                                                                                 (int64_t)nbx * nbx, out); }
+      if ((ndim & 3) == 0)
+          peer_gather_kernel<true><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
+                                                                                           (int64_t)nbx * nbx, out);
+      else
+          peer_gather_kernel<false><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
+                                                                                            (int64_t)nbx * nbx, out); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }
