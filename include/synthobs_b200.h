@@ -244,8 +244,9 @@ int so_img_deposit_batch(const void* plan_workspace, const double* L, const int3
 
 /* so_img_deposit_batch writing `data` into a larger buffer: image (i, c) starts at
  * data + (i * n_chan + c) * data_plane and its rows are data_ld floats apart (data_ld >= ndim).  Used to
- * deposit straight into the zero-padded buffer of the PSF transform (no pad copy); the caller zeroes the
- * padding. */
+ * deposit straight into the zero-padded buffer of the PSF transform (no pad copy); the caller zeroes the WHOLE
+ * buffer (padding and image windows: sub-tiles no particle reaches are not written); a dense `data` (data_ld == ndim,
+ * data_plane == ndim * ndim) is cleared by the call itself. */
 int so_img_deposit_batch_ld(const void* plan_workspace, const double* L, const int32_t* img, int64_t n,
                             int32_t n_chan, int32_t n_img, int32_t ndim, int64_t n_pairs,
                             float* data, int64_t data_ld, int64_t data_plane, float* simple, float* hist,

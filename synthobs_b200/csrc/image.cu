@@ -499,40 +499,51 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     }
 }
 
-// sub-tiles with 0 items -> zeros, 1 item -> already written, >1 -> sum of the partial sub-tiles in a FIXED order
-// (four interleaved running sums, combined pairwise: deterministic, and the loads of four items are in flight).
-// blockIdx.x = work item (+ one per sub-tile for the empty ones), blockIdx.y = channel: only the first item of a split
-// sub-tile does work, so most CTAs exit at once
-__global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParams p, int n_chan, int64_t max_items) {
-    int tile;
-    int64_t i0, i1;
-    if ((int64_t)blockIdx.x < max_items) {
-        const int64_t item = blockIdx.x;
-        if (item >= p.item_start[p.ntiles]) return;
-        tile = p.item_tile[item];
-        i0 = p.item_start[tile]; i1 = p.item_start[tile + 1];
-        if (item != i0 || i1 - i0 == 1) return;            // not the first item of its sub-tile, or written directly
-    } else {
-        tile = (int)((int64_t)blockIdx.x - max_items);
-        i0 = p.item_start[tile]; i1 = p.item_start[tile + 1];
-        if (i1 != i0) return;                              // only the empty sub-tiles are zeroed here
+// Sub-tiles with one work item were written by the deposit kernel, empty ones keep the zeros the image was cleared
+// with; a sub-tile split over several items is the sum of their partial sub-tiles in a FIXED order (four interleaved
+// running sums, combined pairwise: deterministic, and the loads of four items are in flight).
+// One CTA looks at 32 consecutive work items (one per lane of its first warp) and finishes the sub-tiles whose FIRST
+// item is among them (blockIdx.y = channel), so the launch is max_items / 32 x channels CTAs whatever the image size.
+constexpr int kReduceItems = 32;
+__global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParams p, int n_chan) {
+    __shared__ unsigned s_todo;
+    __shared__ int s_tile[kReduceItems];
+    if (threadIdx.x < 32) {
+        const int64_t item = (int64_t)blockIdx.x * kReduceItems + threadIdx.x;
+        bool first = false;
+        int tile = 0;
+        if (item < p.item_start[p.ntiles]) {
+            tile = p.item_tile[item];
+            first = p.item_start[tile] == item && p.item_start[tile + 1] - item > 1;
+        }
+        s_tile[threadIdx.x] = tile;
+        const unsigned m = __ballot_sync(0xffffffffu, first);
+        if (threadIdx.x == 0) s_todo = m;
     }
-    const int chan = blockIdx.y;
-    const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
-    const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
+    __syncthreads();
+    unsigned todo = s_todo;
     const int e = threadIdx.x;
-    const int row = py0 + e / kT, col = px0 + e % kT;
-    const float* src = p.partial + ((size_t)i0 * n_chan + chan) * (kT * kT) + e;
-    const size_t stride = (size_t)n_chan * (kT * kT);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int64_t it = i0;
-    for (; it + 4 <= i1; it += 4) {
-        s0 += src[0]; s1 += src[stride]; s2 += src[2 * stride]; s3 += src[3 * stride];
-        src += 4 * stride;
+    while (todo) {
+        const int tile = s_tile[__ffs(todo) - 1];
+        todo &= todo - 1;
+        const int64_t i0 = p.item_start[tile], i1 = p.item_start[tile + 1];
+        const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
+        const int row = (t_in / p.ntx) * kT + e / kT, col = (t_in % p.ntx) * kT + e % kT;
+        const size_t stride = (size_t)n_chan * (kT * kT);
+        {
+            const int chan = blockIdx.y;
+            const float* src = p.partial + ((size_t)i0 * n_chan + chan) * (kT * kT) + e;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int64_t it = i0;
+            for (; it + 4 <= i1; it += 4) {
+                s0 += src[0]; s1 += src[stride]; s2 += src[2 * stride]; s3 += src[3 * stride];
+                src += 4 * stride;
+            }
+            for (; it < i1; ++it) { s0 += src[0]; src += stride; }
+            if (row < p.ndim && col < p.ndim)
+                p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = (s0 + s1) + (s2 + s3);
+        }
     }
-    for (; it < i1; ++it) { s0 += src[0]; src += stride; }
-    const float s = (s0 + s1) + (s2 + s3);
-    if (row < p.ndim && col < p.ndim) p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = s;
 }
 
 // NGP products: one CTA per sub-tile; shared-memory accumulation (float64 sums, integer counts)
@@ -817,6 +828,9 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
     p.ld = data_ld; p.plane = data_plane;
     p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0; p.wts = d.wts;
     if (data) {
+        // empty sub-tiles are never written: a dense image is cleared here; a window of a larger (padded) buffer is
+        // cleared by the caller together with its padding (contract of so_img_deposit_batch_ld)
+        if (dense) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
         { SO_PROF("weights_kernel", st); weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, pv.rec, n, n_chan, d.wts); }
         SO_LAUNCH_CHECK();
         { SO_PROF("tile_item_count_kernel", st); tile_item_count_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start); }
@@ -838,7 +852,7 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
             SO_LAUNCH_CHECK();
         }
         { SO_PROF("tile_reduce_kernel", st);
-          tile_reduce_kernel<<<dim3((unsigned)(d.max_items + d.ntiles), (unsigned)n_chan), kT * kT, 0, st>>>(p, n_chan, d.max_items); }
+          tile_reduce_kernel<<<dim3((unsigned)((d.max_items + kReduceItems - 1) / kReduceItems), (unsigned)n_chan), kT * kT, 0, st>>>(p, n_chan); }
         SO_LAUNCH_CHECK();
     }
     if (simple || hist) {
