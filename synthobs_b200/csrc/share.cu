@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(256) share_weight_kernel(const int32_t* __rest
 __global__ void __launch_bounds__(256) share_mark_kernel(const int32_t* __restrict__ hist, const unsigned long long* __restrict__ cum,
                                                          const unsigned long long* __restrict__ sat, int nc, int k, int part,
                                                          int n_parts, unsigned char* __restrict__ mark) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one WARP per cell: a sparse cell far out may need a block of thousands of cells around it
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= nc * nc) return;
     const unsigned long long total = cum[nc * nc - 1];
     if (total == 0 || hist[c] == 0 || cell_share(cum, c, total, n_parts) != part) return;
@@ -133,10 +135,12 @@ __global__ void __launch_bounds__(256) share_mark_kernel(const int32_t* __restri
     }
     // k-th neighbour within diag(B_m) = sqrt(2) (2m + 1) cell edges: Chebyshev ring M = ceil of that
     const int M = min(nc, (int)ceil(1.41421356237309515 * (double)(2 * m + 1)));
-    for (int y = max(0, cy - M); y <= min(nc - 1, cy + M); ++y)
-        for (int x = max(0, cx - M); x <= min(nc - 1, cx + M); ++x)
-            mark[sh_spread((uint32_t)x) | (sh_spread((uint32_t)y) << 1)] |= 1;      // racing writers all set bit 0
-    __threadfence();
+    const int x0 = max(0, cx - M), x1 = min(nc - 1, cx + M), y0 = max(0, cy - M), y1 = min(nc - 1, cy + M);
+    const int bw = x1 - x0 + 1, cnt = bw * (y1 - y0 + 1);
+    for (int i = lane; i < cnt; i += 32) {
+        const int x = x0 + i % bw, y = y0 + i / bw;
+        mark[sh_spread((uint32_t)x) | (sh_spread((uint32_t)y) << 1)] = 1;           // racing writers all store the same byte
+    }
 }
 
 __global__ void __launch_bounds__(256) share_own_kernel(const unsigned long long* __restrict__ cum, int nc, int part, int n_parts,
@@ -273,7 +277,7 @@ extern "C" int so_share_plan(const double* X, const double* Y, int64_t n, double
       share_sat_rows_kernel<<<(nc + 1 + 127) / 128, 128, 0, st>>>(hist, nc, l.sat);
       share_sat_cols_kernel<<<(nc + 127) / 128, 128, 0, st>>>(nc, l.sat); }
     SO_LAUNCH_CHECK();
-    { SO_PROF("share_mark_kernel", st); share_mark_kernel<<<(cells + 255) / 256, 256, 0, st>>>(hist, l.cum, l.sat, nc, k, part, n_parts, l.mark); }
+    { SO_PROF("share_mark_kernel", st); share_mark_kernel<<<(unsigned)(((int64_t)cells * 32 + 255) / 256), 256, 0, st>>>(hist, l.cum, l.sat, nc, k, part, n_parts, l.mark); }
     SO_LAUNCH_CHECK();
     { SO_PROF("share_own_kernel", st); share_own_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.cum, nc, part, n_parts, l.mark); }
     SO_LAUNCH_CHECK();
