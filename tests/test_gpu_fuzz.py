@@ -1,7 +1,6 @@
 """Randomised small configurations (ragged sizes, empty inputs, duplicates, inf / NaN coordinates, extreme weights,
 odd image sizes, every smoothing mode, 1..40 filters, missing dust arrays) through the public API against the oracle.
-The generators live in tests/_fuzz_images.py and tests/_fuzz_sed.py; run them directly with other seeds / more cases
-via scratch/fuzz_images.py and scratch/fuzz_sed.py."""
+The generators live in tests/_fuzz_images.py and tests/_fuzz_sed.py (their run(seed, n_cases) take other seeds / more cases)."""
 import pytest
 
 pytestmark = pytest.mark.gpu
