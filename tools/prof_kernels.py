@@ -35,4 +35,9 @@ for _ in range(1):
     images.median_device_pair(Xr, Yr)
     images.particle_device_multi(obs, X, Y, L)
 torch.cuda.synchronize()
+# the reference-named call (per-filter recentring chain + the same pipeline)
+PSFs = {f: synthetic.GaussianPSF(1.5 + 0.2 * i) for i, f in enumerate(filters)}
+images.particle(Xr.clone(), Yr.clone(), {f: L[i] for i, f in enumerate(filters)}, filters, cosmo, 8.0, 512 * 0.031 + 1e-9,
+                smoothing=('adaptive', 8.), PSFs=PSFs, super_sampling=2)
+torch.cuda.synchronize()
 print('done')
