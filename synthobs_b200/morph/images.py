@@ -55,6 +55,18 @@ class empty():
     pass
 
 
+def _report(title, rows):
+    """the verbose=True listing of the reference (images.py:159-178, 343-358): '***** TITLE', then 'name: value' lines
+    ('{:.2f}' unless another format is given), None = a rule of dashes"""
+    print('*' * 5, title)
+    for row in rows:
+        if row is None:
+            print('-' * 10)
+        else:
+            name, value, fmt = row
+            print(name + ': ' + (fmt or '{0:.2f}').format(value))
+
+
 # --------------------------------------------------------------------------
 # building blocks on device tensors
 # --------------------------------------------------------------------------
@@ -709,21 +721,12 @@ class observed():
         self.yoffset = yoffset_pix * self.pixel_scale_kpc
 
         if verbose:
-            print('*' * 5, 'OBSERVED')
-            print('z: {0}'.format(z))
-            print('"/kpc: {0:.2f}'.format(self.arcsec_per_proper_kpc))
-            print('-' * 10)
-            print('target width/": {0:.2f}'.format(self.target_width_arcsec))
-            print('width/": {0:.2f}'.format(self.width_arcsec))
-            print('width/kpc: {0:.2f}'.format(self.width))
-            print('-' * 10)
-            print('native pixel scale/": {0:.2f}'.format(self.native_pixel_scale))
-            print('pixel scale/": {0:.2f}'.format(self.pixel_scale))
-            print('pixel scale/kpc: {0:.2f}'.format(self.pixel_scale_kpc))
-            print('super sampling: {0:.2f}'.format(self.super_sampling))
-            print('resolution/kpc: {0:.2f}'.format(self.resolution))
-            print('ndim: {0:.2f}'.format(self.ndim))
-            print('-' * 10)
+            _report('OBSERVED', [('z', z, '{0}'), ('"/kpc', self.arcsec_per_proper_kpc, None), None,
+                                 ('target width/"', self.target_width_arcsec, None), ('width/"', self.width_arcsec, None),
+                                 ('width/kpc', self.width, None), None,
+                                 ('native pixel scale/"', self.native_pixel_scale, None), ('pixel scale/"', self.pixel_scale, None),
+                                 ('pixel scale/kpc', self.pixel_scale_kpc, None), ('super sampling', self.super_sampling, None),
+                                 ('resolution/kpc', self.resolution, None), ('ndim', self.ndim, None), None])
 
     def psf_kernel(self):
         """PSF image on the super-sampled grid; depends only on the geometry fixed at
@@ -1022,16 +1025,9 @@ def point(flux, filter, target_width_arcsec, resampling_factor=False, pixel_scal
     yoffset_arcsec = yoffset_pix * pixel_scale
 
     if verbose:
-        print('*' * 5, 'POINT')
-        print('-' * 10)
-        print('target width/": {0:.2f}'.format(target_width_arcsec))
-        print('width/": {0:.2f}'.format(width_arcsec))
-        print('-' * 10)
-        print('native pixel scale/": {0:.2f}'.format(native_pixel_scale))
-        print('pixel scale/": {0:.2f}'.format(pixel_scale))
-        print('super sampling: {0:.2f}'.format(super_sampling))
-        print('ndim: {0:.2f}'.format(ndim))
-        print('-' * 10)
+        _report('POINT', [None, ('target width/"', target_width_arcsec, None), ('width/"', width_arcsec, None), None,
+                          ('native pixel scale/"', native_pixel_scale, None), ('pixel scale/"', pixel_scale, None),
+                          ('super sampling', super_sampling, None), ('ndim', ndim, None), None])
 
     host = not dv.is_device_tensor(flux)
     fd = dv.to_dev(np.atleast_1d(np.asarray(flux, dtype=np.float64))) if host else flux.reshape(-1).to(torch.float64)
