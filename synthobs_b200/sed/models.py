@@ -644,8 +644,13 @@ def sed_spectra_device(model, Masses, Ages, Metallicities, tauVs_ISM=False, tauV
         key, order = torch.sort(cell, stable=True)
     else:
         off = dv.to_dev(offsets, torch.int64)
-        gal = torch.repeat_interleave(torch.arange(G, device=M.device, dtype=torch.int64), off[1:] - off[:-1])
-        _, order = torch.sort(gal * (1 << 17) + cell.to(torch.int64), stable=True)     # (galaxy, young, cell)
+        # galaxy of every particle by bisection of the offsets; (galaxy, young, cell) fits 31 bits for up to 2^14
+        # galaxies, so the radix sort runs four 8-bit passes instead of eight
+        gal = torch.searchsorted(off[1:], torch.arange(n, device=M.device, dtype=torch.int64), right=True)
+        if G <= (1 << 14):
+            _, order = torch.sort((gal << 17).to(torch.int32) + cell, stable=True)
+        else:
+            _, order = torch.sort((gal << 17) + cell.to(torch.int64), stable=True)
         key = cell[order]
     order = order.to(torch.int32)
     bc = torch.empty((G, nl), dtype=torch.float32, device=M.device)

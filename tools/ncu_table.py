@@ -1,7 +1,8 @@
 """Summarise an .ncu-rep (first launch of every distinct kernel) as a markdown table."""
 import csv, subprocess, sys
 rep = sys.argv[1]
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+raw = open(rep, errors='replace').read() if rep.endswith('.csv') else \
+    subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
