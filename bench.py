@@ -362,9 +362,9 @@ def run_sed(ctx):
                    'parallelism': 'galaxies sharded by rank, no collective'},
         'particles_per_s': ctx.world * n_part / (ms_step * 1e-3),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
-                     'traffic': 1.0397e9 if n_part == 25600000 else None,
+                     'traffic': 1.0369e9 if n_part == 25600000 else None,
                      'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
-                                       '(profiles/): 1.031 GB read + 8.3 MB written vs 1.024 GB algorithmic',
+                                       '(profiles/r02_ncu_kernels.md): 1.030 GB read + 6.9 MB written vs 1.024 GB algorithmic',
                      'peak_source': ctx.peaks['source'], 'kernel': kname, 'kernel_ms_per_launch': kms,
                      'algorithmic_bytes_per_particle': 40, 'algorithmic_bytes_per_launch': algo_bytes,
                      'step_frac': algo_bytes / (ms_step * 1e-3) / 1e9 / hbm,
@@ -488,10 +488,10 @@ def run_spectra(ctx, model, F):
                              'roofline': {'bound': 'tensor', 'achieved': flops / gms / 1e9, 'peak': tf32_peak,
                                           'unit': 'TFLOP/s', 'frac': flops / gms / 1e9 / tf32_peak,
                                           'executed_frac': 3 * flops / gms / 1e9 / tf32_peak,
-                                          'traffic': 1.96e9 if (M, n_lam, K) == (20000, 9000, 1326) else None,
+                                          'traffic': 1.95e9 if (M, n_lam, K) == (20000, 9000, 1326) else None,
                                           'algorithmic_bytes': 4.0 * (M * K + n_lam * K + M * n_lam),
-                                          'traffic_note': 'ncu dram read 1.26 GB + write 0.70 GB per launch '
-                                                          '(profiles/r01_ncu_kernels.md)',
+                                          'traffic_note': 'ncu dram read 1.25 GB + write 0.70 GB per launch '
+                                                          '(profiles/r02_ncu_kernels.md)',
                                           'peak_source': src,
                                           'note': 'achieved = ALGORITHMIC flops 2*M*N*K (SURVEY 8d: the x3 of 3xTF32 is '
                                                   'implementation overhead); executed_frac counts the three TF32 MMAs '
