@@ -741,7 +741,7 @@ def run_c4(ctx, model, F):
     cat = synthetic.hashed_catalogue(ids)
     del ids
     shards = sdist.shard_galaxies(sizes, ctx.world)
-    share = {'indices': mine, 'offsets': local_off, 'n_total': G, 'all_indices': shards}
+    share = {'indices': mine, 'offsets': torch.from_numpy(local_off).to(dev), 'n_total': G, 'all_indices': shards}   # resident
     share.update({k: cat[k] for k in sdist.SED_KEYS})
     n_local = int(local_off[-1])
     n_total = int(offsets[-1])

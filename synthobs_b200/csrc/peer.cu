@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerPtrs part, const u
 template <bool VEC>
 __global__ void __launch_bounds__(256) peer_gather_kernel(PeerPtrs fin, const unsigned char* __restrict__ masks, int n_ranks, int rank,
                                                           int n_planes, int ndim, int nbx, int64_t n_blocks, float* __restrict__ out) {
-    const int b = blockIdx.x;
+    // every rank starts its sweep at a different block: otherwise all readers would pull from the same owner at the
+    // same time (the blocks of an owner are clustered) and its outgoing links would serialise the whole exchange
+    const int b = (int)(((int64_t)blockIdx.x + (int64_t)rank * (n_blocks / n_ranks)) % n_blocks);
     const int owner = block_owner(masks, n_ranks, n_blocks, b);
     if (owner == rank) return;
     const int y0 = (b / nbx) * kXB, x0 = (b % nbx) * kXB;

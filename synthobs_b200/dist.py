@@ -96,7 +96,7 @@ def gather_rows(local_rows, local_index, n_total, device=None, all_index=None):
         all_index = [t[:int(c)].cpu().numpy() for t, c in zip(all_idx, counts.cpu())]
     cmax, order = _gather_plan(all_index, n_total, dev)
     F = tuple(rows.shape[1:])
-    pad_rows = torch.zeros((cmax,) + F, dtype=rows.dtype, device=dev)
+    pad_rows = torch.empty((cmax,) + F, dtype=rows.dtype, device=dev)        # the padding rows are never read back
     pad_rows[:len(local_index)] = rows.to(dev)
     gathered = torch.empty((ws * cmax,) + F, dtype=rows.dtype, device=dev)
     dist.all_gather_into_tensor(gathered, pad_rows)
