@@ -349,13 +349,11 @@ int so_knn_kth_distance_q(const double* X, const double* Y, const int32_t* ix, i
  *   so_peer_alloc / so_peer_free          device buffers that other processes may map (plain cudaMalloc)
  *   so_ipc_get_handle / so_ipc_open / so_ipc_close   cudaIpc handle (64 bytes, HOST) of such a buffer / mapping of a peer's
  *   so_peer_block_mask   mask[b] = 1 iff block b of the image holds a non-zero pixel (DEVICE uint8[nb * nb])
- *   so_peer_reduce       masks = the N ranks' masks, gathered (DEVICE uint8[N][nb * nb]); partial_ptrs = HOST array of the N
- *                        partial images (DEVICE pointers, the peers' mapped).  For every block whose lowest touching rank is
- *                        `rank`: out = sum over the touching ranks, in rank order.  Blocks of other owners are left alone.
- *   so_peer_gather       final_ptrs = the N ranks' result images; copies the blocks owned by other ranks from their owners
- *                        into out, zeroes the blocks nobody touched.
- * The caller orders the steps across ranks (all partial images complete before so_peer_reduce, all reduces complete
- * before so_peer_gather, all gathers complete before the buffers are written again). */
+ *   so_peer_sum          masks = the N ranks' masks, gathered (DEVICE uint8[N][nb * nb]); partial_ptrs = HOST array of the N
+ *                        partial images (DEVICE pointers, the peers' mapped).  out (DEVICE, this rank's own memory) = for
+ *                        every block the sum over the ranks that touched it, in rank order; zero where nobody did.
+ * The caller orders the steps across ranks: all partial images complete before so_peer_sum (the all-gather of the masks
+ * does that), and no rank rewrites a partial image a peer may still be reading (two alternating buffers). */
 int32_t so_peer_block_edge(void);
 int so_peer_alloc(int64_t bytes, void** ptr);
 int so_peer_free(void* ptr);
@@ -363,10 +361,8 @@ int so_ipc_get_handle(const void* ptr, void* handle64);
 int so_ipc_open(const void* handle64, void** ptr);
 int so_ipc_close(void* ptr);
 int so_peer_block_mask(const float* img, int32_t n_planes, int32_t ndim, int64_t ld, int64_t plane, uint8_t* mask, void* stream);
-int so_peer_reduce(const void* const* partial_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
-                   int32_t n_planes, int32_t ndim, float* out, void* stream);
-int so_peer_gather(const void* const* final_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
-                   int32_t n_planes, int32_t ndim, float* out, void* stream);
+int so_peer_sum(const void* const* partial_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
+                int32_t n_planes, int32_t ndim, float* out, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* measurement support (bench.py); no upstream equivalent                      */

@@ -4,14 +4,13 @@
 // A plain all-reduce moves the whole image 2 (N-1)/N times per rank although every partial image is spatially compact
 // (a rank deposits one share of the particles) and nearly disjoint from the others.  Here the image is cut into
 // 32 x 32 pixel exchange blocks; every rank publishes which blocks its partial image touches (one byte per block),
-// and after one all-gather of those masks two kernels finish the job over peer-mapped memory (cudaIpc, NVLink/NVSwitch
-// loads):
-//   so_peer_reduce   the OWNER of a block -- the lowest rank that touched it, so its own contribution is local --
-//                    adds the touching ranks' partial blocks in rank order (deterministic) into its result image;
-//   so_peer_gather   every rank copies the blocks it does not own from their owners' result images (untouched blocks
-//                    are zeroed locally, nothing is transferred for them).
-// Only overlapping blocks cross the links in the first step and every block crosses at most once per reader in the
-// second.  The ordering between the steps is the caller's (a tiny collective between them; synthobs_b200/dist.py).
+// and after one all-gather of those masks ONE kernel finishes the job over peer-mapped memory (cudaIpc, NVLink/NVSwitch
+// loads): so_peer_sum adds, for every block, the partial blocks of the ranks that touched it, in rank order
+// (deterministic and identical on every rank); untouched blocks are zeroed locally.  A block crosses the links once per
+// reader and touching rank -- (N-1)/N of the image plus the few overlapping blocks, against 2 (N-1)/N for the all-reduce
+// -- and the all-gather of the masks is the only synchronisation (it also marks the point after which every rank's
+// partial image is complete); the caller alternates two partial buffers so that nobody overwrites what a slower
+// peer may still be reading (synthobs_b200/dist.py).
 #include <string.h>
 
 #include "common.cuh"
@@ -48,18 +47,15 @@ __global__ void __launch_bounds__(256) block_mask_kernel(const float* __restrict
     if (threadIdx.x == 0) mask[b] = r ? 1 : 0;
 }
 
-__device__ __forceinline__ int block_owner(const unsigned char* __restrict__ masks, int n_ranks, int64_t n_blocks, int b) {
-    for (int r = 0; r < n_ranks; ++r)
-        if (masks[(size_t)r * n_blocks + b]) return r;
-    return -1;
-}
-
-// one 16-byte load per thread and plane (a 32 x 32 block = 256 float4): peer loads need many bytes in flight
+// out = sum over the ranks whose mask has the block, in rank order (deterministic, the same on every rank); blocks
+// nobody touched are zeroed locally.  One 16-byte load per thread, plane and touching rank (a 32 x 32 block = 256
+// float4): peer loads need many bytes in flight.  Every rank starts its sweep at a different block: otherwise all
+// readers would pull from the same rank at the same time (a rank's blocks are clustered) and its outgoing links would
+// serialise the exchange.
 template <bool VEC>
-__global__ void __launch_bounds__(256) peer_reduce_kernel(PeerPtrs part, const unsigned char* __restrict__ masks, int n_ranks, int rank,
-                                                          int n_planes, int ndim, int nbx, int64_t n_blocks, float* __restrict__ out) {
-    const int b = blockIdx.x;
-    if (block_owner(masks, n_ranks, n_blocks, b) != rank) return;
+__global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs part, const unsigned char* __restrict__ masks, int n_ranks, int rank,
+                                                       int n_planes, int ndim, int nbx, int64_t n_blocks, float* __restrict__ out) {
+    const int b = (int)(((int64_t)blockIdx.x + (int64_t)rank * (n_blocks / n_ranks)) % n_blocks);
     const int y0 = (b / nbx) * kXB, x0 = (b % nbx) * kXB;
     const size_t plane = (size_t)ndim * ndim;
     unsigned touch = 0;
@@ -70,11 +66,10 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerPtrs part, const u
         for (int c = 0; c < n_planes; ++c) {
             const size_t o = (size_t)c * plane + (size_t)y * ndim + x;
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < n_ranks; ++r)
-                if (touch >> r & 1u) {                                             // rank order: deterministic
-                    const float4 v = *reinterpret_cast<const float4*>(part.p[r] + o);
-                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                }
+            for (unsigned t = touch; t; t &= t - 1) {
+                const float4 v = *reinterpret_cast<const float4*>(part.p[__ffs(t) - 1] + o);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
             *reinterpret_cast<float4*>(out + o) = s;
         }
     } else {
@@ -84,45 +79,8 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerPtrs part, const u
                 if (y >= ndim || x >= ndim) continue;
                 const size_t o = (size_t)c * plane + (size_t)y * ndim + x;
                 float s = 0.f;
-                for (int r = 0; r < n_ranks; ++r)
-                    if (touch >> r & 1u) s += part.p[r][o];
+                for (unsigned t = touch; t; t &= t - 1) s += part.p[__ffs(t) - 1][o];
                 out[o] = s;
-            }
-    }
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(256) peer_gather_kernel(PeerPtrs fin, const unsigned char* __restrict__ masks, int n_ranks, int rank,
-                                                          int n_planes, int ndim, int nbx, int64_t n_blocks, float* __restrict__ out) {
-    // every rank starts its sweep at a different block: otherwise all readers would pull from the same owner at the
-    // same time (the blocks of an owner are clustered) and its outgoing links would serialise the whole exchange
-    const int b = (int)(((int64_t)blockIdx.x + (int64_t)rank * (n_blocks / n_ranks)) % n_blocks);
-    const int owner = block_owner(masks, n_ranks, n_blocks, b);
-    if (owner == rank) return;
-    const int y0 = (b / nbx) * kXB, x0 = (b % nbx) * kXB;
-    const size_t plane = (size_t)ndim * ndim;
-    const float* src = owner >= 0 ? fin.p[owner] : nullptr;
-    if (VEC) {
-        const int y = y0 + threadIdx.x / 8, x = x0 + (threadIdx.x % 8) * 4;
-        if (y >= ndim || x >= ndim) return;
-        float4 v[4];
-        for (int c0 = 0; c0 < n_planes; c0 += 4) {                                  // up to four planes' loads in flight
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (c0 + j < n_planes)
-                    v[j] = src ? *reinterpret_cast<const float4*>(src + (size_t)(c0 + j) * plane + (size_t)y * ndim + x)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (c0 + j < n_planes) *reinterpret_cast<float4*>(out + (size_t)(c0 + j) * plane + (size_t)y * ndim + x) = v[j];
-        }
-    } else {
-        for (int c = 0; c < n_planes; ++c)
-            for (int e = threadIdx.x; e < kXB * kXB; e += 256) {
-                const int y = y0 + e / kXB, x = x0 + e % kXB;
-                if (y >= ndim || x >= ndim) continue;
-                const size_t o = (size_t)c * plane + (size_t)y * ndim + x;
-                out[o] = src ? src[o] : 0.f;
             }
     }
 }
@@ -183,36 +141,19 @@ static int peer_args(const void* const* ptrs, int32_t n_ranks, int32_t rank, int
     return SO_OK;
 }
 
-extern "C" int so_peer_reduce(const void* const* partial_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
-                              int32_t n_planes, int32_t ndim, float* out, void* stream) {
+extern "C" int so_peer_sum(const void* const* partial_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
+                           int32_t n_planes, int32_t ndim, float* out, void* stream) {
     PeerPtrs pp{};
     int rc = peer_args(partial_ptrs, n_ranks, rank, n_planes, ndim, &pp);
     if (rc != SO_OK || !masks || !out) return SO_ERR_BAD_ARG;
     const int nbx = (ndim + kXB - 1) / kXB;
-    { SO_PROF("peer_reduce_kernel", (cudaStream_t)stream);
+    { SO_PROF("peer_sum_kernel", (cudaStream_t)stream);
       if ((ndim & 3) == 0)
-          peer_reduce_kernel<true><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
-                                                                                           (int64_t)nbx * nbx, out);
+          peer_sum_kernel<true><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
+                                                                                        (int64_t)nbx * nbx, out);
       else
-          peer_reduce_kernel<false><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
-                                                                                            (int64_t)nbx * nbx, out); }
-    SO_LAUNCH_CHECK();
-    return SO_OK;
-}
-
-extern "C" int so_peer_gather(const void* const* final_ptrs, const uint8_t* masks, int32_t n_ranks, int32_t rank,
-                              int32_t n_planes, int32_t ndim, float* out, void* stream) {
-    PeerPtrs pp{};
-    int rc = peer_args(final_ptrs, n_ranks, rank, n_planes, ndim, &pp);
-    if (rc != SO_OK || !masks || !out) return SO_ERR_BAD_ARG;
-    const int nbx = (ndim + kXB - 1) / kXB;
-    { SO_PROF("peer_gather_kernel", (cudaStream_t)stream);
-      if ((ndim & 3) == 0)
-          peer_gather_kernel<true><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
-                                                                                           (int64_t)nbx * nbx, out);
-      else
-          peer_gather_kernel<false><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
-                                                                                            (int64_t)nbx * nbx, out); }
+          peer_sum_kernel<false><<<(unsigned)(nbx * nbx), 256, 0, (cudaStream_t)stream>>>(pp, masks, n_ranks, rank, n_planes, ndim, nbx,
+                                                                                         (int64_t)nbx * nbx, out); }
     SO_LAUNCH_CHECK();
     return SO_OK;
 }

@@ -155,8 +155,9 @@ class _DevicePtr:
 
 class PeerImage:
     """Peer-mapped buffers for the sum of the ranks' partial images [C, ndim, ndim] without an all-reduce of the whole
-    image (csrc/peer.cu): `partial` (the deposit target) and `result`, allocated with cudaMalloc, exported with cudaIpc
-    and mapped by every other rank of the node over NVLink.  Created collectively, once per image shape."""
+    image (csrc/peer.cu): two alternating `partial` buffers (the deposit target of successive calls), allocated with
+    cudaMalloc, exported with cudaIpc and mapped by every other rank of the node over NVLink.  Created collectively,
+    once per image shape."""
 
     _cache = {}
 
@@ -188,7 +189,7 @@ class PeerImage:
             handles.append(h.raw)
         every = [None] * self.ws
         dist.all_gather_object(every, handles)
-        self.ptrs = [[None] * self.ws, [None] * self.ws]          # [partial | result][rank]
+        self.ptrs = [[None] * self.ws, [None] * self.ws]          # [buffer 0 | 1][rank]
         for r in range(self.ws):
             for b in range(2):
                 if r == self.rank:
@@ -198,31 +199,35 @@ class PeerImage:
                     _cabi.check(_cabi.lib.so_ipc_open(create_string_buffer(every[r][b], 64), byref(q)), 'so_ipc_open')
                     self.ptrs[b][r] = q.value
         shape = (self.n_planes, self.ndim, self.ndim)
-        self.partial = torch.as_tensor(_DevicePtr(own[0], shape), device=self.dev)
-        self.result = torch.as_tensor(_DevicePtr(own[1], shape), device=self.dev)
+        self.partials = [torch.as_tensor(_DevicePtr(own[b], shape), device=self.dev) for b in range(2)]
+        self.parity = 0
         xb = int(_cabi.lib.so_peer_block_edge())
         self.n_blocks = ((self.ndim + xb - 1) // xb) ** 2
         self.mask = torch.empty(self.n_blocks, dtype=torch.uint8, device=self.dev)
         self.masks = torch.empty(self.ws * self.n_blocks, dtype=torch.uint8, device=self.dev)
-        self.token = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.c_ptrs = [(c_void_p * self.ws)(*self.ptrs[b]) for b in range(2)]
         dist.barrier()
 
+    @property
+    def partial(self):
+        """the buffer this call deposits into"""
+        return self.partials[self.parity]
+
     def reduce(self):
-        """sum of the ranks' `partial` images -> `result` on every rank (see csrc/peer.cu); stream-ordered"""
+        """sum of the ranks' current `partial` images -> a new tensor on every rank (csrc/peer.cu); stream-ordered.
+        The next call deposits into the other buffer, so a slower peer may still be reading this one: by the time a
+        buffer comes round again an all-gather (a barrier for the kernels before it) lies in between."""
         from . import _cabi
-        n, C = self.ndim, self.n_planes
-        _cabi.check(_cabi.lib.so_peer_block_mask(_cabi.ptr(self.partial), C, n, n, n * n, _cabi.ptr(self.mask), _cabi.stream()),
+        n, C, b = self.ndim, self.n_planes, self.parity
+        _cabi.check(_cabi.lib.so_peer_block_mask(_cabi.ptr(self.partials[b]), C, n, n, n * n, _cabi.ptr(self.mask), _cabi.stream()),
                     'so_peer_block_mask')
         # the all-gather of the masks is also the point after which every rank's partial image is complete
         dist.all_gather_into_tensor(self.masks, self.mask)
-        _cabi.check(_cabi.lib.so_peer_reduce(self.c_ptrs[0], _cabi.ptr(self.masks), self.ws, self.rank, C, n,
-                                             _cabi.ptr(self.result), _cabi.stream()), 'so_peer_reduce')
-        dist.all_reduce(self.token)          # every owner has finished its blocks (and reading the partial images)
-        _cabi.check(_cabi.lib.so_peer_gather(self.c_ptrs[1], _cabi.ptr(self.masks), self.ws, self.rank, C, n,
-                                             _cabi.ptr(self.result), _cabi.stream()), 'so_peer_gather')
-        dist.all_reduce(self.token)          # every rank has its copy: the buffers may be written again
-        return self.result
+        out = torch.empty((C, n, n), dtype=torch.float32, device=self.dev)
+        _cabi.check(_cabi.lib.so_peer_sum(self.c_ptrs[b], _cabi.ptr(self.masks), self.ws, self.rank, C, n, _cabi.ptr(out),
+                                          _cabi.stream()), 'so_peer_sum')
+        self.parity ^= 1
+        return out
 
 
 def peer_reduce_enabled():
@@ -403,7 +408,7 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
     img = r['data']
     if reduce and ws > 1:
         if peer is not None:
-            img = peer.reduce().clone()      # the peer buffers are written again by the next call
+            img = peer.reduce()
             mark('sum of the partial images over peer memory')
         else:
             img = reduce_image(img)
