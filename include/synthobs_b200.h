@@ -38,6 +38,7 @@ extern "C" {
 
 #define SO_MAX_FILTERS 32 /* filters per so_sed_broadband launch (smem tables) */
 #define SO_TILE 16        /* image sub-tile edge in pixels (so_img_*) */
+#define SO_MAX_PEERS 16   /* ranks of one node that may share a huge image (so_img_deposit_push) */
 
 /* library / build identification; returns a static string */
 const char* so_version(void);
@@ -343,6 +344,35 @@ int so_share_compact(const double* X, const double* Y, const uint8_t* flags, int
 int so_knn_kth_distance_q(const double* X, const double* Y, const int32_t* ix, int64_t n, int32_t k, double half_width,
                           const uint8_t* query_mask, double floor, double* dk, void* workspace,
                           int64_t workspace_bytes, void* stream);
+
+/* so_img_deposit_batch_ld for ONE image shared by the GPUs of a node, with the exchange of the partial images fused into
+ * the deposit (config 5; replaces deposit + ncclAllReduce).  Every pointer array holds one DEVICE pointer per rank
+ * (the peers' mapped with so_ipc_open; entry `rank` is this rank's own buffer):
+ *   partial  the ranks' partial images [n_chan, ndim, ndim]; partial[rank] must be `data` (dense)
+ *   result   the ranks' result images, same layout
+ *   masks    uint8 [n_ranks][ntiles] per rank, ntiles = ceil(ndim / SO_TILE)^2
+ *   flags    uint64 [n_ranks] per rank, zero before the first call
+ *   epoch    generation of this call: starts at 1, +1 per call, the same on every rank
+ * Steps, all stream-ordered: binning; every rank stores which sub-tiles it touches into everybody's masks; barrier
+ * over the flags (release / acquire stores and loads at system scope through NVLink); deposit -- a sub-tile only this
+ * rank touches is stored straight into EVERY rank's result while the deposit runs, so the transfer overlaps the
+ * arithmetic tile by tile; barrier; sub-tiles several ranks touch are summed from their partial images in rank order and
+ * sub-tiles nobody touches are zeroed, by every rank for itself.  Deterministic and identical on all ranks.  The caller
+ * alternates two result (and mask) buffers between calls so that nobody overwrites what a slower rank still uses.  A rank
+ * that never reaches a barrier makes the others trap after ~4 s instead of hanging. */
+typedef struct {
+    int32_t n_ranks, rank;
+    uint64_t epoch;
+    void* partial[SO_MAX_PEERS];
+    void* result[SO_MAX_PEERS];
+    void* masks[SO_MAX_PEERS];
+    void* flags[SO_MAX_PEERS];
+} so_push_t;
+int so_img_deposit_push(const void* plan_workspace, const double* L, const int32_t* img, int64_t n,
+                        int32_t n_chan, int32_t n_img, int32_t ndim, int64_t n_pairs,
+                        float* data, int64_t data_ld, int64_t data_plane, float* simple, float* hist,
+                        int32_t* tile_ids, int32_t* pair_pids,
+                        void* workspace, int64_t workspace_bytes, const so_push_t* push, void* stream);
 
 /* Sum of the ranks' partial images over NVLink peer memory (config 5; instead of ncclAllReduce of the whole image).
  * The image [n_planes, ndim, ndim] (dense float32) is cut into so_peer_block_edge() = 32 pixel square exchange blocks.

@@ -61,6 +61,7 @@ SIGNATURES = {
     'so_img_rebin': (c_int, [P, P, I32, I32, I32, P]),
     'so_img_rebin_ld': (c_int, [P, I64, I64, P, I32, I32, I32, P]),
     'so_img_deposit_batch_ld': (c_int, [P, P, P, I64, I32, I32, I32, I64, P, I64, I64, P, P, P, P, P, I64, P]),
+    'so_img_deposit_push': (c_int, [P, P, P, I64, I32, I32, I32, I64, P, I64, I64, P, P, P, P, P, I64, P, P]),
     'so_complex_mul_bcast': (c_int, [P, P, P, I64, I32, I32, P]),
     'so_median_workspace_bytes': (I64, [I64, I32]),
     'so_median_f64': (c_int, [P, I64, I32, I64, P, P, I64, P]),
@@ -83,6 +84,16 @@ SIGNATURES = {
     'so_prof_enable': (c_int, [I32]),
     'so_prof_report': (I64, [c_char_p, I64]),
 }
+
+SO_MAX_PEERS = 16
+
+
+class PushDesc(ctypes.Structure):
+    """so_push_t of include/synthobs_b200.h"""
+    _fields_ = [('n_ranks', c_int32), ('rank', c_int32), ('epoch', ctypes.c_uint64),
+                ('partial', c_void_p * SO_MAX_PEERS), ('result', c_void_p * SO_MAX_PEERS),
+                ('masks', c_void_p * SO_MAX_PEERS), ('flags', c_void_p * SO_MAX_PEERS)]
+
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)

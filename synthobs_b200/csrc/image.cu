@@ -323,7 +323,19 @@ struct DepositParams {
     int n_chan;               // C_total
     int chan0;                // first channel of this launch
     int ntiles_img;           // sub-tiles per image; tile key = image * ntiles_img + tile (batch of images)
+    // several GPUs, one image (so_img_deposit_push): a sub-tile only THIS rank touches is also stored into every rank's
+    // result image over NVLink while the deposit runs; push_n = 0: off
+    int push_n;
+    float* push_result[SO_MAX_PEERS];          // the ranks' result images, same layout as data
+    const unsigned char* push_masks;           // [push_n][ntiles]: which ranks touch which sub-tile (this rank's copy)
 };
+
+// true when no other rank of a push deposit touches the sub-tile
+__device__ __forceinline__ bool tile_exclusive(const DepositParams& p, int tile) {
+    int cnt = 0;
+    for (int r = 0; r < p.push_n; ++r) cnt += p.push_masks[(size_t)r * p.ntiles + tile] ? 1 : 0;
+    return cnt == 1;
+}
 
 // wts[p][c] = (float)(L[c][p] * wnorm[p]): the weights of a particle in one sector, so the deposit gathers
 // two sectors per (particle, sub-tile) pair (plan record + weights) instead of one per array and channel
@@ -369,6 +381,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     const int64_t start = t0 + (item - p.item_start[tile]) * p.chunk;
     const int64_t end = min(t1, start + p.chunk);
     const bool single = (p.item_start[tile + 1] - p.item_start[tile]) == 1;
+    const bool push = p.push_n > 0 && single && tile_exclusive(p, tile);
     const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
     const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
 
@@ -481,10 +494,17 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
             const int r = py0 + 2 * br + rr;
             if (single) {
                 if (r < p.ndim) {
-                    float* out = p.data + ((size_t)image * p.n_chan + p.chan0 + c) * p.plane + (size_t)r * p.ld + col;
+                    const size_t off = ((size_t)image * p.n_chan + p.chan0 + c) * p.plane + (size_t)r * p.ld + col;
+                    float* out = p.data + off;
                     if (col + 4 <= p.ndim && ((p.ld | p.plane) & 3) == 0) {
                         *reinterpret_cast<float4*>(out) = v;
+                        if (push)
+                            for (int q = 0; q < p.push_n; ++q) *reinterpret_cast<float4*>(p.push_result[q] + off) = v;
                     } else {
+                        if (push)
+                            for (int q = 0; q < p.push_n; ++q)
+                                for (int j = 0; j < 4; ++j)
+                                    if (col + j < p.ndim) p.push_result[q][off + j] = j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
                         if (col < p.ndim) out[0] = v.x;
                         if (col + 1 < p.ndim) out[1] = v.y;
                         if (col + 2 < p.ndim) out[2] = v.z;
@@ -540,8 +560,13 @@ __global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParam
                 src += 4 * stride;
             }
             for (; it < i1; ++it) { s0 += src[0]; src += stride; }
-            if (row < p.ndim && col < p.ndim)
-                p.data[((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col] = (s0 + s1) + (s2 + s3);
+            if (row < p.ndim && col < p.ndim) {
+                const size_t off = ((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col;
+                const float v = (s0 + s1) + (s2 + s3);
+                p.data[off] = v;
+                if (p.push_n > 0 && tile_exclusive(p, tile))
+                    for (int q = 0; q < p.push_n; ++q) p.push_result[q][off] = v;
+            }
         }
     }
 }
@@ -649,6 +674,59 @@ __global__ void complex_mul_kernel(const float2* __restrict__ a, const float2* _
     if (i >= nc) return;
     const float2 x = a[(size_t)blockIdx.y * nc + i], y = b[(b_per_image ? (size_t)blockIdx.y * nc : 0) + i];
     out[(size_t)blockIdx.y * nc + i] = make_float2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+}
+
+// ---- several GPUs, one image: mask exchange, barrier and overlap fix over peer memory (so_img_deposit_push) ----
+struct PeerPtrs {
+    void* p[SO_MAX_PEERS];
+};
+
+// this rank's row of the sub-tile masks (a sub-tile is touched when it has a work item), stored into every rank's copy
+__global__ void __launch_bounds__(256) push_mask_kernel(const int64_t* __restrict__ item_start, int ntiles, PeerPtrs masks, int n_ranks,
+                                                        int rank) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const unsigned char m = item_start[t + 1] > item_start[t] ? 1 : 0;
+    for (int q = 0; q < n_ranks; ++q) reinterpret_cast<unsigned char*>(masks.p[q])[(size_t)rank * ntiles + t] = m;
+}
+
+// Barrier between the ranks' streams over NVLink: lane q publishes `epoch` in rank q's flag array and waits until rank q's
+// epoch has arrived in this rank's.  Kernels of a stream run in order, so everything the peers enqueued before their
+// barrier has completed (and is visible: release / acquire at system scope) when this kernel ends.  A rank that never
+// arrives is a trap after ~4 s, not a hang.
+__global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int n_ranks, int rank, unsigned long long epoch) {
+    const int q = threadIdx.x;
+    if (q >= n_ranks) return;
+    __threadfence_system();
+    unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flags.p[q]) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(flags.p[rank]) + q;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+    __threadfence_system();
+}
+
+// sub-tiles nobody touched are zeroed, sub-tiles several ranks touched are the sum of their partial sub-tiles in rank
+// order (deterministic, the same on every rank); sub-tiles of one rank arrived with its deposit
+__global__ void __launch_bounds__(kT * kT) push_fix_kernel(PeerPtrs partial, const unsigned char* __restrict__ masks, int n_ranks,
+                                                          int ntiles, int ntx, int ndim, int n_chan, float* __restrict__ result) {
+    const int tile = blockIdx.x;
+    unsigned touch = 0;
+    for (int r = 0; r < n_ranks; ++r) touch |= (masks[(size_t)r * ntiles + tile] ? 1u : 0u) << r;
+    if (__popc(touch) == 1) return;
+    const int row = (tile / ntx) * kT + threadIdx.x / kT, col = (tile % ntx) * kT + threadIdx.x % kT;
+    if (row >= ndim || col >= ndim) return;
+    for (int c = 0; c < n_chan; ++c) {
+        const size_t off = ((size_t)c * ndim + row) * ndim + col;
+        float s = 0.f;
+        for (unsigned t = touch; t; t &= t - 1) s += reinterpret_cast<const float*>(partial.p[__ffs(t) - 1])[off];
+        result[off] = s;
+    }
 }
 
 struct DepositLayout {
@@ -785,7 +863,24 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
                                        float* data, int64_t data_ld, int64_t data_plane, float* simple, float* hist,
                                        int32_t* tile_ids, int32_t* pair_pids,
                                        void* workspace, int64_t workspace_bytes, void* stream) {
+    return so_img_deposit_push(plan_workspace, L, img, n, n_chan, n_img, ndim, n_pairs, data, data_ld, data_plane, simple, hist,
+                               tile_ids, pair_pids, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int so_img_deposit_push(const void* plan_workspace, const double* L, const int32_t* img, int64_t n,
+                                   int32_t n_chan, int32_t n_img, int32_t ndim, int64_t n_pairs,
+                                   float* data, int64_t data_ld, int64_t data_plane, float* simple, float* hist,
+                                   int32_t* tile_ids, int32_t* pair_pids,
+                                   void* workspace, int64_t workspace_bytes, const so_push_t* push, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (push) {
+        if (push->n_ranks < 2 || push->n_ranks > SO_MAX_PEERS || push->rank < 0 || push->rank >= push->n_ranks || n_img != 1 ||
+            !data || simple || hist)
+            return SO_ERR_BAD_ARG;
+        for (int r = 0; r < push->n_ranks; ++r)
+            if (!push->result[r] || !push->partial[r] || !push->masks[r] || !push->flags[r]) return SO_ERR_BAD_ARG;
+        if (push->partial[push->rank] != (void*)data) return SO_ERR_BAD_ARG;
+    }
     if (n < 0 || ndim < 1 || n_chan < 1 || n_pairs < 0 || !plan_workspace || n_img < 1) return SO_ERR_BAD_ARG;
     if (data && (data_ld < ndim || data_plane < data_ld * ndim)) return SO_ERR_BAD_ARG;
     const bool dense = data_ld == ndim && data_plane == (int64_t)ndim * ndim;
@@ -799,7 +894,8 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
     DepositLayout d = carve_deposit(workspace, workspace_bytes, n, n_pairs, ndim, n_chan, n_img, &ok);
     if (!ok || !workspace) return SO_ERR_WORKSPACE;
     const size_t img_bytes = (size_t)ndim * ndim * sizeof(float) * n_img;
-    if (n_pairs == 0) {
+    if (push && !(data_ld == ndim && data_plane == (int64_t)ndim * ndim)) return SO_ERR_BAD_ARG;
+    if (n_pairs == 0 && !push) {
         if (data) {
             if (dense) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
             else
@@ -811,11 +907,13 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
         return SO_OK;
     }
     const int ntiles_img = d.ntx * d.ntx;
+    if (n > 0 && n_pairs > 0)
     { SO_PROF("expand_kernel", st); expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, img, ntiles_img, d.keys0, d.vals0); }
     SO_LAUNCH_CHECK();
     int bits = 1;
     while (((int64_t)1 << bits) < d.ntiles) ++bits;
     size_t tmp = (size_t)d.cub_tmp_bytes;
+    if (n_pairs > 0)
     { SO_PROF("cub sort (tile, particle) pairs", st); SO_CUDA(cub::DeviceRadixSort::SortPairs(d.cub_tmp, tmp, d.keys0, d.keys1, d.vals0, d.vals1, (int)n_pairs, 0, bits, st)); }
     { SO_PROF("tile_start_kernel", st); tile_start_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.keys1, n_pairs, d.ntiles, d.tile_start); }
     SO_LAUNCH_CHECK();
@@ -827,10 +925,21 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
     p.pids = d.vals1; p.tile_start = d.tile_start; p.item_start = d.item_start; p.item_tile = d.item_tile;
     p.ld = data_ld; p.plane = data_plane;
     p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0; p.wts = d.wts;
+    p.push_n = 0;
+    PeerPtrs pp_partial{}, pp_masks{}, pp_flags{};
+    if (push) {
+        p.push_n = push->n_ranks;
+        p.push_masks = (const unsigned char*)push->masks[push->rank];
+        for (int r = 0; r < push->n_ranks; ++r) {
+            p.push_result[r] = (float*)push->result[r];
+            pp_partial.p[r] = push->partial[r]; pp_masks.p[r] = push->masks[r]; pp_flags.p[r] = push->flags[r];
+        }
+    }
     if (data) {
-        // empty sub-tiles are never written: a dense image is cleared here; a window of a larger (padded) buffer is
-        // cleared by the caller together with its padding (contract of so_img_deposit_batch_ld)
-        if (dense) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
+        // empty sub-tiles are never written: a dense image is cleared here (a push deposit zeroes them in its result
+        // instead); a window of a larger (padded) buffer is cleared by the caller together with its padding
+        if (dense && !push) SO_CUDA(cudaMemsetAsync(data, 0, img_bytes * n_chan, st));
+        if (n > 0)
         { SO_PROF("weights_kernel", st); weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, pv.rec, n, n_chan, d.wts); }
         SO_LAUNCH_CHECK();
         { SO_PROF("tile_item_count_kernel", st); tile_item_count_kernel<<<(d.ntiles + 1 + 255) / 256, 256, 0, st>>>(d.tile_start, d.ntiles, d.chunk, d.item_start); }
@@ -840,8 +949,15 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
         { SO_PROF("item_tile_kernel", st); item_tile_kernel<<<(unsigned)((d.max_items + 255) / 256), 256, 0, st>>>(d.item_start, d.ntiles, d.max_items,
                                                                               d.item_tile); }
         SO_LAUNCH_CHECK();
+        if (push) {
+            // every rank learns which sub-tiles the others touch before anybody deposits
+            { SO_PROF("push_mask_kernel", st);
+              push_mask_kernel<<<(d.ntiles + 255) / 256, 256, 0, st>>>(d.item_start, d.ntiles, pp_masks, push->n_ranks, push->rank); }
+            { SO_PROF("peer_barrier_kernel", st); peer_barrier_kernel<<<1, 32, 0, st>>>(pp_flags, push->n_ranks, push->rank, 2 * push->epoch); }
+            SO_LAUNCH_CHECK();
+        }
         const unsigned grid = (unsigned)((d.max_items + kDepWarps - 1) / kDepWarps);
-        for (int c0 = 0; c0 < n_chan;) {       // channel groups of 8 / 4 / 2 / 1 share one pass over the lists
+        for (int c0 = 0; c0 < n_chan && n_pairs > 0;) {       // channel groups of 8 / 4 / 2 / 1 share one pass over the lists
             SO_PROF("deposit_kernel", st);
             p.chan0 = c0;
             const int left = n_chan - c0;
@@ -851,9 +967,18 @@ extern "C" int so_img_deposit_batch_ld(const void* plan_workspace, const double*
             else { deposit_kernel<1><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 1; }
             SO_LAUNCH_CHECK();
         }
+        if (n_pairs > 0)
         { SO_PROF("tile_reduce_kernel", st);
           tile_reduce_kernel<<<dim3((unsigned)((d.max_items + kReduceItems - 1) / kReduceItems), (unsigned)n_chan), kT * kT, 0, st>>>(p, n_chan); }
         SO_LAUNCH_CHECK();
+        if (push) {
+            // all ranks have deposited (and pushed their own sub-tiles): finish the shared and the empty ones
+            { SO_PROF("peer_barrier_kernel", st); peer_barrier_kernel<<<1, 32, 0, st>>>(pp_flags, push->n_ranks, push->rank, 2 * push->epoch + 1); }
+            { SO_PROF("push_fix_kernel", st);
+              push_fix_kernel<<<(unsigned)d.ntiles, kT * kT, 0, st>>>(pp_partial, p.push_masks, push->n_ranks, d.ntiles, d.ntx, ndim, n_chan,
+                                                                       (float*)push->result[push->rank]); }
+            SO_LAUNCH_CHECK();
+        }
     }
     if (simple || hist) {
         { SO_PROF("ngp_tile_kernel", st); ngp_tile_kernel<<<(unsigned)d.ntiles, 64, 0, st>>>(p, n_chan, simple, hist); }

@@ -154,10 +154,9 @@ class _DevicePtr:
 
 
 class PeerImage:
-    """Peer-mapped buffers for the sum of the ranks' partial images [C, ndim, ndim] without an all-reduce of the whole
-    image (csrc/peer.cu): two alternating `partial` buffers (the deposit target of successive calls), allocated with
-    cudaMalloc, exported with cudaIpc and mapped by every other rank of the node over NVLink.  Created collectively,
-    once per image shape."""
+    """Peer-mapped buffers of ONE image [C, ndim, ndim] shared by the GPUs of a node (so_img_deposit_push): the partial
+    image, two alternating result images and tile-mask arrays, and the barrier flags -- allocated with cudaMalloc,
+    exported with cudaIpc and mapped by every other rank over NVLink.  Created collectively, once per image shape."""
 
     _cache = {}
 
@@ -174,59 +173,62 @@ class PeerImage:
         from ctypes import byref, c_void_p, create_string_buffer
         from . import _cabi, device as dv
         self.rank, self.ws = world()
+        if self.ws > _cabi.SO_MAX_PEERS:
+            raise ValueError('at most %d ranks share an image' % _cabi.SO_MAX_PEERS)
         self.n_planes, self.ndim = int(n_planes), int(ndim)
         self.dev = dv.device()
-        nbytes = 4 * self.n_planes * self.ndim * self.ndim
-        own = []
-        for _ in range(2):
+        img = 4 * self.n_planes * self.ndim * self.ndim
+        ntiles = ((self.ndim + 15) // 16) ** 2
+        sizes = {'partial': img, 'result0': img, 'result1': img, 'masks0': self.ws * ntiles, 'masks1': self.ws * ntiles,
+                 'flags': 8 * _cabi.SO_MAX_PEERS}
+        self.names = list(sizes)
+        own = {}
+        for k, nbytes in sizes.items():
             p = c_void_p()
             _cabi.check(_cabi.lib.so_peer_alloc(nbytes, byref(p)), 'so_peer_alloc')
-            own.append(p.value)
-        handles = []
-        for p in own:
+            own[k] = p.value
+        handles = {}
+        for k, p in own.items():
             h = create_string_buffer(64)
             _cabi.check(_cabi.lib.so_ipc_get_handle(c_void_p(p), h), 'so_ipc_get_handle')
-            handles.append(h.raw)
+            handles[k] = h.raw
         every = [None] * self.ws
         dist.all_gather_object(every, handles)
-        self.ptrs = [[None] * self.ws, [None] * self.ws]          # [buffer 0 | 1][rank]
+        self.ptrs = {k: [None] * self.ws for k in sizes}           # [buffer][rank]
         for r in range(self.ws):
-            for b in range(2):
+            for k in sizes:
                 if r == self.rank:
-                    self.ptrs[b][r] = own[b]
+                    self.ptrs[k][r] = own[k]
                 else:
                     q = c_void_p()
-                    _cabi.check(_cabi.lib.so_ipc_open(create_string_buffer(every[r][b], 64), byref(q)), 'so_ipc_open')
-                    self.ptrs[b][r] = q.value
+                    _cabi.check(_cabi.lib.so_ipc_open(create_string_buffer(every[r][k], 64), byref(q)), 'so_ipc_open')
+                    self.ptrs[k][r] = q.value
         shape = (self.n_planes, self.ndim, self.ndim)
-        self.partials = [torch.as_tensor(_DevicePtr(own[b], shape), device=self.dev) for b in range(2)]
-        self.parity = 0
-        xb = int(_cabi.lib.so_peer_block_edge())
-        self.n_blocks = ((self.ndim + xb - 1) // xb) ** 2
-        self.mask = torch.empty(self.n_blocks, dtype=torch.uint8, device=self.dev)
-        self.masks = torch.empty(self.ws * self.n_blocks, dtype=torch.uint8, device=self.dev)
-        self.c_ptrs = [(c_void_p * self.ws)(*self.ptrs[b]) for b in range(2)]
+        self.partial = torch.as_tensor(_DevicePtr(own['partial'], shape), device=self.dev)
+        self.results = [torch.as_tensor(_DevicePtr(own['result%d' % b], shape), device=self.dev) for b in range(2)]
+        flags = torch.as_tensor(_DevicePtr(own['flags'], (2 * _cabi.SO_MAX_PEERS,)), device=self.dev)     # uint64 seen as 2 floats
+        flags.zero_()
+        torch.cuda.synchronize()
+        self.calls = 0
         dist.barrier()
 
-    @property
-    def partial(self):
-        """the buffer this call deposits into"""
-        return self.partials[self.parity]
-
-    def reduce(self):
-        """sum of the ranks' current `partial` images -> a new tensor on every rank (csrc/peer.cu); stream-ordered.
-        The next call deposits into the other buffer, so a slower peer may still be reading this one: by the time a
-        buffer comes round again an all-gather (a barrier for the kernels before it) lies in between."""
+    def push_desc(self):
+        """so_push_t of the next call (alternating result / mask buffers, barrier generation)"""
         from . import _cabi
-        n, C, b = self.ndim, self.n_planes, self.parity
-        _cabi.check(_cabi.lib.so_peer_block_mask(_cabi.ptr(self.partials[b]), C, n, n, n * n, _cabi.ptr(self.mask), _cabi.stream()),
-                    'so_peer_block_mask')
-        # the all-gather of the masks is also the point after which every rank's partial image is complete
-        dist.all_gather_into_tensor(self.masks, self.mask)
-        out = torch.empty((C, n, n), dtype=torch.float32, device=self.dev)
-        _cabi.check(_cabi.lib.so_peer_sum(self.c_ptrs[b], _cabi.ptr(self.masks), self.ws, self.rank, C, n, _cabi.ptr(out),
-                                          _cabi.stream()), 'so_peer_sum')
-        self.parity ^= 1
+        b = self.calls % 2
+        d = _cabi.PushDesc()
+        d.n_ranks, d.rank, d.epoch = self.ws, self.rank, self.calls + 1
+        for r in range(self.ws):
+            d.partial[r] = self.ptrs['partial'][r]
+            d.result[r] = self.ptrs['result%d' % b][r]
+            d.masks[r] = self.ptrs['masks%d' % b][r]
+            d.flags[r] = self.ptrs['flags'][r]
+        return d
+
+    def finish(self):
+        """the result image of the call just made (valid until the call after the next one writes it again)"""
+        out = self.results[self.calls % 2]
+        self.calls += 1
         return out
 
 
@@ -403,16 +405,19 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
             warnings.warn('synthobs_b200.dist: peer-memory image reduce unavailable (%r); using ncclAllReduce' % (e,))
             os.environ['SO_PEER_REDUCE'] = '0'
     r = images.deposit_device(Xo, Yo, Lo, resolution, ndim, adaptive_k=int(k), want_ngp=False,
-                              support_sigmas=support_sigmas, dk=dko, out=None if peer is None else peer.partial)
-    mark('plan + binning + deposit of the share')
+                              support_sigmas=support_sigmas, dk=dko, out=None if peer is None else peer.partial,
+                              push=None if peer is None else peer.push_desc())
     img = r['data']
     if reduce and ws > 1:
         if peer is not None:
-            img = peer.reduce()
-            mark('sum of the partial images over peer memory')
+            img = peer.finish()
+            mark('plan + binning + deposit fused with the exchange over peer memory')
         else:
+            mark('plan + binning + deposit of the share')
             img = reduce_image(img)
             mark('all-reduce of the image')
+    else:
+        mark('plan + binning + deposit of the share')
     if stages is not None:
         torch.cuda.synchronize()
         for (_, a), (name, b) in zip(marks[:-1], marks[1:]):

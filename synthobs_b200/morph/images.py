@@ -337,13 +337,15 @@ def share_compact_device(Xd, Yd, flags, bit_mask, m):
 
 def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True, want_ngp=True,
                    support_sigmas=None, dk=None, return_pairs=False, L_event=None, img=None, n_img=1, exact_dk=False,
-                   pad_to=None, out=None):
+                   pad_to=None, out=None, push=None):
     """images.core on device tensors.  Xd, Yd: [n] float64 CUDA; Ld: [C, n] float64
     CUDA (C images sharing positions).  Returns dict of float32 CUDA tensors:
     data [C, ndim, ndim] (adaptive only), simple [C, ndim, ndim], hist [ndim, ndim],
     plus ix, iy, dk and the stats (pairs, deposits, selected, dropped).  pad_to=(py, px): `data` is the
     top-left window of a zero-padded buffer [C, py, px] (returned as 'data_padded') ready for the PSF transform.
-    out: a float32 CUDA tensor [C, ndim, ndim] to deposit into (every pixel is written) instead of a new one."""
+    out: a float32 CUDA tensor [C, ndim, ndim] to deposit into (every pixel is written) instead of a new one.
+    push: a _cabi.PushDesc -- one image shared by several GPUs, the exchange fused into the deposit (dist.PeerImage;
+    `out` is then the peer-mapped partial image and the result is read from the descriptor's result buffer)."""
     _cabi.require_device()
     if Ld.dim() == 1:
         Ld = Ld.reshape(1, -1)
@@ -364,6 +366,8 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
                                       _cabi.ptr(dk) if adaptive else None, n, _cabi.ptr(Gd), ndim, float(R),
                                       _cabi.ptr(pws), pws_b, n_pairs, stats, _cabi.stream()), 'so_img_plan')
     npairs = n_pairs.value
+    if push is not None and npairs > MAX_PAIRS:
+        raise ValueError('a shared (push) deposit takes at most %d (particle, sub-tile) pairs per rank' % MAX_PAIRS)
     if npairs > MAX_PAIRS and n > 1:
         # more (particle, sub-tile) pairs than one binning pass indexes (int32) or should hold in memory:
         # deposit the two halves of the particle list separately and add the images (the sum is associative)
@@ -400,11 +404,12 @@ def deposit_device(Xd, Yd, Ld, resolution, ndim, adaptive_k=None, want_data=True
     if L_event is not None:        # the weights may still be arriving on a copy stream (k-NN and binning need positions only)
         torch.cuda.current_stream().wait_event(L_event)
     ld, plane = (padded.shape[-1], padded.shape[-1] * padded.shape[-2]) if padded is not None else (ndim, ndim * ndim)
-    _cabi.check(_cabi.lib.so_img_deposit_batch_ld(_cabi.ptr(pws), _cabi.ptr(Ld), _cabi.ptr(img), n, C, int(n_img), ndim,
-                                                  npairs, _cabi.ptr(padded if padded is not None else data), ld, plane,
-                                                  _cabi.ptr(simple), _cabi.ptr(hist), _cabi.ptr(tiles), _cabi.ptr(pids),
-                                                  _cabi.ptr(ws), wsb, _cabi.stream()),
-                'so_img_deposit_batch_ld')
+    from ctypes import byref
+    _cabi.check(_cabi.lib.so_img_deposit_push(_cabi.ptr(pws), _cabi.ptr(Ld), _cabi.ptr(img), n, C, int(n_img), ndim,
+                                              npairs, _cabi.ptr(padded if padded is not None else data), ld, plane,
+                                              _cabi.ptr(simple), _cabi.ptr(hist), _cabi.ptr(tiles), _cabi.ptr(pids),
+                                              _cabi.ptr(ws), wsb, None if push is None else byref(push), _cabi.stream()),
+                'so_img_deposit_push')
     return {'data': data, 'data_padded': padded, 'simple': simple, 'hist': hist, 'ix': ix, 'iy': iy, 'dk': dk, 'G': G,
             'stats': {'pairs': stats[0], 'deposits': stats[1], 'selected': stats[2], 'dropped': stats[3]},
             'tiles': tiles, 'pids': pids}

@@ -32,7 +32,7 @@ sdist.image_huge(X, Y, L, res, ndim, 8, stages=st)
 torch.cuda.synchronize()
 if rank == 0:
     print({k[:40]: round(v, 3) for k, v in st.items()})
-    print({k: round(ms, 3) for k, (c, ms) in _cabi.prof_report().items() if 'peer' in k or 'mask' in k})
+    print({k: round(ms, 3) for k, (c, ms) in _cabi.prof_report().items() if 'peer' in k or 'mask' in k or 'push' in k or 'deposit' in k or 'tile_reduce' in k})
 _cabi.prof_enable(False)
 whole = sdist.image_huge(X, Y, L, res, ndim, 8, rank=0, n_ranks=1, reduce=False)
 peak = float(whole.max())
