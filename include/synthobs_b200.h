@@ -356,8 +356,8 @@ int so_knn_kth_distance_q(const double* X, const double* Y, const int32_t* ix, i
  * Steps, all stream-ordered: binning; every rank stores which sub-tiles it touches into everybody's masks; barrier
  * over the flags (release / acquire stores and loads at system scope through NVLink); deposit -- a sub-tile only this
  * rank touches is stored straight into EVERY rank's result while the deposit runs, so the transfer overlaps the
- * arithmetic tile by tile; barrier; sub-tiles several ranks touch are summed from their partial images in rank order and
- * sub-tiles nobody touches are zeroed, by every rank for itself.  Deterministic and identical on all ranks.  The caller
+ * arithmetic tile by tile; barrier; sub-tiles several ranks touch are summed from their partial images in rank order, by
+ * every rank for itself (sub-tiles nobody touches keep the zeros the result was cleared with before the first barrier).  Deterministic and identical on all ranks.  The caller
  * alternates two result (and mask) buffers between calls so that nobody overwrites what a slower rank still uses.  A rank
  * that never reaches a barrier makes the others trap after ~4 s instead of hanging. */
 typedef struct {

@@ -711,22 +711,25 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int n_
     __threadfence_system();
 }
 
-// sub-tiles nobody touched are zeroed, sub-tiles several ranks touched are the sum of their partial sub-tiles in rank
-// order (deterministic, the same on every rank); sub-tiles of one rank arrived with its deposit
-__global__ void __launch_bounds__(kT * kT) push_fix_kernel(PeerPtrs partial, const unsigned char* __restrict__ masks, int n_ranks,
-                                                          int ntiles, int ntx, int ndim, int n_chan, float* __restrict__ result) {
-    const int tile = blockIdx.x;
-    unsigned touch = 0;
-    for (int r = 0; r < n_ranks; ++r) touch |= (masks[(size_t)r * ntiles + tile] ? 1u : 0u) << r;
-    if (__popc(touch) == 1) return;
-    const int row = (tile / ntx) * kT + threadIdx.x / kT, col = (tile % ntx) * kT + threadIdx.x % kT;
-    if (row >= ndim || col >= ndim) return;
-    for (int c = 0; c < n_chan; ++c) {
-        const size_t off = ((size_t)c * ndim + row) * ndim + col;
-        float s = 0.f;
-        for (unsigned t = touch; t; t &= t - 1) s += reinterpret_cast<const float*>(partial.p[__ffs(t) - 1])[off];
-        result[off] = s;
-    }
+// sub-tiles several ranks touched are the sum of their partial sub-tiles in rank order (deterministic, the same on every
+// rank); sub-tiles of one rank arrived with its deposit, untouched ones keep the zeros the result was cleared with.
+// One WARP per sub-tile: almost all of them leave after the mask test.
+__global__ void __launch_bounds__(256) push_fix_kernel(PeerPtrs partial, const unsigned char* __restrict__ masks, int n_ranks,
+                                                       int ntiles, int ntx, int ndim, int n_chan, float* __restrict__ result) {
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (tile >= ntiles) return;
+    const unsigned touch = __ballot_sync(0xffffffffu, lane < n_ranks && masks[(size_t)lane * ntiles + tile]);
+    if (__popc(touch) < 2) return;
+    const int py0 = (tile / ntx) * kT, px0 = (tile % ntx) * kT;
+    for (int c = 0; c < n_chan; ++c)
+        for (int e = lane; e < kT * kT; e += 32) {
+            const int row = py0 + e / kT, col = px0 + e % kT;
+            if (row >= ndim || col >= ndim) continue;
+            const size_t off = ((size_t)c * ndim + row) * ndim + col;
+            float s = 0.f;
+            for (unsigned t = touch; t; t &= t - 1) s += reinterpret_cast<const float*>(partial.p[__ffs(t) - 1])[off];
+            result[off] = s;
+        }
 }
 
 struct DepositLayout {
@@ -907,6 +910,9 @@ extern "C" int so_img_deposit_push(const void* plan_workspace, const double* L, 
         return SO_OK;
     }
     const int ntiles_img = d.ntx * d.ntx;
+    // sub-tiles nobody touches stay zero: the result is cleared before this rank passes the first barrier, i.e. before
+    // any peer stores into it
+    if (push) SO_CUDA(cudaMemsetAsync(push->result[push->rank], 0, img_bytes * n_chan, st));
     if (n > 0 && n_pairs > 0)
     { SO_PROF("expand_kernel", st); expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, ndim, d.ntx, img, ntiles_img, d.keys0, d.vals0); }
     SO_LAUNCH_CHECK();
@@ -972,10 +978,10 @@ extern "C" int so_img_deposit_push(const void* plan_workspace, const double* L, 
           tile_reduce_kernel<<<dim3((unsigned)((d.max_items + kReduceItems - 1) / kReduceItems), (unsigned)n_chan), kT * kT, 0, st>>>(p, n_chan); }
         SO_LAUNCH_CHECK();
         if (push) {
-            // all ranks have deposited (and pushed their own sub-tiles): finish the shared and the empty ones
+            // all ranks have deposited (and pushed their own sub-tiles): finish the shared ones
             { SO_PROF("peer_barrier_kernel", st); peer_barrier_kernel<<<1, 32, 0, st>>>(pp_flags, push->n_ranks, push->rank, 2 * push->epoch + 1); }
             { SO_PROF("push_fix_kernel", st);
-              push_fix_kernel<<<(unsigned)d.ntiles, kT * kT, 0, st>>>(pp_partial, p.push_masks, push->n_ranks, d.ntiles, d.ntx, ndim, n_chan,
+              push_fix_kernel<<<(unsigned)(((int64_t)d.ntiles * 32 + 255) / 256), 256, 0, st>>>(pp_partial, p.push_masks, push->n_ranks, d.ntiles, d.ntx, ndim, n_chan,
                                                                        (float*)push->result[push->rank]); }
             SO_LAUNCH_CHECK();
         }
