@@ -316,7 +316,8 @@ int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, 
  * shares of equal WORK (+- one coarse cell; a particle of a cell too sparse to hold k particles within `floor`, the
  * FWHM floor of synthobs/morph/images.py:89, counts 2.5 times: its query walks the tree and its support is wide) --
  * contiguous Morton ranges of a 2^cb x 2^cb grid over the image -- and flag
- * every particle for share `part`: bit 1 (value 2) = OWN (this share answers its k-NN query and deposits it),
+ * every particle for the share [share_lo, share_hi) of the total work (share p of N equal ones: p / N, (p + 1) / N;
+ * unequal fractions let the caller balance measured times): bit 1 (value 2) = OWN (this share answers its k-NN query and deposits it),
  * bit 0 = LOCAL (own or halo: member of this share's search tree).  The halo is sized from the coarse histogram so
  * that the k-th neighbour distance among the LOCAL particles is exact for every OWN particle (share.cu header).
  * so_share_hist counts the selected particles [begin, end) per coarse cell (DEVICE int32[4^cb], Morton order): with
@@ -326,7 +327,7 @@ int so_share_hist(const double* X, const double* Y, int64_t begin, int64_t end, 
                   int32_t* hist, void* stream);
 int64_t so_share_plan_workspace_bytes(int32_t cb);
 int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, const int32_t* hist,
-                  int32_t k, double floor, int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts,
+                  int32_t k, double floor, double share_lo, double share_hi, uint8_t* flags, uint64_t* counts,
                   void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Stable compaction of the particles whose flag byte has a bit of bit_mask set: out_index[j] = index of the j-th
@@ -351,7 +352,8 @@ int so_knn_kth_distance_q(const double* X, const double* Y, const int32_t* ix, i
  *   partial  the ranks' partial images [n_chan, ndim, ndim]; partial[rank] must be `data` (dense)
  *   result   the ranks' result images, same layout
  *   masks    uint8 [n_ranks][ntiles] per rank, ntiles = ceil(ndim / SO_TILE)^2
- *   flags    uint64 [n_ranks] per rank, zero before the first call
+ *   flags    uint64 [SO_MAX_PEERS + 2] per rank, zero before the first call (the last two slots receive the time [ns] this
+ *            rank spent waiting at the two barriers of the call)
  *   epoch    generation of this call: starts at 1, +1 per call, the same on every rank
  * Steps, all stream-ordered: binning; every rank stores which sub-tiles it touches into everybody's masks; barrier
  * over the flags (release / acquire stores and loads at system scope through NVLink); deposit -- a sub-tile only this

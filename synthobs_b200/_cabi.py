@@ -49,7 +49,7 @@ SIGNATURES = {
     'so_knn_kth_distance_q': (c_int, [P, P, P, I64, I32, D, P, D, P, P, I64, P]),
     'so_share_plan_workspace_bytes': (I64, [I32]),
     'so_share_hist': (c_int, [P, P, I64, I64, D, I32, P, P]),
-    'so_share_plan': (c_int, [P, P, I64, D, I32, P, I32, D, I32, I32, P, P, P, I64, P]),
+    'so_share_plan': (c_int, [P, P, I64, D, I32, P, I32, D, D, D, P, P, P, I64, P]),
     'so_share_compact_workspace_bytes': (I64, [I64]),
     'so_share_compact': (c_int, [P, P, P, I64, I32, I64, P, P, P, P, P, P, I64, P]),
     'so_img_plan_workspace_bytes': (I64, [I64]),

@@ -702,6 +702,8 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int n_
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(flags.p[rank]) + q;
     const long long t0 = clock64();
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     for (;;) {
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
@@ -709,6 +711,11 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int n_
         if (clock64() - t0 > 8000000000LL) __trap();
     }
     __threadfence_system();
+    // how long this rank waited for the slowest one [ns], per barrier of the call (slots SO_MAX_PEERS, SO_MAX_PEERS + 1 of
+    // its own flag array): what a caller needs to balance the shares by measured busy time
+    __syncwarp((1u << n_ranks) - 1u);                 // every lane has seen its rank arrive
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (q == 0) reinterpret_cast<unsigned long long*>(flags.p[rank])[SO_MAX_PEERS + (int)(epoch & 1ull)] = g1 - g0;
 }
 
 // sub-tiles several ranks touched are the sum of their partial sub-tiles in rank order (deterministic, the same on every

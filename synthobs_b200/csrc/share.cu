@@ -94,14 +94,14 @@ __device__ __forceinline__ unsigned long long sat_block(const unsigned long long
     return sat[(size_t)(y1 + 1) * w + x1 + 1] - sat[(size_t)y0 * w + x1 + 1] - sat[(size_t)(y1 + 1) * w + x0] + sat[(size_t)y0 * w + x0];
 }
 
-// cum = inclusive Morton-order prefix of the cells' WORK (share_weight_kernel).  The share of Morton cell c is the part
-// whose work interval holds the MIDDLE of the cell's interval: contiguous ranges of cells, equal work up to one cell.
-__device__ __forceinline__ int cell_share(const unsigned long long* cum, int c, unsigned long long total, int n_parts) {
-    const unsigned long long lo = c ? cum[c - 1] : 0, hi = cum[c];
-    if (hi == lo) return -1;                                  // empty cell: nobody's
-    const unsigned long long mid2 = lo + hi;                  // twice the middle
-    int p = (int)((mid2 * (unsigned long long)n_parts) / (2 * total));
-    return p >= n_parts ? n_parts - 1 : p;
+// cum = inclusive Morton-order prefix of the cells' WORK (share_weight_kernel).  A cell belongs to the share [lo, hi)
+// (fractions of the total work) that holds the MIDDLE of the cell's interval: contiguous ranges of cells, the
+// requested work up to one cell.
+__device__ __forceinline__ bool cell_in_share(const unsigned long long* cum, int c, unsigned long long total, double lo, double hi) {
+    const unsigned long long a = c ? cum[c - 1] : 0, b = cum[c];
+    if (b == a) return false;                                 // empty cell: nobody's
+    const double mid = 0.5 * ((double)a + (double)b) / (double)total;
+    return mid >= lo && mid < hi;
 }
 
 // work of a cell = its particles, counted 2.5 times where the density is below dense_count per cell: there the k-th
@@ -117,14 +117,14 @@ __global__ void __launch_bounds__(256) share_weight_kernel(const int32_t* __rest
 
 // every cell of share `part` marks the cells its queries may need (see header); mark: 1 = local, 2 = own
 __global__ void __launch_bounds__(256) share_mark_kernel(const int32_t* __restrict__ hist, const unsigned long long* __restrict__ cum,
-                                                         const unsigned long long* __restrict__ sat, int nc, int k, int part,
-                                                         int n_parts, unsigned char* __restrict__ mark) {
+                                                         const unsigned long long* __restrict__ sat, int nc, int k, double lo,
+                                                         double hi, unsigned char* __restrict__ mark) {
     // one WARP per cell: a sparse cell far out may need a block of thousands of cells around it
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= nc * nc) return;
     const unsigned long long total = cum[nc * nc - 1];
-    if (total == 0 || hist[c] == 0 || cell_share(cum, c, total, n_parts) != part) return;
+    if (total == 0 || hist[c] == 0 || !cell_in_share(cum, c, total, lo, hi)) return;
     const int cx = (int)sh_compact((uint32_t)c), cy = (int)sh_compact((uint32_t)c >> 1);
     const int w = nc + 1;
     int m = 0;
@@ -143,12 +143,12 @@ __global__ void __launch_bounds__(256) share_mark_kernel(const int32_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(256) share_own_kernel(const unsigned long long* __restrict__ cum, int nc, int part, int n_parts,
+__global__ void __launch_bounds__(256) share_own_kernel(const unsigned long long* __restrict__ cum, int nc, double lo, double hi,
                                                         unsigned char* __restrict__ mark) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc * nc) return;
     const unsigned long long total = cum[nc * nc - 1];
-    if (total && cell_share(cum, c, total, n_parts) == part) mark[c] |= 3;
+    if (total && cell_in_share(cum, c, total, lo, hi)) mark[c] |= 3;
 }
 
 __global__ void __launch_bounds__(512) share_flag_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n,
@@ -251,10 +251,10 @@ extern "C" int64_t so_share_plan_workspace_bytes(int32_t cb) {
 }
 
 extern "C" int so_share_plan(const double* X, const double* Y, int64_t n, double half_width, int32_t cb, const int32_t* hist,
-                             int32_t k, double floor, int32_t part, int32_t n_parts, uint8_t* flags, uint64_t* counts,
+                             int32_t k, double floor, double share_lo, double share_hi, uint8_t* flags, uint64_t* counts,
                              void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (n < 0 || !(half_width > 0.0) || cb < 1 || cb > kMaxCb || k < 1 || n_parts < 1 || part < 0 || part >= n_parts || !counts || !hist)
+    if (n < 0 || !(half_width > 0.0) || cb < 1 || cb > kMaxCb || k < 1 || !(share_lo >= 0.0) || !(share_hi > share_lo) || !counts || !hist)
         return SO_ERR_BAD_ARG;
     if (n > 0 && (!X || !Y || !flags)) return SO_ERR_BAD_ARG;
     bool ok = false;
@@ -277,9 +277,9 @@ extern "C" int so_share_plan(const double* X, const double* Y, int64_t n, double
       share_sat_rows_kernel<<<(nc + 1 + 127) / 128, 128, 0, st>>>(hist, nc, l.sat);
       share_sat_cols_kernel<<<(nc + 127) / 128, 128, 0, st>>>(nc, l.sat); }
     SO_LAUNCH_CHECK();
-    { SO_PROF("share_mark_kernel", st); share_mark_kernel<<<(unsigned)(((int64_t)cells * 32 + 255) / 256), 256, 0, st>>>(hist, l.cum, l.sat, nc, k, part, n_parts, l.mark); }
+    { SO_PROF("share_mark_kernel", st); share_mark_kernel<<<(unsigned)(((int64_t)cells * 32 + 255) / 256), 256, 0, st>>>(hist, l.cum, l.sat, nc, k, share_lo, share_hi, l.mark); }
     SO_LAUNCH_CHECK();
-    { SO_PROF("share_own_kernel", st); share_own_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.cum, nc, part, n_parts, l.mark); }
+    { SO_PROF("share_own_kernel", st); share_own_kernel<<<(cells + 255) / 256, 256, 0, st>>>(l.cum, nc, share_lo, share_hi, l.mark); }
     SO_LAUNCH_CHECK();
     int64_t blocks = (n + 511) / 512;
     if (blocks > 16 * so_num_sms()) blocks = 16 * so_num_sms();

@@ -180,7 +180,7 @@ class PeerImage:
         img = 4 * self.n_planes * self.ndim * self.ndim
         ntiles = ((self.ndim + 15) // 16) ** 2
         sizes = {'partial': img, 'result0': img, 'result1': img, 'masks0': self.ws * ntiles, 'masks1': self.ws * ntiles,
-                 'flags': 8 * _cabi.SO_MAX_PEERS}
+                 'flags': 8 * (_cabi.SO_MAX_PEERS + 2)}
         self.names = list(sizes)
         own = {}
         for k, nbytes in sizes.items():
@@ -206,8 +206,9 @@ class PeerImage:
         shape = (self.n_planes, self.ndim, self.ndim)
         self.partial = torch.as_tensor(_DevicePtr(own['partial'], shape), device=self.dev)
         self.results = [torch.as_tensor(_DevicePtr(own['result%d' % b], shape), device=self.dev) for b in range(2)]
-        flags = torch.as_tensor(_DevicePtr(own['flags'], (2 * _cabi.SO_MAX_PEERS,)), device=self.dev)     # uint64 seen as 2 floats
+        flags = torch.as_tensor(_DevicePtr(own['flags'], (2 * (_cabi.SO_MAX_PEERS + 2),)), device=self.dev)   # uint64 seen as 2 floats
         flags.zero_()
+        self.waits = flags.view(torch.int64)[_cabi.SO_MAX_PEERS:]      # [2] ns this rank waited at the barriers of the last call
         torch.cuda.synchronize()
         self.calls = 0
         dist.barrier()
@@ -230,6 +231,9 @@ class PeerImage:
         out = self.results[self.calls % 2]
         self.calls += 1
         return out
+
+
+_share_balance = {}      # (n, ndim, k, ranks) -> work fractions of the shares, adapted to the measured busy times
 
 
 def peer_reduce_enabled():
@@ -376,14 +380,37 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
     else:
         n = Xd.numel()
         cb = images.share_grid_bits(n, ws)
+        bounds = None
+        bal = None
         if w0 == ws and w0 > 1:
-            # every rank counts its 1/N of the particles; the small table is summed over the ranks (exact integers)
+            # every rank counts its 1/N of the particles; the small table is summed over the ranks (exact integers).
+            # The same all-reduce carries every rank's busy time of the previous call (below)
+            bal = _share_balance.setdefault((n, int(ndim), int(k), ws), {'frac': np.full(ws, 1.0 / ws), 'pending': None})
+            cells = 1 << (2 * cb)
+            buf = torch.zeros(cells + ws, dtype=torch.int32, device=Xd.device)
             b, e = particle_block(n, rank, ws)
-            hist = images.share_hist_device(Xd, Yd, hw, cb, b, e)
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+            images.share_hist_device(Xd, Yd, hw, cb, b, e, out=buf[:cells])
+            if bal['pending'] is not None:
+                e0, e1, waits = bal['pending']
+                e1.synchronize()
+                busy_us = max(1.0, e0.elapsed_time(e1) * 1e3 - float(waits.sum()) * 1e-3)
+                buf[cells + rank] = int(busy_us)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            hist = buf[:cells]
+            if bal['pending'] is not None:
+                t = buf[cells:].cpu().numpy().astype(np.float64)
+                if np.all(t > 0):
+                    # shares proportional to the measured speed of their rank, damped; identical on every rank
+                    f = bal['frac'] * (t.mean() / t) ** 0.7
+                    f = np.clip(f / f.sum(), 0.4 / ws, 2.5 / ws)
+                    bal['frac'] = f / f.sum()
+            bounds = np.concatenate([[0.0], np.cumsum(bal['frac'])])
         else:
             hist = images.share_hist_device(Xd, Yd, hw, cb)
-        flags, counts = images.share_plan_device(Xd, Yd, hw, int(k), rank, ws, cb=cb, hist=hist)
+        flags, counts = images.share_plan_device(Xd, Yd, hw, int(k), rank, ws, cb=cb, hist=hist, bounds=bounds)
+        if bal is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         n_loc, n_own = (int(v) for v in counts.cpu())        # the one host synchronisation: the sizes of the share
         mark('share plan (coarse histogram, halo flags)')
         loc, Xl, Yl, fl = images.share_compact_device(Xd, Yd, flags, 1, n_loc)      # local = own + halo
@@ -408,6 +435,14 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
                               support_sigmas=support_sigmas, dk=dko, out=None if peer is None else peer.partial,
                               push=None if peer is None else peer.push_desc())
     img = r['data']
+    if ws > 1 and ws == w0 and reduce:
+        bal = _share_balance.get((Xd.numel(), int(ndim), int(k), ws))
+        if bal is not None and peer is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            bal['pending'] = (e0, e1, peer.waits.clone())
+        elif bal is not None:
+            bal['pending'] = None
     if reduce and ws > 1:
         if peer is not None:
             img = peer.finish()

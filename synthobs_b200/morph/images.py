@@ -289,31 +289,35 @@ def share_grid_bits(n, n_parts=1):
     return int(min(max(cb, 3), 9))
 
 
-def share_hist_device(Xd, Yd, half_width, cb, begin=0, end=None):
+def share_hist_device(Xd, Yd, half_width, cb, begin=0, end=None, out=None):
     """counts of the selected particles [begin, end) per coarse cell (Morton order), int32 CUDA tensor [4^cb]"""
     n = Xd.numel()
     end = n if end is None else int(end)
-    hist = torch.empty(1 << (2 * cb), dtype=torch.int32, device=Xd.device)
+    hist = torch.empty(1 << (2 * cb), dtype=torch.int32, device=Xd.device) if out is None else out
     _cabi.check(_cabi.lib.so_share_hist(_cabi.ptr(Xd), _cabi.ptr(Yd), int(begin), end, float(half_width), int(cb), _cabi.ptr(hist),
                                         _cabi.stream()), 'so_share_hist')
     return hist
 
 
-def share_plan_device(Xd, Yd, half_width, k, part, n_parts, cb=None, hist=None):
+def share_plan_device(Xd, Yd, half_width, k, part, n_parts, cb=None, hist=None, bounds=None):
     """Flags of share `part` of `n_parts` of one huge image (so_share_plan): uint8 CUDA tensor, bit 0 = local (member
     of the share's search tree: own + halo), bit 1 = own; plus the device counts [local, own].  hist = the coarse
-    histogram of ALL particles (share_hist_device; summed over the ranks when each counted a part)."""
+    histogram of ALL particles (share_hist_device; summed over the ranks when each counted a part).  bounds = the
+    n_parts + 1 cumulative work fractions of the shares (default: equal)."""
     n = Xd.numel()
     cb = share_grid_bits(n, n_parts) if cb is None else int(cb)
     if hist is None:
         hist = share_hist_device(Xd, Yd, half_width, cb)
+    lo, hi = (part / n_parts, (part + 1) / n_parts) if bounds is None else (float(bounds[part]), float(bounds[part + 1]))
+    if part == n_parts - 1:
+        hi = 2.0            # the last share takes everything up to the end
     flags = torch.empty(n, dtype=torch.uint8, device=Xd.device)
     counts = torch.zeros(2, dtype=torch.int64, device=Xd.device)
     wsb = _cabi.lib.so_share_plan_workspace_bytes(cb)
     ws = dv.workspace(wsb)
     _cabi.check(_cabi.lib.so_share_plan(_cabi.ptr(Xd), _cabi.ptr(Yd), n, float(half_width), cb, _cabi.ptr(hist), int(k),
-                                        float(FWHM_FLOOR), int(part), int(n_parts), _cabi.ptr(flags), _cabi.ptr(counts), _cabi.ptr(ws), wsb, _cabi.stream()),
-                'so_share_plan')
+                                        float(FWHM_FLOOR), lo, hi, _cabi.ptr(flags), _cabi.ptr(counts), _cabi.ptr(ws), wsb,
+                                        _cabi.stream()), 'so_share_plan')
     return flags, counts
 
 
