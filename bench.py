@@ -808,7 +808,7 @@ def run_c5(ctx):
 
     def step():
         return sdist.image_huge(X, Y, L, res, ndim, IMG_K)
-    for _ in range(2):
+    for _ in range(4):                 # (the share fractions settle on the measured busy times of the ranks)
         img = step()
     flux = float(img.double().sum())
     ms = timed_loop(ctx, step, max(3, min(args.steps, 5)))
