@@ -1,0 +1,12 @@
+import sys; sys.path.insert(0, '.')
+import numpy as np, torch
+from synthobs_b200 import synthetic
+from synthobs_b200.morph import images
+dev = torch.device('cuda', 0)
+W, ndim = 512 * 0.031 + 1e-9, 1024
+p = synthetic.particles(1000000, seed=200, scale_kpc=3.0)
+X = torch.from_numpy(p['X'] - np.median(p['X'])).to(dev); Y = torch.from_numpy(p['Y'] - np.median(p['Y'])).to(dev)
+width, _, G = images.pixel_grid_device(W / ndim, ndim)
+ix, iy = images.ngp_index_device(X, Y, G, ndim, width / 2.)
+images.knn_device(X, Y, ix, 8, width / 2., floor=images.FWHM_FLOOR)
+torch.cuda.synchronize()
