@@ -808,7 +808,9 @@ def run_c5(ctx):
 
     def step():
         return sdist.image_huge(X, Y, L, res, ndim, IMG_K)
-    for _ in range(4):                 # (the share fractions settle on the measured busy times of the ranks)
+    # warm-up: the share fractions settle on the measured busy times of the ranks and freeze, then both ways of summing
+    # the partial images are timed by the library and the faster one is kept (dist.reduce_mode)
+    for _ in range(sdist.SHARE_ADAPT_CALLS + len(sdist.REDUCE_TRIALS) + 2 if ctx.world > 1 else 3):
         img = step()
     flux = float(img.double().sum())
     ms = timed_loop(ctx, step, max(3, min(args.steps, 5)))
@@ -816,16 +818,24 @@ def run_c5(ctx):
     for _ in range(2):
         sdist.image_huge(X, Y, L, res, ndim, IMG_K, stages=stages)
     stages = {k: ctx.max_over_ranks(v / 2) for k, v in stages.items()}
-    # the same step with a plain ncclAllReduce of the whole image instead of the peer-memory block exchange
-    nccl_ms = None
-    if ctx.world > 1 and sdist.peer_reduce_enabled():
-        os.environ['SO_PEER_REDUCE'] = '0'
+    chosen, forced = 'none (one rank)', {}
+    if ctx.world > 1:
+        bal = sdist._share_balance.get((N, int(ndim), int(IMG_K), ctx.world), {})
+        env0 = os.environ.get('SO_PEER_REDUCE')
+        chosen = {'peer': 'peer-memory block exchange fused into the deposit (csrc/peer.cu)', 'nccl': 'ncclAllReduce of the image',
+                  None: 'forced by SO_PEER_REDUCE=%s' % env0}[bal.get('mode') if sdist.reduce_mode() == 'auto' else None]
+        # the same step with each way forced
         try:
-            for _ in range(2):
-                step()
-            nccl_ms = timed_loop(ctx, step, max(3, min(args.steps, 5)))
+            for name, v in (('peer', '1'), ('nccl', '0')):
+                os.environ['SO_PEER_REDUCE'] = v
+                for _ in range(2):
+                    step()
+                forced[name] = timed_loop(ctx, step, max(3, min(args.steps, 5)))
         finally:
-            os.environ['SO_PEER_REDUCE'] = '1'
+            if env0 is None:
+                os.environ.pop('SO_PEER_REDUCE', None)
+            else:
+                os.environ['SO_PEER_REDUCE'] = env0
     sel = float(((X.abs() < 4 * S) & (Y.abs() < 4 * S)).sum())
     return {'workload': 'config[4] single huge object: %d particles -> %d x %d, (\'adaptive\', %d), Morton-range particle '
                         'shares, partial images summed over NVLink' % (N, ndim, ndim, IMG_K),
@@ -833,9 +843,8 @@ def run_c5(ctx):
             'value': N / (ms * 1e-3), 'unit': 'particles/s', 'selected': sel,
             'flux_conservation': flux / float(L[(X.abs() < 4 * S) & (Y.abs() < 4 * S)].sum()) - 1.0,
             'stages_ms_max_over_ranks': stages, 'image_bytes': 4 * ndim * ndim,
-            'reduce': 'peer-memory block exchange (csrc/peer.cu)' if (ctx.world > 1 and sdist.peer_reduce_enabled()) else
-                      ('ncclAllReduce' if ctx.world > 1 else 'none (one rank)'),
-            'ms_per_step_with_nccl_allreduce': nccl_ms}
+            'reduce': chosen, 'ms_per_step_with_peer_exchange': forced.get('peer'),
+            'ms_per_step_with_nccl_allreduce': forced.get('nccl')}
 
 
 # ------------------------------------------------------------------ CPU baselines (oracle port)

@@ -234,11 +234,26 @@ class PeerImage:
 
 
 _share_balance = {}      # (n, ndim, k, ranks) -> work fractions of the shares, adapted to the measured busy times
+SHARE_ADAPT_CALLS = 6    # calls of one (catalogue size, image, k, ranks) after which the fractions are frozen: reading the
+                         # busy time of the previous call is a host synchronisation per call (measured: ~0.4 ms of a 12 ms step)
 
 
 def peer_reduce_enabled():
     """SO_PEER_REDUCE=0 selects the plain NCCL all-reduce of the whole image"""
-    return os.environ.get('SO_PEER_REDUCE', '1') != '0'
+    return os.environ.get('SO_PEER_REDUCE', 'auto') != '0'
+
+
+def reduce_mode():
+    """How image_huge sums the partial images: 'peer' (SO_PEER_REDUCE=1: the block exchange over peer memory fused into
+    the deposit, csrc/peer.cu), 'nccl' (SO_PEER_REDUCE=0: one ncclAllReduce of the whole image) or 'auto' (default):
+    both are timed on the device in the first calls of a configuration (after the share fractions have settled) and
+    the faster one - the maximum over the ranks decides, so every rank agrees - is kept.  Measured on 8 x B200 with
+    NVSwitch the in-switch all-reduce of the 268 MB image costs ~0.5 ms and wins by 2-4 % at 2, 4 and 8 ranks."""
+    v = os.environ.get('SO_PEER_REDUCE', 'auto')
+    return 'nccl' if v == '0' else ('peer' if v == '1' else 'auto')
+
+
+REDUCE_TRIALS = ('peer', 'peer', 'nccl', 'nccl')      # after SHARE_ADAPT_CALLS calls; the first of each pair is a warm-up
 
 
 SED_KEYS = ('Masses', 'Ages', 'Metallicities', 'tauVs_ISM', 'tauVs_BC')
@@ -385,7 +400,7 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
         if w0 == ws and w0 > 1:
             # every rank counts its 1/N of the particles; the small table is summed over the ranks (exact integers).
             # The same all-reduce carries every rank's busy time of the previous call (below)
-            bal = _share_balance.setdefault((n, int(ndim), int(k), ws), {'frac': np.full(ws, 1.0 / ws), 'pending': None})
+            bal = _share_balance.setdefault((n, int(ndim), int(k), ws), {'frac': np.full(ws, 1.0 / ws), 'pending': None, 'calls': 0})
             cells = 1 << (2 * cb)
             buf = torch.zeros(cells + ws, dtype=torch.int32, device=Xd.device)
             b, e = particle_block(n, rank, ws)
@@ -424,7 +439,28 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
         Lo = Ld.index_select(1, loc.index_select(0, own))
         mark('compaction of the own particles')
     peer = None
-    if reduce and ws > 1 and ws == w0 and peer_reduce_enabled():
+    mode, trial = reduce_mode(), None
+    if reduce and ws > 1 and ws == w0 and mode == 'auto':
+        bal = _share_balance.get((Xd.numel(), int(ndim), int(k), ws))
+        c = bal['calls'] - SHARE_ADAPT_CALLS
+        if bal.get('mode') is not None:
+            mode = bal['mode']
+        elif c < 0:
+            mode = 'peer'
+        elif c < len(REDUCE_TRIALS):
+            mode = trial = REDUCE_TRIALS[c]
+        else:
+            # both timed: the slower rank decides, identically everywhere
+            t = torch.tensor([min(a.elapsed_time(b) for m, a, b in bal['trials'] if m == w and (b.synchronize() or True))
+                              for w in ('peer', 'nccl')], dtype=torch.float64, device=Xd.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = t.cpu().numpy()
+            mode = bal['mode'] = 'peer' if t[0] <= t[1] else 'nccl'
+            bal['trial_ms'] = {'peer': float(t[0]), 'nccl': float(t[1])}
+        if trial is not None:
+            t_start = torch.cuda.Event(enable_timing=True)
+            t_start.record()
+    if reduce and ws > 1 and ws == w0 and mode == 'peer':
         try:
             peer = PeerImage.get(Ld.shape[0], ndim)
         except Exception as e:      # noqa: BLE001  (no peer access between the GPUs of this node: NCCL does the sum)
@@ -437,7 +473,9 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
     img = r['data']
     if ws > 1 and ws == w0 and reduce:
         bal = _share_balance.get((Xd.numel(), int(ndim), int(k), ws))
-        if bal is not None and peer is not None:
+        if bal is not None:
+            bal['calls'] += 1
+        if bal is not None and peer is not None and bal['calls'] < SHARE_ADAPT_CALLS:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             bal['pending'] = (e0, e1, peer.waits.clone())
@@ -453,6 +491,12 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
             mark('all-reduce of the image')
     else:
         mark('plan + binning + deposit of the share')
+    if trial is not None:
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_end.record()
+        # (the second call of each pair counts: the first follows a change of mode)
+        if c % 2 == 1:
+            _share_balance[(Xd.numel(), int(ndim), int(k), ws)].setdefault('trials', []).append((trial, t_start, t_end))
     if stages is not None:
         torch.cuda.synchronize()
         for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
