@@ -440,6 +440,34 @@ def test_observed_particle_batch_equals_loop():
             assert np.isnan(med[g])
 
 
+@pytest.mark.parametrize('k', [1, 4, 8, 16, 30])
+def test_knn_exact_ties_and_stacks_of_identical_positions(k):
+    """the tile search (default for small calls) screens in FP32 and decides in float64: exact ties of the k-th
+    distance (a lattice), more identical positions than a query's list keeps (the hand-over to the quadtree walk),
+    points far outside the bulk and a nearly collinear streak must all come out equal to cKDTree (images.py:83-85)"""
+    from synthobs_b200.morph import images
+    from synthobs_b200 import device as dv
+    rng = np.random.default_rng(7 + k)
+    gx, gy = np.meshgrid(np.arange(40) * 0.05 - 1.0, np.arange(40) * 0.05 - 1.0)       # 1600 lattice points: ties everywhere
+    stack = np.tile([[0.3141, -0.2718]], (60, 1))                                       # 60 identical positions
+    pairs = np.repeat(rng.uniform(-2, 2, (50, 2)), 3, axis=0)                           # triples
+    far = rng.uniform(-3.9, 3.9, (40, 2))
+    streak = np.column_stack([np.linspace(-3, 3, 700), 1e-9 * rng.standard_normal(700) + 2.5])
+    cloud = rng.normal(0, 0.7, (3000, 2))
+    P = np.concatenate([np.column_stack([gx.ravel(), gy.ravel()]), stack, pairs, far, streak, cloud])
+    P = P[rng.permutation(P.shape[0])]
+    X, Y = np.ascontiguousarray(P[:, 0]), np.ascontiguousarray(P[:, 1])
+    hw = 4.0
+    width, G = images.pixel_grid(2 * hw / 100, 100)
+    Xd, Yd = dv.to_dev(X), dv.to_dev(Y)
+    ix, _ = images.ngp_index_device(Xd, Yd, dv.to_dev(G), 100, hw)
+    dk = images.knn_device(Xd, Yd, ix, k, hw).cpu().numpy()
+    sel = image_oracle.select(X, Y, 2 * hw)
+    ref = image_oracle.kth_neighbour_distance(X[sel], Y[sel], k)
+    assert np.array_equal(dk[~sel], np.zeros((~sel).sum()))
+    np.testing.assert_allclose(dk[sel], ref, rtol=4e-16, atol=0)
+
+
 @pytest.mark.parametrize('k', [8, 12])
 def test_knn_floor_shortcut_leaves_the_image_unchanged(k):
     """FWHM = max(dk, 0.01) (images.py:89): with floor = 0.01 the k-NN may return any upper bound <= 0.01 for
