@@ -369,7 +369,7 @@ __device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
 // transpose turns the 32 sets into one particle mask per lane, and the multiply-add loop runs until the longest
 // list is done (about 14 instead of 32 rounds at ~18 pixels per particle; all 32 for wide supports).  The order
 // in which a pixel receives its contributions is still the order of the list: bitwise reproducible.
-template <int C>
+template <int C, bool PUSH>
 __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositParams p) {
     constexpr int CP = (C == 8) ? 12 : C;                      // padded weight row: lanes read different rows at once
     constexpr int FP = 2 * kT + 4;                             // padded factor row
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
     const int64_t start = t0 + (item - p.item_start[tile]) * p.chunk;
     const int64_t end = min(t1, start + p.chunk);
     const bool single = (p.item_start[tile + 1] - p.item_start[tile]) == 1;
-    const bool push = p.push_n > 0 && single && tile_exclusive(p, tile);
+    const bool push = PUSH && single && tile_exclusive(p, tile);      // (PUSH = false: the single-GPU code without these branches)
     const int image = tile / p.ntiles_img, t_in = tile - image * p.ntiles_img;
     const int py0 = (t_in / p.ntx) * kT, px0 = (t_in % p.ntx) * kT;
 
@@ -525,6 +525,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
 // One CTA looks at 32 consecutive work items (one per lane of its first warp) and finishes the sub-tiles whose FIRST
 // item is among them (blockIdx.y = channel), so the launch is max_items / 32 x channels CTAs whatever the image size.
 constexpr int kReduceItems = 32;
+template <bool PUSH>
 __global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParams p, int n_chan) {
     __shared__ unsigned s_todo;
     __shared__ int s_tile[kReduceItems];
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(kT * kT) tile_reduce_kernel(const DepositParam
                 const size_t off = ((size_t)image * n_chan + chan) * p.plane + (size_t)row * p.ld + col;
                 const float v = (s0 + s1) + (s2 + s3);
                 p.data[off] = v;
-                if (p.push_n > 0 && tile_exclusive(p, tile))
+                if (PUSH && tile_exclusive(p, tile))
                     for (int q = 0; q < p.push_n; ++q) p.push_result[q][off] = v;
             }
         }
@@ -974,15 +975,24 @@ extern "C" int so_img_deposit_push(const void* plan_workspace, const double* L, 
             SO_PROF("deposit_kernel", st);
             p.chan0 = c0;
             const int left = n_chan - c0;
-            if (left >= 8) { deposit_kernel<8><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 8; }
-            else if (left >= 4) { deposit_kernel<4><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 4; }
-            else if (left >= 2) { deposit_kernel<2><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 2; }
-            else { deposit_kernel<1><<<grid, kDepWarps * 32, 0, st>>>(p); c0 += 1; }
+#define SO_DEPOSIT(C)                                                                                 \
+            do {                                                                                      \
+                if (p.push_n > 0) deposit_kernel<C, true><<<grid, kDepWarps * 32, 0, st>>>(p);        \
+                else deposit_kernel<C, false><<<grid, kDepWarps * 32, 0, st>>>(p);                    \
+                c0 += C;                                                                              \
+            } while (0)
+            if (left >= 8) SO_DEPOSIT(8);
+            else if (left >= 4) SO_DEPOSIT(4);
+            else if (left >= 2) SO_DEPOSIT(2);
+            else SO_DEPOSIT(1);
+#undef SO_DEPOSIT
             SO_LAUNCH_CHECK();
         }
         if (n_pairs > 0)
         { SO_PROF("tile_reduce_kernel", st);
-          tile_reduce_kernel<<<dim3((unsigned)((d.max_items + kReduceItems - 1) / kReduceItems), (unsigned)n_chan), kT * kT, 0, st>>>(p, n_chan); }
+          const dim3 rg((unsigned)((d.max_items + kReduceItems - 1) / kReduceItems), (unsigned)n_chan);
+          if (p.push_n > 0) tile_reduce_kernel<true><<<rg, kT * kT, 0, st>>>(p, n_chan);
+          else tile_reduce_kernel<false><<<rg, kT * kT, 0, st>>>(p, n_chan); }
         SO_LAUNCH_CHECK();
         if (push) {
             // all ranks have deposited (and pushed their own sub-tiles): finish the shared ones
