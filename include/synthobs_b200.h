@@ -154,9 +154,13 @@ int so_img_ngp_index(const double* X, const double* Y, int64_t n,
 /* K7 — distance to the k-th nearest neighbour in 2-D, counting the particle
  * itself as the first (cKDTree.query(k)[..., -1], synthobs/morph/images.py:83-85).
  * Only particles with ix >= 0 take part; dk = 0 for the others.  dk = +inf when
- * k exceeds the number of selected particles.  Exact (uniform-grid ring search
- * with a conservative stopping rule), float64.  Synchronises once (reads the
- * selected count back). */
+ * k exceeds the number of selected particles.  Exact, float64: the squared distance
+ * is formed with separately rounded products and sum and an IEEE sqrt, like a C loop
+ * (equal to cKDTree to <= 4e-16 relative, ties and identical positions included).
+ * The particles are sorted by the Morton code of their cell; calls of more than 32768
+ * particles walk the implicit quadtree of that order with one thread per query, smaller
+ * ones answer 32 consecutive queries per warp (FP32 screening of shared candidate
+ * tiles, float64 decision; csrc/knn.cu).  Stream-ordered, no host synchronisation. */
 int64_t so_knn_workspace_bytes(int64_t n, int32_t k);
 int so_knn_kth_distance(const double* X, const double* Y, const int32_t* ix, int64_t n,
                         int32_t k, double half_width, double* dk,
