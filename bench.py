@@ -613,6 +613,16 @@ def run_imaging(ctx):
     e2e_ms = wall_loop(ctx, step_e2e, steps)
     stages = imaging_stage_times(obs, Xd, Yd, Ld)
     prof = kernel_profile(step_device)
+    # what the deposit's multiply-add loop really evaluates (so_img_deposit_count: a counting instantiation of the kernel)
+    from synthobs_b200 import _cabi
+    dep_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    _cabi.check(_cabi.lib.so_img_deposit_count(_cabi.ptr(dep_cnt)), 'so_img_deposit_count')
+    try:
+        step_device()
+        torch.cuda.synchronize()
+    finally:
+        _cabi.lib.so_img_deposit_count(None)
+    dep_visits, dep_slots = (float(v) for v in dep_cnt.tolist())
 
     # SED -> images pipeline (examples/morph_image_observed.py:93-95): the catalogue goes up ONCE (56 B/particle), the
     # per-particle fluxes of the 8 filters never leave the GPU, 8 images come back
@@ -643,18 +653,24 @@ def run_imaging(ctx):
     dep_ms = kms('deposit_kernel')
     if dep_ms:
         useful = 2.0 * deposits * IMG_FILTERS                      # 2 flop per in-support (particle, pixel, channel) deposit
-        executed = 2.0 * pairs * 256 * IMG_FILTERS                 # every pair evaluates its whole 16 x 16 sub-tile
+        # a (lane, particle) visit of the multiply-add loop evaluates one 2 x 4 pixel block for all channels; a lane only
+        # visits the staged particles whose support box meets its block (round 1 evaluated 256 pixels per pair)
+        executed = 2.0 * dep_visits * 8 * IMG_FILTERS
+        slots = 2.0 * dep_slots * 8 * IMG_FILTERS                  # issue slots: every round occupies all 32 lanes
         kern['deposit_kernel'] = {
             'bound': 'fp32_fma', 'ms_per_step': dep_ms, 'algorithmic_flops': useful, 'executed_flops': executed,
             'achieved': useful / (dep_ms * 1e-3) / 1e12, 'executed_tflops': executed / (dep_ms * 1e-3) / 1e12,
             'peak': ffma, 'unit': 'TFLOP/s', 'frac': (useful / (dep_ms * 1e-3) / 1e12 / ffma) if ffma else None,
             'executed_frac': (executed / (dep_ms * 1e-3) / 1e12 / ffma) if ffma else None,
             'useful_fma_fraction': useful / executed if executed else None,
+            'issue_slot_flops': slots, 'lanes_busy_fraction': executed / slots if slots else None,
+            'round1_executed_flops': 2.0 * pairs * 256 * IMG_FILTERS,
             'algorithmic_bytes': IMG_PARTICLES * (8 + 8 + 4 + 4 * IMG_FILTERS) + 4 * IMG_FILTERS * (IMG_NDIM * IMG_SS) ** 2,
             'hbm_frac': (IMG_PARTICLES * (20 + 4 * IMG_FILTERS) + 4 * IMG_FILTERS * (IMG_NDIM * IMG_SS) ** 2) / (dep_ms * 1e-3) / 1e9 / hbm,
             'peak_source': 'measured FFMA2 throughput (peaks.fp32_ffma2_tflops)' if ffma else None,
             'note': 'SURVEY 8d: binding roof = max(bytes/HBM, flops/FP32-FMA, exps/MUFU); at ~18 pixels per particle '
-                    'the algorithmic work is tiny against either roof, the kernel\'s time is the evaluated sub-tiles'}
+                    'the algorithmic work is tiny against either roof; executed_flops = multiply-adds of the (lane, particle) '
+                    'visits counted by the kernel itself (so_img_deposit_count), issue_slot_flops = the same for rounds x 32 lanes'}
     for name in ('knn_query_kernel', 'knn_group_kernel'):
         q_ms = kms(name)
         if q_ms:

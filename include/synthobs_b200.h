@@ -194,6 +194,12 @@ int so_knn_kth_distance_ex(const double* X, const double* Y, const int32_t* ix, 
                            double floor, double* dk, int32_t* order_out, int64_t* range_out,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Measurement aid (bench.py's useful-FMA fraction): while `counters` (DEVICE uint64[2], zeroed by the caller) is set, every
+ * single-GPU deposit adds [0] += (lane, staged particle) visits of its multiply-add loop -- each evaluates one 2 x 4 pixel
+ * block for all channels -- and [1] += 32 x the rounds of that loop (the issue slots it occupied).  NULL switches it off
+ * (the counting instantiation of the kernel is a separate one; the normal one is unchanged). */
+int so_img_deposit_count(unsigned long long* counters);
+
 /* K8b..K9 — kernel-smoothed deposition.  Replaces the adaptive loop of
  * images.core (synthobs/morph/images.py:87-97): per particle a Gaussian of
  * FWHM = max(dk, 0.01), normalised by its SUM OVER THE IMAGE PIXELS, times L.

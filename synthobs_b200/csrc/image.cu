@@ -328,6 +328,7 @@ struct DepositParams {
     int push_n;
     float* push_result[SO_MAX_PEERS];          // the ranks' result images, same layout as data
     const unsigned char* push_masks;           // [push_n][ntiles]: which ranks touch which sub-tile (this rank's copy)
+    unsigned long long* visits;                // so_img_deposit_count: [0] += (lane, particle) visits, [1] += rounds x 32
 };
 
 // true when no other rank of a push deposit touches the sub-tile
@@ -369,7 +370,7 @@ __device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
 // transpose turns the 32 sets into one particle mask per lane, and the multiply-add loop runs until the longest
 // list is done (about 14 instead of 32 rounds at ~18 pixels per particle; all 32 for wide supports).  The order
 // in which a pixel receives its contributions is still the order of the list: bitwise reproducible.
-template <int C, bool PUSH>
+template <int C, bool PUSH, bool COUNT = false>
 __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositParams p) {
     constexpr int CP = (C == 8) ? 12 : C;                      // padded weight row: lanes read different rows at once
     constexpr int FP = 2 * kT + 4;                             // padded factor row
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
+    unsigned n_visits = 0, n_rounds = 0;                       // COUNT only
     int pid_next = (start + lane < end) ? p.pids[start + lane] : 0;     // list entries are fetched one phase ahead
     for (int64_t base = start; base < end; base += kP) {
         const int np = (int)min((int64_t)kP, end - base);
@@ -454,6 +456,7 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
         }
         __syncwarp();
         while (__any_sync(0xffffffffu, mine != 0)) {
+            if (COUNT) { ++n_rounds; n_visits += mine != 0; }
             if (mine) {
                 const int q = __ffs(mine) - 1;
                 mine &= mine - 1;
@@ -485,6 +488,11 @@ __global__ void __launch_bounds__(kDepWarps * 32) deposit_kernel(const DepositPa
         }
     }
 
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_visits += __shfl_xor_sync(0xffffffffu, n_visits, o);
+        if (lane == 0) { atomicAdd(p.visits, (unsigned long long)n_visits); atomicAdd(p.visits + 1, 32ull * n_rounds); }
+    }
     const int col = px0 + 4 * bc;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -795,6 +803,13 @@ static DepositLayout carve_deposit(void* ws, int64_t bytes, int64_t n, int64_t n
 
 }  // namespace
 
+// so_img_deposit_count: device counters the next deposits add their (lane, particle) visits to (measurement aid)
+static unsigned long long* g_deposit_visits = nullptr;
+extern "C" int so_img_deposit_count(unsigned long long* counters) {
+    g_deposit_visits = counters;
+    return SO_OK;
+}
+
 extern "C" int so_img_ngp_index(const double* X, const double* Y, int64_t n, const double* G, int32_t ndim,
                                 double half_width, int32_t* ix, int32_t* iy, void* stream) {
     if (n < 0 || ndim < 1 || !G) return SO_ERR_BAD_ARG;
@@ -940,6 +955,7 @@ extern "C" int so_img_deposit_push(const void* plan_workspace, const double* L, 
     p.ld = data_ld; p.plane = data_plane;
     p.chunk = d.chunk; p.data = data; p.partial = d.partial; p.n_chan = n_chan; p.chan0 = 0; p.wts = d.wts;
     p.push_n = 0;
+    p.visits = g_deposit_visits;
     PeerPtrs pp_partial{}, pp_masks{}, pp_flags{};
     if (push) {
         p.push_n = push->n_ranks;
@@ -978,6 +994,7 @@ extern "C" int so_img_deposit_push(const void* plan_workspace, const double* L, 
 #define SO_DEPOSIT(C)                                                                                 \
             do {                                                                                      \
                 if (p.push_n > 0) deposit_kernel<C, true><<<grid, kDepWarps * 32, 0, st>>>(p);        \
+                else if (p.visits) deposit_kernel<C, false, true><<<grid, kDepWarps * 32, 0, st>>>(p); \
                 else deposit_kernel<C, false><<<grid, kDepWarps * 32, 0, st>>>(p);                    \
                 c0 += C;                                                                              \
             } while (0)
