@@ -702,7 +702,7 @@ def run_imaging(ctx):
                 'entry_point': 'images.particle(X, Y, {filter: L}, filters, cosmo, z, width, smoothing=, PSFs=, super_sampling=) '
                                'with pinned CPU tensors; returns {filter: img} NumPy; X, Y recentred in place',
                 'h2d_bytes_per_step': int(IMG_PARTICLES * 8 * (2 + IMG_FILTERS)),
-                'd2h_bytes_per_step': int(2 * IMG_FILTERS * IMG_NDIM * IMG_NDIM * 4 + 16 * IMG_PARTICLES)},
+                'd2h_bytes_per_step': int(2 * IMG_FILTERS * IMG_NDIM * IMG_NDIM * 8 + 16 * IMG_PARTICLES)},
         'pipeline_e2e': {'value': ctx.world * IMG_PARTICLES / (pipe_ms * 1e-3), 'unit': 'particles/s', 'ms_per_step': pipe_ms,
                          'chain': 'pinned catalogue (X, Y, Masses, Ages, Metallicities, tauVs_ISM, tauVs_BC) -> H2D once -> '
                                   'models.generate_Fnu_arrays (8 filters, stays on the GPU) -> images.particle -> 8 images D2H',

@@ -653,6 +653,13 @@ def particle_device_multi(obs_list, Xd, Yd, Ld, L_event=None, offsets_applied=Fa
 _copy_stream = {}
 
 
+def _side_stream(key, dev):
+    st = _copy_stream.get(key)
+    if st is None:
+        st = _copy_stream[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def particle_host_multi(obs_list, Xh, Yh, Lh):
     """particle_device_multi for HOST inputs (NumPy arrays or CPU tensors, ideally pinned): the
     positions go up first, the [C, n] weights follow on a copy stream while the k-NN and the tile
@@ -661,7 +668,7 @@ def particle_host_multi(obs_list, Xh, Yh, Lh):
     final images [C, ndim, ndim] as a float32 CPU tensor plus the run statistics."""
     dev = dv.device()
     main = torch.cuda.current_stream()
-    side = _copy_stream.setdefault(dev.index, torch.cuda.Stream(device=dev))
+    side = _side_stream(dev.index, dev)
     as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))   # noqa: E731
     Xd = as_t(Xh).to(dev, non_blocking=True)
     Yd = as_t(Yh).to(dev, non_blocking=True)
@@ -909,7 +916,7 @@ def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=
     n = len(X)
     if host:
         # positions first (the k-NN and the binning only need them), the weights follow on a copy stream
-        side = _copy_stream.setdefault(dev.index, torch.cuda.Stream(device=dev))
+        side = _side_stream(dev.index, dev)
         XY = torch.empty((2, n), dtype=torch.float64, device=dev)     # one block: both medians in one selection
         XY[0].copy_(_as_cpu_tensor(X), non_blocking=True)
         XY[1].copy_(_as_cpu_tensor(Y), non_blocking=True)
@@ -938,6 +945,28 @@ def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=
     pos = dict(zip(out_steps, recentre_chain_device(Xd, Yd, [obs[f].xoffset for f in filters],
                                                     [obs[f].yoffset for f in filters], out_steps)))
 
+    # the caller's arrays end up exactly as the reference leaves them (recentred once per filter).  For host inputs the
+    # recentred positions go back on a second copy stream as soon as they exist, under the k-NN and the deposit (the
+    # device-to-host direction of the link is idle until the images are ready)
+    Xf, Yf = pos[len(filters)]
+    back, back_done = [], None
+    if host:
+        down = _side_stream((dev.index, 'down'), dev)
+        rc_done = torch.cuda.Event()
+        rc_done.record(main)
+        with torch.cuda.stream(down):
+            down.wait_event(rc_done)
+            for A, Af in ((X, Xf), (Y, Yf)):
+                Af.record_stream(down)
+                if isinstance(A, torch.Tensor) and A.is_pinned() and A.dtype == torch.float64 and A.is_contiguous():
+                    A.copy_(Af, non_blocking=True)      # straight into the caller's page-locked buffer
+                else:
+                    Ah = torch.empty(n, dtype=torch.float64, pin_memory=True)
+                    Ah.copy_(Af, non_blocking=True)
+                    back.append((A, Ah))
+            back_done = torch.cuda.Event()
+            back_done.record(down)
+
     IMGs = {}
     pending = []
     for key, fs in groups.items():
@@ -956,19 +985,9 @@ def particle(X, Y, L, filters, cosmo, z, target_width_arcsec, resampling_factor=
                 img.pixel_scale, img.pixel_scale_kpc = obs[f].pixel_scale, obs[f].pixel_scale_kpc
                 img.no_PSF, img.data = r['no_PSF'][c], r['data'][c]
                 IMGs[f] = img
-    # the caller's arrays end up exactly as the reference leaves them (recentred once per filter)
-    Xf, Yf = pos[len(filters)]
     if host:
-        # D2H of the recentred positions: straight into the caller's buffer when it is page-locked
-        back = []
-        for A, Af in ((X, Xf), (Y, Yf)):
-            if isinstance(A, torch.Tensor) and A.is_pinned() and A.dtype == torch.float64 and A.is_contiguous():
-                A.copy_(Af, non_blocking=True)
-            else:
-                Ah = torch.empty(n, dtype=torch.float64, pin_memory=True)
-                Ah.copy_(Af, non_blocking=True)
-                back.append((A, Ah))
         main.synchronize()
+        back_done.synchronize()
         for A, Ah in back:
             if isinstance(A, torch.Tensor):
                 A.copy_(Ah)
