@@ -147,9 +147,10 @@ __global__ void __launch_bounds__(kKeyThreads) knn_key_kernel(
     __syncthreads();
     unsigned int mine = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const bool sel = ix[i] >= 0;
         const double x = X[i], y = Y[i];
         unsigned long long key = (unsigned long long)n_img << (2 * kBits);
+        // an image id outside [0, n_img) would leave key bits above the sorted range: such a particle counts as outside
+        const bool sel = ix[i] >= 0 && (!img || (unsigned)img[i] < (unsigned long long)n_img);
         if (sel) {
             const int nc = 1 << kBits;
             int cx = (int)((x + hw) * inv_h), cy = (int)((y + hw) * inv_h);
@@ -1044,6 +1045,9 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     const double inv_h = (double)(1 << kBits) / (2.0 * half_width);
     int img_bits = 1;
     while (((int64_t)1 << img_bits) <= n_img) ++img_bits;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("SO_KNN_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
+#define KNN_DBG(what) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[knn] %s: %s\n", what, cudaGetErrorString(e_)); } } while (0)
     SO_CUDA(cudaMemsetAsync(l.counter, 0, 2 * sizeof(unsigned long long), st));
     const unsigned blocks = (unsigned)((n + 255) / 256);
     int64_t key_blocks = (n + kKeyThreads - 1) / kKeyThreads;
@@ -1054,8 +1058,10 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     size_t tmp = (size_t)l.cub_tmp_bytes;
     { SO_PROF("cub sort Morton keys", st); SO_CUDA(cub::DeviceRadixSort::SortPairs(l.cub_tmp, tmp, keys0, keys1, l.vals0, l.vals1, (int)n, 0,
                                             2 * kBits + img_bits, st)); }
+    KNN_DBG("sort");
     { SO_PROF("knn_gather_kernel", st); knn_gather_kernel<<<blocks, 256, 0, st>>>(l.xy, l.vals1, n, l.pts); }
     SO_LAUNCH_CHECK();
+    KNN_DBG("gather");
     // measured on B200 (1e6 clustered particles): the private walk wins for k <= 8 (0.71 vs 0.76 ms), the shared
     // walk for larger k (k = 16: 1.17 vs 1.27 ms).  SO_KNN_PRIVATE=0/1 and SO_KNN_LEAF override (A/B aids).
     static int force_private = -2, leaf = 0;
@@ -1127,6 +1133,7 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     SO_LAUNCH_CHECK();
     tmp = (size_t)l.cub_tmp_bytes;
     SO_CUDA(cub::DeviceScan::InclusiveScan(l.cub_tmp, tmp, l.E, l.E, cub::Max(), (int)ncell, st));
+    KNN_DBG("table");
     const bool private_walk = gate || (force_private >= 0 ? force_private == 1 : k <= 8);
     // half-width of the window of sorted neighbours scanned first (SO_KNN_WIN = multiple of k, default 1)
     static int win_mul = 0;
@@ -1142,6 +1149,8 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
             l.pts, keys1, l.vals1, n, n_img, l.E, Lt, half_width, inv_h, k, part, n_parts, leaf, win, floor2, qmask, dk); }
     }
     SO_LAUNCH_CHECK();
+    KNN_DBG("query");
+#undef KNN_DBG
     if (order_out) SO_CUDA(cudaMemcpyAsync(order_out, l.vals1, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
     if (range_out) {
         { SO_PROF("knn_range_kernel", st); knn_range_kernel<<<1, 1, 0, st>>>(l.counter, part, n_parts, range_out); }

@@ -468,6 +468,39 @@ def test_knn_exact_ties_and_stacks_of_identical_positions(k):
     np.testing.assert_allclose(dk[sel], ref, rtol=4e-16, atol=0)
 
 
+@pytest.mark.parametrize('n', [3000, 50000])
+def test_knn_batch_of_tiny_images_and_invalid_image_ids(n):
+    """batch mode (image id per particle, config 4): many tiny images, some with fewer than k particles (dk = inf),
+    equal to cKDTree per image for both searches (n picks the tile kernel / the quadtree walk); a particle whose image id
+    lies outside [0, n_img) counts as outside its image (dk = 0) instead of corrupting the sort"""
+    import torch
+    from synthobs_b200.morph import images
+    from synthobs_b200 import device as dv
+    rng = np.random.default_rng(n)
+    k, n_img, hw = 6, n // 12, 4.0
+    X, Y = rng.normal(0, 0.8, n), rng.normal(0, 0.8, n)
+    ids = np.sort(rng.integers(0, n_img, n)).astype(np.int32)
+    bad = rng.choice(n, 25, replace=False)
+    ids_in = ids.copy()
+    ids_in[bad[:12]] = n_img + 7
+    ids_in[bad[12:]] = -3
+    width, G = images.pixel_grid(2 * hw / 100, 100)
+    Xd, Yd = dv.to_dev(X), dv.to_dev(Y)
+    ix, _ = images.ngp_index_device(Xd, Yd, dv.to_dev(G), 100, hw)
+    dk = images.knn_device(Xd, Yd, ix, k, hw, img=dv.to_dev(ids_in, torch.int32), n_img=n_img).cpu().numpy()
+    ok = image_oracle.select(X, Y, 2 * hw)
+    ok[bad] = False
+    ref = np.zeros(n)
+    for g in np.unique(ids):
+        m = ok & (ids == g)
+        if m.sum() == 0:
+            continue
+        ref[m] = image_oracle.kth_neighbour_distance(X[m], Y[m], k) if m.sum() >= k else np.inf
+    assert np.array_equal(np.isinf(dk), np.isinf(ref))
+    f = np.isfinite(ref)
+    np.testing.assert_allclose(dk[f], ref[f], rtol=4e-16, atol=0)
+
+
 @pytest.mark.parametrize('k', [8, 12])
 def test_knn_floor_shortcut_leaves_the_image_unchanged(k):
     """FWHM = max(dk, 0.01) (images.py:89): with floor = 0.01 the k-NN may return any upper bound <= 0.01 for
