@@ -321,6 +321,22 @@ int so_median_segmented(const double* x, const int64_t* seg_offsets, int64_t n_s
 int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, const double* med, double shift,
                           void* stream);
 
+/* Line-of-sight metal column density of star particles: the input the reference loads as
+ * MetSurfaceDensities.npy (synthobs/core.py:17-21, :33-37) and turns into tauVs_ISM = 10^5.2 * MetSurfaceDensities
+ * (examples/SED_luminosities.py:69).  The reference does not compute it; specification: oracle/los_oracle.py.
+ *   out[i] = scale * sum over the gas particles j of star i's object with zg[j] > zs[i] of
+ *            mg[j] Zg[j] / hg[j]^2 * F(b_ij / hg[j]),  b_ij = distance in the (x, y) plane,
+ * F = cubic-spline SPH kernel (support r < h) projected along z: `table` = F(i / nt), i = 0..nt (DEVICE float32[nt + 1],
+ * nt <= 2048), interpolated linearly, 0 beyond.  Batch of objects: stars and gas concatenated, star_off / gas_off =
+ * HOST int64[n_obj + 1] CSR offsets (a star only sees its own object's gas).  All other arrays DEVICE float64.
+ * The z test uses the float64 inputs; the kernel sum is FP32 per tile of 256 gas particles, float64 over the tiles,
+ * in a fixed order (bitwise reproducible).  Workspace: so_los_workspace_bytes(n_obj). */
+int64_t so_los_workspace_bytes(int64_t n_obj);
+int so_los_column(const double* xs, const double* ys, const double* zs, const int64_t* star_off_host,
+                  const double* xg, const double* yg, const double* zg, const double* mg, const double* Zg,
+                  const double* hg, const int64_t* gas_off_host, int64_t n_obj, const float* table, int32_t nt,
+                  double scale, double* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* One huge image over several GPUs (BASELINE config 5; the reference images one object in one Python loop,
  * synthobs/morph/images.py:83-97): split the selected particles (|x|, |y| < half_width) into n_parts spatially compact
  * shares of equal WORK (+- one coarse cell; a particle of a cell too sparse to hold k particles within `floor`, the
