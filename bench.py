@@ -48,7 +48,7 @@ Z = 8.0
 C4_GALAXIES = 10000
 C5_PARTICLES = 100000000
 C5_NDIM = 8192
-ALL_SECTIONS = ('peaks', 'sed', 'latency', 'spectra', 'imaging', 'c1', 'c4', 'c5')
+ALL_SECTIONS = ('peaks', 'sed', 'latency', 'spectra', 'imaging', 'c1', 'c4', 'c5', 'los')
 SED_WORKLOAD = ('config[1] SED_fluxes: %d galaxies per step (and per GPU) x 1e5 particles, BPASS-shape grid 51x13x%d, '
                 'ISM+BC LOS dust, %d filters' % (GALAXIES_PER_GPU, N_LAM, N_FILTERS))
 
@@ -711,6 +711,52 @@ def run_imaging(ctx):
     }
 
 
+def run_los(ctx):
+    """Line-of-sight metal column density (synthobs_b200.los, so_los_column): one object of 1e5 star and 1e5
+    gas particles per GPU = 1e10 (star, gas) pairs per step.  Compute-bound pair kernel: reported against the measured
+    FP32 FMA roof with 7 flops per pair (2 subtractions, 2 multiply-adds, 1 multiply: what every pair costs before the
+    support test); the oracle (NumPy, float64) timed on a sample of the same stars is the CPU baseline."""
+    import torch
+    from synthobs_b200 import los
+    dev = ctx.dev
+    ns = ng = 100000
+    g = torch.Generator(device=dev)
+    g.manual_seed(7 + ctx.rank)
+    stars = [1.5 * torch.randn(ns, dtype=torch.float64, device=dev, generator=g) for _ in range(3)]
+    gas = [2.0 * torch.randn(ng, dtype=torch.float64, device=dev, generator=g) for _ in range(3)]
+    m = 1e6 * (0.5 + torch.rand(ng, dtype=torch.float64, device=dev, generator=g))
+    Z = 10 ** (-4 + 2.3 * torch.rand(ng, dtype=torch.float64, device=dev, generator=g))
+    h = 10 ** (-1.3 + 1.3 * torch.rand(ng, dtype=torch.float64, device=dev, generator=g))
+
+    def step():
+        return los.metal_surface_density(*stars, *gas, m, Z, h, scale=1e-6)
+    for _ in range(3):
+        out = step()
+    ms = timed_loop(ctx, step, max(3, min(ctx.args.steps, 10)))
+    pairs = float(ns) * ng
+    ffma = ctx.measured.get('fp32_ffma_tflops')
+    rec = {'metric': 'star-gas pairs / s (line-of-sight metal column density)', 'unit': 'pairs/s',
+           'value': ctx.world * pairs / (ms * 1e-3), 'ms_per_step': ms, 'stars_per_s': ctx.world * ns / (ms * 1e-3),
+           'config': {'workload': '1 object per GPU: %d star x %d gas particles, smoothing lengths 0.05..1 (extent ~2)' % (ns, ng),
+                      'l2_policy': 'inputs 6.4 MB: L2-resident by design (every star reads all the gas)'},
+           'roofline': {'bound': 'fp32_fma', 'algorithmic_flops': 7.0 * pairs, 'achieved': 7.0 * pairs / (ms * 1e-3) / 1e12,
+                        'peak': ffma, 'unit': 'TFLOP/s', 'frac': (7.0 * pairs / (ms * 1e-3) / 1e12 / ffma) if ffma else None,
+                        'kernel': 'los_kernel', 'peak_source': 'measured FFMA throughput (peaks.fp32_ffma_tflops)' if ffma else None},
+           'mean_column_Msol_pc2': float(out.mean())}
+    if ctx.rank == 0 and ctx.world == 1 and not ctx.args.no_cpu:
+        from oracle import los_oracle
+        h_stars = [a[:512].cpu().numpy() for a in stars]
+        h_gas = [a.cpu().numpy() for a in gas] + [m.cpu().numpy(), Z.cpu().numpy(), h.cpu().numpy()]
+        t0 = time.time()
+        ref = los_oracle.metal_surface_density(*h_stars, *h_gas, scale=1e-6)
+        dt = time.time() - t0
+        rec['cpu_baseline'] = {'value': 512.0 * ng / dt, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port',
+                               'sample': 'oracle/los_oracle.metal_surface_density (the specification itself; the reference has no '
+                                         'implementation) for the first 512 stars against all %d gas particles in %.1f s' % (ng, dt),
+                               'max_abs_diff_over_max': float(np.max(np.abs(out[:512].cpu().numpy() - ref)) / np.max(ref))}
+    return rec
+
+
 def run_c1(ctx):
     """config[0]: examples/morph_image_physical.py-style, 1e4 particles onto a 100 x 100 physical image through
     images.core, the three smoothing modes; NumPy in / NumPy out, ms per call."""
@@ -954,6 +1000,8 @@ def run_ours(args):
         rec['config4'] = run_c4(ctx, model, F)
     if 'c5' in sections:
         rec['config5'] = run_c5(ctx)
+    if 'los' in sections:
+        rec['los'] = run_los(ctx)
     sampler.stop()
     rec['clocks'] = sampler.summary(t_start, time.time())     # all timed regions of this run
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:

@@ -329,7 +329,7 @@ int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, 
  * F = cubic-spline SPH kernel (support r < h) projected along z: `table` = F(i / nt), i = 0..nt (DEVICE float32[nt + 1],
  * nt <= 2048), interpolated linearly, 0 beyond.  Batch of objects: stars and gas concatenated, star_off / gas_off =
  * HOST int64[n_obj + 1] CSR offsets (a star only sees its own object's gas).  All other arrays DEVICE float64.
- * The z test uses the float64 inputs; the kernel sum is FP32 per tile of 256 gas particles, float64 over the tiles,
+ * The z test uses the float64 inputs; the kernel sum is FP32 per tile of 128 gas particles, float64 over the tiles,
  * in a fixed order (bitwise reproducible).  Workspace: so_los_workspace_bytes(n_obj). */
 int64_t so_los_workspace_bytes(int64_t n_obj);
 int so_los_column(const double* xs, const double* ys, const double* zs, const int64_t* star_off_host,

@@ -7,10 +7,10 @@
 // F = the cubic-spline SPH kernel (support r < h) projected along the line of sight, tabulated at NT + 1 nodes and
 // interpolated linearly.
 //
-// One thread = one star, one CTA = 256 stars of one object; the object's gas particles pass through shared memory in
-// tiles of 256 (one coalesced load per thread and tile: position relative to the object's first gas particle and
+// One thread = one star, one CTA = 128 stars of one object; the object's gas particles pass through shared memory in
+// tiles of 128 (one coalesced load per thread and tile: position relative to the object's first gas particle and
 // as FP32 head + tail, 1 / h^2, m Z / h^2 in FP32, z in float64), and every thread walks the tile with broadcast loads:
-// 2 subtractions, a multiply-add, one multiply and two compares per pair on the heads; the few pairs inside a kernel's
+// 2 subtractions, a multiply-add and one multiply per pair on the heads, four pairs per round with one branch; the few pairs inside a kernel's
 // support (b < h, in front) redo the difference with the tails (coordinates far from the origin lose nothing), then take
 // one rsqrt and two table loads.  The z test is made on the float64 inputs (a particle counts or does not: no FP32
 // rounding decides that), the smooth part is FP32, summed per tile in FP32 and over the tiles in float64 in a fixed
@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int kLosThreads = 256;
+constexpr int kLosThreads = 128;
 constexpr int kLosMaxTable = 2048;
 
 __global__ void __launch_bounds__(kLosThreads) los_kernel(
@@ -72,23 +72,44 @@ __global__ void __launch_bounds__(kLosThreads) los_kernel(
         }
         __syncthreads();
         float acc = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
-            const float4 p = s_g[j];
-            const float dxc = p.x - sx, dyc = p.y - sy;                 // heads only: off by <= 2^-23 of the coordinates
-            if (fmaf(dxc, dxc, dyc * dyc) * p.z < 1.002f && s_z[j] > sz) {
-                // a pair inside (or at the edge of) the support: the tails make the difference exact to ~1e-7 of h
-                const float2 l = s_lo[j];
-                const float dx = dxc + (l.x - sxl), dy = dyc + (l.y - syl);
-                const float q2 = fmaf(dx, dx, dy * dy) * p.z;           // (b / h)^2
-                if (q2 < 1.f) {
-                    const float t = q2 * rsqrtf(fmaxf(q2, 1e-30f)) * fnt;   // u NT, u = sqrt(q2)
-                    const int k = min((int)t, nt - 1);
-                    const float f = t - (float)k;
-                    const float a = s_tab[k];
-                    acc = fmaf(p.w, fmaf(f, s_tab[k + 1] - a, a), acc);
-                }
+        // a pair inside (or at the edge of) a kernel's support, in front of the star: redo the difference with the tails
+        // (exact to ~1e-7 of h whatever the distance from the origin), then the interpolated kernel
+        auto inside = [&](int j, const float4 p, float dxc, float dyc) {
+            if (!(s_z[j] > sz)) return;
+            const float2 l = s_lo[j];
+            const float dx = dxc + (l.x - sxl), dy = dyc + (l.y - syl);
+            const float q2 = fmaf(dx, dx, dy * dy) * p.z;               // (b / h)^2
+            if (q2 < 1.f) {
+                const float t = q2 * rsqrtf(fmaxf(q2, 1e-30f)) * fnt;    // u NT, u = sqrt(q2)
+                const int k = min((int)t, nt - 1);
+                const float f = t - (float)k;
+                const float a = s_tab[k];
+                acc = fmaf(p.w, fmaf(f, s_tab[k + 1] - a, a), acc);
             }
+        };
+        // four pairs per round on the FP32 heads (off by <= 2^-23 of the coordinates: the test is widened), ONE branch
+        // for the round: the four loads and distance chains are independent and overlap
+        int j = 0;
+        for (; j + 4 <= cnt; j += 4) {
+            float4 p[4];
+            float dxc[4], dyc[4], q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = s_g[j + u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dxc[u] = p[u].x - sx; dyc[u] = p[u].y - sy;
+                q[u] = fmaf(dxc[u], dxc[u], dyc[u] * dyc[u]) * p[u].z;
+            }
+            if (fminf(fminf(q[0], q[1]), fminf(q[2], q[3])) < 1.002f) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (q[u] < 1.002f) inside(j + u, p[u], dxc[u], dyc[u]);
+            }
+        }
+        for (; j < cnt; ++j) {
+            const float4 p = s_g[j];
+            const float dxc = p.x - sx, dyc = p.y - sy;
+            if (fmaf(dxc, dxc, dyc * dyc) * p.z < 1.002f) inside(j, p, dxc, dyc);
         }
         total += (double)acc;
     }

@@ -1,5 +1,5 @@
 """CUDA line-of-sight metal column density (so_los_column) against the specification oracle/los_oracle.py.
-Tolerance: the pair arithmetic is FP32 (relative coordinates, kernel interpolation), summed per tile of 256 gas particles
+Tolerance: the pair arithmetic is FP32 (relative coordinates, kernel interpolation), summed per tile of 128 gas particles
 in FP32 and over the tiles in float64: |a - b| <= 2e-5 max|b| and 1e-5 in L2."""
 import numpy as np
 import pytest
