@@ -329,9 +329,10 @@ int so_recentre_segmented(double* x, const int64_t* seg_offsets, int64_t n_seg, 
  * F = cubic-spline SPH kernel (support r < h) projected along z: `table` = F(i / nt), i = 0..nt (DEVICE float32[nt + 1],
  * nt <= 2048), interpolated linearly, 0 beyond.  Batch of objects: stars and gas concatenated, star_off / gas_off =
  * HOST int64[n_obj + 1] CSR offsets (a star only sees its own object's gas).  All other arrays DEVICE float64.
- * The z test uses the float64 inputs; the kernel sum is FP32 per tile of 128 gas particles, float64 over the tiles,
- * in a fixed order (bitwise reproducible).  Workspace: so_los_workspace_bytes(n_obj). */
-int64_t so_los_workspace_bytes(int64_t n_obj);
+ * The z test uses the float64 inputs; pairs are screened in FP32 (conservatively) and the in-support ones decided from
+ * FP32 head + tail coordinates; the kernel sum is FP32 per tile of 128 gas particles, float64 over the tiles,
+ * in a fixed order (bitwise reproducible).  star_off[0] must be 0.  Workspace: so_los_workspace_bytes(n_obj, n_star). */
+int64_t so_los_workspace_bytes(int64_t n_obj, int64_t n_star);
 int so_los_column(const double* xs, const double* ys, const double* zs, const int64_t* star_off_host,
                   const double* xg, const double* yg, const double* zg, const double* mg, const double* Zg,
                   const double* hg, const int64_t* gas_off_host, int64_t n_obj, const float* table, int32_t nt,

@@ -81,7 +81,7 @@ SIGNATURES = {
     'so_peer_block_mask': (c_int, [P, I32, I32, I64, I64, P, P]),
     'so_peer_sum': (c_int, [POINTER(c_void_p), P, I32, I32, I32, I32, P, P]),
     'so_peak_kernel': (c_int, [I32, I64, I32, P, POINTER(c_double), P]),
-    'so_los_workspace_bytes': (I64, [I64]),
+    'so_los_workspace_bytes': (I64, [I64, I64]),
     'so_los_column': (c_int, [P, P, P, POINTER(c_int64), P, P, P, P, P, P, POINTER(c_int64), I64, P, I32, D, P, P, I64, P]),
     'so_img_deposit_count': (c_int, [P]),
     'so_prof_enable': (c_int, [I32]),

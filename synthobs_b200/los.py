@@ -73,7 +73,7 @@ def metal_surface_density_batch(xs, ys, zs, star_offsets, xg, yg, zg, gas_mass, 
         raise ValueError('star arrays and gas arrays must have one entry per particle')
     _, table = kernel_table()
     out = torch.zeros(d[0].numel(), dtype=torch.float64, device=dv.device())
-    wsb = _cabi.lib.so_los_workspace_bytes(n_obj)
+    wsb = _cabi.lib.so_los_workspace_bytes(n_obj, d[0].numel())
     ws = dv.workspace(wsb)
     i64p = ctypes.POINTER(ctypes.c_int64)
     _cabi.check(_cabi.lib.so_los_column(_cabi.ptr(d[0]), _cabi.ptr(d[1]), _cabi.ptr(d[2]), so.ctypes.data_as(i64p),
