@@ -400,7 +400,7 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
         if w0 == ws and w0 > 1:
             # every rank counts its 1/N of the particles; the small table is summed over the ranks (exact integers).
             # The same all-reduce carries every rank's busy time of the previous call (below)
-            bal = _share_balance.setdefault((n, int(ndim), int(k), ws), {'frac': np.full(ws, 1.0 / ws), 'pending': None, 'calls': 0})
+            bal = _share_balance.setdefault((n, int(ndim), int(k), ws), {'frac': np.full(ws, 1.0 / ws), 'pending': None, 'calls': 0, 'hist': []})
             cells = 1 << (2 * cb)
             buf = torch.zeros(cells + ws, dtype=torch.int32, device=Xd.device)
             b, e = particle_block(n, rank, ws)
@@ -415,10 +415,15 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
             if bal['pending'] is not None:
                 t = buf[cells:].cpu().numpy().astype(np.float64)
                 if np.all(t > 0):
-                    # shares proportional to the measured speed of their rank, damped; identical on every rank
-                    f = bal['frac'] * (t.mean() / t) ** 0.7
-                    f = np.clip(f / f.sum(), 0.4 / ws, 2.5 / ws)
-                    bal['frac'] = f / f.sum()
+                    bal['hist'].append((float(t.max()), bal['frac'].copy()))     # what the previous call's fractions cost
+                    if bal['calls'] < SHARE_ADAPT_CALLS:
+                        # shares proportional to the measured speed of their rank, damped; identical on every rank
+                        f = bal['frac'] * (t.mean() / t) ** 0.7
+                        f = np.clip(f / f.sum(), 0.4 / ws, 2.5 / ws)
+                        bal['frac'] = f / f.sum()
+                    else:
+                        # last measurement: freeze on the best fractions seen (the damped iteration may still be swinging)
+                        bal['frac'] = min(bal['hist'], key=lambda h: h[0])[1]
             bounds = np.concatenate([[0.0], np.cumsum(bal['frac'])])
         else:
             hist = images.share_hist_device(Xd, Yd, hw, cb)
@@ -475,7 +480,7 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
         bal = _share_balance.get((Xd.numel(), int(ndim), int(k), ws))
         if bal is not None:
             bal['calls'] += 1
-        if bal is not None and peer is not None and bal['calls'] < SHARE_ADAPT_CALLS:
+        if bal is not None and peer is not None and bal['calls'] <= SHARE_ADAPT_CALLS:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             bal['pending'] = (e0, e1, peer.waits.clone())
