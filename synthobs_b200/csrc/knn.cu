@@ -1045,7 +1045,7 @@ static int knn_run_keys(const double* X, const double* Y, const int32_t* ix, con
     const double inv_h = (double)(1 << kBits) / (2.0 * half_width);
     int img_bits = 1;
     while (((int64_t)1 << img_bits) <= n_img) ++img_bits;
-    static int dbg = -1;
+    static int dbg = -1;      // SO_KNN_DEBUG=1: synchronise and report after every stage (locates a failing or hanging stage)
     if (dbg < 0) { const char* e = getenv("SO_KNN_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
 #define KNN_DBG(what) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[knn] %s: %s\n", what, cudaGetErrorString(e_)); } } while (0)
     SO_CUDA(cudaMemsetAsync(l.counter, 0, 2 * sizeof(unsigned long long), st));

@@ -164,3 +164,17 @@ def test_core_sed_known_answers():
     # IGM: transparent redward of Lyman alpha in the observed frame, opaque far blueward
     t = providers.madau(np.array([500.0 * 9, 1300.0 * 9, 20000.0]), 8.0)
     assert t[1] == 1.0 and t[2] == 1.0 and t[0] < 1e-3
+
+
+def test_image_reduce_mode_env(monkeypatch):
+    """dist.reduce_mode: SO_PEER_REDUCE = 1 / 0 force the peer-memory exchange / ncclAllReduce, anything else measures"""
+    from synthobs_b200 import dist as sdist
+    monkeypatch.delenv('SO_PEER_REDUCE', raising=False)
+    assert sdist.reduce_mode() == 'auto' and sdist.peer_reduce_enabled()
+    monkeypatch.setenv('SO_PEER_REDUCE', '1')
+    assert sdist.reduce_mode() == 'peer'
+    monkeypatch.setenv('SO_PEER_REDUCE', '0')
+    assert sdist.reduce_mode() == 'nccl' and not sdist.peer_reduce_enabled()
+    # every timed mode is preceded by an untimed call of the same mode
+    assert sdist.REDUCE_TRIALS[0::2] == sdist.REDUCE_TRIALS[1::2] and set(sdist.REDUCE_TRIALS) == {'peer', 'nccl'}
+    assert sdist.SHARE_ADAPT_CALLS >= 2
