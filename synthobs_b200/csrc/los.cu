@@ -152,15 +152,19 @@ __global__ void __launch_bounds__(kLosThreads) los_kernel(
                 const float q = fmaf(p.y, sx[u], fmaf(p.z, sy[u], fmaf(p.w, s2[u], p.x)));
                 m |= (q < 1.f ? 1 : 0) << (7 + u);
             }
-            if (m) {
-                if (n_mine == kLosList) {                             // full: work it off now (in list order, then on)
-                    for (int k = 0; k < kLosList; ++k) entry(mine[k]);
-                    n_mine = 0;
-                }
-                mine[n_mine++] = (unsigned short)(m | j);
+            if (m) mine[n_mine++] = (unsigned short)(m | j);
+            // a full list anywhere in the warp: ALL lanes work theirs off now, together (a lane-private flush would
+            // serialise the warp: with the cell grid a third of the tested pairs are candidates)
+            if (__any_sync(0xffffffffu, n_mine == kLosList)) {
+                for (int k = 0; k < kLosList; ++k)
+                    if (k < n_mine) entry(mine[k]);
+                n_mine = 0;
             }
         }
-        for (int k = 0; k < n_mine; ++k) entry(mine[k]);
+        for (int k = 0; k < kLosList; ++k) {
+            if (!__any_sync(0xffffffffu, k < n_mine)) break;
+            if (k < n_mine) entry(mine[k]);
+        }
 #pragma unroll
         for (int u = 0; u < kLosStars; ++u) total[u] += (double)acc[u];
     }

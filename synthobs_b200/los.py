@@ -83,11 +83,75 @@ def metal_surface_density_batch(xs, ys, zs, star_offsets, xg, yg, zg, gas_mass, 
     return out if on_device else dv.to_host(out)
 
 
-def metal_surface_density(xs, ys, zs, xg, yg, zg, gas_mass, gas_Z, gas_h, scale=1.0):
+GRID_MIN_PAIRS = 5.0e9        # star x gas pairs of one object from which the cell grid pays (building it costs ~2 ms =
+                              # what all pairs cost at ~4e9; measured on B200)
+GRID_CELL = 4.0               # cell edge in units of the median smoothing length (1e5 x 1e5, h = 0.05..1: kernel 2.3 / 2.3 /
+                              # 1.85 / 1.44 ms at 0.5 / 1 / 2 / 4: the widest kernels sit in every list whatever the cell)
+GRID_MAX_ENTRIES = 4.0e7      # (cell, gas) entries the grid may create (the gas arrays are gathered once per entry)
+
+
+def _cell_grid(xs, ys, xg, yg, hg, max_cells=512):
+    """Uniform grid over the stars' bounding box (cell edge ~ 2 median h): the stars sorted by cell and, for every cell
+    that holds stars, the list of the gas particles whose kernel footprint [x - h, x + h] x [y - h, y + h] meets it, in
+    gas order (stable sorts: deterministic).  A star can only lie under kernels of its cell's list, so every cell is one
+    independent 'object' of so_los_column.  Returns (star order, star offsets, gas index per entry, gas offsets), the
+    offsets as host arrays, or None when the entry budget is exceeded (the caller then takes all pairs)."""
+    x0, y0 = float(xs.min()), float(ys.min())
+    ext = max(float(xs.max()) - x0, float(ys.max()) - y0, 0.0)
+    cell = max(GRID_CELL * float(hg.median()), ext / max_cells, 1e-300)      # stars inside one kernel width: a single cell
+    for _ in range(6):
+        n = int(np.floor(ext / cell)) + 1
+        gx0, gx1 = torch.floor((xg - hg - x0) / cell).long(), torch.floor((xg + hg - x0) / cell).long()
+        gy0, gy1 = torch.floor((yg - hg - y0) / cell).long(), torch.floor((yg + hg - y0) / cell).long()
+        ok = (gx1 >= 0) & (gx0 <= n - 1) & (gy1 >= 0) & (gy0 <= n - 1)
+        gx0, gx1, gy0, gy1 = (t.clamp(0, n - 1) for t in (gx0, gx1, gy0, gy1))
+        nx = torch.where(ok, gx1 - gx0 + 1, torch.zeros_like(gx0))
+        cnt = nx * torch.where(ok, gy1 - gy0 + 1, torch.zeros_like(gy0))
+        total = int(cnt.sum())
+        if total <= GRID_MAX_ENTRIES:
+            break
+        cell *= 2.0
+    else:
+        return None
+    sc = ((xs - x0) / cell).long().clamp(0, n - 1) + n * ((ys - y0) / cell).long().clamp(0, n - 1)
+    order = torch.argsort(sc, stable=True)
+    cells, star_cnt = torch.unique_consecutive(sc[order], return_counts=True)
+    gi = torch.repeat_interleave(torch.arange(xg.numel(), device=xg.device), cnt)
+    k = torch.arange(total, device=xg.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+    nxe = nx[gi]
+    ce = (gx0[gi] + k % nxe) + n * (gy0[gi] + k // nxe)
+    has = torch.zeros(n * n, dtype=torch.bool, device=xg.device)
+    has[cells] = True
+    keep = has[ce]
+    gi, ce = gi[keep], ce[keep]
+    o2 = torch.argsort(ce, stable=True)
+    gi, ce = gi[o2], ce[o2]
+    gas_cnt = torch.bincount(torch.searchsorted(cells, ce), minlength=cells.numel())
+    so = np.concatenate([[0], np.cumsum(star_cnt.cpu().numpy())]).astype(np.int64)
+    go = np.concatenate([[0], np.cumsum(gas_cnt.cpu().numpy())]).astype(np.int64)
+    return order, so, gi, go
+
+
+def metal_surface_density(xs, ys, zs, xg, yg, zg, gas_mass, gas_Z, gas_h, scale=1.0, grid='auto'):
     """Sigma_i for the star particles (xs, ys, zs) of ONE object from its gas particles (positions, masses, metallicities,
     smoothing lengths = kernel support radii), line of sight along +z.  scale = 1: units of mass / length^2 of the inputs
-    (M_sol / kpc^2 for kpc and M_sol); 1e-6 gives M_sol / pc^2."""
+    (M_sol / kpc^2 for kpc and M_sol); 1e-6 gives M_sol / pc^2.
+    grid: True / False / 'auto' (from GRID_MIN_PAIRS star x gas pairs on): bin the gas into the cells of a uniform grid
+    over the stars and let every star test only the gas whose footprint meets its cell, instead of all of it.  Same
+    specification, same pair arithmetic; only the float64 summation order over the tiles differs (~1e-16)."""
     ns = int(np.asarray(xs.shape if hasattr(xs, 'shape') else (len(xs),))[0])
     ng = int(np.asarray(xg.shape if hasattr(xg, 'shape') else (len(xg),))[0])
+    use = (float(ns) * ng >= GRID_MIN_PAIRS) if grid == 'auto' else bool(grid)
+    if use and ns > 0 and ng > 0:
+        arrays = (xs, ys, zs, xg, yg, zg, gas_mass, gas_Z, gas_h)
+        on_device = any(dv.is_device_tensor(a) for a in arrays)
+        d = [dv.to_dev(a) for a in arrays]
+        plan = _cell_grid(d[0], d[1], d[3], d[4], d[8])
+        if plan is not None:
+            order, so, gi, go = plan
+            res = metal_surface_density_batch(d[0][order], d[1][order], d[2][order], so, *(a[gi] for a in d[3:]), go, scale=scale)
+            out = torch.empty_like(res)
+            out[order] = res
+            return out if on_device else dv.to_host(out)
     return metal_surface_density_batch(xs, ys, zs, np.array([0, ns]), xg, yg, zg, gas_mass, gas_Z, gas_h,
                                        np.array([0, ng]), scale=scale)

@@ -82,3 +82,19 @@ def test_los_batch_is_a_loop_over_objects():
         np.testing.assert_allclose(one, out[so[k]:so[k + 1]], rtol=1e-13, atol=0)
     with pytest.raises(ValueError):
         los.metal_surface_density_batch(*stars, so[:-1], *gas, m, Z, h, go, scale=1.0)
+
+
+def test_los_cell_grid_equals_all_pairs():
+    """grid=True bins the gas per cell of the stars' grid and runs every cell as one object of the same kernel: same
+    numbers as all pairs (float64 sum order over tiles differs) and as the specification"""
+    from synthobs_b200 import los
+    rng = np.random.default_rng(21)
+    stars, gas, m, Z, h = _galaxy(rng, 20000, 30000, centre=(40.0, -25.0, 3.0))
+    a = los.metal_surface_density(*stars, *gas, m, Z, h, scale=1e-6, grid=True)
+    b = los.metal_surface_density(*stars, *gas, m, Z, h, scale=1e-6, grid=False)
+    np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-9 * b.max())    # FP32 tile sums are cut differently
+    ref = lo.metal_surface_density(*stars[:, :2000], *gas, m, Z, h, scale=1e-6)
+    _close(a[:2000], ref)
+    # one star, and gas far larger than the stars' box
+    one = los.metal_surface_density(*stars[:, :1], *gas, m, Z, np.full(h.size, 3.0), grid=True)
+    _close(one, lo.metal_surface_density(*stars[:, :1], *gas, m, Z, np.full(h.size, 3.0)))

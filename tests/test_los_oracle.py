@@ -63,3 +63,32 @@ def test_product_table_is_the_specified_one():
     exec(compile(ast.Module([fn], []), 'los.py', 'exec'), ns)
     u = np.arange(lo.NT + 1) / float(lo.NT)
     assert np.max(np.abs(ns['_projected_spline'](u) - lo.projected_kernel(u))) < 1e-14
+
+
+def test_cell_grid_is_exact():
+    """the cell grid of synthobs_b200/los.py (torch ops; run here on CPU tensors): every star's cell list holds all the gas
+    whose kernel can cover it, so the oracle over the cells equals the oracle over all pairs (float64 sum order only)"""
+    import torch
+    src = open(os.path.join(ROOT, 'synthobs_b200', 'los.py')).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == '_cell_grid'][0]
+    ns_ = {'np': np, 'torch': torch, 'GRID_MAX_ENTRIES': 4.0e7, 'GRID_CELL': 4.0}
+    exec(compile(ast.Module([fn], []), 'los.py', 'exec'), ns_)
+    rng = np.random.default_rng(1)
+    for ns, ng, hlo in ((3000, 8000, -1.3), (500, 4000, -2.0), (1, 300, -0.5)):
+        xs, ys, zs = rng.normal(0, 1.5, (3, ns)) + np.array([[40.0], [-25.0], [3.0]])
+        xg, yg, zg = rng.normal(0, 2.0, (3, ng)) + np.array([[40.0], [-25.0], [3.0]])
+        m, Z, h = rng.uniform(0.5e6, 2e6, ng), 10 ** rng.uniform(-4, -1.7, ng), 10 ** rng.uniform(hlo, 0.0, ng)
+        T = torch.from_numpy
+        order, so, gi, go = ns_['_cell_grid'](T(xs), T(ys), T(xg), T(yg), T(h))
+        order, gi = order.numpy(), gi.numpy()
+        assert so[-1] == ns and go[-1] == gi.size and np.array_equal(np.sort(order), np.arange(ns))
+        o = lo.metal_surface_density_batch((xs[order], ys[order], zs[order]), so, (xg[gi], yg[gi], zg[gi], m[gi], Z[gi], h[gi]), go)
+        out = np.empty(ns)
+        out[order] = o
+        ref = lo.metal_surface_density(xs, ys, zs, xg, yg, zg, m, Z, h)
+        assert np.max(np.abs(out - ref)) <= 1e-13 * max(ref.max(), 1e-300)
+        if ns > 1:
+            assert np.sum(np.diff(so) * np.diff(go)) < 0.7 * ns * ng          # and it saves work
+    # entry budget exceeded -> None (the caller takes all pairs)
+    ns_['GRID_MAX_ENTRIES'] = 10.0
+    assert ns_['_cell_grid'](T(xs), T(ys), T(xg), T(yg), T(np.full(ng, 50.0))) is None
