@@ -421,7 +421,7 @@ def image_huge(X, Y, L, resolution, ndim, k, support_sigmas=None, stages=None, r
                         f = bal['frac'] * (t.mean() / t) ** 0.7
                         f = np.clip(f / f.sum(), 0.4 / ws, 2.5 / ws)
                         bal['frac'] = f / f.sum()
-                    else:
+                    elif bal['hist']:
                         # last measurement: freeze on the best fractions seen (the damped iteration may still be swinging)
                         bal['frac'] = min(bal['hist'], key=lambda h: h[0])[1]
             bounds = np.concatenate([[0.0], np.cumsum(bal['frac'])])
