@@ -744,7 +744,7 @@ def run_los(ctx):
     ffma = ctx.measured.get('fp32_ffma_tflops')
     rec = {'metric': 'star-gas pairs / s (line-of-sight metal column density)', 'unit': 'pairs/s',
            'value': ctx.world * pairs / (ms * 1e-3), 'ms_per_step': ms, 'stars_per_s': ctx.world * ns / (ms * 1e-3),
-           'pairs_tested_with_the_cell_grid': tested, 'cell_grid_objects': int(plan[1].size - 1) if plan is not None else None,
+           'pairs_tested_with_the_cell_grid': tested, 'cell_grid_cells_with_stars': int((np.diff(plan[1]) > 0).sum()) if plan is not None else None,
            'all_pairs': {'ms_per_step': ms_all, 'value': ctx.world * pairs / (ms_all * 1e-3)},
            'config': {'workload': '1 object per GPU: %d star x %d gas particles, smoothing lengths 0.05..1 (extent ~2); value = '
                                   'pairs of the specification (N_star x N_gas) per second, whatever subset the grid tests' % (ns, ng),

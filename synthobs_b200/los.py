@@ -91,14 +91,17 @@ GRID_MAX_ENTRIES = 4.0e7      # (cell, gas) entries the grid may create (the gas
 
 
 def _cell_grid(xs, ys, xg, yg, hg, max_cells=512):
-    """Uniform grid over the stars' bounding box (cell edge ~ 2 median h): the stars sorted by cell and, for every cell
-    that holds stars, the list of the gas particles whose kernel footprint [x - h, x + h] x [y - h, y + h] meets it, in
-    gas order (stable sorts: deterministic).  A star can only lie under kernels of its cell's list, so every cell is one
-    independent 'object' of so_los_column.  Returns (star order, star offsets, gas index per entry, gas offsets), the
-    offsets as host arrays, or None when the entry budget is exceeded (the caller then takes all pairs)."""
-    x0, y0 = float(xs.min()), float(ys.min())
-    ext = max(float(xs.max()) - x0, float(ys.max()) - y0, 0.0)
-    cell = max(GRID_CELL * float(hg.median()), ext / max_cells, 1e-300)      # stars inside one kernel width: a single cell
+    """Uniform grid over the stars' bounding box (cell edge ~ GRID_CELL median h): the stars sorted by cell and, for every
+    cell, the list of the gas particles whose kernel footprint [x - h, x + h] x [y - h, y + h] meets it, in gas order
+    (stable sorts: deterministic).  A star can only lie under kernels of its cell's list, so every cell is one independent
+    'object' of so_los_column (cells without stars cost nothing there).  Returns (star order, star offsets, gas index per
+    entry, gas offsets), the offsets over ALL n x n cells as host arrays, or None when the entry budget is exceeded (the
+    caller then takes all pairs).  Three host synchronisations: bounds, number of entries, offsets."""
+    dev = xs.device
+    b = torch.stack([xs.min(), ys.min(), xs.max(), ys.max(), hg.median()]).cpu().tolist()
+    x0, y0 = b[0], b[1]
+    ext = max(b[2] - x0, b[3] - y0, 0.0)
+    cell = max(GRID_CELL * b[4], ext / max_cells, 1e-300)      # stars inside one kernel width: a single cell
     for _ in range(6):
         n = int(np.floor(ext / cell)) + 1
         gx0, gx1 = torch.floor((xg - hg - x0) / cell).long(), torch.floor((xg + hg - x0) / cell).long()
@@ -113,23 +116,19 @@ def _cell_grid(xs, ys, xg, yg, hg, max_cells=512):
         cell *= 2.0
     else:
         return None
+    ncell = n * n
     sc = ((xs - x0) / cell).long().clamp(0, n - 1) + n * ((ys - y0) / cell).long().clamp(0, n - 1)
     order = torch.argsort(sc, stable=True)
-    cells, star_cnt = torch.unique_consecutive(sc[order], return_counts=True)
-    gi = torch.repeat_interleave(torch.arange(xg.numel(), device=xg.device), cnt)
-    k = torch.arange(total, device=xg.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+    star_cnt = torch.zeros(ncell, dtype=torch.int64, device=dev).index_add_(0, sc, torch.ones_like(sc))
+    gi = torch.repeat_interleave(torch.arange(xg.numel(), device=dev), cnt, output_size=total)
+    k = torch.arange(total, device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt, output_size=total)
     nxe = nx[gi]
     ce = (gx0[gi] + k % nxe) + n * (gy0[gi] + k // nxe)
-    has = torch.zeros(n * n, dtype=torch.bool, device=xg.device)
-    has[cells] = True
-    keep = has[ce]
-    gi, ce = gi[keep], ce[keep]
-    o2 = torch.argsort(ce, stable=True)
-    gi, ce = gi[o2], ce[o2]
-    gas_cnt = torch.bincount(torch.searchsorted(cells, ce), minlength=cells.numel())
-    so = np.concatenate([[0], np.cumsum(star_cnt.cpu().numpy())]).astype(np.int64)
-    go = np.concatenate([[0], np.cumsum(gas_cnt.cpu().numpy())]).astype(np.int64)
-    return order, so, gi, go
+    gi = gi[torch.argsort(ce, stable=True)]
+    gas_cnt = torch.zeros(ncell, dtype=torch.int64, device=dev).index_add_(0, ce, torch.ones_like(ce))
+    zero = torch.zeros(1, dtype=torch.int64, device=dev)
+    off = torch.cat([zero, torch.cumsum(star_cnt, 0), zero, torch.cumsum(gas_cnt, 0)]).cpu().numpy()
+    return order, np.ascontiguousarray(off[:ncell + 1]), gi, np.ascontiguousarray(off[ncell + 1:])
 
 
 def metal_surface_density(xs, ys, zs, xg, yg, zg, gas_mass, gas_Z, gas_h, scale=1.0, grid='auto'):
